@@ -1,0 +1,169 @@
+/*
+ * tt_b200.h -- C ABI of the B200-native two-tower DSSM hot path.
+ *
+ * The reference (juankim834/RecommendSystemProject) has no FFI or operator
+ * registry: its hot path is Python calling ATen ops.  Each entry point below
+ * replaces one group of those ATen call sites (reference file:line given per
+ * function) and is what a
+ * ctypes / torch custom-op binding on the reference side would load (see
+ * INTEGRATION.md).
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless a name ends in _host;
+ *  - every function enqueues work on `stream` (a cudaStream_t passed as
+ *    void*) and returns without synchronising; scalars that would force a
+ *    host sync (unique-row counts, loss, clip coefficient, NaN flags, Adam
+ *    step) live in device memory;
+ *  - return value: 0 on success, a positive cudaError_t value for CUDA
+ *    failures, a negative TT_E_* code for argument errors; no exception ever
+ *    crosses the ABI; tt_last_error() returns a thread-local message;
+ *  - caller allocates outputs and workspaces (size queries provided);
+ *  - matrices are row-major, ids are int64 at the boundary;
+ *  - no global state besides cached function attributes.
+ */
+#ifndef TT_B200_H
+#define TT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TT_API __attribute__((visibility("default")))
+#else
+#define TT_API
+#endif
+
+#define TT_E_BADARG (-1)      /* null pointer / non-positive size / bad enum      */
+#define TT_E_UNSUPPORTED (-2) /* shape outside what the kernels implement         */
+#define TT_E_WORKSPACE (-3)   /* workspace smaller than the size query returned    */
+#define TT_E_DEVICE (-4)      /* not an sm_100 device                             */
+
+/* pooling modes (GenericTower.py:155-160, SequenceFeatureProcessor.py:64-68) */
+#define TT_POOL_NONE 0 /* L must be 1: plain row gather                           */
+#define TT_POOL_SUM 1
+#define TT_POOL_MEAN 2 /* divides by L (pads included), as the reference does     */
+#define TT_POOL_MAX 3
+
+/* element types of embedding tables / activations */
+#define TT_F32 0
+#define TT_BF16 1
+
+TT_API int tt_abi_version(void);
+TT_API const char *tt_last_error(void);
+/* sm count, compute capability; returns TT_E_DEVICE when the current device is not cc 10.x */
+TT_API int tt_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
+
+/* ------------------------------------------------------------------------
+ * 1. Embedding gather + pooling forward.
+ * Replaces aten::embedding (+ mean/sum/max over dim 1) at
+ * GenericTower.py:153-160,182 and SequenceFeatureProcessor.py:60-68.
+ *   out[b, :] = pool_{l<L} table[ids[b, l], :]      (never materialises [B,L,D])
+ * Padding positions (ids == padding_idx) contribute table[padding_idx] like
+ * any other id (the reference pools over all L positions); the kernel counts
+ * them and adds the pad row once.  padding_idx < 0: no id is special.
+ * out rows are `out_stride` floats apart so a feature can be written straight
+ * into its column slice of the tower's concat buffer.
+ * argmax (int32 [B, D], TT_POOL_MAX only, may be NULL): position l of the max.
+ * ---------------------------------------------------------------------- */
+TT_API int tt_emb_gather_pool_fwd(const void *table, int table_dtype, int64_t vocab, int dim,
+                           const int64_t *ids, int64_t n_rows, int len, int mode, int64_t padding_idx,
+                           float *out, int64_t out_stride, int32_t *argmax, int *oob_flag, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 2. Sparse embedding gradient: deterministic sorted-segment scatter-add and
+ *    the fused row-wise optimizer.
+ * Replaces embedding_dense_backward (autograd of the call sites above,
+ * training_utils.py:51) and, for tables, clip_grad_norm_ + Adam.step
+ * (training_utils.py:53-56, train_twotower.py:111).
+ *
+ * tt_emb_segment_grad: positions p = b*len + l, id = ids[p]; source gradient
+ * row = grad_out[b] (pooled modes; scaled 1/len for MEAN; routed by argmax
+ * for MAX) or grad_out[p] (len == 1).  Positions with id == padding_idx are
+ * dropped (nn.Embedding padding_idx semantics).  Outputs, all device:
+ *   unique_rows[U] ascending, row_grad[U, dim] fp32, *n_unique = U,
+ *   *sq_norm += sum(row_grad^2)   (fixed-order reduction, deterministic).
+ * The dense [V, D] gradient is never formed.
+ * ---------------------------------------------------------------------- */
+TT_API int tt_emb_segment_grad_workspace(int64_t n_pos, int dim, size_t *bytes_host);
+TT_API int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, int mode, int64_t padding_idx,
+                        int64_t vocab, const float *grad_out, int64_t grad_stride, const int32_t *argmax,
+                        int dim, int64_t *unique_rows, float *row_grad, int32_t *n_unique, float *sq_norm,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* Adam on the touched rows only ("lazy" Adam; equals dense Adam the first
+ * time a row is touched).  g = row_grad * (*clip_coef) (NULL -> 1).  The step
+ * count t is read from *step_dev (so CUDA graphs can replay). */
+TT_API int tt_emb_rowwise_adam(void *table, int table_dtype, float *exp_avg, float *exp_avg_sq, int dim,
+                        const int64_t *unique_rows, const float *row_grad, const int32_t *n_unique,
+                        int64_t max_rows, const float *clip_coef, float lr, float beta1, float beta2, float eps,
+                        const int64_t *step_dev, void *stream);
+
+/* dense[rows[u], :] += row_grad[u, :]  -- builds the dense .grad the drop-in
+ * modules expose to an unmodified torch.optim.Adam. */
+TT_API int tt_emb_scatter_rows(float *dense, int dim, const int64_t *unique_rows, const float *row_grad,
+                        const int32_t *n_unique, int64_t max_rows, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Dense-parameter side of clip_grad_norm_ + Adam (training_utils.py:53-56).
+ * ---------------------------------------------------------------------- */
+/* *out += sum(x[i]^2), fixed-order two-level reduction */
+TT_API int tt_sq_norm_accum(const float *x, int64_t n, float *out, void *workspace, size_t workspace_bytes, void *stream);
+/* *coef = min(1, max_norm / (sqrt(sum_k sq_terms[k]) + 1e-6)); also *total_norm if not NULL */
+TT_API int tt_clip_coef(const float *sq_terms, int n_terms, float max_norm, float *coef, float *total_norm, void *stream);
+/* flat dense Adam over n contiguous floats, g scaled by *clip_coef */
+TT_API int tt_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                 const float *clip_coef, float lr, float beta1, float beta2, float eps,
+                 const int64_t *step_dev, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 3. Fused in-batch (+ hard-negative) softmax cross-entropy.
+ * Replaces mm/div/eq/masked_fill/bmm/cat/log_softmax/nll_loss at
+ * TwoTowerModel.py:95-140 and their autograd.  The B x (B+H) logit matrix is
+ * never written to HBM.
+ *   Z = [ mask(U I^T * inv_T) , <U, HN_row> * inv_T , U Pool^T * inv_T ]
+ *   loss = mean_b( logsumexp(Z_b) - Z_bb )
+ * item_ids (nullable): in-batch logits with item_ids[b]==item_ids[j], b!=j
+ * are set to -1e9 after scaling.  hn_rows [B,N,D] is the reference's per-row
+ * form; pool [H,D] is the shared-pool form (== hn_rows = pool expanded).
+ * nan_flags bits: 1 user, 2 item, 4 hard negative (device int, OR-ed).
+ * fp32 variant: exact SIMT path.  bf16 variant: tcgen05/TMA tensor-core path
+ * (requires D == 64 or 128 and 16-byte aligned rows).
+ * ---------------------------------------------------------------------- */
+TT_API int tt_ce_workspace(int64_t batch, int64_t pool, int n_rowneg, int dim, size_t *bytes_host);
+TT_API int tt_ce_fwd_f32(const float *user, const float *item, const int64_t *item_ids, const float *hn_rows,
+                  int n_rowneg, const float *pool, int64_t pool_rows, int64_t batch, int dim, float inv_temp,
+                  float *loss, float *row_lse, float *row_pos, int *nan_flags, void *workspace,
+                  size_t workspace_bytes, void *stream);
+TT_API int tt_ce_bwd_f32(const float *user, const float *item, const int64_t *item_ids, const float *hn_rows,
+                  int n_rowneg, const float *pool, int64_t pool_rows, int64_t batch, int dim, float inv_temp,
+                  const float *row_lse, const float *grad_loss, float *d_user, float *d_item, float *d_hn_rows,
+                  float *d_pool, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 4. Corpus scoring + top-K for retrieval evaluation.
+ * Replaces matmul + per-user -inf masking + topk at training_utils.py:220-258.
+ * Scores are never written to HBM.  Selection is two-stage: an fp32 scoring
+ * pass keeps the best K+margin candidates per query, which are re-scored in
+ * fp64 and ordered by (score descending, corpus row ascending) -- the stated
+ * tie-break.  out_idx = local corpus row + row_offset.  mask_offsets/mask_rows
+ * (nullable): CSR list of LOCAL corpus rows excluded per query (history mask).
+ * ---------------------------------------------------------------------- */
+TT_API int tt_score_topk_workspace(int64_t n_query, int64_t n_corpus, int dim, int k, size_t *bytes_host);
+TT_API int tt_score_topk_f32(const float *query, int64_t n_query, const float *corpus, int64_t n_corpus, int dim, int k,
+                      int64_t row_offset, const int64_t *mask_offsets, const int64_t *mask_rows,
+                      double *out_scores, int64_t *out_idx, void *workspace, size_t workspace_bytes,
+                      void *stream);
+/* merge W per-shard lists [W, n_query, k] into the global top-k with the same tie-break */
+TT_API int tt_topk_merge(const double *scores, const int64_t *idx, int n_shards, int64_t n_query, int k,
+                  double *out_scores, int64_t *out_idx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H */

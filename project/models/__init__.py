@@ -1,0 +1,1 @@
+"""Import-path shim: the reference's `project.*` module paths, served by recommendsystemproject_b200."""

@@ -1,0 +1,8 @@
+"""B200-native two-tower DSSM hot path (sm_100a CUDA kernels behind the
+reference's YAML-driven model classes).  No CPU fallback."""
+from . import _lib  # noqa: F401
+from .modules import GenericTower, MLP_Tower, SequenceEncoder, SequenceFeatureProcessor, TwoTowerModel
+from .optim import FusedTwoTowerOptimizer, GraphedTrainStep
+
+__all__ = ["GenericTower", "MLP_Tower", "SequenceEncoder", "SequenceFeatureProcessor", "TwoTowerModel",
+           "FusedTwoTowerOptimizer", "GraphedTrainStep"]

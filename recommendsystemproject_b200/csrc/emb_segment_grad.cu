@@ -1,0 +1,558 @@
+// Sparse embedding gradient: deterministic sorted-segment scatter-add, plus
+// the fused row-wise Adam (kernel 2 of the hot path).
+//
+// Replaces embedding_dense_backward (autograd of GenericTower.py:153-160,182,
+// SequenceFeatureProcessor.py:60-68; training_utils.py:51) and, for the
+// tables, clip_grad_norm_ + Adam.step (training_utils.py:53-56,
+// train_twotower.py:111).  The dense [V, D] gradient is never formed.
+//
+// Pipeline (all on one stream, no host sync; U lives in device memory):
+//   keys   : key[p] = id (pad -> V so it sorts last), val[p] = p
+//   sort   : stable LSD radix sort over ceil(log2(V+1)) bits (cub::DeviceRadixSort)
+//   heads  : head[i] = key[i] != key[i-1]; exclusive scan -> segment index
+//   chunks : segments longer than CHUNK positions are cut into CHUNK-sized
+//            pieces reduced by separate warps (heavy hitters under Zipf ids)
+//   reduce : LPR lanes per segment, 16-byte loads of grad_out rows, fp32
+//            accumulation in sorted (= ascending position) order -> bitwise
+//            reproducible; one row_grad[U, D] write; per-segment sum of squares
+//   norm   : fixed-order tree over the per-segment squares
+//   adam   : one pass over the U touched rows of table / exp_avg / exp_avg_sq
+// HBM-bound: algorithmic bytes = n_pos*(8 + D*4) + U*D*4 (segment grad) and
+// U*D*(4 + 3*4 + 3*4) (row-wise Adam, fp32 state).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace tt {
+
+constexpr int SEG_CHUNK = 128;
+
+__global__ void seg_build_keys(const int64_t *__restrict__ ids, int64_t n, int64_t pad, int64_t vocab,
+                               uint32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n;
+         p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t id = ids[p];
+        const bool drop = (id == pad) || id < 0 || id >= vocab;
+        keys[p] = drop ? static_cast<uint32_t>(vocab) : static_cast<uint32_t>(id);
+        vals[p] = static_cast<int32_t>(p);
+    }
+}
+
+__global__ void seg_heads(const uint32_t *__restrict__ keys, int64_t n, uint32_t sentinel,
+                          int32_t *__restrict__ head) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t k = keys[i];
+        head[i] = (k != sentinel && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+    }
+}
+
+// seg_start[s], unique_rows[s]; counters[0] = U, counters[1] = n_valid
+__global__ void seg_starts(const uint32_t *__restrict__ keys, const int32_t *__restrict__ head,
+                           const int32_t *__restrict__ seg_id, int64_t n, uint32_t sentinel,
+                           int32_t *__restrict__ seg_start, int64_t *__restrict__ unique_rows,
+                           int32_t *__restrict__ counters) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t k = keys[i];
+        if (head[i]) {
+            seg_start[seg_id[i]] = static_cast<int32_t>(i);
+            unique_rows[seg_id[i]] = static_cast<int64_t>(k);
+        }
+        if (k == sentinel && (i == 0 || keys[i - 1] != sentinel)) counters[1] = static_cast<int32_t>(i);
+        if (i == n - 1) {
+            counters[0] = seg_id[i] + head[i];
+            if (k != sentinel) counters[1] = static_cast<int32_t>(n);
+        }
+    }
+}
+
+// number of CHUNK pieces of each long segment (0 for short ones); also closes seg_start[U] = n_valid
+__global__ void seg_chunk_counts(int32_t *__restrict__ seg_start, const int32_t *__restrict__ counters,
+                                 int64_t n, int32_t *__restrict__ n_chunks) {
+    const int32_t U = counters[0];
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < n;
+         s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int32_t c = 0;
+        if (s < U) {
+            const int32_t end = (s + 1 < U) ? seg_start[s + 1] : counters[1];
+            const int32_t len = end - seg_start[s];
+            if (len > SEG_CHUNK) c = (len + SEG_CHUNK - 1) / SEG_CHUNK;
+        }
+        n_chunks[s] = c;
+    }
+}
+
+struct GradSrc {
+    const float *grad_out;
+    int64_t grad_stride;
+    const int32_t *argmax;
+    int len;
+    int mode;
+    int dim;
+};
+
+// accumulate positions [p0, p1) of the sorted order into acc (LPR lanes per row, 4 floats per lane)
+template <int LPR>
+__device__ __forceinline__ void seg_accumulate(const GradSrc &g, const int32_t *__restrict__ sorted_pos, int p0,
+                                               int p1, int c, bool col_ok, float (&acc)[4]) {
+    constexpr int UNROLL = 4;
+    for (int i = p0; i < p1; i += UNROLL) {
+        float4 v[UNROLL];
+        int slot[UNROLL];
+        bool use[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            use[u] = (i + u) < p1 && col_ok;
+            slot[u] = 0;
+            if (use[u]) {
+                const int32_t p = __ldg(sorted_pos + i + u);
+                int64_t src = p;
+                if (g.len > 1) { src = p / g.len; slot[u] = p - static_cast<int32_t>(src) * g.len; }
+                v[u] = __ldg(reinterpret_cast<const float4 *>(g.grad_out + src * g.grad_stride + c * 4));
+                if (g.mode == TT_POOL_MAX) {
+                    const int4 am = __ldg(reinterpret_cast<const int4 *>(g.argmax + src * g.dim + c * 4));
+                    if (am.x != slot[u]) v[u].x = 0.f;
+                    if (am.y != slot[u]) v[u].y = 0.f;
+                    if (am.z != slot[u]) v[u].z = 0.f;
+                    if (am.w != slot[u]) v[u].w = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (use[u]) { acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w; }
+        }
+    }
+}
+
+// one LPR-lane group per CHUNK piece of a long segment -> partial[c, D]
+template <int LPR>
+__global__ void __launch_bounds__(256)
+seg_reduce_chunks(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
+                  const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
+                  int32_t total_chunks_idx, float *__restrict__ partial) {
+    const int U = counters[0];
+    if (U == 0) return;
+    const int n_valid = counters[1];
+    const int total = chunk_base[U - 1] + 0;  // exclusive scan value at U-1 ...
+    (void)total_chunks_idx;
+    const int vpr = g.dim / 4;
+    const int sub = threadIdx.x % LPR;
+    const int64_t group0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+    const int64_t n_groups = static_cast<int64_t>(gridDim.x) * blockDim.x / LPR;
+    // total chunks = chunk_base[U-1] + chunks of the last segment
+    const int last_end = n_valid;
+    const int last_len = last_end - seg_start[U - 1];
+    const int n_total = total + (last_len > SEG_CHUNK ? (last_len + SEG_CHUNK - 1) / SEG_CHUNK : 0);
+    for (int64_t ck = group0; ck < n_total; ck += n_groups) {
+        // upper_bound(chunk_base, ck) - 1 over segments [0, U)
+        int lo = 0, hi = U;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (chunk_base[mid] <= ck) lo = mid; else hi = mid;
+        }
+        // skip zero-chunk segments that share the same base: lo is the LAST segment with base <= ck,
+        // and only a long segment advances the base, so lo is the owner.
+        const int s = lo;
+        const int send = (s + 1 < U) ? seg_start[s + 1] : n_valid;
+        const int p0 = seg_start[s] + static_cast<int>(ck - chunk_base[s]) * SEG_CHUNK;
+        const int p1 = min(p0 + SEG_CHUNK, send);
+        for (int c0 = 0; c0 < vpr; c0 += LPR) {
+            const int c = c0 + sub;
+            const bool col_ok = c < vpr;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            seg_accumulate<LPR>(g, sorted_pos, p0, p1, c, col_ok, acc);
+            if (col_ok)
+                *reinterpret_cast<float4 *>(partial + ck * g.dim + c * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+    }
+}
+
+// one LPR-lane group per segment -> row_grad[s, D], sq[s]
+template <int LPR>
+__global__ void __launch_bounds__(256)
+seg_reduce_rows(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
+                const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
+                const float *__restrict__ partial, float scale, float *__restrict__ row_grad,
+                float *__restrict__ seg_sq) {
+    const int U = counters[0];
+    const int n_valid = counters[1];
+    const int vpr = g.dim / 4;
+    const int sub = threadIdx.x % LPR;
+    const int lane = threadIdx.x & 31;
+    const int grp_in_warp = lane / LPR;
+    const int groups_per_block = blockDim.x / LPR;
+    const int64_t warp_first = static_cast<int64_t>(blockIdx.x) * groups_per_block + threadIdx.x / LPR - grp_in_warp;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * groups_per_block;
+    for (int64_t base = warp_first; base < U; base += stride) {
+        const int64_t s = base + grp_in_warp;
+        const bool ok = s < U;
+        float sq = 0.f;
+        if (ok) {
+            const int p0 = seg_start[s];
+            const int p1 = (s + 1 < U) ? seg_start[s + 1] : n_valid;
+            const int len = p1 - p0;
+            for (int c0 = 0; c0 < vpr; c0 += LPR) {
+                const int c = c0 + sub;
+                const bool col_ok = c < vpr;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                if (len <= SEG_CHUNK) {
+                    seg_accumulate<LPR>(g, sorted_pos, p0, p1, c, col_ok, acc);
+                } else if (col_ok) {
+                    const int nck = (len + SEG_CHUNK - 1) / SEG_CHUNK;
+                    const int64_t cb = chunk_base[s];
+                    for (int k = 0; k < nck; ++k) {
+                        const float4 v = *reinterpret_cast<const float4 *>(partial + (cb + k) * g.dim + c * 4);
+                        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+                    }
+                }
+                if (col_ok) {
+                    acc[0] *= scale; acc[1] *= scale; acc[2] *= scale; acc[3] *= scale;
+                    *reinterpret_cast<float4 *>(row_grad + s * g.dim + c * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    sq += acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] + acc[3] * acc[3];
+                }
+            }
+        }
+        // fixed-order reduction over the LPR lanes of the group
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (ok && sub == 0) seg_sq[s] = sq;
+    }
+}
+
+// generic-D fallback (D % 4 != 0 or unaligned grad rows): one thread per (segment, d)
+__global__ void seg_reduce_rows_scalar(GradSrc g, const int32_t *__restrict__ sorted_pos,
+                                       const int32_t *__restrict__ seg_start, const int32_t *__restrict__ counters,
+                                       float scale, float *__restrict__ row_grad) {
+    const int U = counters[0];
+    const int n_valid = counters[1];
+    const int64_t total = static_cast<int64_t>(U) * g.dim;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int s = static_cast<int>(t / g.dim);
+        const int d = static_cast<int>(t % g.dim);
+        const int p1 = (s + 1 < U) ? seg_start[s + 1] : n_valid;
+        float acc = 0.f;
+        for (int i = seg_start[s]; i < p1; ++i) {
+            const int32_t p = sorted_pos[i];
+            int64_t src = p;
+            int slot = 0;
+            if (g.len > 1) { src = p / g.len; slot = p - static_cast<int32_t>(src) * g.len; }
+            float v = g.grad_out[src * g.grad_stride + d];
+            if (g.mode == TT_POOL_MAX && g.argmax[src * g.dim + d] != slot) v = 0.f;
+            acc += v;
+        }
+        row_grad[t] = acc * scale;
+    }
+}
+
+__global__ void seg_sq_scalar(const float *__restrict__ row_grad, const int32_t *__restrict__ counters, int dim,
+                              float *__restrict__ seg_sq) {
+    const int U = counters[0];
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < U;
+         s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float sq = 0.f;
+        for (int d = 0; d < dim; ++d) { const float v = row_grad[s * dim + d]; sq += v * v; }
+        seg_sq[s] = sq;
+    }
+}
+
+// *out += sum(x[0..n)) with n read from device; single block, fixed order
+__global__ void __launch_bounds__(1024)
+sum_fixed_order(const float *__restrict__ x, const int32_t *__restrict__ n_dev, int64_t n_host,
+                float *__restrict__ out, int32_t *__restrict__ n_unique_out) {
+    __shared__ float sh[1024];
+    const int64_t n = n_dev ? static_cast<int64_t>(*n_dev) : n_host;
+    float acc = 0.f;
+    // strided ownership with a fixed block size -> the summation order depends only on n
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += x[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *out += sh[0];
+        if (n_unique_out) *n_unique_out = static_cast<int32_t>(n);
+    }
+}
+
+static inline unsigned grid_for(int64_t n, int threads) {
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<unsigned>(b);
+}
+
+struct SegPlan {
+    size_t cub_sort, cub_scan, cub_bytes;
+    int64_t max_chunks;
+};
+
+static SegPlan seg_plan(int64_t n) {
+    SegPlan p{};
+    cub::DeviceRadixSort::SortPairs(nullptr, p.cub_sort, static_cast<uint32_t *>(nullptr),
+                                    static_cast<uint32_t *>(nullptr), static_cast<int32_t *>(nullptr),
+                                    static_cast<int32_t *>(nullptr), static_cast<int>(n), 0, 32);
+    cub::DeviceScan::ExclusiveSum(nullptr, p.cub_scan, static_cast<int32_t *>(nullptr),
+                                  static_cast<int32_t *>(nullptr), static_cast<int>(n));
+    p.cub_bytes = p.cub_sort > p.cub_scan ? p.cub_sort : p.cub_scan;
+    p.max_chunks = 2 * (n / SEG_CHUNK) + 2;  // each long segment wastes at most one partial chunk
+    return p;
+}
+
+template <int LPR>
+static int launch_reduce(const GradSrc &g, const int32_t *sorted_pos, const int32_t *seg_start,
+                         const int32_t *chunk_base, const int32_t *counters, float *partial, int64_t max_chunks,
+                         float scale, float *row_grad, float *seg_sq, int64_t n, cudaStream_t st) {
+    const int threads = 256;
+    const int gpb = threads / LPR;
+    if (n > SEG_CHUNK) {
+        seg_reduce_chunks<LPR><<<grid_for(max_chunks * LPR, threads), threads, 0, st>>>(
+            g, sorted_pos, seg_start, chunk_base, counters, 0, partial);
+        TT_LAUNCH_CHECK("seg_reduce_chunks");
+    }
+    int64_t blocks = (n + gpb - 1) / gpb;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    seg_reduce_rows<LPR><<<static_cast<unsigned>(blocks), threads, 0, st>>>(g, sorted_pos, seg_start, chunk_base,
+                                                                           counters, partial, scale, row_grad, seg_sq);
+    TT_LAUNCH_CHECK("seg_reduce_rows");
+    return 0;
+}
+
+}  // namespace tt
+
+extern "C" int tt_emb_segment_grad_workspace(int64_t n_pos, int dim, size_t *bytes_host) {
+    TT_CHECK_ARG(bytes_host && n_pos > 0 && dim > 0, "bad size");
+    TT_CHECK_ARG(n_pos < (int64_t(1) << 31) - 2, "more than 2^31 positions per call");
+    const tt::SegPlan p = tt::seg_plan(n_pos);
+    size_t b = 0;
+    auto add = [&](size_t x) { b = tt::align_up(b, 256) + x; };
+    add(sizeof(uint32_t) * n_pos);      // keys in
+    add(sizeof(uint32_t) * n_pos);      // keys out
+    add(sizeof(int32_t) * n_pos);       // vals in
+    add(sizeof(int32_t) * n_pos);       // vals out (sorted positions)
+    add(sizeof(int32_t) * n_pos);       // head flags / chunk counts
+    add(sizeof(int32_t) * n_pos);       // seg ids / chunk bases
+    add(sizeof(int32_t) * (n_pos + 1)); // seg starts
+    add(sizeof(float) * n_pos);         // per-segment squares
+    add(sizeof(int32_t) * 4);           // counters
+    add(sizeof(float) * p.max_chunks * dim);
+    add(p.cub_bytes);
+    *bytes_host = tt::align_up(b, 256) + 256;
+    return 0;
+}
+
+extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, int mode, int64_t padding_idx,
+                                   int64_t vocab, const float *grad_out, int64_t grad_stride, const int32_t *argmax,
+                                   int dim, int64_t *unique_rows, float *row_grad, int32_t *n_unique,
+                                   float *sq_norm, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(ids && grad_out && unique_rows && row_grad && n_unique && workspace, "null pointer");
+    TT_CHECK_ARG(n_rows > 0 && len > 0 && dim > 0 && vocab > 0, "non-positive size");
+    TT_CHECK_ARG(mode >= TT_POOL_NONE && mode <= TT_POOL_MAX, "unknown pooling mode");
+    TT_CHECK_ARG(mode != TT_POOL_MAX || argmax, "TT_POOL_MAX needs argmax");
+    TT_CHECK_ARG(mode != TT_POOL_NONE || len == 1, "TT_POOL_NONE needs len == 1");
+    TT_CHECK_ARG(vocab < (int64_t(1) << 31) - 1, "vocab must fit 31 bits");
+    const int64_t n = n_rows * len;
+    TT_CHECK_ARG(n < (int64_t(1) << 31) - 2, "more than 2^31 positions per call");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const SegPlan plan = seg_plan(n);
+
+    Workspace ws(workspace, workspace_bytes);
+    uint32_t *keys_in = ws.take<uint32_t>(n);
+    uint32_t *keys_out = ws.take<uint32_t>(n);
+    int32_t *vals_in = ws.take<int32_t>(n);
+    int32_t *vals_out = ws.take<int32_t>(n);
+    int32_t *head = ws.take<int32_t>(n);
+    int32_t *seg_id = ws.take<int32_t>(n);
+    int32_t *seg_start = ws.take<int32_t>(n + 1);
+    float *seg_sq = ws.take<float>(n);
+    int32_t *counters = ws.take<int32_t>(4);
+    float *partial = ws.take<float>(plan.max_chunks * dim);
+    void *cub_tmp = ws.take<char>(plan.cub_bytes);
+    if (!ws.ok()) { set_error("segment_grad workspace too small: need %zu have %zu", ws.off, workspace_bytes); return TT_E_WORKSPACE; }
+
+    const int threads = 256;
+    const unsigned g1 = grid_for(n, threads);
+    seg_build_keys<<<g1, threads, 0, st>>>(ids, n, padding_idx, vocab, keys_in, vals_in);
+    TT_LAUNCH_CHECK("seg_build_keys");
+    int end_bit = 1;
+    while ((int64_t(1) << end_bit) <= vocab) ++end_bit;  // keys are in [0, vocab]
+    size_t tmp = plan.cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, keys_in, keys_out, vals_in, vals_out,
+                                                    static_cast<int>(n), 0, end_bit, st);
+    if (e != cudaSuccess) return cuda_status(e, "cub SortPairs");
+    const uint32_t sentinel = static_cast<uint32_t>(vocab);
+    seg_heads<<<g1, threads, 0, st>>>(keys_out, n, sentinel, head);
+    TT_LAUNCH_CHECK("seg_heads");
+    tmp = plan.cub_bytes;
+    e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, head, seg_id, static_cast<int>(n), st);
+    if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum");
+    seg_starts<<<g1, threads, 0, st>>>(keys_out, head, seg_id, n, sentinel, seg_start, unique_rows, counters);
+    TT_LAUNCH_CHECK("seg_starts");
+    // reuse head -> chunk counts, seg_id -> chunk bases
+    int32_t *n_chunks = head;
+    int32_t *chunk_base = seg_id;
+    seg_chunk_counts<<<g1, threads, 0, st>>>(seg_start, counters, n, n_chunks);
+    TT_LAUNCH_CHECK("seg_chunk_counts");
+    tmp = plan.cub_bytes;
+    e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, n_chunks, chunk_base, static_cast<int>(n), st);
+    if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum(chunks)");
+
+    GradSrc g{grad_out, grad_stride, argmax, len, mode, dim};
+    const float scale = (mode == TT_POOL_MEAN) ? 1.0f / static_cast<float>(len) : 1.0f;
+    const bool vec = (dim % 4 == 0) && (grad_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(grad_out) % 16 == 0) &&
+                     (reinterpret_cast<uintptr_t>(row_grad) % 16 == 0);
+    int rc = 0;
+    if (!vec) {
+        seg_reduce_rows_scalar<<<grid_for(n * dim, threads), threads, 0, st>>>(g, vals_out, seg_start, counters, scale,
+                                                                                row_grad);
+        TT_LAUNCH_CHECK("seg_reduce_rows_scalar");
+        seg_sq_scalar<<<g1, threads, 0, st>>>(row_grad, counters, dim, seg_sq);
+        TT_LAUNCH_CHECK("seg_sq_scalar");
+    } else {
+        const int vpr = dim / 4;
+        if (vpr <= 1) rc = launch_reduce<1>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
+        else if (vpr <= 2) rc = launch_reduce<2>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
+        else if (vpr <= 4) rc = launch_reduce<4>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
+        else if (vpr <= 8) rc = launch_reduce<8>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
+        else if (vpr <= 16) rc = launch_reduce<16>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
+        else rc = launch_reduce<32>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
+        if (rc) return rc;
+    }
+    // *sq_norm += sum(seg_sq[0..U)), *n_unique = U
+    float *sq_target = sq_norm ? sq_norm : seg_sq + (n - 1);  // dummy target when the caller does not want the norm
+    sum_fixed_order<<<1, 1024, 0, st>>>(seg_sq, counters, 0, sq_target, n_unique);
+    TT_LAUNCH_CHECK("sum_fixed_order");
+    return 0;
+}
+
+namespace tt {
+
+template <typename T, int LPR>
+__global__ void __launch_bounds__(256)
+rowwise_adam_kernel(T *__restrict__ table, float *__restrict__ m, float *__restrict__ v, int dim,
+                    const int64_t *__restrict__ rows, const float *__restrict__ row_grad,
+                    const int32_t *__restrict__ n_unique, const float *__restrict__ clip_coef, float lr, float beta1,
+                    float beta2, float eps, const int64_t *__restrict__ step_dev) {
+    const int U = *n_unique;
+    const float coef = clip_coef ? *clip_coef : 1.0f;
+    const double t = static_cast<double>(*step_dev);
+    const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
+    const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+    const float step_size = lr / bc1;
+    const int vpr = dim / 4;
+    const int sub = threadIdx.x % LPR;
+    const int64_t g0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+    const int64_t ng = static_cast<int64_t>(gridDim.x) * blockDim.x / LPR;
+    for (int64_t s = g0; s < U; s += ng) {
+        const int64_t r = rows[s];
+        for (int c = sub; c < vpr; c += LPR) {
+            const float4 g4 = *reinterpret_cast<const float4 *>(row_grad + s * dim + c * 4);
+            float4 m4 = *reinterpret_cast<float4 *>(m + r * dim + c * 4);
+            float4 v4 = *reinterpret_cast<float4 *>(v + r * dim + c * 4);
+            float p[4];
+            if (sizeof(T) == 4) {
+                const float4 p4 = *reinterpret_cast<const float4 *>(reinterpret_cast<float *>(table) + r * dim + c * 4);
+                p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w;
+            } else {
+                const uint2 raw = *reinterpret_cast<const uint2 *>(reinterpret_cast<__nv_bfloat16 *>(table) + r * dim + c * 4);
+                p[0] = __uint_as_float(raw.x << 16); p[1] = __uint_as_float(raw.x & 0xffff0000u);
+                p[2] = __uint_as_float(raw.y << 16); p[3] = __uint_as_float(raw.y & 0xffff0000u);
+            }
+            const float gg[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
+            float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+            float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                mm[e] = beta1 * mm[e] + (1.0f - beta1) * gg[e];
+                vv[e] = beta2 * vv[e] + (1.0f - beta2) * gg[e] * gg[e];
+                const float denom = sqrtf(vv[e]) / bc2_sqrt + eps;
+                p[e] -= step_size * (mm[e] / denom);
+            }
+            *reinterpret_cast<float4 *>(m + r * dim + c * 4) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            *reinterpret_cast<float4 *>(v + r * dim + c * 4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            if (sizeof(T) == 4) {
+                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(table) + r * dim + c * 4) = make_float4(p[0], p[1], p[2], p[3]);
+            } else {
+                __nv_bfloat162 a = __floats2bfloat162_rn(p[0], p[1]);
+                __nv_bfloat162 b = __floats2bfloat162_rn(p[2], p[3]);
+                uint2 raw;
+                raw.x = *reinterpret_cast<uint32_t *>(&a);
+                raw.y = *reinterpret_cast<uint32_t *>(&b);
+                *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(table) + r * dim + c * 4) = raw;
+            }
+        }
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(float *__restrict__ dense, int dim, const int64_t *__restrict__ rows,
+                    const float *__restrict__ row_grad, const int32_t *__restrict__ n_unique) {
+    const int U = *n_unique;
+    const int sub = threadIdx.x % LPR;
+    const int64_t g0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+    const int64_t ng = static_cast<int64_t>(gridDim.x) * blockDim.x / LPR;
+    for (int64_t s = g0; s < U; s += ng) {
+        const int64_t r = rows[s];
+        for (int d = sub; d < dim; d += LPR) dense[r * dim + d] += row_grad[s * dim + d];  // rows are unique: no race
+    }
+}
+
+}  // namespace tt
+
+extern "C" int tt_emb_rowwise_adam(void *table, int table_dtype, float *exp_avg, float *exp_avg_sq, int dim,
+                                   const int64_t *unique_rows, const float *row_grad, const int32_t *n_unique,
+                                   int64_t max_rows, const float *clip_coef, float lr, float beta1, float beta2,
+                                   float eps, const int64_t *step_dev, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(table && exp_avg && exp_avg_sq && unique_rows && row_grad && n_unique && step_dev, "null pointer");
+    TT_CHECK_ARG(dim > 0 && dim % 4 == 0, "row-wise Adam needs dim % 4 == 0");
+    TT_CHECK_ARG(table_dtype == TT_F32 || table_dtype == TT_BF16, "unknown table dtype");
+    if (max_rows <= 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int vpr = dim / 4;
+    const int lpr = vpr >= 32 ? 32 : (vpr >= 16 ? 16 : (vpr >= 8 ? 8 : (vpr >= 4 ? 4 : (vpr >= 2 ? 2 : 1))));
+    const unsigned grid = grid_for(max_rows * lpr, 256);
+#define TT_ADAM(T, L)                                                                                              \
+    rowwise_adam_kernel<T, L><<<grid, 256, 0, st>>>(static_cast<T *>(table), exp_avg, exp_avg_sq, dim, unique_rows, \
+                                                   row_grad, n_unique, clip_coef, lr, beta1, beta2, eps, step_dev)
+#define TT_ADAM_T(T)                                   \
+    switch (lpr) {                                     \
+        case 1: TT_ADAM(T, 1); break;                  \
+        case 2: TT_ADAM(T, 2); break;                  \
+        case 4: TT_ADAM(T, 4); break;                  \
+        case 8: TT_ADAM(T, 8); break;                  \
+        case 16: TT_ADAM(T, 16); break;                \
+        default: TT_ADAM(T, 32); break;                \
+    }
+    if (table_dtype == TT_F32) { TT_ADAM_T(float) } else { TT_ADAM_T(__nv_bfloat16) }
+#undef TT_ADAM_T
+#undef TT_ADAM
+    TT_LAUNCH_CHECK("rowwise_adam_kernel");
+    return 0;
+}
+
+extern "C" int tt_emb_scatter_rows(float *dense, int dim, const int64_t *unique_rows, const float *row_grad,
+                                   const int32_t *n_unique, int64_t max_rows, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(dense && unique_rows && row_grad && n_unique && dim > 0, "bad argument");
+    if (max_rows <= 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int lpr = dim >= 32 ? 32 : (dim >= 16 ? 16 : (dim >= 8 ? 8 : 4));
+    const unsigned grid = grid_for(max_rows * lpr, 256);
+    switch (lpr) {
+        case 4: scatter_rows_kernel<4><<<grid, 256, 0, st>>>(dense, dim, unique_rows, row_grad, n_unique); break;
+        case 8: scatter_rows_kernel<8><<<grid, 256, 0, st>>>(dense, dim, unique_rows, row_grad, n_unique); break;
+        case 16: scatter_rows_kernel<16><<<grid, 256, 0, st>>>(dense, dim, unique_rows, row_grad, n_unique); break;
+        default: scatter_rows_kernel<32><<<grid, 256, 0, st>>>(dense, dim, unique_rows, row_grad, n_unique); break;
+    }
+    TT_LAUNCH_CHECK("scatter_rows_kernel");
+    return 0;
+}

@@ -1,0 +1,338 @@
+"""Drop-in model classes for the reference's two-tower DSSM (same class names,
+constructor signatures, attribute names and therefore ``state_dict`` keys),
+running on hand-written sm_100a kernels.
+
+Reference classes mirrored (paths relative to the reference root):
+  MLP_Tower                 project/models/TwoTower/Tower.py:5-41
+  SequenceFeatureProcessor  project/utils/SequenceFeatureProcessor.py:5-85
+  SequenceEncoder           project/models/TwoTower/SequenceEncoder.py:5-74
+  GenericTower              project/models/TwoTower/GenericTower.py:7-237
+  TwoTowerModel             project/models/TwoTower/TwoTowerModel.py:5-150
+
+What runs where: embedding gathers + pooling, their sparse backward, the
+in-batch softmax CE (forward + backward) and retrieval top-K are libtt_b200
+kernels; the small dense GEMMs / BatchNorm / Transformer blocks are cuBLAS /
+cuDNN calls through torch ("torch GEMM acceptable
+initially").  Modules are constructed on the CPU exactly like the reference
+(same torch init calls in the same order, so the same seed gives the same
+weights) and must be moved to a CUDA device before ``forward``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import TTError
+
+
+def _need_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise TTError(f"{what}: recommendsystemproject_b200 modules run on CUDA (B200) only; "
+                      "move the model and the batch to the device (there is no CPU fallback)")
+
+
+class MLP_Tower(nn.Module):
+    """[Linear -> BatchNorm1d -> ReLU -> Dropout] x len(hidden) -> Linear -> L2 normalise
+    (Tower.py:9-41)."""
+
+    def __init__(self, input_dim, hidden_dims, output_dim, dropout=0.1):
+        super().__init__()
+        layers = []
+        curr = input_dim
+        for h in hidden_dims:
+            layers += [nn.Linear(curr, h), nn.BatchNorm1d(h), nn.ReLU(), nn.Dropout(dropout)]
+            curr = h
+        layers.append(nn.Linear(curr, output_dim))
+        self.mlp = nn.Sequential(*layers)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):  # Tower.py:28-35
+        if isinstance(m, nn.Linear):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.BatchNorm1d):
+            nn.init.constant_(m.weight, 1)
+            nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        return F.normalize(self.mlp(x), p=2, dim=1)
+
+
+class SequenceFeatureProcessor(nn.Module):
+    """Per-position sequence feature embedder (SequenceFeatureProcessor.py:6-85)."""
+
+    def __init__(self, feature_config_list, target_dim, max_seq_len, dropout=0.1):
+        super().__init__()
+        self.feature_config_list = feature_config_list
+        self.target_dim = target_dim
+        self.dropout = dropout
+        self.embeddings = nn.ModuleDict()
+        total = 0
+        for feat in feature_config_list:
+            # NB: the reference reads 'padding_index' (sic), so YAML 'padding_idx' is ignored here
+            self.embeddings[feat["name"]] = nn.Embedding(feat["vocab_size"], feat["embedding_dim"],
+                                                         padding_idx=feat.get("padding_index", 0))
+            total += feat["embedding_dim"]
+        self.feature_projection = nn.Sequential(nn.Linear(total, target_dim), nn.Dropout(dropout))
+        self.pos_emb = nn.Embedding(max_seq_len, target_dim)
+        self.sparse_sink: Optional[ops.SparseGradSink] = None
+
+    def forward(self, input_dict):
+        specs, tables = [], []
+        shape = None
+        for feat in self.feature_config_list:
+            name = feat["name"]
+            if name not in input_dict:
+                print(f"Configuration Error: Unable to find {name} in the input dictionary, {name} has skipped")
+                continue
+            x = input_dict[name]
+            _need_cuda(x, "SequenceFeatureProcessor")
+            pad = feat.get("padding_index", 0)
+            if x.dim() == 2:
+                ids, mode = x.reshape(-1, 1), ops.POOL_NONE
+            elif x.dim() == 3:
+                pooling = feat.get("pooling", None)
+                if pooling not in ("mean", "sum"):
+                    raise ValueError(f"sequence feature {name}: [B, L, Tags] input needs pooling 'mean' or 'sum'")
+                ids, mode = x.reshape(-1, x.shape[2]), ops.POOL_MODES[pooling]
+            else:
+                raise ValueError(f"sequence feature {name}: expected [B, L] or [B, L, Tags] ids")
+            shape = x.shape[:2]
+            specs.append((ids.contiguous(), mode, pad, False))
+            tables.append(self.embeddings[name].weight)
+        if not specs:
+            raise ValueError("Configuration Error: No valid features were processed!")
+        concat = ops.MultiGatherPool.apply(specs, self.sparse_sink, *tables)  # [B*L, sum d]
+        total = self.feature_projection(concat).reshape(shape[0], shape[1], self.target_dim)
+        total = total + self.pos_emb.weight[: shape[1]].unsqueeze(0)
+        return F.dropout(total, p=self.dropout, training=self.training)
+
+
+class SequenceEncoder(nn.Module):
+    """Transformer behaviour encoder + last-valid gather (SequenceEncoder.py:6-74)."""
+
+    def __init__(self, feature_config_list, model_dim=64, dim_feedforward=4 * 64, max_seq_len=20, n_head=4,
+                 n_layers=1, dropout=0.1):
+        super().__init__()
+        self.feature_embedder = SequenceFeatureProcessor(feature_config_list, model_dim, max_seq_len, dropout=dropout)
+        layer = nn.TransformerEncoderLayer(d_model=model_dim, nhead=n_head, dim_feedforward=dim_feedforward,
+                                           dropout=dropout, batch_first=True)
+        self.transformer_backbone = nn.TransformerEncoder(layer, num_layers=n_layers, enable_nested_tensor=False)
+
+    def forward(self, input_dict):
+        main = self.feature_embedder.feature_config_list[0]
+        main_seq = input_dict[main["name"]]
+        padding_mask = main_seq == main.get("padding_index", 0)
+        # rows that are all padding get their LAST position unmasked (SequenceEncoder.py:43-46);
+        # written without the reference's `.any()` host sync
+        all_pad = padding_mask.all(dim=1)
+        padding_mask = padding_mask.clone()
+        padding_mask[:, -1] &= ~all_pad
+        seq_emb = self.feature_embedder(input_dict)
+        ctx = self.transformer_backbone(src=seq_emb, src_key_padding_mask=padding_mask)
+        return self._gather_last_valid(ctx, padding_mask)
+
+    def _gather_last_valid(self, seq_output, padding_mask):
+        B = seq_output.shape[0]
+        idx = ((~padding_mask).long().sum(dim=1) - 1).clamp(min=0)  # assumes right padding, like the reference
+        return seq_output[torch.arange(B, device=seq_output.device), idx]
+
+
+class GenericTower(nn.Module):
+    """YAML-driven tower (GenericTower.py:9-237): sparse / pooled / dense /
+    sequence features -> concat -> BatchNorm1d -> MLP_Tower."""
+
+    def __init__(self, cfg, tower_name):
+        super().__init__()
+        model_cfg = cfg.get("two_tower", {})
+        if len(model_cfg.get(tower_name, {})) == 0:
+            raise ValueError(f"TwoTower Model initializing failed, {tower_name} has no features")
+        tcfg = model_cfg.get(tower_name)
+        hidden = tcfg["mlp_hidden_dim"]
+        out_dims = tcfg["output_dims"]
+        dropout = tcfg["dropout"]
+        self.tower_embedding_dim = tcfg["embedding_dim"]
+        self.embeddings = nn.ModuleDict()
+        self.pooling_config = {}
+        self.sparse_features = tcfg.get("sparse_features", None)
+        self.dense_features = tcfg.get("dense_features", None)
+        self.seq_features = tcfg.get("sequence_features", None)
+        self.sparse_sink: Optional[ops.SparseGradSink] = None  # set by optim.FusedTwoTowerOptimizer
+        self.sparse_grad_tables = set()
+
+        sparse_total = 0
+        if self.sparse_features is not None:
+            for feat in self.sparse_features:
+                for field in self.sparse_features:
+                    missing = [k for k in ("name", "vocab_size", "embedding_dim") if k not in field]
+                    if missing:
+                        raise ValueError(f"Sparse feature config missing keys {missing}: {feat}")
+                name = feat["name"]
+                self.embeddings[name] = nn.Embedding(feat["vocab_size"], feat["embedding_dim"],
+                                                     padding_idx=feat.get("padding_idx", 0))
+                nn.init.xavier_uniform_(self.embeddings[name].weight)  # overwrites the zeroed pad row (:51)
+                if "pooling" in feat:
+                    self.pooling_config[name] = feat["pooling"]
+                sparse_total += feat["embedding_dim"]
+        dense_total = 0
+        if self.dense_features is not None:
+            for feat in self.dense_features:
+                for field in self.dense_features:
+                    missing = [k for k in ("name", "dim", "embedding_dim") if k not in field]
+                    if missing:
+                        raise ValueError(f"Dense feature config missing keys {missing}: {field}, tower initializing failed")
+                self.embeddings[feat["name"]] = nn.Sequential(nn.Linear(feat["dim"], feat["embedding_dim"]))
+                dense_total += feat["embedding_dim"]
+        seq_total = 0
+        # the reference leaves self.seq_encoder undefined for `sequence_features: []`
+        # (AttributeError in forward); fixed here: None.
+        self.seq_encoder = None
+        if self.seq_features is not None and len(self.seq_features) > 0:
+            model_dim = tcfg.get("embedding_dim", 32)
+            tp = tcfg.get("transformer_parameters", {})
+            n_head = tp.get("n_head", 4)
+            if model_dim % n_head != 0:
+                raise ValueError(f"Transformer initializing failed, embedding dim {model_dim} must be divisible by n_head {n_head}")
+            self.seq_encoder = SequenceEncoder(feature_config_list=self.seq_features, model_dim=model_dim,
+                                               dim_feedforward=tp.get("FFN_dim", 4 * model_dim),
+                                               max_seq_len=tp.get("max_seq_len", 20), n_head=n_head,
+                                               n_layers=tp.get("n_layers", 1), dropout=tp.get("dropout", 0.1))
+            seq_total = model_dim
+        self.total_embed_dim = sparse_total + dense_total + seq_total
+        self.feature_bn = nn.BatchNorm1d(self.total_embed_dim)
+        self.mlp = MLP_Tower(input_dim=self.total_embed_dim, hidden_dims=hidden, output_dim=out_dims, dropout=dropout)
+
+    # ------------------------------------------------------------------
+    def _sparse_specs(self, input_dict, mapping):
+        specs, tables = [], []
+        sparse_matrix = input_dict["sparse"]
+        seq_dict = input_dict.get("sequence", {})
+        for feat in self.sparse_features:
+            name = feat["name"]
+            pad = feat.get("padding_idx", 0)
+            if "pooling" in feat:
+                if name not in seq_dict:
+                    print(f"Warning: Pooled feature {name} missing from sequence dict")
+                    continue
+                ids = seq_dict[name]
+                if ids.dim() == 1:
+                    ids = ids.unsqueeze(1)
+                pooling = self.pooling_config[name]
+                if pooling not in ("mean", "sum", "max"):
+                    raise ValueError(f"pooled feature {name}: unknown pooling '{pooling}'")
+                mode = ops.POOL_MODES[pooling]
+            else:
+                if sparse_matrix is None:
+                    continue
+                if mapping and "sparse" in mapping:
+                    col = mapping["sparse"].get(name)
+                    if col is None:
+                        raise ValueError(f"Feature '{name}' not found in column mapping")
+                else:
+                    col = [f["name"] for f in self.sparse_features if "pooling" not in f].index(name)
+                ids = sparse_matrix[:, col].unsqueeze(1)
+                mode = ops.POOL_NONE
+            _need_cuda(ids, "GenericTower")
+            specs.append((ids.contiguous().long(), mode, pad, name in self.sparse_grad_tables))
+            tables.append(self.embeddings[name].weight)
+        return specs, tables
+
+    def forward(self, input_dict, feature_column_mapping=None):
+        feats = []
+        if self.sparse_features and "sparse" in input_dict:
+            specs, tables = self._sparse_specs(input_dict, feature_column_mapping)
+            if specs:
+                feats.append(ops.MultiGatherPool.apply(specs, self.sparse_sink, *tables))
+        if self.dense_features and "dense" in input_dict:
+            dense = input_dict["dense"]
+            for feat in self.dense_features:
+                name = feat["name"]
+                if feature_column_mapping and "dense" in feature_column_mapping:
+                    col = feature_column_mapping["dense"].get(name)
+                    if col is None:
+                        raise ValueError(f"Dense feature '{name}' not found in column mapping")
+                else:
+                    col = [f["name"] for f in self.dense_features].index(name)
+                x = dense[:, col:col + 1]
+                if x.dtype != torch.float32:
+                    x = x.float()
+                feats.append(self.embeddings[name](x))
+        if self.seq_encoder is not None and "sequence" in input_dict:
+            seq = input_dict["sequence"]
+            if seq:
+                feats.append(self.seq_encoder(seq))
+        if not feats:
+            raise RuntimeError("Tower received no valid features. Check if input_dict matches config")
+        x = feats[0] if len(feats) == 1 else torch.cat(feats, dim=1)
+        x = self.feature_bn(x)
+        return self.mlp(x)
+
+
+class TwoTowerModel(nn.Module):
+    """Two-tower wrapper + fused in-batch softmax loss (TwoTowerModel.py:6-150)."""
+
+    def __init__(self, user_tower, item_tower, user_feature_mapping=None, item_feature_mapping=None):
+        super().__init__()
+        self.user_tower = user_tower
+        self.item_tower = item_tower
+        self.user_feature_mapping = user_feature_mapping
+        self.item_feature_mapping = item_feature_mapping
+        # the reference does three isnan().any() host syncs per loss call; here the kernels
+        # set a device flag that is read once (or never, when strict_nan_check is False /
+        # the stream is being captured into a CUDA graph)
+        self.strict_nan_check = True
+        self.last_nan_flags: Optional[torch.Tensor] = None
+
+    def set_feature_mappings(self, user_mapping, item_mapping):
+        self.user_feature_mapping = user_mapping
+        self.item_feature_mapping = item_mapping
+
+    def forward(self, batch_data):
+        user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping)
+        item_emb = self.item_tower(batch_data["item_tower"], self.item_feature_mapping)
+        hard_neg_emb = None
+        if "hard_negatives" in batch_data and batch_data["hard_negatives"]:
+            # one item-tower pass per slab: each slab keeps its own BatchNorm batch
+            # statistics and running-stat update, like the reference (:54-60)
+            slabs = [self.item_tower(neg, self.item_feature_mapping) for neg in batch_data["hard_negatives"]]
+            hard_neg_emb = torch.stack(slabs, dim=1)
+        return user_emb, item_emb, hard_neg_emb
+
+    def predict(self, batch_data):
+        user_emb, item_emb, _ = self.forward(batch_data)
+        return (user_emb * item_emb).sum(dim=1)
+
+    def get_item_embeddings(self, item_inputs):
+        return self.item_tower(item_inputs, self.item_feature_mapping)
+
+    def check_nan_flags(self):
+        """Raise the reference's RuntimeErrors from the device flag word (one host sync)."""
+        if self.last_nan_flags is None:
+            return
+        flags = int(self.last_nan_flags.item())
+        if flags & 1:
+            raise RuntimeError("Found NaN in User Embedding")
+        if flags & 2:
+            raise RuntimeError("Found NaN in Item Embedding")
+        if flags & 4:
+            raise RuntimeError("Found NaN in Hard Negative Embedding")
+
+    def compute_loss(self, user_emb, item_emb, item_ids=None, hard_neg_emb=None, temperature=0.1,
+                     hard_neg_pool=None):
+        """In-batch (+ per-row hard negative [B,N,D], + shared pool [H,D]) softmax CE.
+        ``hard_neg_pool`` is an extension: it equals ``hard_neg_emb = pool.expand(B,H,D)``."""
+        _need_cuda(user_emb, "compute_loss")
+        if hard_neg_emb is not None:
+            assert hard_neg_emb.dim() == 3, f"Expected shape [B, N, D], got {hard_neg_emb.shape}"
+            assert hard_neg_emb.size(0) == user_emb.shape[0], "Batch size mismatch"
+        loss, _, flags = ops.fused_inbatch_ce(user_emb, item_emb, item_ids=item_ids, hn_rows=hard_neg_emb,
+                                              pool=hard_neg_pool, temperature=temperature)
+        self.last_nan_flags = flags
+        if self.strict_nan_check and not torch.cuda.is_current_stream_capturing():
+            self.check_nan_flags()
+        return loss

@@ -1,0 +1,306 @@
+"""Thin torch custom-op layer over the C ABI (include/tt_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only;
+every op below runs a hand-written sm_100a kernel from libtt_b200.so.  There
+is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import TTError, check
+
+POOL_NONE, POOL_SUM, POOL_MEAN, POOL_MAX = 0, 1, 2, 3
+POOL_MODES = {None: POOL_NONE, "none": POOL_NONE, "sum": POOL_SUM, "mean": POOL_MEAN, "max": POOL_MAX}
+_DTYPES = {torch.float32: 0, torch.bfloat16: 1}
+
+# count of kernel-launching C-ABI calls (bench.py reports it as gpu_launches evidence)
+launch_counter = {"calls": 0}
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TTError("recommendsystemproject_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _count(n=1):
+    launch_counter["calls"] += n
+
+
+# --------------------------------------------------------------------------
+# 1. embedding gather + pooling
+# --------------------------------------------------------------------------
+def gather_pool_into(table: torch.Tensor, ids: torch.Tensor, mode: int, padding_idx: int, out: torch.Tensor,
+                     argmax: Optional[torch.Tensor], oob_flag: torch.Tensor):
+    """out[b, :D] (a column slice view of a row-major buffer) = pool_l table[ids[b, l]]."""
+    _need_cuda(table, ids, out)
+    lib = _lib.load()
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.dim() == 2
+    assert out.dtype == torch.float32 and out.stride(1) == 1
+    n_rows, length = ids.shape
+    check(lib.tt_emb_gather_pool_fwd(_p(table), _DTYPES[table.dtype], table.shape[0], table.shape[1], _p(ids), n_rows,
+                                     length, mode, -1 if padding_idx is None else int(padding_idx), _p(out),
+                                     out.stride(0), _p(argmax), _p(oob_flag), _stream()), "tt_emb_gather_pool_fwd")
+    _count()
+
+
+def segment_grad(ids: torch.Tensor, mode: int, padding_idx: Optional[int], vocab: int, grad_out: torch.Tensor,
+                 argmax: Optional[torch.Tensor], dim: int, sq_norm: Optional[torch.Tensor] = None):
+    """Sorted-segment scatter-add.  Returns (unique_rows[int64, n_pos], row_grad[n_pos, D], n_unique[int32, 1]);
+    only the first n_unique entries are meaningful (n_unique stays on the device)."""
+    _need_cuda(ids, grad_out)
+    lib = _lib.load()
+    n_rows, length = ids.shape
+    n_pos = n_rows * length
+    dev = ids.device
+    assert grad_out.dtype == torch.float32 and grad_out.stride(1) == 1
+    nbytes = ctypes.c_size_t(0)
+    check(lib.tt_emb_segment_grad_workspace(n_pos, dim, ctypes.byref(nbytes)), "tt_emb_segment_grad_workspace")
+    ws = _ws(nbytes.value, dev)
+    rows = torch.empty(n_pos, dtype=torch.int64, device=dev)
+    row_grad = torch.empty(n_pos, dim, dtype=torch.float32, device=dev)
+    n_unique = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib.tt_emb_segment_grad(_p(ids), n_rows, length, mode, -1 if padding_idx is None else int(padding_idx),
+                                  vocab, _p(grad_out), grad_out.stride(0), _p(argmax), dim, _p(rows), _p(row_grad),
+                                  _p(n_unique), _p(sq_norm), _p(ws), ws.numel(), _stream()), "tt_emb_segment_grad")
+    _count(10)
+    return rows, row_grad, n_unique
+
+
+def scatter_rows_(dense: torch.Tensor, rows: torch.Tensor, row_grad: torch.Tensor, n_unique: torch.Tensor):
+    lib = _lib.load()
+    check(lib.tt_emb_scatter_rows(_p(dense), dense.shape[1], _p(rows), _p(row_grad), _p(n_unique), rows.numel(),
+                                  _stream()), "tt_emb_scatter_rows")
+    _count()
+
+
+def rowwise_adam_(table: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, rows: torch.Tensor,
+                  row_grad: torch.Tensor, n_unique: torch.Tensor, clip_coef: Optional[torch.Tensor], lr: float,
+                  beta1: float, beta2: float, eps: float, step_dev: torch.Tensor):
+    lib = _lib.load()
+    check(lib.tt_emb_rowwise_adam(_p(table), _DTYPES[table.dtype], _p(exp_avg), _p(exp_avg_sq), table.shape[1],
+                                  _p(rows), _p(row_grad), _p(n_unique), rows.numel(), _p(clip_coef), lr, beta1, beta2,
+                                  eps, _p(step_dev), _stream()), "tt_emb_rowwise_adam")
+    _count()
+
+
+class SparseGradSink:
+    """Collects (table, rows, row_grad, n_unique) produced by backward when a
+    table runs in sparse-gradient mode (consumed by optim.FusedTwoTowerOptimizer)."""
+
+    def __init__(self):
+        self.entries: List[Tuple[torch.nn.Parameter, torch.Tensor, torch.Tensor, torch.Tensor]] = []
+        self.sq_norm: Optional[torch.Tensor] = None
+
+    def clear(self):
+        self.entries = []
+
+
+class _GatherSpec:
+    __slots__ = ("ids", "mode", "pad", "col", "dim", "vocab", "argmax")
+
+
+class MultiGatherPool(torch.autograd.Function):
+    """All sparse features of one tower in one autograd node: every feature is
+    gathered/pooled straight into its column slice of one [B, W] buffer
+    (GenericTower.py:141-183, concat at :233)."""
+
+    @staticmethod
+    def forward(ctx, specs: Sequence[tuple], sink: Optional[SparseGradSink], *tables: torch.Tensor):
+        # specs[i] = (ids [B, L] int64, mode, padding_idx, sparse_grad: bool)
+        dev = tables[0].device
+        B = specs[0][0].shape[0]
+        width = sum(t.shape[1] for t in tables)
+        out = torch.empty(B, width, dtype=torch.float32, device=dev)
+        oob = torch.zeros(1, dtype=torch.int32, device=dev)
+        col = 0
+        saved = []
+        for (ids, mode, pad, sparse_grad), table in zip(specs, tables):
+            D = table.shape[1]
+            argmax = torch.empty(B, D, dtype=torch.int32, device=dev) if mode == POOL_MAX else None
+            gather_pool_into(table.detach(), ids, mode, pad, out[:, col:col + D], argmax, oob)
+            saved.append((ids, mode, pad, sparse_grad, col, D, table.shape[0], argmax))
+            col += D
+        ctx.saved_specs = saved
+        ctx.sink = sink
+        ctx.tables = tables
+        ctx.oob = oob
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        grads = []
+        grad_out = grad_out.contiguous()
+        for n, ((ids, mode, pad, sparse_grad, col, D, V, argmax), table) in enumerate(zip(ctx.saved_specs, ctx.tables)):
+            if not ctx.needs_input_grad[2 + n]:
+                grads.append(None)
+                continue
+            g = grad_out[:, col:col + D]
+            sq = ctx.sink.sq_norm if (sparse_grad and ctx.sink is not None) else None
+            rows, row_grad, n_unique = segment_grad(ids, mode, pad, V, g, argmax, D, sq)
+            if sparse_grad and ctx.sink is not None:
+                ctx.sink.entries.append((table, rows, row_grad, n_unique))
+                grads.append(None)
+            else:
+                dense = torch.zeros(V, D, dtype=torch.float32, device=g.device)
+                scatter_rows_(dense, rows, row_grad, n_unique)
+                grads.append(dense)
+        return (None, None, *grads)
+
+
+def gather_rows(table: torch.Tensor, ids: torch.Tensor, mode: Optional[str], padding_idx: Optional[int],
+                sink: Optional[SparseGradSink] = None, sparse_grad: bool = False) -> torch.Tensor:
+    """Single-feature convenience wrapper; ids [B] or [B, L] -> [B, D]."""
+    if ids.dim() == 1:
+        ids = ids.unsqueeze(1)
+    m = POOL_MODES[mode]
+    if m == POOL_NONE and ids.shape[1] != 1:
+        raise TTError("unpooled gather needs one id per row")
+    return MultiGatherPool.apply([(ids.contiguous(), m, padding_idx, sparse_grad)], sink, table)
+
+
+# --------------------------------------------------------------------------
+# 3. fused in-batch softmax cross-entropy
+# --------------------------------------------------------------------------
+class FusedInBatchCE(torch.autograd.Function):
+    """loss = mean_b(logsumexp(Z_b) - Z_bb), Z as in TwoTowerModel.py:95-134; the
+    logits never reach HBM.  Inputs fp32 [B, D]; hn_rows [B, N, D] and/or pool
+    [H, D] optional; item_ids int64 [B] optional."""
+
+    @staticmethod
+    def forward(ctx, user, item, hn_rows, pool, item_ids, inv_temp: float, nan_flags):
+        _need_cuda(user, item)
+        lib = _lib.load()
+        user = user.contiguous().float()
+        item = item.contiguous().float()
+        hn_rows = None if hn_rows is None else hn_rows.contiguous().float()
+        pool = None if pool is None else pool.contiguous().float()
+        item_ids = None if item_ids is None else item_ids.reshape(-1).contiguous().long()
+        B, D = user.shape
+        N = 0 if hn_rows is None else hn_rows.shape[1]
+        H = 0 if pool is None else pool.shape[0]
+        dev = user.device
+        nbytes = ctypes.c_size_t(0)
+        check(lib.tt_ce_workspace(B, H, N, D, ctypes.byref(nbytes)), "tt_ce_workspace")
+        ws = _ws(nbytes.value, dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        row_lse = torch.empty(B, dtype=torch.float32, device=dev)
+        row_pos = torch.empty(B, dtype=torch.float32, device=dev)
+        check(lib.tt_ce_fwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D, float(inv_temp),
+                                _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(ws), ws.numel(), _stream()),
+              "tt_ce_fwd_f32")
+        _count(3)
+        ctx.save_for_backward(user, item, hn_rows, pool, item_ids, row_lse)
+        ctx.inv_temp = float(inv_temp)
+        ctx.ws_bytes = nbytes.value
+        ctx.mark_non_differentiable(row_lse)
+        return loss, row_lse
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_lse):
+        lib = _lib.load()
+        user, item, hn_rows, pool, item_ids, row_lse = ctx.saved_tensors
+        B, D = user.shape
+        N = 0 if hn_rows is None else hn_rows.shape[1]
+        H = 0 if pool is None else pool.shape[0]
+        dev = user.device
+        ws = _ws(ctx.ws_bytes, dev)
+        g = grad_loss.reshape(1).contiguous().float()
+        d_user = torch.empty_like(user)
+        d_item = torch.empty_like(item)
+        d_hn = None if hn_rows is None else torch.empty_like(hn_rows)
+        d_pool = None if pool is None else torch.empty_like(pool)
+        check(lib.tt_ce_bwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D, ctx.inv_temp,
+                                _p(row_lse), _p(g), _p(d_user), _p(d_item), _p(d_hn), _p(d_pool), _p(ws), ws.numel(),
+                                _stream()), "tt_ce_bwd_f32")
+        _count(6)
+        return d_user, d_item, d_hn, d_pool, None, None, None
+
+
+def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, temperature: float = 0.1,
+                     nan_flags: Optional[torch.Tensor] = None):
+    if nan_flags is None:
+        nan_flags = torch.zeros(1, dtype=torch.int32, device=user.device)
+    loss, row_lse = FusedInBatchCE.apply(user, item, hn_rows, pool, item_ids, 1.0 / float(temperature), nan_flags)
+    return loss, row_lse, nan_flags
+
+
+# --------------------------------------------------------------------------
+# 4. corpus scoring + top-K
+# --------------------------------------------------------------------------
+def score_topk(query: torch.Tensor, corpus: torch.Tensor, k: int, row_offset: int = 0,
+               mask_offsets: Optional[torch.Tensor] = None, mask_rows: Optional[torch.Tensor] = None):
+    """Top-k corpus rows per query under (score desc, row asc).  Returns
+    (scores float64 [Bq, k], rows int64 [Bq, k]); rows = local row + row_offset."""
+    _need_cuda(query, corpus)
+    lib = _lib.load()
+    query = query.contiguous().float()
+    corpus = corpus.contiguous().float()
+    Bq, D = query.shape
+    Nc = corpus.shape[0]
+    dev = query.device
+    nbytes = ctypes.c_size_t(0)
+    check(lib.tt_score_topk_workspace(Bq, Nc, D, k, ctypes.byref(nbytes)), "tt_score_topk_workspace")
+    ws = _ws(nbytes.value, dev)
+    scores = torch.empty(Bq, k, dtype=torch.float64, device=dev)
+    idx = torch.empty(Bq, k, dtype=torch.int64, device=dev)
+    if mask_offsets is not None:
+        mask_offsets = mask_offsets.contiguous().long()
+        mask_rows = mask_rows.contiguous().long()
+    check(lib.tt_score_topk_f32(_p(query), Bq, _p(corpus), Nc, D, k, row_offset, _p(mask_offsets), _p(mask_rows),
+                                _p(scores), _p(idx), _p(ws), ws.numel(), _stream()), "tt_score_topk_f32")
+    _count(2)
+    return scores, idx
+
+
+def topk_merge(scores: torch.Tensor, idx: torch.Tensor):
+    """[W, Bq, k] per-shard lists -> global (scores [Bq, k], rows [Bq, k])."""
+    lib = _lib.load()
+    W, Bq, k = scores.shape
+    scores = scores.contiguous().double()
+    idx = idx.contiguous().long()
+    out_s = torch.empty(Bq, k, dtype=torch.float64, device=scores.device)
+    out_i = torch.empty(Bq, k, dtype=torch.int64, device=scores.device)
+    check(lib.tt_topk_merge(_p(scores), _p(idx), W, Bq, k, _p(out_s), _p(out_i), _stream()), "tt_topk_merge")
+    _count()
+    return out_s, out_i
+
+
+# --------------------------------------------------------------------------
+# dense clip + Adam
+# --------------------------------------------------------------------------
+def sq_norm_accum_(x: torch.Tensor, out: torch.Tensor, ws: torch.Tensor):
+    lib = _lib.load()
+    check(lib.tt_sq_norm_accum(_p(x), x.numel(), _p(out), _p(ws), ws.numel(), _stream()), "tt_sq_norm_accum")
+    _count(2)
+
+
+def clip_coef_(sq_terms: torch.Tensor, max_norm: float, coef: torch.Tensor, total_norm: Optional[torch.Tensor]):
+    lib = _lib.load()
+    check(lib.tt_clip_coef(_p(sq_terms), sq_terms.numel(), float(max_norm), _p(coef), _p(total_norm), _stream()),
+          "tt_clip_coef")
+    _count()
+
+
+def adam_flat_(param, grad, exp_avg, exp_avg_sq, clip_coef, lr, beta1, beta2, eps, step_dev):
+    lib = _lib.load()
+    check(lib.tt_adam_flat(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), _p(clip_coef), lr, beta1,
+                           beta2, eps, _p(step_dev), _stream()), "tt_adam_flat")
+    _count()

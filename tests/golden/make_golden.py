@@ -144,6 +144,7 @@ def run_case(name, cfg, make_batch, make_corpus, seed):
     batch, (umap, imap) = make_batch(gen, B)
     batch2, _ = make_batch(gen, B)
     model = TwoTowerModel(GenericTower(cfg, "user_tower"), GenericTower(cfg, "item_tower"), umap, imap)
+    state_init = copy.deepcopy(model.state_dict())  # what torch.manual_seed(seed) + construction gives
     # give BN affine params / biases non-trivial values so they are exercised
     with torch.no_grad():
         for n, p in model.named_parameters():
@@ -181,7 +182,7 @@ def run_case(name, cfg, make_batch, make_corpus, seed):
         scores = uq @ corpus.t()
         topv, topi = torch.topk(scores, k=5, dim=1)
     save_case(os.path.join(HERE, name + ".npz"), cfg,
-              state0=state0, batch=batch, batch2=batch2,
+              state_init=state_init, seed=torch.tensor(seed), state0=state0, batch=batch, batch2=batch2,
               maps={"user": _enc_map(umap), "item": _enc_map(imap)},
               eval0={"u": ue, "i": ie, "hn": hne},
               step0=steps[0], step1=steps[1],

@@ -1,0 +1,92 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the
+header declares; the drop-in classes construct like the reference (same seed
+-> same weights, same state_dict keys) and refuse to run without a GPU."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from golden_io import unflatten
+from helpers import load_golden
+import recommendsystemproject_b200 as tt
+from recommendsystemproject_b200 import _lib, ops, synth
+from recommendsystemproject_b200._lib import TTError
+
+
+def test_library_exports_every_declared_symbol():
+    names = _lib.declared_symbols()
+    assert len(names) >= 17
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/tt_b200.h but not exported"
+    assert set(names) == set(_lib._SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.load().tt_abi_version() == 1
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    assert lib.tt_emb_segment_grad_workspace(0, 8, ctypes.byref(n)) == -1
+    assert b"bad" in lib.tt_last_error()
+    assert lib.tt_emb_segment_grad_workspace(1000, 64, ctypes.byref(n)) == 0 and n.value > 0
+    assert lib.tt_ce_workspace(512, 0, 10, 128, ctypes.byref(n)) == 0 and n.value > 0
+    assert lib.tt_score_topk_workspace(64, 1000, 128, 10, ctypes.byref(n)) == 0 and n.value > 0
+
+
+@pytest.mark.parametrize("name", ["pool_small", "seq_small"])
+def test_same_seed_same_weights_and_keys(name):
+    npz, cfg = load_golden(name)
+    init = unflatten(npz, "state_init")
+    torch.manual_seed(int(npz["seed"]))
+    model = tt.TwoTowerModel(tt.GenericTower(cfg, "user_tower"), tt.GenericTower(cfg, "item_tower"))
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(init.keys())
+    for k, v in init.items():
+        assert torch.equal(sd[k], v), k
+    model.load_state_dict(unflatten(npz, "state0"))  # reference checkpoints load unchanged
+
+
+def test_shipped_config_parameter_count():
+    cfg = synth.config_c2()
+    model = tt.TwoTowerModel(tt.GenericTower(cfg, "user_tower"), tt.GenericTower(cfg, "item_tower"))
+    assert sum(p.numel() for p in model.parameters()) == 865760
+
+
+def test_config_errors_match_reference():
+    with pytest.raises(ValueError):
+        tt.GenericTower({"two_tower": {}}, "user_tower")
+    cfg = synth.config_c1()
+    del cfg["two_tower"]["user_tower"]["sparse_features"][0]["vocab_size"]
+    with pytest.raises(ValueError):
+        tt.GenericTower(cfg, "user_tower")
+    cfg = synth.config_c2()
+    cfg["two_tower"]["user_tower"]["transformer_parameters"]["n_head"] = 5
+    with pytest.raises(ValueError):
+        tt.GenericTower(cfg, "user_tower")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback():
+    cfg = synth.config_c1()
+    model = tt.TwoTowerModel(tt.GenericTower(cfg, "user_tower"), tt.GenericTower(cfg, "item_tower"), *synth.MAPS_C1)
+    batch = synth.make_batch_c1(B=8, L=5)
+    with pytest.raises(TTError):
+        model(batch)
+    with pytest.raises(TTError):
+        model.compute_loss(torch.eye(2), torch.eye(2))
+    with pytest.raises(TTError):
+        ops.score_topk(torch.eye(2), torch.eye(2), 1)
+    with pytest.raises(TTError):
+        _lib.require_device()
+
+
+def test_synthetic_batches_follow_collate_contract():
+    b = synth.make_batch_c2(B=16, n_neg=2)
+    assert b["user_tower"]["sparse"].dtype == torch.int64 and b["user_tower"]["sparse"].shape == (16, 1)
+    assert b["user_tower"]["dense"].dtype == torch.float32
+    assert b["user_tower"]["sequence"]["hist_genre_ids"].shape == (16, 20, 3)
+    assert len(b["hard_negatives"]) == 2 and b["hard_negatives"][0]["sparse"].shape == (16, 2)
+    h = b["user_tower"]["sequence"]["hist_movie_ids"]
+    # right padded: once a 0 appears everything after it is 0
+    assert ((h == 0).long().diff(dim=1) >= 0).all()
