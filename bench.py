@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the two-tower DSSM hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1]
+
+Prints ONE JSON line (rank 0).  A "step" is one full training step of the
+reference loop (training_utils.py:28-60: zero_grad -> model(batch) ->
+compute_loss -> backward -> clip_grad_norm_(1.0) -> Adam.step) on one batch of
+synthetic input shaped like BASELINE.json configs[1] (shipped config.yaml:
+Transformer 2L/4H/d64 user tower, B=512, 10 hard-negative slabs per step).
+
+  value : samples/s with the batch already resident in HBM (CUDA-graph replay,
+          CUDA events, L2 flushed between steps outside the timed region)
+  e2e   : same metric through the public API with HOST (pinned) batches: H2D
+          copy of the batch + step + D2H read of the loss inside the timed region
+  roofline / kernels : the dominant kernel of the step and the hot-path kernels
+          at their BASELINE-scale shapes, algorithmic bytes (flops) / CUDA-event
+          time against MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle port of the same step (oracle/twotower_oracle.py)
+          timed on this box's host cores, bounded sample
+
+--impl reference runs ONLY the CPU port (no GPU work) on the same config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def tree_to(obj, device, pin=False):
+    if isinstance(obj, torch.Tensor):
+        if pin:
+            return obj.pin_memory()
+        return obj.to(device, non_blocking=True)
+    if isinstance(obj, dict):
+        return {k: tree_to(v, device, pin) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [tree_to(v, device, pin) for v in obj]
+    return obj
+
+
+def tree_bytes(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.numel() * obj.element_size()
+    if isinstance(obj, dict):
+        return sum(tree_bytes(v) for v in obj.values())
+    if isinstance(obj, list):
+        return sum(tree_bytes(v) for v in obj)
+    return 0
+
+
+def workload(name):
+    from recommendsystemproject_b200 import synth
+    if name == "c2":
+        return dict(cfg=synth.config_c2(), maps=synth.MAPS_C2, batch_fn=lambda seed: synth.make_batch_c2(512, 20, 10, seed),
+                    B=512, T=0.15, lr=5e-4,
+                    desc="BASELINE configs[1]: shipped config.yaml (Transformer 2L/4H/d64/FFN256, L=20, 3 tags), "
+                         "B=512, 10 hard-negative slabs, shipped dropout, fwd+bwd+clip+Adam")
+    if name == "c1":
+        cfg = synth.config_c1(dropout=0.1)
+        return dict(cfg=cfg, maps=synth.MAPS_C1, batch_fn=lambda seed: synth.make_batch_c1(1024, 50, seed),
+                    B=1024, T=0.15, lr=5e-4,
+                    desc="BASELINE configs[0]: ML-1M-shaped, mean-pooled L=50 history, dim 64, B=1024, dropout 0.1")
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ----------------------------------------------------------------------------- CPU port (reference arm)
+def cpu_port_steps(wl, steps, warmup, seed=2):
+    """Time the CPU oracle port of the training step with all host threads."""
+    from oracle import twotower_oracle as O
+    import recommendsystemproject_b200 as tt
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = wl["cfg"]
+    # parity runs use dropout 0; the port has no dropout, which only makes the CPU arm faster
+    torch.manual_seed(0)
+    model = tt.TwoTowerModel(tt.GenericTower(cfg, "user_tower"), tt.GenericTower(cfg, "item_tower"), *wl["maps"])
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    opt = {"step": 0, "m": {}, "v": {}}
+    batch = wl["batch_fn"](seed)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(batch, state, opt, cfg, *wl["maps"], temperature=wl["T"], lr=wl["lr"])
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(args.workload)
+    steps = max(1, min(args.steps, 20))
+    times = cpu_port_steps(wl, steps, max(1, min(args.warmup, 3)))
+    total = sum(times)
+    value = wl["B"] * len(times) / total
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "train samples/sec (fwd+bwd+clip+Adam)", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "arm": "CPU port of the reference step (oracle/twotower_oracle.py), torch fp32, "
+                                                  "dropout omitted"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} full steps of B={wl['B']}"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- kernel rooflines
+def time_op(fn, reps, flush):
+    """Mean CUDA-event duration (ms) of fn() on the current stream, L2 flushed before each rep."""
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sum(ts) / len(ts), min(ts)
+
+
+def kernel_rooflines(peaks, flush, quick=False):
+    """Hot-path kernels at BASELINE-scale shapes (per-GPU slices of C3/C4/C5)."""
+    from recommendsystemproject_b200 import ops
+    dev = "cuda"
+    out = []
+    gen = torch.Generator(device=dev).manual_seed(3)
+    # --- C3-shaped gather + pool: B=65536 samples, L=200 ragged history, D=128, 10M-row fp32 table (5.1 GB)
+    B, L, D, V = (16384, 200, 128, 2_000_000) if quick else (65536, 200, 128, 10_000_001)
+    table = torch.empty(V, D, device=dev).uniform_(-0.01, 0.01)
+    ids = torch.randint(1, V, (B, L), device=dev, generator=gen)
+    lens = torch.randint(1, L + 1, (B,), device=dev, generator=gen)
+    ids[torch.arange(L, device=dev)[None, :] >= lens[:, None]] = 0
+    n_valid = int((ids != 0).sum().item())
+    outbuf = torch.empty(B, D, device=dev)
+    oob = torch.zeros(1, dtype=torch.int32, device=dev)
+    ms, best = time_op(lambda: ops.gather_pool_into(table, ids, ops.POOL_MEAN, 0, outbuf, None, oob), 5, flush)
+    alg = n_valid * D * 4 + B * L * 8 + B * D * 4  # rows actually read (pads are counted, not read) + ids + out
+    out.append({"kernel": "gather_pool_kernel", "workload": f"C3 slice: B={B} L={L} ragged mean-pool D={D} fp32, V={V}",
+                "bound": "hbm", "ms": ms, "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg})
+    # --- sorted-segment gradient + row-wise Adam on the same ids
+    g = torch.randn(B, D, device=dev)
+    sq = torch.zeros(1, device=dev)
+    res = {}
+
+    def seg():
+        res["r"] = ops.segment_grad(ids, ops.POOL_MEAN, 0, V, g, None, D, sq)
+    ms, best = time_op(seg, 3, flush)
+    rows, row_grad, nu = res["r"]
+    U = int(nu.item())
+    alg = B * L * 8 + n_valid * D * 4 + U * (D * 4 + 8)
+    out.append({"kernel": "emb_segment_grad (sort + seg_reduce_rows)", "workload": f"same ids, U={U} unique rows",
+                "bound": "hbm", "ms": ms, "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg})
+    m = torch.zeros_like(table)
+    v = torch.zeros_like(table)
+    step = torch.ones(1, dtype=torch.int64, device=dev)
+    coef = torch.ones(1, device=dev)
+    ms, best = time_op(lambda: ops.rowwise_adam_(table, m, v, rows, row_grad, nu, coef, 5e-4, 0.9, 0.999, 1e-8, step), 5, flush)
+    alg = U * (D * 4 * 7 + 8)  # grad read + 3 state reads + 3 state writes
+    out.append({"kernel": "rowwise_adam_kernel", "workload": f"U={U} rows x D={D} fp32 state", "bound": "hbm", "ms": ms,
+                "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg})
+    del table, m, v, ids, g, rows, row_grad, res
+    torch.cuda.empty_cache()
+    # --- C4-shaped fused CE (fp32 SIMT path): B x (B+H) logits never materialised
+    Bc, Hc, Dc = (8192, 1024, 128) if quick else (32768, 4096, 128)
+    u = torch.nn.functional.normalize(torch.randn(Bc, Dc, device=dev), dim=1).requires_grad_(True)
+    it = torch.nn.functional.normalize(torch.randn(Bc, Dc, device=dev), dim=1).requires_grad_(True)
+    pool = torch.nn.functional.normalize(torch.randn(Hc, Dc, device=dev), dim=1).requires_grad_(True)
+    item_ids = torch.randint(1, Bc * 50, (Bc,), device=dev)
+    res = {}
+
+    def ce_f():
+        res["l"] = ops.fused_inbatch_ce(u, it, item_ids, None, pool, 0.05)[0]
+    ms_f, _ = time_op(ce_f, 2, flush)
+    ms_b, _ = time_op(lambda: (ce_f(), res["l"].backward()), 2, flush)
+    flops = 6.0 * Bc * (Bc + Hc) * Dc
+    ms = ms_b  # fwd + bwd
+    out.append({"kernel": "ce_fwd_tiles + ce_bwd_pass (fp32 SIMT)", "workload": f"C4 slice: B={Bc} H={Hc} D={Dc} fwd+bwd",
+                "bound": "tensor", "ms": ms, "ms_fwd": ms_f, "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["bf16_tflops"], "alg_flops": flops})
+    del u, it, pool
+    # --- C5-shaped scoring + top-100
+    Q, N, K = (1024, 200_000, 100) if quick else (4096, 1_000_000, 100)
+    q = torch.nn.functional.normalize(torch.randn(Q, 128, device=dev), dim=1)
+    e = torch.nn.functional.normalize(torch.randn(N, 128, device=dev), dim=1)
+    ms, _ = time_op(lambda: ops.score_topk(q, e, K), 2, flush)
+    flops = 2.0 * Q * N * 128
+    out.append({"kernel": "topk_stage1 + topk_stage2 (fp32 SIMT)", "workload": f"C5 slice: Q={Q} N={N} D=128 K={K}",
+                "bound": "tensor", "ms": ms, "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": flops / ms / 1e9 / peaks["bf16_tflops"], "queries_per_s": Q / ms * 1e3, "alg_flops": flops})
+    return out
+
+
+# ----------------------------------------------------------------------------- main GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
+    ap.add_argument("--quick", action="store_true", help="smaller kernel-roofline shapes")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
+    import recommendsystemproject_b200 as tt
+    from recommendsystemproject_b200 import _lib, ops
+    torch.cuda.set_device(local_rank)
+    _lib.require_device()
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    wl = workload(args.workload)
+
+    torch.manual_seed(0)
+    model = tt.TwoTowerModel(tt.GenericTower(wl["cfg"], "user_tower"), tt.GenericTower(wl["cfg"], "item_tower"),
+                             *wl["maps"]).to(dev).train()
+    opt = tt.FusedTwoTowerOptimizer(model, lr=wl["lr"], max_grad_norm=1.0, table_mode="dense")
+    host_batches = [tree_to(wl["batch_fn"](100 + rank * 17 + s), None, pin=True) for s in range(4)]
+    dev_batch = tree_to(host_batches[0], dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        from recommendsystemproject_b200.dist import DataParallelStep
+        step = DataParallelStep(model, opt, dev_batch, wl["T"])
+    else:
+        step = tt.GraphedTrainStep(model, opt, dev_batch, wl["T"])
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.fill_(1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    calls0 = ops.launch_counter["calls"]
+    step.count_launches = True
+    for _ in range(args.warmup):
+        step()
+    launches_per_step = getattr(step, "launches_per_step", None)
+
+    # ---- value: device-resident batch, per-step CUDA events, L2 flushed (untimed) between steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- e2e: pinned host batch -> H2D -> step -> D2H loss, every step, one timed region
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for s in range(args.steps):
+        loss = step(host_batches[s % len(host_batches)])
+        loss_host.copy_(loss, non_blocking=False)
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    final_loss = float(loss_host)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    B = wl["B"]
+    value = world * B * args.steps / (dev_ms / 1e3)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    h2d = tree_bytes(host_batches[0])
+
+    kernels = []
+    if not args.no_kernels:
+        try:
+            kernels = kernel_rooflines(peaks, flush, quick=args.quick)
+        except torch.cuda.OutOfMemoryError as ex:  # report, never hide
+            kernels = [{"error": f"kernel roofline section skipped: {ex}"}]
+    # dominant kernel of the C2 step = the fused-CE backward pass (see profiles/); its standalone roofline
+    roof = step_roofline(model, wl, dev, peaks, flush)
+
+    cpu = None
+    try:
+        times = cpu_port_steps(wl, args.cpu_steps, 1)
+        cpu = {"value": B * len(times) / sum(times), "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{len(times)} full steps of B={B} (oracle/twotower_oracle.py, torch fp32, all host threads)"}
+    except Exception as ex:  # noqa: BLE001
+        cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {ex}"}
+
+    line = {
+        "metric": "train samples/sec (fwd+bwd+clip+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": "flushed between steps by an untimed 256 MiB write; step = one CUDA-graph replay",
+                   "table_mode": "dense Adam on every table row (reference semantics)", "peaks": peaks["source"]},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": (launches_per_step or 0) * args.steps * 2,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "final_loss": final_loss,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def step_roofline(model, wl, dev, peaks, flush):
+    """Roofline of the dominant hand-written kernel inside the C2 step: the fused-CE backward passes
+    (ce_bwd_pass) at the step's own shape, timed standalone with CUDA events."""
+    from recommendsystemproject_b200 import ops
+    B = wl["B"]
+    D = wl["cfg"]["two_tower"]["user_tower"]["output_dims"]
+    N = 10 if "hard" in wl["desc"] else 0
+    u = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1).requires_grad_(True)
+    it = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1).requires_grad_(True)
+    hn = torch.nn.functional.normalize(torch.randn(B, N, D, device=dev), dim=2).requires_grad_(True) if N else None
+    ids = torch.randint(1, 3500, (B,), device=dev)
+    res = {}
+
+    def fwd():
+        res["l"] = ops.fused_inbatch_ce(u, it, ids, hn, None, wl["T"])[0]
+    ms_f, _ = time_op(fwd, 10, flush)
+    ms_fb, _ = time_op(lambda: (fwd(), res["l"].backward()), 10, flush)
+    flops = 6.0 * B * (B + N) * D
+    return {"bound": "tensor", "kernel": "fused in-batch CE fwd+bwd (ce_fwd_tiles, ce_bwd_pass; fp32 SIMT path)",
+            "achieved": flops / ms_fb / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": flops / ms_fb / 1e9 / peaks["bf16_tflops"], "traffic": None, "ms": ms_fb, "ms_fwd": ms_f,
+            "alg_flops": flops, "note": "B=512: launch/latency-bound; see `kernels` for BASELINE-scale shapes"}
+
+
+if __name__ == "__main__":
+    main()

@@ -101,7 +101,7 @@ TT_API int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, int 
  * count t is read from *step_dev (so CUDA graphs can replay). */
 TT_API int tt_emb_rowwise_adam(void *table, int table_dtype, float *exp_avg, float *exp_avg_sq, int dim,
                         const int64_t *unique_rows, const float *row_grad, const int32_t *n_unique,
-                        int64_t max_rows, const float *clip_coef, float lr, float beta1, float beta2, float eps,
+                        int64_t max_rows, const float *clip_coef, double lr, double beta1, double beta2, double eps,
                         const int64_t *step_dev, void *stream);
 
 /* dense[rows[u], :] += row_grad[u, :]  -- builds the dense .grad the drop-in
@@ -118,7 +118,7 @@ TT_API int tt_sq_norm_accum(const float *x, int64_t n, float *out, void *workspa
 TT_API int tt_clip_coef(const float *sq_terms, int n_terms, float max_norm, float *coef, float *total_norm, void *stream);
 /* flat dense Adam over n contiguous floats, g scaled by *clip_coef */
 TT_API int tt_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
-                 const float *clip_coef, float lr, float beta1, float beta2, float eps,
+                 const float *clip_coef, double lr, double beta1, double beta2, double eps,
                  const int64_t *step_dev, void *stream);
 
 /* ------------------------------------------------------------------------

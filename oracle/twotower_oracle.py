@@ -400,7 +400,12 @@ def score_topk(q: np.ndarray, e: np.ndarray, k: int, row_offset: int = 0,
     Scores are the float64 dot products of the stored (fp32/bf16-valued)
     embeddings; ``hist_mask[i]`` lists corpus rows set to -inf for query i
     (training_utils.py:238-252).  Returns (scores float64 [Bq,k], rows int64 [Bq,k])."""
-    s = q.astype(np.float64) @ e.astype(np.float64).T
+    # fixed-order accumulation over d (NOT a BLAS call): duplicate corpus rows must give bitwise-equal
+    # scores so that the row-index tie-break is well defined
+    q64, e64 = q.astype(np.float64), e.astype(np.float64)
+    s = np.zeros((q64.shape[0], e64.shape[0]), dtype=np.float64)
+    for d in range(q64.shape[1]):
+        s += q64[:, d:d + 1] * e64[None, :, d]
     if hist_mask is not None:
         for r, cols in enumerate(hist_mask):
             if len(cols):

@@ -23,11 +23,11 @@ _SIGNATURES = {
     "tt_emb_segment_grad_workspace": (c_int, [c_int64, c_int, P]),
     "tt_emb_segment_grad": (c_int, [P, c_int64, c_int, c_int, c_int64, c_int64, P, c_int64, P, c_int, P, P, P, P, P,
                                     c_size_t, P]),
-    "tt_emb_rowwise_adam": (c_int, [P, c_int, P, P, c_int, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, P, P]),
+    "tt_emb_rowwise_adam": (c_int, [P, c_int, P, P, c_int, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, P, P]),
     "tt_emb_scatter_rows": (c_int, [P, c_int, P, P, P, c_int64, P]),
     "tt_sq_norm_accum": (c_int, [P, c_int64, P, P, c_size_t, P]),
     "tt_clip_coef": (c_int, [P, c_int, c_float, P, P, P]),
-    "tt_adam_flat": (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, P, P]),
+    "tt_adam_flat": (c_int, [P, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, P, P]),
     "tt_ce_workspace": (c_int, [c_int64, c_int64, c_int, c_int, P]),
     "tt_ce_fwd_f32": (c_int, [P, P, P, P, c_int, P, c_int64, c_int64, c_int, c_float, P, P, P, P, P, c_size_t, P]),
     "tt_ce_bwd_f32": (c_int, [P, P, P, P, c_int, P, c_int64, c_int64, c_int, c_float, P, P, P, P, P, P, P, c_size_t, P]),

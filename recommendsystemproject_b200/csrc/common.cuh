@@ -52,6 +52,33 @@ struct Workspace {
     bool ok() const { return off <= size; }
 };
 
+// Adam hyper-parameters: doubles as the host gave them (torch computes 1-beta and the bias
+// corrections in double) plus the fp32 constants the element loop uses.
+struct AdamHyper {
+    double lr, beta1, beta2;
+    float b1, omb1, b2, omb2, eps;
+};
+inline AdamHyper make_adam(double lr, double beta1, double beta2, double eps) {
+    AdamHyper h;
+    h.lr = lr; h.beta1 = beta1; h.beta2 = beta2;
+    h.b1 = static_cast<float>(beta1); h.omb1 = static_cast<float>(1.0 - beta1);
+    h.b2 = static_cast<float>(beta2); h.omb2 = static_cast<float>(1.0 - beta2);
+    h.eps = static_cast<float>(eps);
+    return h;
+}
+__device__ __forceinline__ void adam_step_consts(const AdamHyper &h, const int64_t *step_dev, float &step_size,
+                                                 float &bc2_sqrt) {
+    const double t = static_cast<double>(*step_dev);
+    step_size = static_cast<float>(h.lr / (1.0 - pow(h.beta1, t)));
+    bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(h.beta2, t)));
+}
+__device__ __forceinline__ void adam_elem(const AdamHyper &h, float step_size, float bc2_sqrt, float g, float &p,
+                                          float &m, float &v) {
+    m = h.b1 * m + h.omb1 * g;
+    v = h.b2 * v + h.omb2 * g * g;
+    p -= step_size * (m / (sqrtf(v) / bc2_sqrt + h.eps));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

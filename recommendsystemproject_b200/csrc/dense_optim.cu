@@ -66,21 +66,17 @@ __global__ void clip_coef_kernel(const float *__restrict__ sq_terms, int n_terms
 
 __global__ void __launch_bounds__(256)
 adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                 int64_t n, const float *__restrict__ clip_coef, float lr, float beta1, float beta2, float eps,
-                 const int64_t *__restrict__ step_dev) {
+                 int64_t n, const float *__restrict__ clip_coef, AdamHyper h, const int64_t *__restrict__ step_dev) {
     const float coef = clip_coef ? *clip_coef : 1.0f;
-    const double t = static_cast<double>(*step_dev);
-    const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
-    const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
-    const float step_size = lr / bc1;
+    float step_size, bc2_sqrt;
+    adam_step_consts(h, step_dev, step_size, bc2_sqrt);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float gg = g[i] * coef;
-        const float mm = beta1 * m[i] + (1.0f - beta1) * gg;
-        const float vv = beta2 * v[i] + (1.0f - beta2) * gg * gg;
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam_elem(h, step_size, bc2_sqrt, g[i] * coef, pp, mm, vv);
         m[i] = mm;
         v[i] = vv;
-        p[i] -= step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+        p[i] = pp;
     }
 }
 
@@ -110,7 +106,7 @@ extern "C" int tt_clip_coef(const float *sq_terms, int n_terms, float max_norm, 
 }
 
 extern "C" int tt_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
-                            const float *clip_coef, float lr, float beta1, float beta2, float eps,
+                            const float *clip_coef, double lr, double beta1, double beta2, double eps,
                             const int64_t *step_dev, void *stream) {
     TT_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_dev && n >= 0, "bad argument");
     if (n == 0) return 0;
@@ -118,7 +114,7 @@ extern "C" int tt_adam_flat(float *param, const float *grad, float *exp_avg, flo
     const int64_t cap = static_cast<int64_t>(tt::sm_count()) * 16;
     if (blocks > cap) blocks = cap;
     tt::adam_flat_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        param, grad, exp_avg, exp_avg_sq, n, clip_coef, lr, beta1, beta2, eps, step_dev);
+        param, grad, exp_avg, exp_avg_sq, n, clip_coef, tt::make_adam(lr, beta1, beta2, eps), step_dev);
     TT_LAUNCH_CHECK("adam_flat_kernel");
     return 0;
 }

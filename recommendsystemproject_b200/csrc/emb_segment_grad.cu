@@ -438,14 +438,12 @@ template <typename T, int LPR>
 __global__ void __launch_bounds__(256)
 rowwise_adam_kernel(T *__restrict__ table, float *__restrict__ m, float *__restrict__ v, int dim,
                     const int64_t *__restrict__ rows, const float *__restrict__ row_grad,
-                    const int32_t *__restrict__ n_unique, const float *__restrict__ clip_coef, float lr, float beta1,
-                    float beta2, float eps, const int64_t *__restrict__ step_dev) {
+                    const int32_t *__restrict__ n_unique, const float *__restrict__ clip_coef, AdamHyper h,
+                    const int64_t *__restrict__ step_dev) {
     const int U = *n_unique;
     const float coef = clip_coef ? *clip_coef : 1.0f;
-    const double t = static_cast<double>(*step_dev);
-    const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
-    const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
-    const float step_size = lr / bc1;
+    float step_size, bc2_sqrt;
+    adam_step_consts(h, step_dev, step_size, bc2_sqrt);
     const int vpr = dim / 4;
     const int sub = threadIdx.x % LPR;
     const int64_t g0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
@@ -469,12 +467,7 @@ rowwise_adam_kernel(T *__restrict__ table, float *__restrict__ m, float *__restr
             float mm[4] = {m4.x, m4.y, m4.z, m4.w};
             float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                mm[e] = beta1 * mm[e] + (1.0f - beta1) * gg[e];
-                vv[e] = beta2 * vv[e] + (1.0f - beta2) * gg[e] * gg[e];
-                const float denom = sqrtf(vv[e]) / bc2_sqrt + eps;
-                p[e] -= step_size * (mm[e] / denom);
-            }
+            for (int e = 0; e < 4; ++e) adam_elem(h, step_size, bc2_sqrt, gg[e], p[e], mm[e], vv[e]);
             *reinterpret_cast<float4 *>(m + r * dim + c * 4) = make_float4(mm[0], mm[1], mm[2], mm[3]);
             *reinterpret_cast<float4 *>(v + r * dim + c * 4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
             if (sizeof(T) == 4) {
@@ -509,8 +502,8 @@ scatter_rows_kernel(float *__restrict__ dense, int dim, const int64_t *__restric
 
 extern "C" int tt_emb_rowwise_adam(void *table, int table_dtype, float *exp_avg, float *exp_avg_sq, int dim,
                                    const int64_t *unique_rows, const float *row_grad, const int32_t *n_unique,
-                                   int64_t max_rows, const float *clip_coef, float lr, float beta1, float beta2,
-                                   float eps, const int64_t *step_dev, void *stream) {
+                                   int64_t max_rows, const float *clip_coef, double lr, double beta1, double beta2,
+                                   double eps, const int64_t *step_dev, void *stream) {
     using namespace tt;
     TT_CHECK_ARG(table && exp_avg && exp_avg_sq && unique_rows && row_grad && n_unique && step_dev, "null pointer");
     TT_CHECK_ARG(dim > 0 && dim % 4 == 0, "row-wise Adam needs dim % 4 == 0");
@@ -520,9 +513,10 @@ extern "C" int tt_emb_rowwise_adam(void *table, int table_dtype, float *exp_avg,
     const int vpr = dim / 4;
     const int lpr = vpr >= 32 ? 32 : (vpr >= 16 ? 16 : (vpr >= 8 ? 8 : (vpr >= 4 ? 4 : (vpr >= 2 ? 2 : 1))));
     const unsigned grid = grid_for(max_rows * lpr, 256);
+    const AdamHyper hyper = make_adam(lr, beta1, beta2, eps);
 #define TT_ADAM(T, L)                                                                                              \
     rowwise_adam_kernel<T, L><<<grid, 256, 0, st>>>(static_cast<T *>(table), exp_avg, exp_avg_sq, dim, unique_rows, \
-                                                   row_grad, n_unique, clip_coef, lr, beta1, beta2, eps, step_dev)
+                                                   row_grad, n_unique, clip_coef, hyper, step_dev)
 #define TT_ADAM_T(T)                                   \
     switch (lpr) {                                     \
         case 1: TT_ADAM(T, 1); break;                  \

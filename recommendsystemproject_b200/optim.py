@@ -150,8 +150,11 @@ class GraphedTrainStep:
         for k, (m, v) in snap_opt[3].items():
             optimizer.table_state[k][0].copy_(m)
             optimizer.table_state[k][1].copy_(v)
+        c0 = ops.launch_counter["calls"]
         with torch.cuda.graph(self.graph):
             self.static_loss = self._step_eager()
+        # hand-written kernels recorded in the graph (torch/cuBLAS/cub kernels are not counted)
+        self.launches_per_step = ops.launch_counter["calls"] - c0
         torch.cuda.synchronize()
 
     def _step_eager(self):
