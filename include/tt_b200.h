@@ -145,6 +145,16 @@ TT_API int tt_ce_bwd_f32(const float *user, const float *item, const int64_t *it
                   const float *row_lse, const float *grad_loss, float *d_user, float *d_item, float *d_hn_rows,
                   float *d_pool, void *workspace, size_t workspace_bytes, void *stream);
 
+/* bf16 tensor-core path (tcgen05.mma + TMEM accumulators + TMA operand staging).  Same contract as
+ * tt_ce_fwd_f32; inputs are the fp32 activations, converted to bf16 (and permuted into item-id order,
+ * which turns the false-negative mask into a contiguous column run per row) inside the call.
+ * dim must be 64 or 128.  The workspace must stay alive until the matching backward has run. */
+TT_API int tt_ce_tc_workspace(int64_t batch, int64_t pool, int n_rowneg, int dim, size_t *bytes_host);
+TT_API int tt_ce_fwd_tc(const float *user, const float *item, const int64_t *item_ids, const float *hn_rows,
+                 int n_rowneg, const float *pool, int64_t pool_rows, int64_t batch, int dim, float inv_temp,
+                 float *loss, float *row_lse, float *row_pos, int *nan_flags, void *workspace,
+                 size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------
  * 4. Corpus scoring + top-K for retrieval evaluation.
  * Replaces matmul + per-user -inf masking + topk at training_utils.py:220-258.

@@ -185,7 +185,7 @@ class FusedInBatchCE(torch.autograd.Function):
     [H, D] optional; item_ids int64 [B] optional."""
 
     @staticmethod
-    def forward(ctx, user, item, hn_rows, pool, item_ids, inv_temp: float, nan_flags):
+    def forward(ctx, user, item, hn_rows, pool, item_ids, inv_temp: float, nan_flags, precision: str = "fp32"):
         _need_cuda(user, item)
         lib = _lib.load()
         user = user.contiguous().float()
@@ -199,14 +199,26 @@ class FusedInBatchCE(torch.autograd.Function):
         dev = user.device
         nbytes = ctypes.c_size_t(0)
         check(lib.tt_ce_workspace(B, H, N, D, ctypes.byref(nbytes)), "tt_ce_workspace")
-        ws = _ws(nbytes.value, dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         row_lse = torch.empty(B, dtype=torch.float32, device=dev)
         row_pos = torch.empty(B, dtype=torch.float32, device=dev)
-        check(lib.tt_ce_fwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D, float(inv_temp),
-                                _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(ws), ws.numel(), _stream()),
-              "tt_ce_fwd_f32")
-        _count(3)
+        if precision == "bf16":
+            # tcgen05 / TMA tensor-core path (D in {64, 128})
+            tcbytes = ctypes.c_size_t(0)
+            check(lib.tt_ce_tc_workspace(B, H, N, D, ctypes.byref(tcbytes)), "tt_ce_tc_workspace")
+            tcws = _ws(tcbytes.value, dev)
+            check(lib.tt_ce_fwd_tc(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D,
+                                   float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(tcws),
+                                   tcws.numel(), _stream()), "tt_ce_fwd_tc")
+            _count(7 + (1 if pool is not None else 0) + (1 if item_ids is not None else 0))
+        elif precision == "fp32":
+            ws = _ws(nbytes.value, dev)
+            check(lib.tt_ce_fwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D,
+                                    float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(ws),
+                                    ws.numel(), _stream()), "tt_ce_fwd_f32")
+            _count(3)
+        else:
+            raise TTError(f"unknown precision '{precision}' (use 'fp32' or 'bf16')")
         ctx.save_for_backward(user, item, hn_rows, pool, item_ids, row_lse)
         ctx.inv_temp = float(inv_temp)
         ctx.ws_bytes = nbytes.value
@@ -231,14 +243,16 @@ class FusedInBatchCE(torch.autograd.Function):
                                 _p(row_lse), _p(g), _p(d_user), _p(d_item), _p(d_hn), _p(d_pool), _p(ws), ws.numel(),
                                 _stream()), "tt_ce_bwd_f32")
         _count(6)
-        return d_user, d_item, d_hn, d_pool, None, None, None
+        return d_user, d_item, d_hn, d_pool, None, None, None, None
 
 
 def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, temperature: float = 0.1,
-                     nan_flags: Optional[torch.Tensor] = None):
+                     nan_flags: Optional[torch.Tensor] = None, precision: str = "fp32"):
+    """precision='fp32': exact SIMT path; 'bf16': tcgen05/TMA tensor-core path (dim 64 or 128)."""
     if nan_flags is None:
         nan_flags = torch.zeros(1, dtype=torch.int32, device=user.device)
-    loss, row_lse = FusedInBatchCE.apply(user, item, hn_rows, pool, item_ids, 1.0 / float(temperature), nan_flags)
+    loss, row_lse = FusedInBatchCE.apply(user, item, hn_rows, pool, item_ids, 1.0 / float(temperature), nan_flags,
+                                         precision)
     return loss, row_lse, nan_flags
 
 

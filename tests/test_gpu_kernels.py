@@ -371,3 +371,37 @@ def test_topk_k_larger_than_corpus_pads_with_minus_one():
     assert (idx[:, 5:] == -1).all() and (idx[:, :5] >= 0).all()
     vals_ref, idx_ref = O.score_topk(q.numpy(), e.numpy(), 5)
     assert np.array_equal(idx[:, :5].cpu().numpy(), idx_ref)
+
+
+# ---------------------------------------------------------------- fused CE, tcgen05 / TMA bf16 path
+def _bf16_round(t):
+    return None if t is None else t.bfloat16().float()
+
+
+@pytest.mark.parametrize("B,D,N,H,ids", [(128, 128, 0, 0, False), (256, 64, 0, 0, True), (1000, 128, 0, 300, True),
+                                         (2048, 128, 4, 512, True), (4096, 64, 0, 0, True), (300, 128, 0, 0, True)])
+def test_ce_tc_forward_matches_oracle_on_bf16_rounded_inputs(B, D, N, H, ids):
+    """tcgen05 path: products of bf16-rounded inputs accumulate in fp32, so against the oracle evaluated on the
+    SAME bf16-rounded U/I/pool the only differences are accumulation order and ex2.approx: tolerance 2e-4 on
+    lse; against the unrounded fp32 oracle the stated bf16 tolerance is 3e-2 on lse at T=0.05."""
+    gen = torch.Generator().manual_seed(B + D + N + H)
+    u, i, hn, pool, item_ids, T = _ce_case(gen, B, D, N, H, ids, temperature=0.05)
+    ud, idv = u.to(DEV), i.to(DEV)
+    loss, lse, flags = ops.fused_inbatch_ce(ud, idv, None if item_ids is None else item_ids.to(DEV),
+                                            None if hn is None else hn.to(DEV), None if pool is None else pool.to(DEV),
+                                            T, precision="bf16")
+    assert int(flags.item()) == 0
+    lse_r, pos_r = O.row_logsumexp(_bf16_round(u), _bf16_round(i), item_ids, hn, T, _bf16_round(pool))
+    if N:  # per-row negatives are scored from the fp32 inputs (tiny [B,N] block)
+        lse_r, pos_r = None, None
+        z = O.build_logits(_bf16_round(u).double(), _bf16_round(i).double(), item_ids, None, T, _bf16_round(pool).double()
+                           if pool is not None else None)
+        zh = torch.einsum("bd,bnd->bn", u.double(), hn.double()) / T
+        zz = torch.cat([z, zh], dim=1)
+        lse_r = torch.logsumexp(zz, dim=1)
+        pos_r = z[torch.arange(B), torch.arange(B)]
+    assert torch.allclose(lse.cpu().double(), lse_r, atol=2e-4, rtol=1e-5), float((lse.cpu().double() - lse_r).abs().max())
+    assert abs(float(loss) - float((lse_r - pos_r).mean())) < 2e-4
+    lse_f, pos_f = O.row_logsumexp(u, i, item_ids, hn, T, pool)
+    assert torch.allclose(lse.cpu().double(), lse_f, atol=3e-2)
+    assert abs(float(loss) - float((lse_f - pos_f).mean())) < 1e-2
