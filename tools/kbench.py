@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmarks (CUDA events, L2 flushed between reps).  Usage:
+    python tools/kbench.py ce_tc [B H D]      fused CE forward, tcgen05 path vs fp32 SIMT path
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from bench import load_peaks, time_op  # noqa: E402
+from recommendsystemproject_b200 import ops  # noqa: E402
+
+
+def main():
+    what = sys.argv[1]
+    dev = "cuda"
+    peaks = load_peaks()
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush = lambda: flush_buf.fill_(1)  # noqa: E731
+    if what == "ce_tc":
+        B, H, D = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (65536, 4096, 128)
+        u = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1)
+        it = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1)
+        pool = torch.nn.functional.normalize(torch.randn(H, D, device=dev), dim=1) if H else None
+        ids = torch.randint(1, B * 50, (B,), device=dev)
+        out = {}
+        for prec in ("bf16", "fp32") if B <= 32768 else ("bf16",):
+            res = {}
+
+            def f():
+                res["l"] = ops.fused_inbatch_ce(u, it, ids, None, pool, 0.05, precision=prec)[0]
+            ms, best = time_op(f, 5, flush)
+            flops = 2.0 * B * (B + H) * D
+            out[prec] = {"ms": ms, "best_ms": best, "tflops": flops / ms / 1e9,
+                         "frac_of_bf16_peak": flops / ms / 1e9 / peaks["bf16_tflops"], "loss": float(res["l"])}
+        print(json.dumps({"kernel": "ce_fwd", "B": B, "H": H, "D": D, **out}))
+
+
+if __name__ == "__main__":
+    main()
