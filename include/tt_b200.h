@@ -155,6 +155,18 @@ TT_API int tt_ce_fwd_tc(const float *user, const float *item, const int64_t *ite
                  float *loss, float *row_lse, float *row_pos, int *nan_flags, void *workspace,
                  size_t workspace_bytes, void *stream);
 
+/* Backward of tt_ce_fwd_tc on the tensor cores: two passes of one tcgen05 kernel (dU; dI + dPool) that
+ * recompute each 128x128 logit tile into TMEM, turn it into bf16 (P - onehot) in TMEM and feed it straight
+ * back to the tensor core as the A operand of the gradient product (the W tile in shared memory is read a
+ * second time through an MN-major descriptor).  `fwd_workspace` is the workspace the forward call filled
+ * (bf16 operands in item-id order, permutation, collision runs); row_lse is the forward's output.
+ * Gradients are fp32, in the caller's (unsorted) row order. */
+TT_API int tt_ce_bwd_tc_workspace(int64_t batch, int64_t pool, int n_rowneg, int dim, size_t *bytes_host);
+TT_API int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowneg, int64_t pool_rows, int64_t batch, int dim,
+                 float inv_temp, const float *row_lse, const float *grad_loss, float *d_user, float *d_item,
+                 float *d_hn_rows, float *d_pool, void *fwd_workspace, size_t fwd_workspace_bytes, void *workspace,
+                 size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------
  * 4. Corpus scoring + top-K for retrieval evaluation.
  * Replaces matmul + per-user -inf masking + topk at training_utils.py:220-258.

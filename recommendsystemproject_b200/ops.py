@@ -222,6 +222,8 @@ class FusedInBatchCE(torch.autograd.Function):
         ctx.save_for_backward(user, item, hn_rows, pool, item_ids, row_lse)
         ctx.inv_temp = float(inv_temp)
         ctx.ws_bytes = nbytes.value
+        ctx.precision = precision
+        ctx.tcws = tcws if precision == "bf16" else None  # bf16 operands / permutation / runs for the backward
         ctx.mark_non_differentiable(row_lse)
         return loss, row_lse
 
@@ -233,12 +235,21 @@ class FusedInBatchCE(torch.autograd.Function):
         N = 0 if hn_rows is None else hn_rows.shape[1]
         H = 0 if pool is None else pool.shape[0]
         dev = user.device
-        ws = _ws(ctx.ws_bytes, dev)
         g = grad_loss.reshape(1).contiguous().float()
         d_user = torch.empty_like(user)
         d_item = torch.empty_like(item)
         d_hn = None if hn_rows is None else torch.empty_like(hn_rows)
         d_pool = None if pool is None else torch.empty_like(pool)
+        if ctx.precision == "bf16":
+            nbytes = ctypes.c_size_t(0)
+            check(lib.tt_ce_bwd_tc_workspace(B, H, N, D, ctypes.byref(nbytes)), "tt_ce_bwd_tc_workspace")
+            ws = _ws(nbytes.value, dev)
+            check(lib.tt_ce_bwd_tc(_p(user), _p(hn_rows), N, H, B, D, ctx.inv_temp, _p(row_lse), _p(g), _p(d_user),
+                                   _p(d_item), _p(d_hn), _p(d_pool), _p(ctx.tcws), ctx.tcws.numel(), _p(ws), ws.numel(),
+                                   _stream()), "tt_ce_bwd_tc")
+            _count(5 + (1 if hn_rows is not None else 0) + (1 if pool is not None else 0))
+            return d_user, d_item, d_hn, d_pool, None, None, None, None
+        ws = _ws(ctx.ws_bytes, dev)
         check(lib.tt_ce_bwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D, ctx.inv_temp,
                                 _p(row_lse), _p(g), _p(d_user), _p(d_item), _p(d_hn), _p(d_pool), _p(ws), ws.numel(),
                                 _stream()), "tt_ce_bwd_f32")

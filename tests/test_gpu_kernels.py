@@ -405,3 +405,61 @@ def test_ce_tc_forward_matches_oracle_on_bf16_rounded_inputs(B, D, N, H, ids):
     lse_f, pos_f = O.row_logsumexp(u, i, item_ids, hn, T, pool)
     assert torch.allclose(lse.cpu().double(), lse_f, atol=3e-2)
     assert abs(float(loss) - float((lse_f - pos_f).mean())) < 1e-2
+
+
+@pytest.mark.parametrize("B,D,N,H,ids", [(128, 128, 0, 0, False), (256, 64, 0, 0, True), (1000, 128, 0, 300, True),
+                                         (2048, 128, 4, 512, True), (4096, 64, 0, 200, True), (300, 128, 2, 0, True),
+                                         (77, 128, 0, 5, True)])
+def test_ce_tc_backward_matches_oracle_on_bf16_rounded_inputs(B, D, N, H, ids):
+    """tcgen05 backward (two passes: dU; dI + dPool).  The recomputed probabilities are rounded to bf16 before they
+    re-enter the tensor core (relative 2^-9 per element, unbiased), so against the closed-form fp64 gradients of the
+    oracle on the SAME bf16-rounded U/I/pool the stated tolerance is 1e-2 relative Frobenius error per gradient and
+    3e-2 of the largest reference entry elementwise; dHN (fp32 SIMT, tiny) keeps 1e-3."""
+    gen = torch.Generator().manual_seed(B + D + N + H + 1)
+    u, i, hn, pool, item_ids, T = _ce_case(gen, B, D, N, H, ids, temperature=0.05)
+    if ids:  # force collisions (and a run crossing a 128-row tile boundary after sorting)
+        item_ids[: min(B, 40)] = item_ids[0]
+    ud, idv = u.to(DEV).requires_grad_(True), i.to(DEV).requires_grad_(True)
+    hnd = None if hn is None else hn.to(DEV).requires_grad_(True)
+    pd = None if pool is None else pool.to(DEV).requires_grad_(True)
+    loss, lse, flags = ops.fused_inbatch_ce(ud, idv, None if item_ids is None else item_ids.to(DEV), hnd, pd, T,
+                                            precision="bf16")
+    (2.0 * loss).backward()
+    du_r, di_r, dhn_r, dpool_r = O.loss_grads_closed_form(_bf16_round(u), _bf16_round(i), item_ids, hn, T,
+                                                          _bf16_round(pool), grad_loss=2.0)
+
+    def close(got, ref, what, rel=1e-2, elem=3e-2):
+        got = got.detach().cpu().double()
+        ref = ref.double()
+        err = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+        mx = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        assert err < rel and mx < elem, f"{what}: rel Frobenius {err:.3e}, max elem {mx:.3e}"
+
+    close(ud.grad, du_r, "dU")
+    close(idv.grad, di_r, "dI")
+    if H:
+        close(pd.grad, dpool_r, "dPool")
+    if N:
+        # dHN's own error is the lse error only; u is NOT rounded on this (fp32 SIMT) path
+        _, _, dhn_f, _ = O.loss_grads_closed_form(u, _bf16_round(i), item_ids, hn, T, _bf16_round(pool), grad_loss=2.0)
+        close(hnd.grad, dhn_f, "dHN", rel=3e-2, elem=5e-2)
+
+
+def test_ce_tc_backward_large_properties():
+    """B=8192, H=1024 (a 300 MB logit matrix if it were materialised) through the tensor-core fwd+bwd, compared
+    with this library's exact fp32 SIMT path on the same inputs (itself oracle-checked at small sizes): loss within
+    1e-2, every gradient within 3e-2 relative Frobenius error (bf16 operands + bf16 probabilities)."""
+    gen = torch.Generator().manual_seed(99)
+    B, D, H = 8192, 128, 1024
+    u, i, _, pool, item_ids, T = _ce_case(gen, B, D, 0, H, True, 0.05)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        ud, idv, pd = (t.to(DEV).requires_grad_(True) for t in (u, i, pool))
+        loss, _, _ = ops.fused_inbatch_ce(ud, idv, item_ids.to(DEV), None, pd, T, precision=prec)
+        loss.backward()
+        outs[prec] = (float(loss), ud.grad.double(), idv.grad.double(), pd.grad.double())
+    assert abs(outs["fp32"][0] - outs["bf16"][0]) < 1e-2
+    for k, name in ((1, "dU"), (2, "dI"), (3, "dPool")):
+        a, b = outs["fp32"][k], outs["bf16"][k]
+        rel = float((a - b).norm() / a.norm())
+        assert rel < 3e-2, f"{name}: bf16 tensor-core path differs from the fp32 path by {rel:.3e} (relative Frobenius)"

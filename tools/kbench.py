@@ -21,9 +21,9 @@ def main():
     flush = lambda: flush_buf.fill_(1)  # noqa: E731
     if what == "ce_tc":
         B, H, D = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (65536, 4096, 128)
-        u = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1)
-        it = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1)
-        pool = torch.nn.functional.normalize(torch.randn(H, D, device=dev), dim=1) if H else None
+        u = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1).requires_grad_(True)
+        it = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1).requires_grad_(True)
+        pool = torch.nn.functional.normalize(torch.randn(H, D, device=dev), dim=1).requires_grad_(True) if H else None
         ids = torch.randint(1, B * 50, (B,), device=dev)
         out = {}
         for prec in ("bf16", "fp32") if B <= 32768 else ("bf16",):
@@ -35,6 +35,10 @@ def main():
             flops = 2.0 * B * (B + H) * D
             out[prec] = {"ms": ms, "best_ms": best, "tflops": flops / ms / 1e9,
                          "frac_of_bf16_peak": flops / ms / 1e9 / peaks["bf16_tflops"], "loss": float(res["l"])}
+            if prec == "bf16" or B <= 16384:
+                ms_fb, best_fb = time_op(lambda: (f(), res["l"].backward()), 5, flush)
+                out[prec].update({"fwd_bwd_ms": ms_fb, "fwd_bwd_best_ms": best_fb, "fwd_bwd_tflops": 3 * flops / ms_fb / 1e9,
+                                  "fwd_bwd_frac_of_bf16_peak": 3 * flops / ms_fb / 1e9 / peaks["bf16_tflops"]})
         print(json.dumps({"kernel": "ce_fwd", "B": B, "H": H, "D": D, **out}))
 
 
