@@ -167,6 +167,10 @@ TT_API int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowneg, i
                  float *d_hn_rows, float *d_pool, void *fwd_workspace, size_t fwd_workspace_bytes, void *workspace,
                  size_t workspace_bytes, void *stream);
 
+/* developer hook (tools/ce_trace.py): SM-clock stamps of CTA 0's pipeline events of the next tcgen05 CE
+ * launches are written to dbg[11][256] (device memory); NULL disables.  Not used by the product path. */
+TT_API int tt_ce_tc_debug_trace(long long *dbg);
+
 /* ------------------------------------------------------------------------
  * 4. Corpus scoring + top-K for retrieval evaluation.
  * Replaces matmul + per-user -inf masking + topk at training_utils.py:220-258.

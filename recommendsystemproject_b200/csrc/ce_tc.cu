@@ -1,22 +1,35 @@
 // Fused in-batch (+ shared-pool) softmax cross-entropy on the 5th-gen tensor
-// cores: tcgen05.mma with TMEM accumulators, operands staged by TMA
-// (kernel 3 of the hot path, bf16 path; ce_f32.cu is the exact fp32 path).
+// cores, forward AND backward: tcgen05.mma with TMEM accumulators, operands
+// staged by TMA (kernel 3 of the hot path, bf16 path; ce_f32.cu is the exact
+// fp32 path).
 //
 // Replaces mm / div / masked_fill / cat / log_softmax / nll_loss at
-// TwoTowerModel.py:95-140 of the reference.  The B x (B+H) logits live only in
-// TMEM: a CTA owns 128 user rows, streams 128-row item tiles through a 4-stage
-// TMA ring, one elected thread issues tcgen05.mma (M=128, N=128, K=16 x D/16)
-// into one of four 128-column TMEM accumulators, and four epilogue warps read
-// them back with tcgen05.ld (thread = row) and fold them into an online
-// (max, sum) in the exp2 domain.
+// TwoTowerModel.py:95-140 of the reference and their autograd.  The B x (B+H)
+// logits and probabilities live only in TMEM.
+//
+// ONE persistent kernel template, three modes:
+//   FWD    X = U rows,            W = [item ; pool] tiles   -> per-row online (max, sum)
+//   BWD_X  X = U rows,            W = [item ; pool] tiles   -> dU  = c (P - 1) W
+//   BWD_Y  X = item / pool rows,  W = U tiles               -> dI, dPool = c (P - 1)^T U
+// The 128x128 tiles (X row tile m, W tile n) are numbered m * n_tiles + n and
+// cut into one contiguous range per CTA (stream-K: every SM gets the same
+// number of tiles +-1, a row tile that straddles CTAs leaves one partial per
+// CTA, merged in a fixed order afterwards).  Per CTA, 10 warps:
+//   warp 0      TMA producer: the X tile + a 5-stage (D=128) ring of W tiles, SWIZZLE_128B
+//   warp 1      one thread issues tcgen05.mma:  S = X W^T (SS, K-major)  into one of two TMEM buffers and, for
+//               the backward,  Out += G W  (TS: A = G from TMEM, B = the same smem W tile, MN-major descriptor)
+//   warps 2..9  two softmax groups of 4 warps (thread = row) that alternate tiles: tcgen05.ld the whole S row
+//               into registers, release the buffer, then exp2 on the MUFU while the tensor pipe already runs the
+//               next S; the backward packs bf16 (P - onehot) and tcgen05.st's it back to TMEM as the A operand.
 //
 // False-negative mask without per-element id compares: rows are processed in
 // item-id-sorted order (U and I permuted together while they are converted to
 // bf16; the loss is invariant to that permutation), so the columns that collide
 // with row p are the contiguous run [lo_p, hi_p) around the diagonal and only
-// tiles intersecting that run take the masked path.
+// tiles intersecting that run take the per-element path.
 //
-// Roofline: tensor pipe.  Algorithmic flops fwd = 2*B*(B+H)*D.
+// Roofline: tensor pipe.  Algorithmic flops fwd = 2*B*(B+H)*D, bwd = 4*B*(B+H)*D
+// (the recomputation of S in the two backward passes is overhead, not counted).
 #include <cub/cub.cuh>
 
 #include "tc_common.cuh"
@@ -27,10 +40,13 @@ using namespace tt::tc;
 
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 128;
-constexpr int TC_STAGES = 4;
-constexpr int TC_ACC = 4;
-constexpr int TC_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+// W-tile ring depth: 1 X tile + ST W tiles of 128 x D bf16 must fit in 227 KB
+template <int D> struct TcStages { static constexpr int value = D == 128 ? 5 : 8; };
+constexpr int TC_THREADS = 320;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr uint32_t TM_S = 0, TM_G = 256, TM_OUT = 384;   // TMEM columns: S[2] x 128, G[2] x 64, Out x D
+
+enum { MODE_FWD = 0, MODE_BWD_X = 1, MODE_BWD_Y = 2 };
 
 // ---------------------------------------------------------------- prep kernels
 // out[p, :] = bf16(in[perm ? perm[p] : p, :]); one warp per row; NaN detection for the flag word
@@ -85,188 +101,429 @@ __global__ void tc_runs(const int64_t *__restrict__ sorted_ids, int64_t n, int32
     }
 }
 
+// ---------------------------------------------------------------- stream-K schedule
+// Tiles g = m * n_tiles + n, CTA k owns [k * per_cta, (k + 1) * per_cta).  A row tile m is cut into
+// segments seg = k - first_cta(m); every segment leaves one partial (two for FWD: one per softmax group).
+struct Sched {
+    int m_tiles, n_tiles;
+    int64_t total, per_cta;
+    int grid, max_seg;
+};
+
+static Sched make_sched(int m_tiles, int n_tiles) {
+    Sched s;
+    s.m_tiles = m_tiles; s.n_tiles = n_tiles;
+    s.total = static_cast<int64_t>(m_tiles) * n_tiles;
+    int64_t g = (s.total + 1) / 2;               // at least 2 tiles per CTA
+    if (g > sm_count()) g = sm_count();
+    if (g < 1) g = 1;
+    s.per_cta = (s.total + g - 1) / g;
+    s.grid = static_cast<int>((s.total + s.per_cta - 1) / s.per_cta);
+    s.max_seg = static_cast<int>((n_tiles + s.per_cta - 2) / s.per_cta) + 1;
+    return s;
+}
+
+__host__ __device__ __forceinline__ int sched_first_cta(int m, int n_tiles, int64_t per_cta) {
+    return static_cast<int>((static_cast<int64_t>(m) * n_tiles) / per_cta);
+}
+__host__ __device__ __forceinline__ int sched_last_cta(int m, int n_tiles, int64_t per_cta) {
+    return static_cast<int>((static_cast<int64_t>(m + 1) * n_tiles - 1) / per_cta);
+}
+
+// position of a role inside its CTA's tile range
+struct Cursor {
+    int i;        // local tile index
+    int m, n;     // row tile, W tile
+    int r;        // local row counter (0 for the first row tile this CTA touches)
+    int n_tiles;
+    __device__ __forceinline__ void init(int64_t g0, int nt) {
+        n_tiles = nt; i = 0; r = 0;
+        m = static_cast<int>(g0 / nt);
+        n = static_cast<int>(g0 - static_cast<int64_t>(m) * nt);
+    }
+    __device__ __forceinline__ void next() {
+        ++i;
+        if (++n == n_tiles) { n = 0; ++m; ++r; }
+    }
+};
+
 // ---------------------------------------------------------------- main kernel
 struct CeTcParams {
     int64_t batch;       // rows of U / I
     int64_t pool_rows;   // rows of the shared pool (0 if none)
-    int tiles_item, tiles_total, splits;
+    int tiles_item, tiles_pool;
+    int m_tiles, n_tiles;
+    int64_t per_cta, total;
+    int max_seg;
     float scale2;        // inv_temp * log2(e)
     const int32_t *lo, *hi;
-    float *part_m, *part_s;  // [splits, batch] in the exp2 domain
+    const float *lse2p;      // BWD: [tiles_item * 128] lse * log2(e) in sorted order, +inf past batch
+    float *part_m, *part_s;  // FWD: [2 * max_seg][batch]  (raw-logit max, sum of exp2)
+    float *part;             // BWD: [max_seg][m_tiles * 128][D] raw fp32 accumulators
+    long long *dbg;          // optional timeline of CTA 0 (tools/ce_trace.py): [event][tile] SM clock stamps
 };
 
-template <int D>
+#define TT_DBG(ev, i)                                                                              \
+    do {                                                                                           \
+        if (prm.dbg != nullptr && blockIdx.x == 0 && (i) < 256 && (threadIdx.x & 31) == ((ev) == 0 || (ev) == 2 ? (threadIdx.x & 31) : 0)) \
+            prm.dbg[(ev) * 256 + (i)] = clock64();                                                 \
+    } while (0)
+
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+template <int D, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-ce_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i,
-                 const __grid_constant__ CUtensorMap map_p, const CeTcParams prm) {
+ce_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i,
+             const __grid_constant__ CUtensorMap map_p, const CeTcParams prm) {
+    constexpr bool BWD = MODE != MODE_FWD;
+    constexpr bool TRANS = MODE == MODE_BWD_Y;
     constexpr int KB = D / 64;                       // 64-column (128-byte) K blocks
     constexpr int TILE_BYTES = TC_BN * D * 2;        // one operand tile
     constexpr int KBLOCK_BYTES = TC_BN * 128;        // one 64-column box of 128 rows
+    constexpr int LSE_BYTES = TC_BN * 4;
+    constexpr int TC_STAGES = TcStages<D>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *u_tile = smem;
-    uint8_t *y_tiles = smem + TILE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(y_tiles + TC_STAGES * TILE_BYTES);
-    uint64_t *full = bars;                     // [TC_STAGES]
-    uint64_t *empty = full + TC_STAGES;        // [TC_STAGES]
-    uint64_t *tfull = empty + TC_STAGES;       // [TC_ACC]
-    uint64_t *tempty = tfull + TC_ACC;         // [TC_ACC]
-    uint64_t *ufull = tempty + TC_ACC;         // [1]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ufull + 1);
+    uint8_t *x_tile = smem;
+    uint8_t *w_tiles = smem + TILE_BYTES;                           // [TC_STAGES]
+    float *lse_s = reinterpret_cast<float *>(w_tiles + TC_STAGES * TILE_BYTES);  // [TC_STAGES][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(lse_s + TC_STAGES * TC_BN);
+    uint64_t *full = bars;                   // [ST]  TMA -> MMA (and softmax, for lse_s)
+    uint64_t *empty = full + TC_STAGES;      // [ST]  MMA -> TMA
+    uint64_t *sfull = empty + TC_STAGES;     // [2]   S tile complete
+    uint64_t *sfree = sfull + 2;             // [2]   S tile copied to registers (128 arrivals)
+    uint64_t *gfull = sfree + 2;             // [2]   G tile written (128 arrivals)
+    uint64_t *gfree = gfull + 2;             // [2]   Out MMA that read G retired
+    uint64_t *xfull = gfree + 2;             // [1]   one completion per row segment
+    uint64_t *xfree = xfull + 1;             // [1]   last S MMA of the row retired
+    uint64_t *ofull = xfree + 1;             // [1]   last Out MMA of the row retired
+    uint64_t *ofree = ofull + 1;             // [1]   Out drained (256 arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ofree + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row_tile = blockIdx.x, split = blockIdx.y;
-    const int tiles_per = (prm.tiles_total + prm.splits - 1) / prm.splits;
-    const int t0 = split * tiles_per;
-    const int t1 = min(prm.tiles_total, t0 + tiles_per);
+    const int64_t g0 = static_cast<int64_t>(blockIdx.x) * prm.per_cta;
+    const int64_t g1 = min(prm.total, g0 + prm.per_cta);
+    const int n_local = static_cast<int>(max(g1 - g0, static_cast<int64_t>(0)));
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_u);
         prefetch_tensormap(&map_i);
         if (prm.pool_rows > 0) prefetch_tensormap(&map_p);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < TC_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
-        mbar_init(ufull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&sfull[a], 1); mbar_init(&sfree[a], 128);
+            mbar_init(&gfull[a], 128); mbar_init(&gfree[a], 1);
+        }
+        mbar_init(xfull, 1);
+        mbar_init(xfree, 1);
+        mbar_init(ofull, 1);
+        mbar_init(ofree, 256);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<TC_ACC * TC_BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            mbar_arrive_expect_tx(ufull, TILE_BYTES);
-            for (int kb = 0; kb < KB; ++kb)
-                tma_load_2d(u_tile + kb * KBLOCK_BYTES, &map_u, ufull, kb * 64, row_tile * TC_BM);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = t0; t < t1; ++t) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
-                const bool item = t < prm.tiles_item;
-                const CUtensorMap *m = item ? &map_i : &map_p;
-                const int row0 = (item ? t : t - prm.tiles_item) * TC_BN;
-                for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(y_tiles + stage * TILE_BYTES + kb * KBLOCK_BYTES, m, &full[stage], kb * 64, row0);
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        // ===== TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues =====
+        Cursor c;
+        c.init(g0, prm.n_tiles);
+        for (; c.i < n_local; c.next()) {
+            if (c.i == 0 || c.n == 0) {      // first tile of a row segment: (re)load X
+                if (c.r >= 1) mbar_wait(xfree, (c.r - 1) & 1);   // every S MMA of the previous row has retired
+                const bool x_item = !TRANS || c.m < prm.tiles_item;
+                const CUtensorMap *mx = !TRANS ? &map_u : (x_item ? &map_i : &map_p);
+                const int x_row0 = (x_item ? c.m : c.m - prm.tiles_item) * TC_BM;
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(xfull, TILE_BYTES);
+                    for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_tile + kb * KBLOCK_BYTES, mx, xfull, kb * 64, x_row0);
+                }
+                __syncwarp();
             }
+            const int stage = c.i % TC_STAGES;
+            mbar_wait(&empty[stage], ((c.i / TC_STAGES) & 1) ^ 1);
+            const CUtensorMap *mw;
+            int row0;
+            if (TRANS) { mw = &map_u; row0 = c.n * TC_BN; }
+            else if (c.n < prm.tiles_item) { mw = &map_i; row0 = c.n * TC_BN; }
+            else { mw = &map_p; row0 = (c.n - prm.tiles_item) * TC_BN; }
+            if (elect_one_sync()) {
+                TT_DBG(0, c.i);
+                mbar_arrive_expect_tx(&full[stage], TILE_BYTES + (TRANS ? LSE_BYTES : 0));
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(w_tiles + stage * TILE_BYTES + kb * KBLOCK_BYTES, mw, &full[stage], kb * 64, row0);
+                if (TRANS)
+                    bulk_load_1d(lse_s + stage * TC_BN, prm.lse2p + static_cast<int64_t>(c.n) * TC_BN, LSE_BYTES, &full[stage]);
+            }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16_f32(TC_BM, TC_BN);
-            mbar_wait(ufull, 0);
-            tc_fence_after();
-            const uint32_t u_addr = smem_u32(u_tile);
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, aphase = 0;
-            for (int t = t0; t < t1; ++t) {
-                mbar_wait(&tempty[acc], aphase ^ 1);
-                mbar_wait(&full[stage], phase);
+        // ===== MMA issuer: whole warp in uniform control flow, one elected lane issues =====
+        if (n_local > 0) {
+            constexpr uint32_t idesc_s = idesc_bf16_f32(TC_BM, TC_BN, 0, 0);
+            constexpr uint32_t idesc_o = idesc_bf16_f32(TC_BM, D, 0, 1);   // B operand MN-major
+            const uint64_t xdesc = smem_desc_k_sw128(smem_u32(x_tile));
+            const uint64_t wdesc_k = smem_desc_k_sw128(smem_u32(w_tiles));
+            const uint64_t wdesc_mn = smem_desc_mn_sw128(smem_u32(w_tiles), KBLOCK_BYTES, 1024);
+            Cursor cs, co;   // S cursor, Out cursor
+            cs.init(g0, prm.n_tiles);
+            co.init(g0, prm.n_tiles);
+            auto issue_s = [&]() {
+                const int i = cs.i, b = i & 1, stage = i % TC_STAGES;
+                if (i >= 2) mbar_wait(&sfree[b], ((i >> 1) - 1) & 1);     // softmax(i-2) holds S[b] in registers
+                if (i == 0 || cs.n == 0) mbar_wait(xfull, cs.r & 1);
+                TT_DBG(1, i);
+                mbar_wait(&full[stage], (i / TC_STAGES) & 1);
                 tc_fence_after();
-                const uint32_t y_addr = smem_u32(y_tiles + stage * TILE_BYTES);
+                if (elect_one_sync()) {
+                TT_DBG(2, i);
+                // descriptors differ from the precomputed bases only in the 16-byte-unit start address field
+                const uint64_t wd = wdesc_k + static_cast<uint64_t>(stage * (TILE_BYTES >> 4));
+                const uint32_t acc = tmem_base + TM_S + b * TC_BN;
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k) {
-                    const uint32_t off = (k / 4) * KBLOCK_BYTES + (k % 4) * 32;  // 16 bf16 = 32 B inside the 128-B swizzle atom
-                    umma_f16(tmem_base + acc * TC_BN, smem_desc_k_sw128(u_addr + off), smem_desc_k_sw128(y_addr + off),
-                             idesc, k > 0 ? 1u : 0u);
+                    constexpr int dummy = 0; (void)dummy;
+                    const uint32_t off = ((k / 4) * KBLOCK_BYTES + (k % 4) * 32) >> 4;  // 16 bf16 = 32 B inside the swizzle atom
+                    if (k == 0) umma_f16_first(acc, xdesc + off, wd + off, idesc_s);
+                    else umma_f16_acc(acc, xdesc + off, wd + off, idesc_s);
                 }
-                umma_commit(&empty[stage]);   // smem slot reusable once these MMAs retire
-                umma_commit(&tfull[acc]);     // accumulator ready for the epilogue
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-                if (++acc == TC_ACC) { acc = 0; aphase ^= 1; }
+                if (!BWD) umma_commit(&empty[stage]);        // forward: the W tile is not needed again
+                umma_commit(&sfull[b]);
+                if (cs.n == prm.n_tiles - 1 || i == n_local - 1) umma_commit(xfree);
+                }
+                __syncwarp();
+                cs.next();
+            };
+            auto issue_out = [&]() {
+                const int i = co.i, b = i & 1, stage = i % TC_STAGES;
+                const bool first = (i == 0 || co.n == 0), last = (co.n == prm.n_tiles - 1 || i == n_local - 1);
+                TT_DBG(3, i);
+                mbar_wait(&gfull[b], (i >> 1) & 1);
+                TT_DBG(4, i);
+                if (first && co.r >= 1) mbar_wait(ofree, (co.r - 1) & 1);  // previous row's Out has been drained
+                tc_fence_after();
+                if (elect_one_sync()) {
+                const uint64_t wd = wdesc_mn + static_cast<uint64_t>(stage * (TILE_BYTES >> 4));
+                const uint32_t gaddr = tmem_base + TM_G + b * (TC_BN / 2);
+                if (first) umma_f16_ts_first(tmem_base + TM_OUT, gaddr, wd, idesc_o);
+                else umma_f16_ts_acc(tmem_base + TM_OUT, gaddr, wd, idesc_o);
+#pragma unroll
+                for (int k = 1; k < TC_BN / 16; ++k)
+                    umma_f16_ts_acc(tmem_base + TM_OUT, gaddr + k * 8, wd + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o);
+                umma_commit(&empty[stage]);
+                umma_commit(&gfree[b]);
+                if (last) umma_commit(ofull);
+                }
+                __syncwarp();
+                co.next();
+            };
+            if (!BWD) {
+                while (cs.i < n_local) issue_s();
+            } else {
+                // issue order follows the order in which the softmax groups produce their events:
+                // S(0) S(1) | S(2) | S(3) Out(0) | S(4) Out(1) | ...  (the tensor pipe retires in issue order)
+                issue_s();
+                if (n_local > 1) issue_s();
+                for (int j = 0; j <= n_local; ++j) {
+                    // a row's last Out goes first: the softmax groups drain the row (they wait for ofull) before
+                    // they load the next S tile, which issue_s(j + 2) below waits for
+                    const bool out_first = j >= 1 && (co.n == prm.n_tiles - 1 || co.i == n_local - 1);
+                    if (out_first) issue_out();
+                    if (j + 2 < n_local) issue_s();
+                    if (j >= 1 && !out_first) issue_out();
+                }
             }
         }
     } else {
-        // ===== epilogue: 4 warps, thread = row =====
-        const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        // ===== softmax: two groups of 4 warps alternate tiles; thread = X row =====
+        const int quarter = warp & 3;
+        const int grp = (warp - 2) >> 2;
         const int r_in_tile = quarter * 32 + lane;
-        const int64_t p = static_cast<int64_t>(row_tile) * TC_BM + r_in_tile;
-        const bool row_ok = p < prm.batch;
-        const int lo = row_ok ? prm.lo[p] : 0, hi = row_ok ? prm.hi[p] : 0;
-        float m = -INFINITY, s = 0.f;
-        int acc = 0;
-        uint32_t aphase = 0;
-        for (int t = t0; t < t1; ++t) {
-            const bool item = t < prm.tiles_item;
-            const int64_t col0 = static_cast<int64_t>(item ? t : t - prm.tiles_item) * TC_BN;
-            const int64_t ncol = item ? prm.batch : prm.pool_rows;
-            const bool special = (col0 + TC_BN > ncol) || (item && hi > col0 && lo < col0 + TC_BN);
-            mbar_wait(&tfull[acc], aphase);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * TC_BN + c * 32, r);
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        Cursor c;
+        c.init(g0, prm.n_tiles);
+        // per-row state, reloaded at every row segment
+        int lo = 0, hi = 0, p = 0;
+        bool x_item = true;
+        float row_stat = 0.f;             // BWD_X: lse2 of this row
+        float m_run = -INFINITY, s_run = 0.f;   // FWD: running max of the raw logits / sum of exp2
+        for (; c.i < n_local; c.next()) {
+            const int i = c.i;
+            if (i == 0 || c.n == 0) {
+                x_item = !TRANS || c.m < prm.tiles_item;
+                p = (x_item ? c.m : c.m - prm.tiles_item) * TC_BM + r_in_tile;   // row index inside its matrix
+                lo = hi = 0;
+                if (x_item && p < prm.batch) { lo = prm.lo[p]; hi = prm.hi[p]; }
+                if (MODE == MODE_BWD_X) row_stat = (p < prm.batch) ? prm.lse2p[p] : INFINITY;
+                m_run = -INFINITY; s_run = 0.f;
+            }
+            if ((i & 1) == grp) {
+                const int b = i & 1, k = i >> 1;
+                const bool w_item = TRANS || c.n < prm.tiles_item;
+                const int col0 = (w_item ? c.n : c.n - prm.tiles_item) * TC_BN;
+                const int ncol = static_cast<int>(w_item ? prm.batch : prm.pool_rows);
+                // per-element path: columns past the end (zero-filled W rows would count as logit 0; BWD_Y handles
+                // them through lse = +inf) and the collision run / diagonal of this row
+                const bool special = (!TRANS && col0 + TC_BN > ncol) || (x_item && w_item && hi > col0 && lo < col0 + TC_BN);
+                if (TRANS) mbar_wait(&full[i % TC_STAGES], (i / TC_STAGES) & 1);   // lse_s of this stage has landed
+                if (lane == 0 && quarter == 0) TT_DBG(5, i);
+                mbar_wait(&sfull[b], k & 1);
+                tc_fence_after();
+                if (lane == 0 && quarter == 0) TT_DBG(6, i);
+                uint32_t r[4][32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld_32x32(lane_addr + TM_S + b * TC_BN + q * 32, r[q]);
                 tmem_ld_wait();
-                float x[32];
+                tc_fence_before();
+                mbar_arrive(&sfree[b]);          // the tensor pipe may overwrite S[b] with tile i+2 now
+                if (lane == 0 && quarter == 0) TT_DBG(7, i);
+                if (MODE == MODE_FWD) {
+                    if (special) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * prm.scale2;
-                if (special) {
+                        for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int64_t col = col0 + c * 32 + j;
-                        const bool dead = (col >= ncol) || (item && col >= lo && col < hi && col != p);
-                        if (dead) x[j] = -INFINITY;
+                            for (int j = 0; j < 32; ++j) {
+                                const int col = col0 + q * 32 + j;
+                                const bool dead = (col >= ncol) || (w_item && col >= lo && col < hi && col != p);
+                                if (dead) r[q][j] = 0xff800000u;   // -inf
+                            }
                     }
-                }
-                float cmax = x[0];
+                    float c0 = __uint_as_float(r[0][0]), c1 = __uint_as_float(r[1][0]);
+                    float c2 = __uint_as_float(r[2][0]), c3 = __uint_as_float(r[3][0]);
 #pragma unroll
-                for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, x[j]);
-                if (cmax > m) {
-                    s *= ex2_approx(m - cmax);  // m = -inf -> 0 * s(=0)
-                    m = cmax;
-                }
-                if (m > -INFINITY) {
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        a0 += ex2_approx(x[j] - m);
-                        a1 += ex2_approx(x[j + 1] - m);
-                        a2 += ex2_approx(x[j + 2] - m);
-                        a3 += ex2_approx(x[j + 3] - m);
+                    for (int j = 1; j < 32; ++j) {
+                        c0 = fmaxf(c0, __uint_as_float(r[0][j]));
+                        c1 = fmaxf(c1, __uint_as_float(r[1][j]));
+                        c2 = fmaxf(c2, __uint_as_float(r[2][j]));
+                        c3 = fmaxf(c3, __uint_as_float(r[3][j]));
                     }
-                    s += (a0 + a1) + (a2 + a3);
+                    const float cmax = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+                    if (cmax > m_run) {
+                        s_run *= ex2_approx((m_run - cmax) * prm.scale2);   // m_run = -inf -> 0 * 0
+                        m_run = cmax;
+                    }
+                    if (m_run > -INFINITY) {
+                        const float neg = -m_run * prm.scale2;
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            a0 += ex2_approx(fmaf(__uint_as_float(r[0][j]), prm.scale2, neg));
+                            a1 += ex2_approx(fmaf(__uint_as_float(r[1][j]), prm.scale2, neg));
+                            a2 += ex2_approx(fmaf(__uint_as_float(r[2][j]), prm.scale2, neg));
+                            a3 += ex2_approx(fmaf(__uint_as_float(r[3][j]), prm.scale2, neg));
+                        }
+                        s_run += (a0 + a1) + (a2 + a3);
+                    }
+                } else {
+                    const float *ls = lse_s + (i % TC_STAGES) * TC_BN;
+                    uint32_t g[2][32];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int qq = 0; qq < 2; ++qq) {
+                            const int q = h * 2 + qq;
+                            float e[32];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 st = make_float4(row_stat, row_stat, row_stat, row_stat);
+                                if (TRANS) st = *reinterpret_cast<const float4 *>(ls + q * 32 + j);
+                                e[j] = ex2_approx(fmaf(__uint_as_float(r[q][j]), prm.scale2, -st.x));
+                                e[j + 1] = ex2_approx(fmaf(__uint_as_float(r[q][j + 1]), prm.scale2, -st.y));
+                                e[j + 2] = ex2_approx(fmaf(__uint_as_float(r[q][j + 2]), prm.scale2, -st.z));
+                                e[j + 3] = ex2_approx(fmaf(__uint_as_float(r[q][j + 3]), prm.scale2, -st.w));
+                            }
+                            if (special) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int col = col0 + q * 32 + j;
+                                    if (col >= ncol) e[j] = 0.f;
+                                    else if (x_item && w_item && col >= lo && col < hi) e[j] = (col == p) ? e[j] - 1.0f : 0.f;
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) g[h][qq * 16 + j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+                        }
+                    }
+                    if (lane == 0 && quarter == 0) TT_DBG(8, i);
+                    if (k >= 1) mbar_wait(&gfree[b], (k - 1) & 1);   // Out(i-2) has consumed G[b] (long ago, normally)
+                    if (lane == 0 && quarter == 0) TT_DBG(9, i);
+                    tmem_st_32x32(lane_addr + TM_G + b * (TC_BN / 2), g[0]);
+                    tmem_st_32x32(lane_addr + TM_G + b * (TC_BN / 2) + 32, g[1]);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&gfull[b]);
+                    if (lane == 0 && quarter == 0) TT_DBG(10, i);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tempty[acc]);
-            if (++acc == TC_ACC) { acc = 0; aphase ^= 1; }
-        }
-        if (row_ok) {
-            prm.part_m[static_cast<int64_t>(split) * prm.batch + p] = m;
-            prm.part_s[static_cast<int64_t>(split) * prm.batch + p] = s;
+            // ---- end of a row segment: flush
+            if (c.n == prm.n_tiles - 1 || i == n_local - 1) {
+                const int seg = static_cast<int>(blockIdx.x) - sched_first_cta(c.m, prm.n_tiles, prm.per_cta);
+                if (MODE == MODE_FWD) {
+                    if (p < prm.batch) {
+                        const int64_t slot = static_cast<int64_t>(2 * seg + grp) * prm.batch + p;
+                        prm.part_m[slot] = m_run;
+                        prm.part_s[slot] = s_run;
+                    }
+                } else {
+                    // both groups drain Out (group = column half) once its last MMA has retired
+                    mbar_wait(ofull, c.r & 1);
+                    tc_fence_after();
+                    float *dst = prm.part + ((static_cast<int64_t>(seg) * prm.m_tiles + c.m) * TC_BM + r_in_tile) * D + grp * (D / 2);
+#pragma unroll
+                    for (int cc = 0; cc < D / 64; ++cc) {
+                        uint32_t o[32];
+                        tmem_ld_32x32(lane_addr + TM_OUT + grp * (D / 2) + cc * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<uint4 *>(dst + cc * 32 + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(ofree);
+                }
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        tmem_dealloc<TC_ACC * TC_BN>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
-// one warp per (sorted) row: merge splits (exp2 domain), per-row hard negatives, positive logit
+// ---------------------------------------------------------------- forward epilogue kernels
+// one warp per (sorted) row: merge the stream-K partials, per-row hard negatives, positive logit
 __global__ void __launch_bounds__(256)
 ce_tc_finalize(const __nv_bfloat16 *__restrict__ ub, const __nv_bfloat16 *__restrict__ ib,
                const float *__restrict__ user32, const float *__restrict__ hn_rows, int n_rowneg,
-               const int32_t *__restrict__ perm, int64_t B, int dim, float inv_temp, int splits,
+               const int32_t *__restrict__ perm, int64_t B, int dim, float inv_temp, int n_tiles, int64_t per_cta,
                const float *__restrict__ part_m, const float *__restrict__ part_s, float *__restrict__ row_lse,
-               float *__restrict__ row_pos, float *__restrict__ row_loss, float *__restrict__ lse_sorted,
-               int *__restrict__ nan_flags) {
+               float *__restrict__ row_pos, float *__restrict__ row_loss, int *__restrict__ nan_flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     const float scale2 = inv_temp * LOG2E;
     for (int64_t p = warp; p < B; p += n_warps) {
+        const int mt = static_cast<int>(p / TC_BM);
+        const int n_slots = 2 * (sched_last_cta(mt, n_tiles, per_cta) - sched_first_cta(mt, n_tiles, per_cta) + 1);
         float m = -INFINITY, s = 0.f;  // exp2 domain
-        for (int k = 0; k < splits; ++k) {
-            const float mk = part_m[static_cast<int64_t>(k) * B + p];
+        for (int k = 0; k < n_slots; ++k) {
+            const float mk = part_m[static_cast<int64_t>(k) * B + p] * scale2;
             const float sk = part_s[static_cast<int64_t>(k) * B + p];
-            if (mk == -INFINITY) continue;
+            if (!(mk > -INFINITY)) continue;
             const float mn = fmaxf(m, mk);
             s = ((m == -INFINITY) ? 0.f : s * exp2f(m - mn)) + sk * exp2f(mk - mn);
             m = mn;
@@ -296,7 +553,6 @@ ce_tc_finalize(const __nv_bfloat16 *__restrict__ ub, const __nv_bfloat16 *__rest
             row_lse[orig] = lse;
             row_pos[orig] = pos;
             row_loss[p] = lse - pos;
-            lse_sorted[p] = lse;
         }
     }
 }
@@ -314,325 +570,7 @@ __global__ void __launch_bounds__(1024) ce_tc_mean(const float *__restrict__ x, 
     if (threadIdx.x == 0) *out = sh[0] / static_cast<float>(n);
 }
 
-struct CeTcPlan {
-    int row_tiles, tiles_item, tiles_pool, tiles_total, splits;
-    size_t sort_bytes;
-};
-
-static CeTcPlan ce_tc_plan(int64_t batch, int64_t pool_rows) {
-    CeTcPlan p;
-    p.row_tiles = static_cast<int>((batch + TC_BM - 1) / TC_BM);
-    p.tiles_item = static_cast<int>((batch + TC_BN - 1) / TC_BN);
-    p.tiles_pool = static_cast<int>((pool_rows + TC_BN - 1) / TC_BN);
-    p.tiles_total = p.tiles_item + p.tiles_pool;
-    int want = (4 * sm_count() + p.row_tiles - 1) / p.row_tiles;  // ~4 CTAs per SM over the launch
-    int cap = p.tiles_total / 8;                                  // keep >= 8 tiles per CTA
-    if (cap < 1) cap = 1;
-    if (want > cap) want = cap;
-    if (want < 1) want = 1;
-    p.splits = want;
-    p.sort_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, p.sort_bytes, static_cast<int64_t *>(nullptr),
-                                    static_cast<int64_t *>(nullptr), static_cast<int32_t *>(nullptr),
-                                    static_cast<int32_t *>(nullptr), static_cast<int>(batch));
-    return p;
-}
-
-struct CeTcWs {
-    __nv_bfloat16 *ub, *ib, *pb;
-    int64_t *keys_in, *keys_out;
-    int32_t *vals_in, *perm, *lo, *hi;
-    float *part_m, *part_s, *row_loss, *lse_sorted;
-    void *cub_tmp;
-    bool ok;
-    size_t used;
-};
-
-static CeTcWs ce_tc_carve(void *workspace, size_t bytes, int64_t batch, int64_t pool_rows, int dim, const CeTcPlan &pl) {
-    Workspace ws(workspace, bytes);
-    CeTcWs w;
-    w.ub = ws.take<__nv_bfloat16>(batch * dim);
-    w.ib = ws.take<__nv_bfloat16>(batch * dim);
-    w.pb = ws.take<__nv_bfloat16>((pool_rows > 0 ? pool_rows : 1) * dim);
-    w.keys_in = ws.take<int64_t>(batch);
-    w.keys_out = ws.take<int64_t>(batch);
-    w.vals_in = ws.take<int32_t>(batch);
-    w.perm = ws.take<int32_t>(batch);
-    w.lo = ws.take<int32_t>(batch);
-    w.hi = ws.take<int32_t>(batch);
-    w.part_m = ws.take<float>(static_cast<size_t>(pl.splits) * batch);
-    w.part_s = ws.take<float>(static_cast<size_t>(pl.splits) * batch);
-    w.row_loss = ws.take<float>(batch);
-    w.lse_sorted = ws.take<float>(batch);
-    w.cub_tmp = ws.take<char>(pl.sort_bytes);
-    w.ok = ws.ok();
-    w.used = ws.off;
-    return w;
-}
-
-template <int D>
-static int launch_ce_tc_fwd(const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mp, const CeTcParams &prm,
-                            int row_tiles, cudaStream_t st) {
-    constexpr size_t smem = 1024 + static_cast<size_t>(TC_BN) * D * 2 * (1 + TC_STAGES) + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ce_tc_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(ce_tc_fwd_kernel)");
-        attr_set = true;
-    }
-    dim3 grid(row_tiles, prm.splits);
-    ce_tc_fwd_kernel<D><<<grid, TC_THREADS, smem, st>>>(mu, mi, mp, prm);
-    TT_LAUNCH_CHECK("ce_tc_fwd_kernel");
-    return 0;
-}
-
-static inline unsigned tc_grid(int64_t n, int threads) {
-    int64_t b = (n + threads - 1) / threads;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
-    if (b > cap) b = cap;
-    if (b < 1) b = 1;
-    return static_cast<unsigned>(b);
-}
-
-
-// ================================================================== backward
-// dU = c * sum_j (P - delta)[b, j] * Y_j ,  dY = c * sum_b (P - delta)[b, j] * U_b ,  c = grad_loss / (B * T),
-// P = exp(z - lse) recomputed tile by tile (flash-attention style) -- two passes of ONE kernel:
-//   TRANS = false : X = U rows (CTA owns 128 of them), W = [item ; pool] tiles, row statistic lse[x]
-//   TRANS = true  : X = item / pool rows,               W = U tiles,           column statistic lse[w]
-// Per W tile:  S = X W^T (SS tcgen05.mma into TMEM)  ->  8 softmax warps read S (tcgen05.ld, thread = row),
-// G = bf16(P - delta) written back to TMEM (tcgen05.st, packed pairs)  ->  Out += G W (TS tcgen05.mma: A from
-// TMEM, B = the SAME smem tile read through an MN-major descriptor).  S and G are double buffered; the tensor
-// pipe executes in issue order, which is what makes the two extra "buffer free" barriers unnecessary (see the
-// MMA warp).  Neither S nor G ever leaves the SM.
-constexpr int BW_THREADS = 320;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: softmax (2 per lane quarter)
-constexpr int BW_STAGES = 4;
-constexpr uint32_t BW_TMEM_S = 0, BW_TMEM_G = 256, BW_TMEM_OUT = 384;
-
-struct CeBwdParams {
-    int64_t batch, pool_rows;
-    int tiles_item, tiles_pool;
-    int n_tiles;   // W tiles in this pass
-    int splits;
-    float scale2;  // inv_temp * log2(e)
-    const int32_t *lo, *hi;
-    const float *lse2p;  // [tiles_item * 128] lse * log2(e) in sorted order, +inf past batch
-    float *part;         // [splits][part_rows][D] raw fp32 accumulators
-    int64_t part_rows;
-};
-
-__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-
-template <int D, bool TRANS>
-__global__ void __launch_bounds__(BW_THREADS, 1)
-ce_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i,
-                 const __grid_constant__ CUtensorMap map_p, const CeBwdParams prm) {
-    constexpr int KB = D / 64;
-    constexpr int TILE_BYTES = TC_BN * D * 2;
-    constexpr int KBLOCK_BYTES = TC_BN * 128;
-    constexpr int LSE_BYTES = TC_BN * 4;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *x_tile = smem;
-    uint8_t *w_tiles = smem + TILE_BYTES;
-    float *lse_s = reinterpret_cast<float *>(w_tiles + BW_STAGES * TILE_BYTES);  // [BW_STAGES][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(lse_s + BW_STAGES * TC_BN);
-    uint64_t *full = bars;                  // [BW_STAGES]  TMA -> MMA (+ softmax for lse_s)
-    uint64_t *empty = full + BW_STAGES;     // [BW_STAGES]  MMA -> TMA
-    uint64_t *sfull = empty + BW_STAGES;    // [2]          S tile ready
-    uint64_t *gfull = sfull + 2;            // [2]          G tile written (256 arrivals)
-    uint64_t *xfull = gfull + 2;            // [1]
-    uint64_t *ofull = xfull + 1;            // [1]          all Out MMAs retired
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ofull + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, split = blockIdx.y;
-    const int tiles_per = (prm.n_tiles + prm.splits - 1) / prm.splits;
-    const int t0 = split * tiles_per;
-    const int t1 = min(prm.n_tiles, t0 + tiles_per);
-    const int n_local = max(t1 - t0, 0);
-    const bool x_is_item = !TRANS || m_tile < prm.tiles_item;   // TRANS: X rows are item rows (else pool rows)
-    const int x_row0 = (TRANS && !x_is_item ? m_tile - prm.tiles_item : m_tile) * TC_BM;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&map_u);
-        prefetch_tensormap(&map_i);
-        if (prm.pool_rows > 0) prefetch_tensormap(&map_p);
-        for (int s = 0; s < BW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&sfull[a], 1); mbar_init(&gfull[a], 256); }
-        mbar_init(xfull, 1);
-        mbar_init(ofull, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0 && n_local > 0) {
-            const CUtensorMap *mx = !TRANS ? &map_u : (x_is_item ? &map_i : &map_p);
-            mbar_arrive_expect_tx(xfull, TILE_BYTES);
-            for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_tile + kb * KBLOCK_BYTES, mx, xfull, kb * 64, x_row0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = t0; t < t1; ++t) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], TILE_BYTES + (TRANS ? LSE_BYTES : 0));
-                const CUtensorMap *m;
-                int row0;
-                if (TRANS) { m = &map_u; row0 = t * TC_BN; }
-                else if (t < prm.tiles_item) { m = &map_i; row0 = t * TC_BN; }
-                else { m = &map_p; row0 = (t - prm.tiles_item) * TC_BN; }
-                for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(w_tiles + stage * TILE_BYTES + kb * KBLOCK_BYTES, m, &full[stage], kb * 64, row0);
-                if (TRANS) bulk_load_1d(lse_s + stage * TC_BN, prm.lse2p + static_cast<int64_t>(t) * TC_BN, LSE_BYTES, &full[stage]);
-                if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0 && n_local > 0) {
-            constexpr uint32_t idesc_s = idesc_bf16_f32(TC_BM, TC_BN, 0, 0);
-            constexpr uint32_t idesc_o = idesc_bf16_f32(TC_BM, D, 0, 1);   // B operand MN-major
-            mbar_wait(xfull, 0);
-            tc_fence_after();
-            const uint32_t x_addr = smem_u32(x_tile);
-            auto issue_s = [&](int i) {
-                const int stage = i % BW_STAGES;
-                mbar_wait(&full[stage], (i / BW_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t w_addr = smem_u32(w_tiles + stage * TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < D / 16; ++k) {
-                    const uint32_t off = (k / 4) * KBLOCK_BYTES + (k % 4) * 32;
-                    umma_f16(tmem_base + BW_TMEM_S + (i & 1) * TC_BN, smem_desc_k_sw128(x_addr + off),
-                             smem_desc_k_sw128(w_addr + off), idesc_s, k > 0 ? 1u : 0u);
-                }
-                umma_commit(&sfull[i & 1]);
-            };
-            issue_s(0);
-            for (int i = 0; i < n_local; ++i) {
-                // S(i+1) goes into the buffer softmax(i-1) read; it finished before gfull(i-1) completed, which
-                // this thread waited for in the previous iteration.
-                if (i + 1 < n_local) issue_s(i + 1);
-                mbar_wait(&gfull[i & 1], (i >> 1) & 1);
-                tc_fence_after();
-                const int stage = i % BW_STAGES;
-                const uint32_t w_addr = smem_u32(w_tiles + stage * TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BN / 16; ++k)
-                    umma_f16_ts(tmem_base + BW_TMEM_OUT, tmem_base + BW_TMEM_G + (i & 1) * (TC_BN / 2) + k * 8,
-                                smem_desc_mn_sw128(w_addr + k * 2048, KBLOCK_BYTES, 1024), idesc_o,
-                                (i > 0 || k > 0) ? 1u : 0u);
-                // retiring Out(i) frees the smem stage; it also precedes S(i+2) on the in-order tensor pipe, so
-                // sfull(i+2) implies G(i) has been consumed and may be overwritten
-                umma_commit(&empty[stage]);
-            }
-            umma_commit(ofull);
-        }
-    } else {
-        // ===== softmax warps: thread = X row, each warp a 32-lane quarter x 64-column half =====
-        const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int r_in_tile = quarter * 32 + lane;
-        const int64_t p = static_cast<int64_t>(x_row0) + r_in_tile;       // row index inside its matrix
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        int lo = 0, hi = 0;
-        float row_stat = 0.f;
-        if (x_is_item && p < prm.batch) { lo = prm.lo[p]; hi = prm.hi[p]; }
-        if (!TRANS) row_stat = (p < prm.batch) ? prm.lse2p[p] : INFINITY;
-        for (int i = 0; i < n_local; ++i) {
-            const int t = t0 + i;
-            const bool w_is_item = TRANS || t < prm.tiles_item;
-            const int64_t col0 = static_cast<int64_t>(w_is_item ? t : t - prm.tiles_item) * TC_BN;
-            const int64_t ncol = w_is_item ? prm.batch : prm.pool_rows;
-            // columns that need the per-element path: past the end (zero-filled rows of W would count as logit 0;
-            // TRANS handles them through lse = +inf) and the collision run / diagonal of this row
-            const bool special = (!TRANS && col0 + TC_BN > ncol) ||
-                                 (x_is_item && w_is_item && hi > col0 && lo < col0 + TC_BN);
-            if (TRANS) mbar_wait(&full[i % BW_STAGES], (i / BW_STAGES) & 1);   // lse_s of this stage has landed
-            mbar_wait(&sfull[i & 1], (i >> 1) & 1);
-            tc_fence_after();
-            uint32_t ra[32], rb[32];
-            const uint32_t s_addr = lane_addr + BW_TMEM_S + (i & 1) * TC_BN + half * 64;
-            tmem_ld_32x32(s_addr, ra);
-            tmem_ld_32x32(s_addr + 32, rb);
-            tmem_ld_wait();
-            const float *ls = lse_s + (i % BW_STAGES) * TC_BN + half * 64;
-            uint32_t g[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float e[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 st = make_float4(row_stat, row_stat, row_stat, row_stat);
-                    if (TRANS) st = *reinterpret_cast<const float4 *>(ls + c * 32 + j);
-                    const uint32_t *r = c == 0 ? ra : rb;
-                    e[j] = ex2_approx(fmaf(__uint_as_float(r[j]), prm.scale2, -st.x));
-                    e[j + 1] = ex2_approx(fmaf(__uint_as_float(r[j + 1]), prm.scale2, -st.y));
-                    e[j + 2] = ex2_approx(fmaf(__uint_as_float(r[j + 2]), prm.scale2, -st.z));
-                    e[j + 3] = ex2_approx(fmaf(__uint_as_float(r[j + 3]), prm.scale2, -st.w));
-                }
-                if (special) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int64_t col = col0 + half * 64 + c * 32 + j;
-                        if (col >= ncol) e[j] = 0.f;
-                        else if (x_is_item && w_is_item && col >= lo && col < hi) e[j] = (col == p) ? e[j] - 1.0f : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) g[c * 16 + j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
-            }
-            tmem_st_32x32(lane_addr + BW_TMEM_G + (i & 1) * (TC_BN / 2) + half * 32, g);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&gfull[i & 1]);
-        }
-        // final: raw accumulators -> this split's partial (scaled / un-permuted by ce_tc_reduce_rows)
-        if (n_local > 0) {
-            mbar_wait(ofull, 0);
-            tc_fence_after();
-        }
-        float *dst = prm.part + (static_cast<int64_t>(split) * prm.part_rows + static_cast<int64_t>(m_tile) * TC_BM + r_in_tile) * D +
-                     half * (D / 2);
-#pragma unroll
-        for (int c = 0; c < D / 64; ++c) {
-            uint32_t r[32];
-            if (n_local > 0) {
-                tmem_ld_32x32(lane_addr + BW_TMEM_OUT + half * (D / 2) + c * 32, r);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<uint4 *>(dst + c * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
-
+// ---------------------------------------------------------------- backward helper kernels
 // lse2p[p] = lse[perm[p]] * log2(e) for p < B, +inf for the padding up to a multiple of 128
 __global__ void ce_tc_bwd_prep(const float *__restrict__ row_lse, const int32_t *__restrict__ perm, int64_t B,
                                int64_t padded, float *__restrict__ lse2p) {
@@ -667,20 +605,22 @@ ce_tc_bwd_hn_rows(const float *__restrict__ user, const float *__restrict__ hn_r
     }
 }
 
-// out[dst(p), :] = (*grad_loss * scale) * sum_s part[s][row_begin + p, :] (+ extra_scale * extra[dst(p), :]);
-// dst(p) = perm ? perm[p] : p.  Fixed summation order.
+// out[dst(p), :] = (*grad_loss * scale) * sum_seg part[seg][row_begin + p, :] (+ extra_scale * extra[dst(p), :]);
+// dst(p) = perm ? perm[p] : p.  Segments of the row tile in fixed (CTA) order.
 __global__ void __launch_bounds__(256)
-ce_tc_reduce_rows(const float *__restrict__ part, int splits, int64_t part_rows, int64_t row_begin, int64_t n_rows,
-                  int dim, const int32_t *__restrict__ perm, const float *__restrict__ grad_loss, float scale,
-                  const float *__restrict__ extra, float extra_scale, float *__restrict__ out) {
+ce_tc_reduce_rows(const float *__restrict__ part, int64_t part_rows, int n_tiles, int64_t per_cta, int64_t row_begin,
+                  int64_t n_rows, int dim, const int32_t *__restrict__ perm, const float *__restrict__ grad_loss,
+                  float scale, const float *__restrict__ extra, float extra_scale, float *__restrict__ out) {
     const int vpr = dim / 4;
     const float c = (*grad_loss) * scale;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_rows * vpr;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t p = i / vpr;
         const int c4 = static_cast<int>(i - p * vpr) * 4;
+        const int mt = static_cast<int>((row_begin + p) / TC_BM);
+        const int n_seg = sched_last_cta(mt, n_tiles, per_cta) - sched_first_cta(mt, n_tiles, per_cta) + 1;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < splits; ++s) {
+        for (int s = 0; s < n_seg; ++s) {
             const float4 v = *reinterpret_cast<const float4 *>(part + (static_cast<int64_t>(s) * part_rows + row_begin + p) * dim + c4);
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
@@ -695,56 +635,117 @@ ce_tc_reduce_rows(const float *__restrict__ part, int splits, int64_t part_rows,
     }
 }
 
-static int bwd_splits(int m_tiles, int n_tiles) {
-    int want = (4 * sm_count() + m_tiles - 1) / m_tiles;
-    int cap = n_tiles / 8;
-    if (cap < 1) cap = 1;
-    if (want > cap) want = cap;
-    if (want < 1) want = 1;
-    return want;
+// ---------------------------------------------------------------- host side
+struct CeTcPlan {
+    int tiles_item, tiles_pool, tiles_total;
+    Sched fwd, bwd_x, bwd_y;
+    size_t sort_bytes;
+};
+
+static CeTcPlan ce_tc_plan(int64_t batch, int64_t pool_rows) {
+    CeTcPlan p;
+    p.tiles_item = static_cast<int>((batch + TC_BN - 1) / TC_BN);
+    p.tiles_pool = static_cast<int>((pool_rows + TC_BN - 1) / TC_BN);
+    p.tiles_total = p.tiles_item + p.tiles_pool;
+    p.fwd = make_sched(p.tiles_item, p.tiles_total);
+    p.bwd_x = p.fwd;
+    p.bwd_y = make_sched(p.tiles_total, p.tiles_item);
+    p.sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, p.sort_bytes, static_cast<int64_t *>(nullptr),
+                                    static_cast<int64_t *>(nullptr), static_cast<int32_t *>(nullptr),
+                                    static_cast<int32_t *>(nullptr), static_cast<int>(batch));
+    return p;
 }
 
-struct CeBwdWs {
-    float *lse2p, *extra, *part_u, *part_y;
-    int splits_u, splits_y;
-    int64_t rows_u, rows_y;
+struct CeTcWs {
+    __nv_bfloat16 *ub, *ib, *pb;
+    int64_t *keys_in, *keys_out;
+    int32_t *vals_in, *perm, *lo, *hi;
+    float *part_m, *part_s, *row_loss;
+    void *cub_tmp;
     bool ok;
     size_t used;
 };
 
-static CeBwdWs ce_bwd_carve(void *workspace, size_t bytes, int64_t batch, int64_t pool_rows, int n_rowneg, int dim,
-                            const CeTcPlan &pl) {
+static CeTcWs ce_tc_carve(void *workspace, size_t bytes, int64_t batch, int64_t pool_rows, int dim, const CeTcPlan &pl) {
     Workspace ws(workspace, bytes);
-    CeBwdWs w;
-    w.splits_u = bwd_splits(pl.tiles_item, pl.tiles_total);
-    w.splits_y = bwd_splits(pl.tiles_total, pl.tiles_item);
-    w.rows_u = static_cast<int64_t>(pl.tiles_item) * TC_BM;
-    w.rows_y = static_cast<int64_t>(pl.tiles_total) * TC_BM;
-    w.lse2p = ws.take<float>(w.rows_u);
-    w.extra = ws.take<float>(n_rowneg > 0 ? batch * dim : 1);
-    w.part_u = ws.take<float>(static_cast<size_t>(w.splits_u) * w.rows_u * dim);
-    w.part_y = ws.take<float>(static_cast<size_t>(w.splits_y) * w.rows_y * dim);
-    (void)pool_rows;
+    CeTcWs w;
+    w.ub = ws.take<__nv_bfloat16>(batch * dim);
+    w.ib = ws.take<__nv_bfloat16>(batch * dim);
+    w.pb = ws.take<__nv_bfloat16>((pool_rows > 0 ? pool_rows : 1) * dim);
+    w.keys_in = ws.take<int64_t>(batch);
+    w.keys_out = ws.take<int64_t>(batch);
+    w.vals_in = ws.take<int32_t>(batch);
+    w.perm = ws.take<int32_t>(batch);
+    w.lo = ws.take<int32_t>(batch);
+    w.hi = ws.take<int32_t>(batch);
+    w.part_m = ws.take<float>(static_cast<size_t>(2 * pl.fwd.max_seg) * batch);
+    w.part_s = ws.take<float>(static_cast<size_t>(2 * pl.fwd.max_seg) * batch);
+    w.row_loss = ws.take<float>(batch);
+    w.cub_tmp = ws.take<char>(pl.sort_bytes);
     w.ok = ws.ok();
     w.used = ws.off;
     return w;
 }
 
-template <int D, bool TRANS>
-static int launch_ce_tc_bwd(const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mp, const CeBwdParams &prm,
-                            int m_tiles, cudaStream_t st) {
-    constexpr size_t smem = 1024 + static_cast<size_t>(TC_BN) * D * 2 * (1 + BW_STAGES) + BW_STAGES * TC_BN * 4 + 256;
+struct CeBwdWs {
+    float *lse2p, *extra, *part_x, *part_y;
+    int64_t rows_x, rows_y;
+    bool ok;
+    size_t used;
+};
+
+static CeBwdWs ce_bwd_carve(void *workspace, size_t bytes, int64_t batch, int n_rowneg, int dim, const CeTcPlan &pl) {
+    Workspace ws(workspace, bytes);
+    CeBwdWs w;
+    w.rows_x = static_cast<int64_t>(pl.tiles_item) * TC_BM;
+    w.rows_y = static_cast<int64_t>(pl.tiles_total) * TC_BM;
+    w.lse2p = ws.take<float>(w.rows_x);
+    w.extra = ws.take<float>(n_rowneg > 0 ? batch * dim : 1);
+    w.part_x = ws.take<float>(static_cast<size_t>(pl.bwd_x.max_seg) * w.rows_x * dim);
+    w.part_y = ws.take<float>(static_cast<size_t>(pl.bwd_y.max_seg) * w.rows_y * dim);
+    w.ok = ws.ok();
+    w.used = ws.off;
+    return w;
+}
+
+template <int D, int MODE>
+static int launch_ce_tc(const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mp, const CeTcParams &prm,
+                        int grid, cudaStream_t st) {
+    constexpr int ST = TcStages<D>::value;
+    constexpr size_t smem = 1024 + static_cast<size_t>(TC_BN) * D * 2 * (1 + ST) + ST * TC_BN * 4 + 256;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ce_tc_bwd_kernel<D, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(ce_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
-        if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(ce_tc_bwd_kernel)");
+        if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(ce_tc_kernel)");
         attr_set = true;
     }
-    dim3 grid(m_tiles, prm.splits);
-    ce_tc_bwd_kernel<D, TRANS><<<grid, BW_THREADS, smem, st>>>(mu, mi, mp, prm);
-    TT_LAUNCH_CHECK("ce_tc_bwd_kernel");
+    ce_tc_kernel<D, MODE><<<grid, TC_THREADS, smem, st>>>(mu, mi, mp, prm);
+    TT_LAUNCH_CHECK("ce_tc_kernel");
     return 0;
+}
+
+template <int MODE>
+static int launch_ce_tc_dim(int dim, const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mp,
+                            const CeTcParams &prm, int grid, cudaStream_t st) {
+    return dim == 128 ? launch_ce_tc<128, MODE>(mu, mi, mp, prm, grid, st) : launch_ce_tc<64, MODE>(mu, mi, mp, prm, grid, st);
+}
+
+static long long *g_ce_dbg = nullptr;   // set by tt_ce_tc_debug_trace (developer tool, not part of the product path)
+
+static void fill_sched(CeTcParams &prm, const Sched &s) {
+    prm.dbg = g_ce_dbg;
+    prm.m_tiles = s.m_tiles; prm.n_tiles = s.n_tiles;
+    prm.per_cta = s.per_cta; prm.total = s.total; prm.max_seg = s.max_seg;
+}
+
+static inline unsigned tc_grid(int64_t n, int threads) {
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<unsigned>(b);
 }
 
 }  // namespace tt
@@ -766,7 +767,8 @@ extern "C" int tt_ce_fwd_tc(const float *user, const float *item, const int64_t 
     TT_CHECK_ARG(user && item && loss && row_lse && row_pos && nan_flags && workspace, "null pointer");
     TT_CHECK_ARG((hn_rows != nullptr) == (n_rowneg > 0), "hn_rows / n_rowneg mismatch");
     TT_CHECK_ARG((pool != nullptr) == (pool_rows > 0), "pool / pool_rows mismatch");
-    TT_CHECK_ARG(batch > 0 && batch < (int64_t(1) << 31), "bad batch");
+    TT_CHECK_ARG(batch > 0 && batch < (int64_t(1) << 30) && pool_rows < (int64_t(1) << 30), "bad batch");
+    TT_CHECK_ARG(inv_temp > 0.f, "temperature must be positive");
     if (dim != 64 && dim != 128) { set_error("tensor-core CE path supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const CeTcPlan pl = ce_tc_plan(batch, pool_rows);
@@ -798,18 +800,17 @@ extern "C" int tt_ce_fwd_tc(const float *user, const float *item, const int64_t 
     if ((rc = make_tmap_bf16_rows(&mu, w.ub, batch, dim, TC_BM))) return rc;
     if ((rc = make_tmap_bf16_rows(&mi, w.ib, batch, dim, TC_BN))) return rc;
     if ((rc = make_tmap_bf16_rows(&mp, pool ? w.pb : w.ib, pool ? pool_rows : batch, dim, TC_BN))) return rc;
-    CeTcParams prm;
+    CeTcParams prm{};
     prm.batch = batch; prm.pool_rows = pool_rows;
-    prm.tiles_item = pl.tiles_item; prm.tiles_total = pl.tiles_total; prm.splits = pl.splits;
+    prm.tiles_item = pl.tiles_item; prm.tiles_pool = pl.tiles_pool;
+    fill_sched(prm, pl.fwd);
     prm.scale2 = inv_temp * LOG2E;
     prm.lo = w.lo; prm.hi = w.hi; prm.part_m = w.part_m; prm.part_s = w.part_s;
-    rc = (dim == 128) ? launch_ce_tc_fwd<128>(mu, mi, mp, prm, pl.row_tiles, st)
-                      : launch_ce_tc_fwd<64>(mu, mi, mp, prm, pl.row_tiles, st);
-    if (rc) return rc;
+    if ((rc = launch_ce_tc_dim<MODE_FWD>(dim, mu, mi, mp, prm, pl.fwd.grid, st))) return rc;
     // 4. finalize
     ce_tc_finalize<<<tc_grid(batch * 32, 256), 256, 0, st>>>(w.ub, w.ib, user, hn_rows, n_rowneg, w.perm, batch, dim,
-                                                            inv_temp, pl.splits, w.part_m, w.part_s, row_lse, row_pos,
-                                                            w.row_loss, w.lse_sorted, nan_flags);
+                                                            inv_temp, pl.fwd.n_tiles, pl.fwd.per_cta, w.part_m, w.part_s,
+                                                            row_lse, row_pos, w.row_loss, nan_flags);
     TT_LAUNCH_CHECK("ce_tc_finalize");
     ce_tc_mean<<<1, 1024, 0, st>>>(w.row_loss, batch, loss);
     TT_LAUNCH_CHECK("ce_tc_mean");
@@ -820,7 +821,7 @@ extern "C" int tt_ce_bwd_tc_workspace(int64_t batch, int64_t pool, int n_rowneg,
     using namespace tt;
     TT_CHECK_ARG(bytes_host && batch > 0 && pool >= 0 && n_rowneg >= 0 && dim > 0, "bad size");
     const CeTcPlan pl = ce_tc_plan(batch, pool);
-    const CeBwdWs w = ce_bwd_carve(nullptr, ~size_t(0), batch, pool, n_rowneg, dim, pl);
+    const CeBwdWs w = ce_bwd_carve(nullptr, ~size_t(0), batch, n_rowneg, dim, pl);
     *bytes_host = w.used + 1024;
     return 0;
 }
@@ -833,38 +834,36 @@ extern "C" int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowne
     TT_CHECK_ARG(user && row_lse && grad_loss && d_user && d_item && fwd_workspace && workspace, "null pointer");
     TT_CHECK_ARG((hn_rows != nullptr) == (n_rowneg > 0), "hn_rows / n_rowneg mismatch");
     TT_CHECK_ARG(pool_rows == 0 || d_pool != nullptr, "d_pool required with a pool");
-    TT_CHECK_ARG(batch > 0 && batch < (int64_t(1) << 31), "bad batch");
+    TT_CHECK_ARG(batch > 0 && batch < (int64_t(1) << 30) && pool_rows < (int64_t(1) << 30), "bad batch");
     if (dim != 64 && dim != 128) { set_error("tensor-core CE path supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const CeTcPlan pl = ce_tc_plan(batch, pool_rows);
     const CeTcWs f = ce_tc_carve(fwd_workspace, fwd_workspace_bytes, batch, pool_rows, dim, pl);
     if (!f.ok) { set_error("ce_tc forward workspace too small: need %zu have %zu", f.used, fwd_workspace_bytes); return TT_E_WORKSPACE; }
-    const CeBwdWs w = ce_bwd_carve(workspace, workspace_bytes, batch, pool_rows, n_rowneg, dim, pl);
+    const CeBwdWs w = ce_bwd_carve(workspace, workspace_bytes, batch, n_rowneg, dim, pl);
     if (!w.ok) { set_error("ce_tc backward workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) { set_error("ce_tc workspace must be 256-byte aligned"); return TT_E_BADARG; }
 
-    ce_tc_bwd_prep<<<tc_grid(w.rows_u, 256), 256, 0, st>>>(row_lse, f.perm, batch, w.rows_u, w.lse2p);
+    ce_tc_bwd_prep<<<tc_grid(w.rows_x, 256), 256, 0, st>>>(row_lse, f.perm, batch, w.rows_x, w.lse2p);
     TT_LAUNCH_CHECK("ce_tc_bwd_prep");
     CUtensorMap mu, mi, mp;
     int rc;
     if ((rc = make_tmap_bf16_rows(&mu, f.ub, batch, dim, TC_BM))) return rc;
     if ((rc = make_tmap_bf16_rows(&mi, f.ib, batch, dim, TC_BN))) return rc;
     if ((rc = make_tmap_bf16_rows(&mp, pool_rows ? f.pb : f.ib, pool_rows ? pool_rows : batch, dim, TC_BN))) return rc;
-    CeBwdParams prm;
+    CeTcParams prm{};
     prm.batch = batch; prm.pool_rows = pool_rows;
     prm.tiles_item = pl.tiles_item; prm.tiles_pool = pl.tiles_pool;
     prm.scale2 = inv_temp * LOG2E;
     prm.lo = f.lo; prm.hi = f.hi; prm.lse2p = w.lse2p;
     // pass 1: dU
-    prm.n_tiles = pl.tiles_total; prm.splits = w.splits_u; prm.part = w.part_u; prm.part_rows = w.rows_u;
-    rc = (dim == 128) ? launch_ce_tc_bwd<128, false>(mu, mi, mp, prm, pl.tiles_item, st)
-                      : launch_ce_tc_bwd<64, false>(mu, mi, mp, prm, pl.tiles_item, st);
-    if (rc) return rc;
+    fill_sched(prm, pl.bwd_x);
+    prm.part = w.part_x;
+    if ((rc = launch_ce_tc_dim<MODE_BWD_X>(dim, mu, mi, mp, prm, pl.bwd_x.grid, st))) return rc;
     // pass 2: dI, dPool
-    prm.n_tiles = pl.tiles_item; prm.splits = w.splits_y; prm.part = w.part_y; prm.part_rows = w.rows_y;
-    rc = (dim == 128) ? launch_ce_tc_bwd<128, true>(mu, mi, mp, prm, pl.tiles_total, st)
-                      : launch_ce_tc_bwd<64, true>(mu, mi, mp, prm, pl.tiles_total, st);
-    if (rc) return rc;
+    fill_sched(prm, pl.bwd_y);
+    prm.part = w.part_y;
+    if ((rc = launch_ce_tc_dim<MODE_BWD_Y>(dim, mu, mi, mp, prm, pl.bwd_y.grid, st))) return rc;
     if (hn_rows) {
         ce_tc_bwd_hn_rows<<<tc_grid(batch * 32, 256), 256, 0, st>>>(user, hn_rows, n_rowneg, batch, dim, inv_temp, row_lse,
                                                                    grad_loss, d_hn_rows, w.extra);
@@ -872,14 +871,23 @@ extern "C" int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowne
     }
     const float scale = inv_temp / static_cast<float>(batch);
     const int64_t vec = dim / 4;
-    ce_tc_reduce_rows<<<tc_grid(batch * vec, 256), 256, 0, st>>>(w.part_u, w.splits_u, w.rows_u, 0, batch, dim, f.perm,
-                                                                grad_loss, scale, hn_rows ? w.extra : nullptr, inv_temp, d_user);
-    ce_tc_reduce_rows<<<tc_grid(batch * vec, 256), 256, 0, st>>>(w.part_y, w.splits_y, w.rows_y, 0, batch, dim, f.perm,
-                                                                grad_loss, scale, nullptr, 0.f, d_item);
+    ce_tc_reduce_rows<<<tc_grid(batch * vec, 256), 256, 0, st>>>(w.part_x, w.rows_x, pl.bwd_x.n_tiles, pl.bwd_x.per_cta, 0,
+                                                                batch, dim, f.perm, grad_loss, scale,
+                                                                hn_rows ? w.extra : nullptr, inv_temp, d_user);
+    ce_tc_reduce_rows<<<tc_grid(batch * vec, 256), 256, 0, st>>>(w.part_y, w.rows_y, pl.bwd_y.n_tiles, pl.bwd_y.per_cta, 0,
+                                                                batch, dim, f.perm, grad_loss, scale, nullptr, 0.f, d_item);
     if (pool_rows > 0)
-        ce_tc_reduce_rows<<<tc_grid(pool_rows * vec, 256), 256, 0, st>>>(w.part_y, w.splits_y, w.rows_y,
-                                                                        static_cast<int64_t>(pl.tiles_item) * TC_BM, pool_rows,
-                                                                        dim, nullptr, grad_loss, scale, nullptr, 0.f, d_pool);
+        ce_tc_reduce_rows<<<tc_grid(pool_rows * vec, 256), 256, 0, st>>>(w.part_y, w.rows_y, pl.bwd_y.n_tiles,
+                                                                        pl.bwd_y.per_cta,
+                                                                        static_cast<int64_t>(pl.tiles_item) * TC_BM,
+                                                                        pool_rows, dim, nullptr, grad_loss, scale, nullptr,
+                                                                        0.f, d_pool);
     TT_LAUNCH_CHECK("ce_tc_reduce_rows");
+    return 0;
+}
+
+/* developer hook: record SM-clock stamps of CTA 0's pipeline events into dbg[11][256] (NULL disables) */
+extern "C" int tt_ce_tc_debug_trace(long long *dbg) {
+    tt::g_ce_dbg = dbg;
     return 0;
 }
