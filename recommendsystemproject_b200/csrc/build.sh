@@ -9,7 +9,7 @@ mkdir -p build
 pids=()
 for f in *.cu; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/tt_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ tc_common.cuh -nt "$o" ] || [ topk_common.cuh -nt "$o" ] || [ ../../include/tt_b200.h -nt "$o" ]; then
     ( $NVCC $FLAGS ${EXTRA_NVCC_FLAGS:-} -c "$f" -o "$o" ) &
     pids+=($!)
   fi

@@ -269,5 +269,52 @@ inline int make_tmap_bf16_rows(CUtensorMap *map, const void *base, int64_t rows,
     return 0;
 }
 
+// ---------------------------------------------------------------- stream-K schedule
+// Tiles g = m * n_tiles + n, CTA k owns [k * per_cta, (k + 1) * per_cta).  A row tile m is cut into
+// segments seg = k - first_cta(m); every segment leaves one partial (two for FWD: one per softmax group).
+struct Sched {
+    int m_tiles, n_tiles;
+    int64_t total, per_cta;
+    int grid, max_seg;
+};
+
+inline Sched make_sched(int m_tiles, int n_tiles) {
+    Sched s;
+    s.m_tiles = m_tiles; s.n_tiles = n_tiles;
+    s.total = static_cast<int64_t>(m_tiles) * n_tiles;
+    int64_t g = (s.total + 1) / 2;               // at least 2 tiles per CTA
+    if (g > sm_count()) g = sm_count();
+    if (g < 1) g = 1;
+    s.per_cta = (s.total + g - 1) / g;
+    s.grid = static_cast<int>((s.total + s.per_cta - 1) / s.per_cta);
+    s.max_seg = static_cast<int>((n_tiles + s.per_cta - 2) / s.per_cta) + 1;
+    return s;
+}
+
+__host__ __device__ __forceinline__ int sched_first_cta(int m, int n_tiles, int64_t per_cta) {
+    return static_cast<int>((static_cast<int64_t>(m) * n_tiles) / per_cta);
+}
+__host__ __device__ __forceinline__ int sched_last_cta(int m, int n_tiles, int64_t per_cta) {
+    return static_cast<int>((static_cast<int64_t>(m + 1) * n_tiles - 1) / per_cta);
+}
+
+// position of a role inside its CTA's tile range
+struct Cursor {
+    int i;        // local tile index
+    int m, n;     // row tile, W tile
+    int r;        // local row counter (0 for the first row tile this CTA touches)
+    int n_tiles;
+    __device__ __forceinline__ void init(int64_t g0, int nt) {
+        n_tiles = nt; i = 0; r = 0;
+        m = static_cast<int>(g0 / nt);
+        n = static_cast<int>(g0 - static_cast<int64_t>(m) * nt);
+    }
+    __device__ __forceinline__ void next() {
+        ++i;
+        if (++n == n_tiles) { n = 0; ++m; ++r; }
+    }
+};
+
+
 }  // namespace tc
 }  // namespace tt

@@ -13,7 +13,7 @@
 // Stage 2 (exact re-rank): one CTA per query gathers the <= splits*K'
 // candidates, re-scores them in fp64 and sorts by (score desc, row asc) --
 // the stated tie-break -- and emits the first K.
-#include "common.cuh"
+#include "topk_common.cuh"
 
 namespace tt {
 
@@ -22,42 +22,6 @@ constexpr int TK_THREADS = 256;
 constexpr int TK_CAP = 512;     // per (query, split) candidate list capacity
 constexpr int TK_MARGIN = 8;    // extra candidates kept beyond K for the fp64 re-rank
 constexpr int TK_MAX_K = 256;
-constexpr int TK_STAGE2_MAX = 2048;
-
-template <typename V, typename I>
-__device__ __forceinline__ bool tk_before(V va, I ia, V vb, I ib) {
-    return va > vb || (va == vb && ia < ib);
-}
-
-// bitonic sort of n (power of two) pairs so that "before" elements come first; `nthreads` cooperating
-// threads with id `tid`; SYNC() separates stages.
-template <typename V, typename I, typename SyncFn>
-__device__ __forceinline__ void tk_bitonic(V *v, I *ix, int n, int tid, int nthreads, SyncFn sync) {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < n / 2; t += nthreads) {
-                const int i = 2 * j * (t / j) + (t % j);
-                const int p = i + j;
-                const bool asc = (i & k) == 0;
-                const V va = v[i], vb = v[p];
-                const I ia = ix[i], ib = ix[p];
-                const bool swap = asc ? tk_before(vb, ib, va, ia) : tk_before(va, ia, vb, ib);
-                if (swap) { v[i] = vb; v[p] = va; ix[i] = ib; ix[p] = ia; }
-            }
-            sync();
-        }
-    }
-}
-
-__device__ __forceinline__ bool tk_masked(const int64_t *__restrict__ mask_rows, int64_t lo, int64_t hi, int64_t row) {
-    while (lo < hi) {  // sorted ascending
-        const int64_t mid = (lo + hi) >> 1;
-        const int64_t v = mask_rows[mid];
-        if (v == row) return true;
-        if (v < row) lo = mid + 1; else hi = mid;
-    }
-    return false;
-}
 
 __device__ __forceinline__ void tk_load_tile(float *__restrict__ dst, const float *__restrict__ src, int64_t row0,
                                              int64_t n, int dim, int stride) {

@@ -1,0 +1,572 @@
+// Corpus scoring + top-K for retrieval evaluation on the 5th-gen tensor cores
+// (kernel 4 of the hot path, bf16 scoring; topk_f32.cu is the fp32 SIMT path).
+//
+// Replaces `scores = U @ E^T` -> per-user -inf masking -> torch.topk at
+// training_utils.py:220-258 of the reference.  The [Bq, Nc] score matrix
+// lives only in TMEM, 128 x 256 fp32 at a time.
+//
+// Exactness (bit-exact row indices under the stated tie-break) with bf16 scoring:
+//   stage 1 is a FILTER.  Every (query, CTA segment, column half) keeps a candidate list: a score enters when it
+//     beats the list's threshold tau; a full list is pruned to its best ~K' = K + margin and tau rises to the
+//     score of the last survivor, so "approx score <= tau" holds for everything that was ever left out.
+//   stage 2 keeps the K' best candidates by approximate score, re-scores them in fp64 from the fp32 inputs and
+//     sorts by (score desc, row asc).  The result is PROVABLY the exact top-K whenever
+//         exact_score[K-th] > tau_max + eps_q,   eps_q = (1.02 * 2^-8 + 2^-16) * |q| * max|e|
+//     (bf16 rounding of both operands is at most 2^-9 relative per element, fp32 accumulation ~1e-5): nothing left
+//     out can reach the K-th exact score.  Queries that fail the test are flagged; the caller re-runs them on the
+//     exact fp32 path (rare: the margin puts tau_max ~10 eps below the K-th score on the 10M-item config).
+//
+// Main kernel = the persistent stream-K / warp-specialised shape of ce_tc.cu:
+//   warp 0 TMA (query tile + 3-stage ring of 256-row corpus tiles, SWIZZLE_128B), warp 1 one elected lane issues
+//   tcgen05.mma M=128 N=256 K=16 (N=256 because a 128-wide MMA is issue-bound at ~100 cycles on this part:
+//   tools/tc_selftest), warps 2..9 = two groups (column halves) x four lane quarters, thread = query row:
+//   tcgen05.ld 128 scores, release the TMEM buffer, max-reduce 32 at a time against tau (one FMNMX per score),
+//   rare append path, warp-cooperative prune by value bisection.
+//
+// Roofline: tensor pipe, 2*Q*N*D flops; one pass over the bf16 corpus per 128 queries per CTA (L2-resident ring).
+#include "tc_common.cuh"
+#include "topk_common.cuh"
+
+namespace tt {
+
+using namespace tt::tc;
+
+constexpr int KT_BM = 128;
+constexpr int KT_BN = 256;
+constexpr int KT_HALF = 128;     // columns per softmax group
+constexpr int KT_THREADS = 320;
+constexpr int KT_CAP = 512;      // candidate list capacity
+constexpr int KT_SLACK = 32;     // a prune keeps between K' and K' + KT_SLACK entries
+constexpr int KT_MAX_KP = 256;
+template <int D> struct KtStages { static constexpr int value = D == 128 ? 3 : 6; };
+
+struct TopkTcParams {
+    int64_t n_query, n_corpus;
+    int m_tiles, n_tiles;
+    int64_t per_cta, total;
+    int max_seg, kp;
+    const int64_t *mask_offsets, *mask_rows;
+    float *cand_v;       // [n_query][2 * max_seg][KT_CAP] approximate scores
+    int32_t *cand_i;     //                               corpus rows
+    int32_t *cand_n;     // [n_query][2 * max_seg] entries (-1: the list overflowed)
+    float *cand_tau;     // [n_query][2 * max_seg] everything left out scored <= tau
+};
+
+// ---------------------------------------------------------------- prep: fp32 -> bf16 rows (+ max row norm)
+__global__ void __launch_bounds__(256)
+tk_convert_rows(const float *__restrict__ in, int64_t n, int dim, __nv_bfloat16 *__restrict__ out,
+                unsigned int *__restrict__ max_norm_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    float best = 0.f;
+    for (int64_t p = warp; p < n; p += n_warps) {
+        float ss = 0.f;
+        for (int c = lane * 4; c < dim; c += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(in + p * dim + c));
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+            uint2 raw;
+            raw.x = *reinterpret_cast<uint32_t *>(&a);
+            raw.y = *reinterpret_cast<uint32_t *>(&b);
+            *reinterpret_cast<uint2 *>(out + p * dim + c) = raw;
+        }
+        best = fmaxf(best, warp_sum(ss));
+    }
+    if (max_norm_bits != nullptr && lane == 0 && best > 0.f)
+        atomicMax(max_norm_bits, __float_as_uint(sqrtf(best) * 1.000001f));   // non-negative floats order like their bits
+}
+
+// ---------------------------------------------------------------- list prune (one warp, one list)
+// Keeps the entries with score >= t where t is found by bisection so that between kp and kp + KT_SLACK entries
+// survive (more only if many scores are equal).  Returns the new count; *tau_new = t if anything was dropped.
+__device__ __forceinline__ int tk_prune_list(float *__restrict__ lv, int32_t *__restrict__ li, int n, int kp, int lane,
+                                             float *tau_new) {
+    float v[KT_CAP / 32];
+    int32_t ix[KT_CAP / 32];
+#pragma unroll
+    for (int t = 0; t < KT_CAP / 32; ++t) {
+        const int idx = t * 32 + lane;
+        const bool ok = idx < n;
+        v[t] = ok ? lv[idx] : -INFINITY;
+        ix[t] = ok ? li[idx] : 0;
+    }
+    float hi = v[0], lo = (lane < n) ? v[0] : INFINITY;
+#pragma unroll
+    for (int t = 1; t < KT_CAP / 32; ++t) {
+        hi = fmaxf(hi, v[t]);
+        if (t * 32 + lane < n) lo = fminf(lo, v[t]);
+    }
+    hi = warp_max(hi);
+    lo = -warp_max(-lo);
+    int c_lo = n;
+    if (n > kp + KT_SLACK) {
+        for (int it = 0; it < 26; ++it) {
+            const float mid = lo + 0.5f * (hi - lo);
+            if (!(mid > lo && mid < hi)) break;
+            int c = 0;
+#pragma unroll
+            for (int t = 0; t < KT_CAP / 32; ++t) c += (v[t] >= mid) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= kp) {
+                lo = mid;
+                c_lo = c;
+                if (c <= kp + KT_SLACK) break;
+            } else {
+                hi = mid;
+            }
+        }
+    }
+    *tau_new = (c_lo < n) ? lo : -INFINITY;
+    if (c_lo == n) return n;
+    __syncwarp();
+    int mine = 0;
+#pragma unroll
+    for (int t = 0; t < KT_CAP / 32; ++t) mine += (v[t] >= lo) ? 1 : 0;
+    int pos = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, pos, o);
+        if (lane >= o) pos += x;
+    }
+    pos -= mine;
+#pragma unroll
+    for (int t = 0; t < KT_CAP / 32; ++t)
+        if (v[t] >= lo) { lv[pos] = v[t]; li[pos] = ix[t]; ++pos; }
+    __syncwarp();
+    return c_lo;
+}
+
+// ---------------------------------------------------------------- main kernel
+template <int D>
+__global__ void __launch_bounds__(KT_THREADS, 1)
+topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
+               const TopkTcParams prm) {
+    constexpr int KB = D / 64;
+    constexpr int ST = KtStages<D>::value;
+    constexpr int X_BYTES = KT_BM * D * 2;
+    constexpr int W_BYTES = KT_BN * D * 2;
+    constexpr int XK_BYTES = KT_BM * 128;     // one 64-column block of the query tile
+    constexpr int WK_BYTES = KT_BN * 128;     // one 64-column block of a corpus tile
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *x_tile = smem;
+    uint8_t *w_tiles = smem + X_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(w_tiles + ST * W_BYTES);
+    uint64_t *full = bars;              // [ST]
+    uint64_t *empty = full + ST;        // [ST]
+    uint64_t *sfull = empty + ST;       // [2]
+    uint64_t *sfree = sfull + 2;        // [2]  256 arrivals
+    uint64_t *xfull = sfree + 2;        // [1]
+    uint64_t *xfree = xfull + 1;        // [1]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xfree + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g0 = static_cast<int64_t>(blockIdx.x) * prm.per_cta;
+    const int64_t g1 = min(prm.total, g0 + prm.per_cta);
+    const int n_local = static_cast<int>(max(g1 - g0, static_cast<int64_t>(0)));
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_q);
+        prefetch_tensormap(&map_e);
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&sfull[a], 1); mbar_init(&sfree[a], 256); }
+        mbar_init(xfull, 1);
+        mbar_init(xfree, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (whole warp in uniform control flow, one elected lane issues) =====
+        Cursor c;
+        c.init(g0, prm.n_tiles);
+        for (; c.i < n_local; c.next()) {
+            if (c.i == 0 || c.n == 0) {
+                if (c.r >= 1) mbar_wait(xfree, (c.r - 1) & 1);
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(xfull, X_BYTES);
+                    for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_tile + kb * XK_BYTES, &map_q, xfull, kb * 64, c.m * KT_BM);
+                }
+                __syncwarp();
+            }
+            const int stage = c.i % ST;
+            mbar_wait(&empty[stage], ((c.i / ST) & 1) ^ 1);
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&full[stage], W_BYTES);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(w_tiles + stage * W_BYTES + kb * WK_BYTES, &map_e, &full[stage], kb * 64, c.n * KT_BN);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = idesc_bf16_f32(KT_BM, KT_BN, 0, 0);
+        const uint64_t xdesc = smem_desc_k_sw128(smem_u32(x_tile));
+        const uint64_t wdesc = smem_desc_k_sw128(smem_u32(w_tiles));
+        Cursor c;
+        c.init(g0, prm.n_tiles);
+        for (; c.i < n_local; c.next()) {
+            const int i = c.i, b = i & 1, stage = i % ST;
+            if (i >= 2) mbar_wait(&sfree[b], ((i >> 1) - 1) & 1);
+            if (i == 0 || c.n == 0) mbar_wait(xfull, c.r & 1);
+            mbar_wait(&full[stage], (i / ST) & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t wd = wdesc + static_cast<uint64_t>(stage * (W_BYTES >> 4));
+                const uint32_t acc = tmem_base + b * KT_BN;
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k) {
+                    const uint32_t xo = ((k / 4) * XK_BYTES + (k % 4) * 32) >> 4;
+                    const uint32_t wo = ((k / 4) * WK_BYTES + (k % 4) * 32) >> 4;
+                    if (k == 0) umma_f16_first(acc, xdesc + xo, wd + wo, idesc);
+                    else umma_f16_acc(acc, xdesc + xo, wd + wo, idesc);
+                }
+                umma_commit(&empty[stage]);
+                umma_commit(&sfull[b]);
+                if (c.n == prm.n_tiles - 1 || i == n_local - 1) umma_commit(xfree);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== filter warps: group = column half, thread = query row =====
+        const int quarter = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const int r_in_tile = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        Cursor c;
+        c.init(g0, prm.n_tiles);
+        float tau = INFINITY;
+        int cnt = 0;
+        bool ovf = false, row_ok = false;
+        int64_t q = 0, list = 0, m_lo = 0, m_hi = 0;
+        for (; c.i < n_local; c.next()) {
+            const int i = c.i, b = i & 1;
+            if (i == 0 || c.n == 0) {
+                q = static_cast<int64_t>(c.m) * KT_BM + r_in_tile;
+                row_ok = q < prm.n_query;
+                const int seg = static_cast<int>(blockIdx.x) - sched_first_cta(c.m, prm.n_tiles, prm.per_cta);
+                list = q * (2 * prm.max_seg) + 2 * seg + grp;
+                tau = row_ok ? -INFINITY : INFINITY;
+                cnt = 0;
+                ovf = false;
+                m_lo = m_hi = 0;
+                if (row_ok && prm.mask_offsets != nullptr) { m_lo = prm.mask_offsets[q]; m_hi = prm.mask_offsets[q + 1]; }
+            }
+            float *lv = prm.cand_v + list * KT_CAP;
+            int32_t *li = prm.cand_i + list * KT_CAP;
+            mbar_wait(&sfull[b], (i >> 1) & 1);
+            tc_fence_after();
+            uint32_t r[4][32];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) tmem_ld_32x32(lane_addr + b * KT_BN + grp * KT_HALF + qq * 32, r[qq]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&sfree[b]);
+            const int64_t col0 = static_cast<int64_t>(c.n) * KT_BN + grp * KT_HALF;
+            // The column index inside its 32-column chunk rides in the 5 low mantissa bits of the score (a 2^-18
+            // relative perturbation, far below the bf16 error budget): one FMNMX tree then yields the best score AND
+            // where it is, so the append path needs no dynamically indexed registers and stays compact.
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[qq][j] = (r[qq][j] & 0xffffffe0u) | static_cast<uint32_t>(j);
+            if (col0 + KT_HALF > prm.n_corpus) {   // last tile: rows past the corpus were zero-filled by TMA
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + qq * 32 + j >= prm.n_corpus) r[qq][j] = 0xff800000u;
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                float m0 = fmaxf(__uint_as_float(r[qq][0]), __uint_as_float(r[qq][1]));
+                float m1 = fmaxf(__uint_as_float(r[qq][2]), __uint_as_float(r[qq][3]));
+#pragma unroll
+                for (int j = 4; j < 32; j += 2) {
+                    m0 = fmaxf(m0, __uint_as_float(r[qq][j]));
+                    m1 = fmaxf(m1, __uint_as_float(r[qq][j + 1]));
+                }
+                float best = fmaxf(m0, m1);
+#pragma unroll 1
+                while (best > tau) {      // expected K' ln(N / K') times per list over the whole stream
+                    const int64_t col = col0 + qq * 32 + static_cast<int>(__float_as_uint(best) & 31u);
+                    if (!(m_hi > m_lo && tk_masked(prm.mask_rows, m_lo, m_hi, col))) {
+                        if (cnt < KT_CAP) { lv[cnt] = best; li[cnt] = static_cast<int32_t>(col); ++cnt; }
+                        else ovf = true;
+                    }
+                    // next best of the chunk: strictly below `best` (packed scores of a chunk are distinct)
+                    float n0 = -INFINITY, n1 = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float x0 = __uint_as_float(r[qq][j]), x1 = __uint_as_float(r[qq][j + 1]);
+                        n0 = fmaxf(n0, x0 < best ? x0 : -INFINITY);
+                        n1 = fmaxf(n1, x1 < best ? x1 : -INFINITY);
+                    }
+                    best = fmaxf(n0, n1);
+                }
+            }
+            const bool seg_end = (c.n == prm.n_tiles - 1 || i == n_local - 1);
+            // a list must have room for a whole 128-column step; at the end of the segment it is cut to ~K'
+            const bool need = row_ok && (seg_end ? cnt > prm.kp + KT_SLACK : cnt > KT_CAP - KT_HALF);
+            unsigned todo = __ballot_sync(0xffffffffu, need);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t l2 = __shfl_sync(0xffffffffu, list, src);
+                const int n2 = __shfl_sync(0xffffffffu, cnt, src);
+                float t_new;
+                __syncwarp();
+                const int kept = tk_prune_list(prm.cand_v + l2 * KT_CAP, prm.cand_i + l2 * KT_CAP, n2, prm.kp, lane, &t_new);
+                if (lane == src) { cnt = kept; tau = fmaxf(tau, t_new); }
+            }
+            if (seg_end && row_ok) {
+                prm.cand_n[list] = ovf ? -1 : cnt;
+                prm.cand_tau[list] = tau;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------- stage 2: K' best by approximate score -> exact
+// one CTA (128 threads) per query
+__global__ void __launch_bounds__(128)
+topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus, int dim, int k, int kp, int max_seg,
+               int n_tiles, int64_t per_cta, int64_t row_offset, const float *__restrict__ cand_v,
+               const int32_t *__restrict__ cand_i, const int32_t *__restrict__ cand_n,
+               const float *__restrict__ cand_tau, const unsigned int *__restrict__ emax_bits,
+               double *__restrict__ out_scores, int64_t *__restrict__ out_idx, int32_t *__restrict__ unverified) {
+    __shared__ float av[TK_STAGE2_MAX];
+    __shared__ int32_t ai[TK_STAGE2_MAX];
+    __shared__ double ev[KT_MAX_KP];
+    __shared__ int32_t ei[KT_MAX_KP];
+    __shared__ float s_tau;
+    __shared__ int s_bad;
+    __shared__ double s_qn;
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mt = static_cast<int>(q / KT_BM);
+    const int n_lists = 2 * (sched_last_cta(mt, n_tiles, per_cta) - sched_first_cta(mt, n_tiles, per_cta) + 1);
+    if (tid == 0) { s_tau = -INFINITY; s_bad = 0; }
+    __syncthreads();
+    int tot = 0;   // entries in av/ai (uniform across the CTA)
+    auto reduce_to_kp = [&]() {   // keep the kp best by approximate score; what falls out bounds tau from below
+        int np2 = 32;
+        while (np2 < tot) np2 <<= 1;
+        for (int t = tid; t < np2; t += blockDim.x)
+            if (t >= tot) { av[t] = -INFINITY; ai[t] = 0x7fffffff; }
+        __syncthreads();
+        tk_bitonic(av, ai, np2, tid, static_cast<int>(blockDim.x), [] { __syncthreads(); });
+        if (tot > kp) {
+            if (tid == 0) s_tau = fmaxf(s_tau, av[kp]);
+            tot = kp;
+        }
+        __syncthreads();
+    };
+    for (int l = 0; l < n_lists; ++l) {
+        const int64_t list = q * (2 * max_seg) + l;
+        const int n = cand_n[list];
+        if (tid == 0) {
+            s_tau = fmaxf(s_tau, cand_tau[list]);
+            if (n < 0) s_bad = 1;
+        }
+        const int take = n < 0 ? KT_CAP : n;
+        if (tot + take > TK_STAGE2_MAX) reduce_to_kp();
+        for (int t = tid; t < take; t += blockDim.x) { av[tot + t] = cand_v[list * KT_CAP + t]; ai[tot + t] = cand_i[list * KT_CAP + t]; }
+        tot += take;
+        __syncthreads();
+    }
+    reduce_to_kp();
+    // exact fp64 re-score of the survivors (fixed summation order: lane-strided, then xor tree)
+    const float *qv = query + q * dim;
+    for (int c = warp; c < tot; c += 4) {
+        const float *e = corpus + static_cast<int64_t>(ai[c]) * dim;
+        double d = 0.0;
+        for (int t = lane; t < dim; t += 32) d = fma(static_cast<double>(qv[t]), static_cast<double>(e[t]), d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) { ev[c] = d; ei[c] = ai[c]; }
+    }
+    if (warp == 0) {
+        double n2 = 0.0;
+        for (int t = lane; t < dim; t += 32) n2 = fma(static_cast<double>(qv[t]), static_cast<double>(qv[t]), n2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        if (lane == 0) s_qn = sqrt(n2);
+    }
+    int np2 = 32;
+    while (np2 < tot) np2 <<= 1;
+    __syncthreads();
+    for (int t = tid; t < np2; t += blockDim.x)
+        if (t >= tot) { ev[t] = -INFINITY; ei[t] = 0x7fffffff; }
+    __syncthreads();
+    tk_bitonic(ev, ei, np2, tid, static_cast<int>(blockDim.x), [] { __syncthreads(); });
+    for (int t = tid; t < k; t += blockDim.x) {
+        const bool ok = t < tot;
+        out_scores[q * k + t] = ok ? ev[t] : -INFINITY;
+        out_idx[q * k + t] = ok ? static_cast<int64_t>(ei[t]) + row_offset : -1;
+    }
+    if (tid == 0) {
+        // nothing was ever left out (tau = -inf): exact by construction.  Otherwise the K-th exact score must clear
+        // the best score anything left out could have.
+        bool good = s_bad == 0;
+        if (good && s_tau > -INFINITY) {
+            const double eps = (1.02 * 0.00390625 + 1.6e-5) * s_qn * static_cast<double>(__uint_as_float(*emax_bits)) + 1e-30;
+            good = (tot >= k) && (ev[k - 1] > static_cast<double>(s_tau) + eps);
+        }
+        unverified[q] = good ? 0 : 1;
+    }
+}
+
+struct KtPlan {
+    Sched sched;
+    int kp;
+};
+
+static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k) {
+    KtPlan p;
+    p.sched = make_sched(static_cast<int>((n_query + KT_BM - 1) / KT_BM), static_cast<int>((n_corpus + KT_BN - 1) / KT_BN));
+    int margin = k / 2;
+    if (margin < 32) margin = 32;
+    p.kp = k + margin;
+    if (p.kp > KT_MAX_KP) p.kp = KT_MAX_KP;
+    return p;
+}
+
+struct KtWs {
+    __nv_bfloat16 *qb, *eb;
+    unsigned int *emax;
+    float *cand_v, *cand_tau;
+    int32_t *cand_i, *cand_n;
+    bool ok;
+    size_t used;
+};
+
+static KtWs kt_carve(void *workspace, size_t bytes, int64_t n_query, int64_t n_corpus, int dim, bool own_corpus,
+                     const KtPlan &pl) {
+    Workspace ws(workspace, bytes);
+    KtWs w;
+    const size_t lists = static_cast<size_t>(n_query) * 2 * pl.sched.max_seg;
+    w.qb = ws.take<__nv_bfloat16>(n_query * dim);
+    w.eb = ws.take<__nv_bfloat16>(own_corpus ? n_corpus * dim : 1);
+    w.emax = ws.take<unsigned int>(1);
+    w.cand_v = ws.take<float>(lists * KT_CAP);
+    w.cand_i = ws.take<int32_t>(lists * KT_CAP);
+    w.cand_n = ws.take<int32_t>(lists);
+    w.cand_tau = ws.take<float>(lists);
+    w.ok = ws.ok();
+    w.used = ws.off;
+    return w;
+}
+
+static inline unsigned kt_grid(int64_t n, int threads) {
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<unsigned>(b);
+}
+
+// row-major bf16 [rows, dim] -> boxes of {64 columns, box_rows rows}, 128B swizzle (box_rows up to 256)
+template <int D>
+static int launch_topk_tc(const CUtensorMap &mq, const CUtensorMap &me, const TopkTcParams &prm, int grid, cudaStream_t st) {
+    constexpr int ST = KtStages<D>::value;
+    constexpr size_t smem = 1024 + static_cast<size_t>(KT_BM) * D * 2 + static_cast<size_t>(ST) * KT_BN * D * 2 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(topk_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(topk_tc_kernel)");
+        attr_set = true;
+    }
+    topk_tc_kernel<D><<<grid, KT_THREADS, smem, st>>>(mq, me, prm);
+    TT_LAUNCH_CHECK("topk_tc_kernel");
+    return 0;
+}
+
+}  // namespace tt
+
+extern "C" int tt_topk_tc_prepare_corpus(const float *corpus, int64_t n_corpus, int dim, void *corpus_bf16,
+                                         float *max_norm, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(corpus && corpus_bf16 && max_norm && n_corpus > 0, "null pointer / empty corpus");
+    if (dim != 64 && dim != 128) { set_error("tensor-core top-K supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(max_norm, 0, sizeof(float), st);
+    if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(max_norm)");
+    tk_convert_rows<<<kt_grid(n_corpus * 32, 256), 256, 0, st>>>(corpus, n_corpus, dim, static_cast<__nv_bfloat16 *>(corpus_bf16),
+                                                                reinterpret_cast<unsigned int *>(max_norm));
+    TT_LAUNCH_CHECK("tk_convert_rows");
+    return 0;
+}
+
+extern "C" int tt_score_topk_tc_workspace(int64_t n_query, int64_t n_corpus, int dim, int k, int own_corpus,
+                                          size_t *bytes_host) {
+    using namespace tt;
+    TT_CHECK_ARG(bytes_host && n_query > 0 && n_corpus > 0 && dim > 0 && k > 0, "bad size");
+    const KtPlan pl = kt_plan(n_query, n_corpus, k);
+    const KtWs w = kt_carve(nullptr, ~size_t(0), n_query, n_corpus, dim, own_corpus != 0, pl);
+    *bytes_host = w.used + 1024;
+    return 0;
+}
+
+extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float *corpus, const void *corpus_bf16,
+                                const float *corpus_max_norm, int64_t n_corpus, int dim, int k, int64_t row_offset,
+                                const int64_t *mask_offsets, const int64_t *mask_rows, double *out_scores,
+                                int64_t *out_idx, int32_t *unverified, void *workspace, size_t workspace_bytes,
+                                void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(query && corpus && out_scores && out_idx && unverified && workspace, "null pointer");
+    TT_CHECK_ARG(n_query > 0 && n_corpus > 0 && k > 0, "non-positive size");
+    TT_CHECK_ARG((mask_offsets == nullptr) == (mask_rows == nullptr), "mask_offsets / mask_rows mismatch");
+    TT_CHECK_ARG((corpus_bf16 == nullptr) == (corpus_max_norm == nullptr), "corpus_bf16 / corpus_max_norm mismatch");
+    if (dim != 64 && dim != 128) { set_error("tensor-core top-K supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
+    if (k > KT_MAX_KP - 32) { set_error("tensor-core top-K supports k <= %d (got %d)", KT_MAX_KP - 32, k); return TT_E_UNSUPPORTED; }
+    if (n_corpus >= (int64_t(1) << 31)) { set_error("corpus shard must have < 2^31 rows"); return TT_E_UNSUPPORTED; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const KtPlan pl = kt_plan(n_query, n_corpus, k);
+    const bool own = corpus_bf16 == nullptr;
+    const KtWs w = kt_carve(workspace, workspace_bytes, n_query, n_corpus, dim, own, pl);
+    if (!w.ok) { set_error("top-K (tensor core) workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) { set_error("top-K workspace must be 256-byte aligned"); return TT_E_BADARG; }
+
+    tk_convert_rows<<<kt_grid(n_query * 32, 256), 256, 0, st>>>(query, n_query, dim, w.qb, nullptr);
+    const __nv_bfloat16 *eb = static_cast<const __nv_bfloat16 *>(corpus_bf16);
+    const unsigned int *emax = reinterpret_cast<const unsigned int *>(corpus_max_norm);
+    if (own) {
+        cudaError_t e = cudaMemsetAsync(w.emax, 0, sizeof(unsigned int), st);
+        if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(emax)");
+        tk_convert_rows<<<kt_grid(n_corpus * 32, 256), 256, 0, st>>>(corpus, n_corpus, dim, w.eb, w.emax);
+        eb = w.eb;
+        emax = w.emax;
+    }
+    TT_LAUNCH_CHECK("tk_convert_rows");
+    CUtensorMap mq, me;
+    int rc;
+    if ((rc = make_tmap_bf16_rows(&mq, w.qb, n_query, dim, KT_BM))) return rc;
+    if ((rc = make_tmap_bf16_rows(&me, eb, n_corpus, dim, KT_BN))) return rc;
+    TopkTcParams prm{};
+    prm.n_query = n_query; prm.n_corpus = n_corpus;
+    prm.m_tiles = pl.sched.m_tiles; prm.n_tiles = pl.sched.n_tiles;
+    prm.per_cta = pl.sched.per_cta; prm.total = pl.sched.total; prm.max_seg = pl.sched.max_seg;
+    prm.kp = pl.kp;
+    prm.mask_offsets = mask_offsets; prm.mask_rows = mask_rows;
+    prm.cand_v = w.cand_v; prm.cand_i = w.cand_i; prm.cand_n = w.cand_n; prm.cand_tau = w.cand_tau;
+    rc = (dim == 128) ? launch_topk_tc<128>(mq, me, prm, pl.sched.grid, st) : launch_topk_tc<64>(mq, me, prm, pl.sched.grid, st);
+    if (rc) return rc;
+    topk_tc_stage2<<<static_cast<unsigned>(n_query), 128, 0, st>>>(query, corpus, dim, k, pl.kp, pl.sched.max_seg,
+                                                                   pl.sched.n_tiles, pl.sched.per_cta, row_offset, w.cand_v,
+                                                                   w.cand_i, w.cand_n, w.cand_tau, emax, out_scores, out_idx,
+                                                                   unverified);
+    TT_LAUNCH_CHECK("topk_tc_stage2");
+    return 0;
+}

@@ -270,10 +270,74 @@ def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, tempera
 # --------------------------------------------------------------------------
 # 4. corpus scoring + top-K
 # --------------------------------------------------------------------------
+class PreparedCorpus:
+    """bf16 copy of a corpus shard + its largest row norm for the tensor-core top-K path (built once per
+    catalog encode, reused for every query batch)."""
+
+    def __init__(self, corpus: torch.Tensor):
+        _need_cuda(corpus)
+        lib = _lib.load()
+        self.corpus = corpus.contiguous().float()
+        n, d = self.corpus.shape
+        self.bf16 = torch.empty(n, d, dtype=torch.bfloat16, device=corpus.device)
+        self.max_norm = torch.zeros(1, dtype=torch.float32, device=corpus.device)
+        check(lib.tt_topk_tc_prepare_corpus(_p(self.corpus), n, d, _p(self.bf16), _p(self.max_norm), _stream()),
+              "tt_topk_tc_prepare_corpus")
+        _count()
+
+
+# statistics of the last tensor-core top-K call (tests / bench report the fallback rate)
+topk_stats = {"queries": 0, "unverified": 0}
+TOPK_TC_QUERY_CHUNK = 32768
+
+
+def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepared: Optional["PreparedCorpus"]):
+    lib = _lib.load()
+    Bq, D = query.shape
+    Nc = corpus.shape[0]
+    dev = query.device
+    scores = torch.empty(Bq, k, dtype=torch.float64, device=dev)
+    idx = torch.empty(Bq, k, dtype=torch.int64, device=dev)
+    bad = torch.empty(Bq, dtype=torch.int32, device=dev)
+    own = 0 if prepared is not None else 1
+    for q0 in range(0, Bq, TOPK_TC_QUERY_CHUNK):
+        q1 = min(Bq, q0 + TOPK_TC_QUERY_CHUNK)
+        nq = q1 - q0
+        nbytes = ctypes.c_size_t(0)
+        check(lib.tt_score_topk_tc_workspace(nq, Nc, D, k, own, ctypes.byref(nbytes)), "tt_score_topk_tc_workspace")
+        ws = _ws(nbytes.value, dev)
+        mo = None if mask_offsets is None else mask_offsets[q0:q1 + 1].contiguous()
+        check(lib.tt_score_topk_tc(_p(query[q0:q1]), nq, _p(corpus), _p(None if prepared is None else prepared.bf16),
+                                   _p(None if prepared is None else prepared.max_norm), Nc, D, k, row_offset, _p(mo),
+                                   _p(mask_rows), _p(scores[q0:q1]), _p(idx[q0:q1]), _p(bad[q0:q1]), _p(ws), ws.numel(),
+                                   _stream()), "tt_score_topk_tc")
+        _count(3 + own)
+    # proof obligation failed for these queries (see include/tt_b200.h): exact fp32 path, one host read
+    redo = torch.nonzero(bad, as_tuple=False).reshape(-1)
+    topk_stats["queries"] = Bq
+    topk_stats["unverified"] = int(redo.numel())
+    if redo.numel() > 0:
+        sub_mo = sub_mr = None
+        if mask_offsets is not None:
+            lens = (mask_offsets[1:] - mask_offsets[:-1])[redo]
+            sub_mo = torch.zeros(redo.numel() + 1, dtype=torch.int64, device=dev)
+            sub_mo[1:] = torch.cumsum(lens, 0)
+            pieces = [mask_rows[int(mask_offsets[r]):int(mask_offsets[r + 1])] for r in redo.tolist()]
+            sub_mr = torch.cat(pieces) if pieces else mask_rows[:0]
+            if sub_mr.numel() == 0:
+                sub_mr = torch.zeros(1, dtype=torch.int64, device=dev)
+        s2, i2 = score_topk(query[redo], corpus, k, row_offset, sub_mo, sub_mr, precision="fp32")
+        scores[redo] = s2
+        idx[redo] = i2
+    return scores, idx
+
+
 def score_topk(query: torch.Tensor, corpus: torch.Tensor, k: int, row_offset: int = 0,
-               mask_offsets: Optional[torch.Tensor] = None, mask_rows: Optional[torch.Tensor] = None):
+               mask_offsets: Optional[torch.Tensor] = None, mask_rows: Optional[torch.Tensor] = None,
+               precision: str = "fp32", prepared: Optional[PreparedCorpus] = None):
     """Top-k corpus rows per query under (score desc, row asc).  Returns
-    (scores float64 [Bq, k], rows int64 [Bq, k]); rows = local row + row_offset."""
+    (scores float64 [Bq, k], rows int64 [Bq, k]); rows = local row + row_offset.
+    precision='bf16': tcgen05 scoring as a filter + exact fp64 re-rank (same bit-exact rows; dim 64/128, k <= 224)."""
     _need_cuda(query, corpus)
     lib = _lib.load()
     query = query.contiguous().float()
@@ -281,6 +345,13 @@ def score_topk(query: torch.Tensor, corpus: torch.Tensor, k: int, row_offset: in
     Bq, D = query.shape
     Nc = corpus.shape[0]
     dev = query.device
+    if mask_offsets is not None:
+        mask_offsets = mask_offsets.contiguous().long()
+        mask_rows = mask_rows.contiguous().long()
+    if precision == "bf16":
+        return _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepared)
+    if precision != "fp32":
+        raise TTError(f"unknown precision '{precision}' (use 'fp32' or 'bf16')")
     nbytes = ctypes.c_size_t(0)
     check(lib.tt_score_topk_workspace(Bq, Nc, D, k, ctypes.byref(nbytes)), "tt_score_topk_workspace")
     ws = _ws(nbytes.value, dev)

@@ -463,3 +463,71 @@ def test_ce_tc_backward_large_properties():
         a, b = outs["fp32"][k], outs["bf16"][k]
         rel = float((a - b).norm() / a.norm())
         assert rel < 3e-2, f"{name}: bf16 tensor-core path differs from the fp32 path by {rel:.3e} (relative Frobenius)"
+
+
+# ---------------------------------------------------------------- scoring + top-K, tcgen05 (bf16 filter + exact re-rank)
+@pytest.mark.parametrize("Bq,Nc,D,K", [(1, 50, 64, 5), (33, 1000, 64, 10), (64, 3416, 128, 50), (100, 20000, 128, 100),
+                                       (5, 130, 128, 128), (300, 70000, 128, 100), (129, 257, 64, 20)])
+def test_topk_tc_bit_exact_vs_oracle(Bq, Nc, D, K):
+    """Tensor-core scoring is only a filter: the rows that come back (after the on-device proof obligation and, if it
+    fails, the fp32 re-run) must be the oracle's, bit for bit and in order."""
+    gen = torch.Generator().manual_seed(Bq + Nc + 1)
+    q = torch.nn.functional.normalize(torch.randn(Bq, D, generator=gen), dim=1)
+    e = torch.nn.functional.normalize(torch.randn(Nc, D, generator=gen), dim=1)
+    vals_ref, idx_ref = O.score_topk(q.numpy(), e.numpy(), K, row_offset=1000)
+    s, idx = ops.score_topk(q.to(DEV), e.to(DEV), K, row_offset=1000, precision="bf16")
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+    assert np.allclose(s.cpu().numpy(), vals_ref, atol=1e-12)
+    if Nc >= 20000:   # on a real-sized corpus the filter must carry the result itself (no fp32 re-runs)
+        assert ops.topk_stats["unverified"] == 0, ops.topk_stats
+
+
+def test_topk_tc_ties_unnormalised_and_prepared_corpus():
+    gen = torch.Generator().manual_seed(19)
+    base = torch.randn(40, 64, generator=gen) * 3.0          # unnormalised, duplicated rows: exact ties
+    e = base[torch.randint(0, 40, (3000,), generator=gen)]
+    q = torch.randn(70, 64, generator=gen) * 0.5
+    vals_ref, idx_ref = O.score_topk(q.numpy(), e.numpy(), 60)
+    prep = ops.PreparedCorpus(e.to(DEV))
+    _, idx = ops.score_topk(q.to(DEV), e.to(DEV), 60, precision="bf16", prepared=prep)
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+    _, idx2 = ops.score_topk(q.to(DEV), e.to(DEV), 60, precision="bf16")
+    assert np.array_equal(idx2.cpu().numpy(), idx_ref)
+
+
+def test_topk_tc_history_mask_and_merge():
+    gen = torch.Generator().manual_seed(20)
+    Bq, Nc, D, K = 150, 9000, 128, 20
+    q = torch.nn.functional.normalize(torch.randn(Bq, D, generator=gen), dim=1)
+    e = torch.nn.functional.normalize(torch.randn(Nc, D, generator=gen), dim=1)
+    full_ref, full_idx = O.score_topk(q.numpy(), e.numpy(), K)
+    hist = [np.unique(np.concatenate([np.random.RandomState(r).choice(Nc, size=r % 7 * 30, replace=False), full_idx[r, :3]]))
+            for r in range(Bq)]
+    off = np.zeros(Bq + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(h) for h in hist])
+    flat = np.concatenate(hist).astype(np.int64)
+    vals_ref, idx_ref = O.score_topk(q.numpy(), e.numpy(), K, hist_mask=hist)
+    s, idx = ops.score_topk(q.to(DEV), e.to(DEV), K, 0, torch.from_numpy(off).to(DEV), torch.from_numpy(flat).to(DEV),
+                            precision="bf16")
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+    W = 3
+    shard = Nc // W
+    ss, ii = [], []
+    for w in range(W):
+        a, b = ops.score_topk(q.to(DEV), e[w * shard:(w + 1) * shard].to(DEV), K, row_offset=w * shard, precision="bf16")
+        ss.append(a)
+        ii.append(b)
+    ms, mi = ops.topk_merge(torch.stack(ss), torch.stack(ii))
+    assert np.array_equal(mi.cpu().numpy(), full_idx)
+
+
+def test_topk_tc_equals_fp32_path_at_scale():
+    """Q=2048 x N=400k (an 3.3 GB score matrix if materialised): the tensor-core path and the fp32 SIMT path of this
+    library must return identical rows (both claim the oracle's answer; the fp32 path is oracle-checked above)."""
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    q = torch.nn.functional.normalize(torch.randn(2048, 128, device=DEV, generator=gen), dim=1)
+    e = torch.nn.functional.normalize(torch.randn(400_000, 128, device=DEV, generator=gen), dim=1)
+    _, i32 = ops.score_topk(q, e, 100)
+    _, i16 = ops.score_topk(q, e, 100, precision="bf16")
+    assert torch.equal(i32, i16)
+    assert ops.topk_stats["unverified"] == 0, ops.topk_stats

@@ -42,5 +42,28 @@ def main():
         print(json.dumps({"kernel": "ce_fwd", "B": B, "H": H, "D": D, **out}))
 
 
+def bench_topk():
+    dev = "cuda"
+    peaks = load_peaks()
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush = lambda: flush_buf.fill_(1)  # noqa: E731
+    Q, N, K = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (16384, 1_250_000, 100)
+    q = torch.nn.functional.normalize(torch.randn(Q, 128, device=dev), dim=1)
+    e = torch.nn.functional.normalize(torch.randn(N, 128, device=dev), dim=1)
+    prep = ops.PreparedCorpus(e)
+    out = {}
+    ms, best = time_op(lambda: ops.score_topk(q, e, K, precision="bf16", prepared=prep), 3, flush)
+    flops = 2.0 * Q * N * 128
+    out["bf16"] = {"ms": ms, "best_ms": best, "tflops": flops / best / 1e9, "frac_of_bf16_peak": flops / best / 1e9 / peaks["bf16_tflops"],
+                   "queries_per_s": Q / best * 1e3, "unverified": ops.topk_stats["unverified"]}
+    if Q * N <= 4096 * 1_000_000:
+        ms, best = time_op(lambda: ops.score_topk(q, e, K), 2, flush)
+        out["fp32"] = {"ms": ms, "best_ms": best, "tflops": flops / best / 1e9, "queries_per_s": Q / best * 1e3}
+    print(json.dumps({"kernel": "score_topk", "Q": Q, "N": N, "K": K, **out}))
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "topk":
+        bench_topk()
+        sys.exit(0)
     main()
