@@ -160,6 +160,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint64_t *xfull = sfree + 2;        // [1]
     uint64_t *xfree = xfull + 1;        // [1]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xfree + 1);
+    // thresholds published to the other column-half group (same query rows): tau_sh[grp][row], tagged per warp with
+    // the row tile they belong to
+    float *tau_sh = reinterpret_cast<float *>(tmem_slot + 2);            // [2][128]
+    volatile int *tau_tag = reinterpret_cast<volatile int *>(tau_sh + 2 * KT_BM);   // [8]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g0 = static_cast<int64_t>(blockIdx.x) * prm.per_cta;
@@ -174,6 +178,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         mbar_init(xfull, 1);
         mbar_init(xfree, 1);
         fence_barrier_init();
+        for (int w = 0; w < 8; ++w) tau_tag[w] = -1;
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
@@ -256,6 +261,15 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 ovf = false;
                 m_lo = m_hi = 0;
                 if (row_ok && prm.mask_offsets != nullptr) { m_lo = prm.mask_offsets[q]; m_hi = prm.mask_offsets[q + 1]; }
+                tau_sh[grp * KT_BM + r_in_tile] = -INFINITY;
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) tau_tag[grp * 4 + quarter] = c.m;
+            }
+            // the other group's K'-th best so far bounds the row's K'-th best from below just as well as ours does
+            if (tau_tag[(grp ^ 1) * 4 + quarter] == c.m) {
+                const float other = *reinterpret_cast<volatile float *>(tau_sh + (grp ^ 1) * KT_BM + r_in_tile);
+                if (row_ok) tau = fmaxf(tau, other);
             }
             float *lv = prm.cand_v + list * KT_CAP;
             int32_t *li = prm.cand_i + list * KT_CAP;
@@ -322,7 +336,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 float t_new;
                 __syncwarp();
                 const int kept = tk_prune_list(prm.cand_v + l2 * KT_CAP, prm.cand_i + l2 * KT_CAP, n2, prm.kp, lane, &t_new);
-                if (lane == src) { cnt = kept; tau = fmaxf(tau, t_new); }
+                if (lane == src) { cnt = kept; tau = fmaxf(tau, t_new); tau_sh[grp * KT_BM + r_in_tile] = tau; }
             }
             if (seg_end && row_ok) {
                 prm.cand_n[list] = ovf ? -1 : cnt;
@@ -481,7 +495,7 @@ static inline unsigned kt_grid(int64_t n, int threads) {
 template <int D>
 static int launch_topk_tc(const CUtensorMap &mq, const CUtensorMap &me, const TopkTcParams &prm, int grid, cudaStream_t st) {
     constexpr int ST = KtStages<D>::value;
-    constexpr size_t smem = 1024 + static_cast<size_t>(KT_BM) * D * 2 + static_cast<size_t>(ST) * KT_BN * D * 2 + 256;
+    constexpr size_t smem = 1024 + static_cast<size_t>(KT_BM) * D * 2 + static_cast<size_t>(ST) * KT_BN * D * 2 + 256 + 2 * KT_BM * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(topk_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
