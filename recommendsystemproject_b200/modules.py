@@ -35,6 +35,38 @@ def _need_cuda(t: torch.Tensor, what: str):
                       "move the model and the batch to the device (there is no CPU fallback)")
 
 
+def grouped_batch_norm(bn: nn.BatchNorm1d, x: torch.Tensor, groups: int) -> torch.Tensor:
+    """BatchNorm1d applied to `groups` independent slabs in ONE call.  Rows of x are ordered (sample, slab), so
+    x.view(B, groups*C) turns "statistics per slab" into plain per-channel statistics over B rows: numerically the
+    same as the reference's one-item-tower-pass-per-hard-negative-slab (TwoTowerModel.py:54-60: every pass
+    normalises with its own batch statistics and updates the running statistics once), in one kernel instead of
+    1+N.  Running statistics receive the 1+N updates in slab order:
+        r <- (1-m)^G r + m * sum_g (1-m)^(G-1-g) stat_g ."""
+    if groups == 1 or not bn.training:
+        return bn(x)
+    rows, C = x.shape
+    B = rows // groups
+    w = bn.weight.repeat(groups)
+    b = bn.bias.repeat(groups)
+    mean = x.new_zeros(groups * C)
+    var = x.new_ones(groups * C)
+    y = F.batch_norm(x.view(B, groups * C), mean, var, w, b, True, 1.0, bn.eps)   # momentum 1: mean/var = batch stats
+    if bn.track_running_stats:
+        with torch.no_grad():
+            m = bn.momentum
+            cache = bn.__dict__.setdefault("_tt_group_coef", {})   # built once (eagerly), reused under graph capture
+            key = (groups, x.device, x.dtype)
+            if key not in cache:
+                cache[key] = torch.tensor([m * (1.0 - m) ** (groups - 1 - g) for g in range(groups)], dtype=x.dtype,
+                                          device=x.device)
+            coef = cache[key]
+            decay = (1.0 - m) ** groups
+            bn.running_mean.mul_(decay).add_(coef @ mean.view(groups, C))
+            bn.running_var.mul_(decay).add_(coef @ var.view(groups, C))
+            bn.num_batches_tracked.add_(groups)
+    return y.view(rows, C)
+
+
 class MLP_Tower(nn.Module):
     """[Linear -> BatchNorm1d -> ReLU -> Dropout] x len(hidden) -> Linear -> L2 normalise
     (Tower.py:9-41)."""
@@ -59,8 +91,12 @@ class MLP_Tower(nn.Module):
             nn.init.constant_(m.weight, 1)
             nn.init.constant_(m.bias, 0)
 
-    def forward(self, x):
-        return F.normalize(self.mlp(x), p=2, dim=1)
+    def forward(self, x, groups: int = 1):
+        if groups == 1:
+            return F.normalize(self.mlp(x), p=2, dim=1)
+        for layer in self.mlp:
+            x = grouped_batch_norm(layer, x, groups) if isinstance(layer, nn.BatchNorm1d) else layer(x)
+        return F.normalize(x, p=2, dim=1)
 
 
 class SequenceFeatureProcessor(nn.Module):
@@ -242,7 +278,26 @@ class GenericTower(nn.Module):
             tables.append(self.embeddings[name].weight)
         return specs, tables
 
-    def forward(self, input_dict, feature_column_mapping=None):
+    def forward_grouped(self, input_dicts, feature_column_mapping=None):
+        """The tower over G input dicts of B rows each in ONE pass -> [B, G, D]; every dict keeps its own BatchNorm
+        batch statistics (see grouped_batch_norm).  Used for [positive items] + hard-negative slabs."""
+        G = len(input_dicts)
+        first = input_dicts[0]
+
+        def stack(ts):
+            t = torch.stack(ts, dim=1)                      # [B, G, ...]: row order (sample, slab)
+            return t.reshape(t.shape[0] * G, *t.shape[2:])
+
+        merged = {}
+        for key in ("sparse", "dense"):
+            if key in first and first[key] is not None:
+                merged[key] = stack([d[key] for d in input_dicts])
+        if "sequence" in first and first["sequence"]:
+            merged["sequence"] = {n: stack([d["sequence"][n] for d in input_dicts]) for n in first["sequence"]}
+        out = self.forward(merged, feature_column_mapping, groups=G)
+        return out.view(out.shape[0] // G, G, out.shape[1])
+
+    def forward(self, input_dict, feature_column_mapping=None, groups: int = 1):
         feats = []
         if self.sparse_features and "sparse" in input_dict:
             specs, tables = self._sparse_specs(input_dict, feature_column_mapping)
@@ -269,8 +324,22 @@ class GenericTower(nn.Module):
         if not feats:
             raise RuntimeError("Tower received no valid features. Check if input_dict matches config")
         x = feats[0] if len(feats) == 1 else torch.cat(feats, dim=1)
-        x = self.feature_bn(x)
-        return self.mlp(x)
+        x = grouped_batch_norm(self.feature_bn, x, groups)
+        return self.mlp(x, groups)
+
+
+def _same_layout(item_dict, negs) -> bool:
+    """True when every hard-negative slab has the item batch's keys and shapes (so they can be stacked)."""
+    def sig(d):
+        out = []
+        for key in ("sparse", "dense"):
+            t = d.get(key)
+            out.append(None if t is None else tuple(t.shape))
+        seq = d.get("sequence") or {}
+        out.append(tuple(sorted((n, tuple(t.shape)) for n, t in seq.items())))
+        return out
+    ref = sig(item_dict)
+    return all(sig(n) == ref for n in negs)
 
 
 class TwoTowerModel(nn.Module):
@@ -287,6 +356,9 @@ class TwoTowerModel(nn.Module):
         # the stream is being captured into a CUDA graph)
         self.strict_nan_check = True
         self.last_nan_flags: Optional[torch.Tensor] = None
+        # positives + hard-negative slabs through the item tower in one grouped pass (same numbers, 1/(1+N) of the
+        # launches); False = one pass per slab, op for op like the reference
+        self.group_hard_negatives = True
 
     def set_feature_mappings(self, user_mapping, item_mapping):
         self.user_feature_mapping = user_mapping
@@ -294,6 +366,10 @@ class TwoTowerModel(nn.Module):
 
     def forward(self, batch_data):
         user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping)
+        negs = batch_data.get("hard_negatives") or []
+        if negs and self.group_hard_negatives and _same_layout(batch_data["item_tower"], negs):
+            both = self.item_tower.forward_grouped([batch_data["item_tower"]] + list(negs), self.item_feature_mapping)
+            return user_emb, both[:, 0], both[:, 1:]
         item_emb = self.item_tower(batch_data["item_tower"], self.item_feature_mapping)
         hard_neg_emb = None
         if "hard_negatives" in batch_data and batch_data["hard_negatives"]:

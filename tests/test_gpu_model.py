@@ -45,21 +45,32 @@ def test_forward_matches_reference(name):
     assert abs(float(loss) - float(s0["loss"])) < 5e-6
 
 
-def _check_state(model, gold, cfg, step):
+def _check_state(model, gold, cfg, step, grad_noise=0.0, carried=None):
+    """Parameters / buffers after the optimizer step against the reference's.  Adam's normalised step
+    lr * m / (sqrt(v) + eps) is chaotic in gradient elements that are pure rounding noise (|g| ~ 1e-8: the quotient
+    g / (|g| + eps) moves by O(1) when g moves by 1e-9, see tests/test_oracle_golden.py), and proportionally sensitive
+    otherwise (|dp| <= lr |dg| / |g|).  `carried` accumulates, per element, the deviation those two effects allow over
+    the steps taken so far; everything else must match to the base tolerance."""
+    lr = cfg["train"]["learning_rate"]
     coef = min(1.0, 1.0 / (float(gold["total_norm"]) + 1e-6))
     sd = model.state_dict()
+    carried = {} if carried is None else carried
     for k, v in gold["state_after"].items():
         got = sd[k].cpu()
         if not v.is_floating_point():
             assert torch.equal(got, v), k
             continue
-        atol = 2e-5 if step == 0 else 0.02 * cfg["train"]["learning_rate"]
+        atol = 2e-5 if step == 0 else 0.02 * lr
         if step > 0 and k.endswith("running_mean"):
-            atol = 2.0 * cfg["train"]["learning_rate"]
+            atol = 2.0 * lr
         ok = torch.isclose(got, v, atol=atol, rtol=1e-4)
         if k in gold["grads"]:
-            ok = ok | (gold["grads"][k].abs() * coef < 1e-6)  # see tests/test_oracle_golden.py
+            g = gold["grads"][k].abs() * coef
+            allow = torch.where(g < 1e-6, torch.full_like(g, 2 * lr), (lr * grad_noise / (g + 1e-30)).clamp(max=2 * lr))
+            carried[k] = carried.get(k, torch.zeros_like(g)) + allow
+            ok = ok | ((got - v).abs() <= carried[k] + atol)
         assert ok.all(), (step, k, float((got - v).abs().max()))
+    return carried
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -71,6 +82,13 @@ def test_two_training_steps_match_reference(name, opt_kind):
     npz, cfg = load_golden(name)
     model = _build(npz, cfg)
     model.train()
+    # "torch" = the pure drop-in: torch.optim.Adam and one item-tower pass per hard-negative slab, op for op like the
+    # reference.  The fused kinds run the hard-negative slabs as ONE grouped pass (same statistics per slab, different
+    # fp32 summation order; test_grouped_hard_negative_pass_equals_one_pass_per_slab bounds the gradient difference by
+    # 2e-6).  Adam's normalised step turns a relative gradient perturbation into the same relative step perturbation,
+    # so after step 1 each element is allowed lr * 4e-6 / |g| on top of the base tolerance.
+    model.group_hard_negatives = opt_kind != "torch"
+    grad_noise = 0.0 if opt_kind == "torch" else 4e-6
     T, lr = cfg["train"]["temperature"], cfg["train"]["learning_rate"]
     batches = [to_device(unflatten(npz, b), DEV) for b in ("batch", "batch2")]
     if opt_kind == "torch":
@@ -78,6 +96,7 @@ def test_two_training_steps_match_reference(name, opt_kind):
     else:
         opt = tt.FusedTwoTowerOptimizer(model, lr=lr, max_grad_norm=1.0, table_mode="dense")
     graphed = tt.GraphedTrainStep(model, opt, batches[0], T) if opt_kind == "graphed" else None
+    carried = None
     for step, batch in enumerate(batches):
         gold = unflatten(npz, f"step{step}")
         if graphed is not None:
@@ -100,7 +119,7 @@ def test_two_training_steps_match_reference(name, opt_kind):
         if opt_kind != "graphed":
             for k, g in gold["grads"].items():
                 assert torch.allclose(grads[k].cpu(), g, atol=2e-5, rtol=2e-4), (step, k, float((grads[k].cpu() - g).abs().max()))
-        _check_state(model, gold, cfg, step)
+        carried = _check_state(model, gold, cfg, step, grad_noise, carried)
 
 
 def test_sparse_table_mode_first_step_equals_dense_adam():
@@ -197,3 +216,34 @@ def test_full_size_c2_step_runs_and_is_finite():
     losses = [float(step(batch)) for _ in range(5)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
     model.check_nan_flags()
+
+
+def test_grouped_hard_negative_pass_equals_one_pass_per_slab():
+    """group_hard_negatives=True runs positives + N hard-negative slabs through the item tower in one pass with
+    per-slab BatchNorm statistics; it must reproduce the reference's 1+N separate passes (TwoTowerModel.py:54-60):
+    embeddings, loss, gradients and the BatchNorm running statistics after the 1+N sequential updates."""
+    cfg = synth.config_c2(dropout_scale=0.0)
+    batch = to_device(synth.make_batch_c2(B=96, n_neg=4, seed=11), DEV)
+    outs = {}
+    for grouped in (False, True):
+        torch.manual_seed(3)
+        model = tt.TwoTowerModel(tt.GenericTower(cfg, "user_tower"), tt.GenericTower(cfg, "item_tower"), *synth.MAPS_C2)
+        model = model.to(DEV).train()
+        model.group_hard_negatives = grouped
+        u, i, hn = model(batch)
+        loss = model.compute_loss(u, i, item_ids=batch["item_tower"]["sparse"][:, 0], hard_neg_emb=hn, temperature=0.15)
+        loss.backward()
+        outs[grouped] = (u.detach(), i.detach(), hn.detach(), loss.detach(),
+                         {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
+                         {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k})
+    a, b = outs[False], outs[True]
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.allclose(x, y, atol=2e-6)
+    assert abs(float(a[3]) - float(b[3])) < 2e-6
+    for k in a[4]:
+        assert torch.allclose(a[4][k], b[4][k], atol=2e-6, rtol=1e-4), k
+    for k in a[5]:
+        if a[5][k].is_floating_point():
+            assert torch.allclose(a[5][k], b[5][k], atol=1e-6, rtol=1e-5), k
+        else:
+            assert torch.equal(a[5][k], b[5][k]), k
