@@ -234,8 +234,8 @@ def kernel_rooflines(peaks, flush, quick=False):
                 "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg})
     del table, m, v, ids, g, rows, row_grad, res
     torch.cuda.empty_cache()
-    # --- C4-shaped fused CE (fp32 SIMT path): B x (B+H) logits never materialised
-    Bc, Hc, Dc = (8192, 1024, 128) if quick else (32768, 4096, 128)
+    # --- C4 fused CE, tcgen05/TMA bf16 path, forward + backward: the B x (B+H) logits live only in TMEM
+    Bc, Hc, Dc = (8192, 1024, 128) if quick else (65536, 4096, 128)
     u = torch.nn.functional.normalize(torch.randn(Bc, Dc, device=dev), dim=1).requires_grad_(True)
     it = torch.nn.functional.normalize(torch.randn(Bc, Dc, device=dev), dim=1).requires_grad_(True)
     pool = torch.nn.functional.normalize(torch.randn(Hc, Dc, device=dev), dim=1).requires_grad_(True)
@@ -243,24 +243,50 @@ def kernel_rooflines(peaks, flush, quick=False):
     res = {}
 
     def ce_f():
-        res["l"] = ops.fused_inbatch_ce(u, it, item_ids, None, pool, 0.05)[0]
-    ms_f, _ = time_op(ce_f, 2, flush)
-    ms_b, _ = time_op(lambda: (ce_f(), res["l"].backward()), 2, flush)
+        res["l"] = ops.fused_inbatch_ce(u, it, item_ids, None, pool, 0.05, precision="bf16")[0]
+    ms_f, best_f = time_op(ce_f, 5, flush)
+    ms_b, best_b = time_op(lambda: (ce_f(), res["l"].backward()), 5, flush)
     flops = 6.0 * Bc * (Bc + Hc) * Dc
-    ms = ms_b  # fwd + bwd
-    out.append({"kernel": "ce_fwd_tiles + ce_bwd_pass (fp32 SIMT)", "workload": f"C4 slice: B={Bc} H={Hc} D={Dc} fwd+bwd",
-                "bound": "tensor", "ms": ms, "ms_fwd": ms_f, "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"],
-                "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["bf16_tflops"], "alg_flops": flops})
+    out.append({"kernel": "ce_tc_kernel<fwd> + ce_tc_kernel<bwd dU> + ce_tc_kernel<bwd dI,dPool> (tcgen05, bf16 in / fp32 acc)",
+                "workload": f"C4: B={Bc} H={Hc} D={Dc} T=0.05, fwd+bwd incl. id sort + bf16 conversion", "bound": "tensor",
+                "ms": ms_b, "best_ms": best_b, "ms_fwd": ms_f, "achieved": flops / ms_b / 1e9, "peak": peaks["bf16_tflops"],
+                "peak_sustained": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": flops / ms_b / 1e9 / peaks["bf16_tflops"], "frac_of_sustained": flops / ms_b / 1e9 / peaks["bf16_tflops_sustained"],
+                "alg_flops": flops, "loss": float(res["l"])})
+    if not quick:   # the exact fp32 SIMT path at a quarter of the rows, for comparison
+        Bs = 16384
+        u2, it2 = u[:Bs].detach().requires_grad_(True), it[:Bs].detach().requires_grad_(True)
+        res2 = {}
+
+        def ce32():
+            res2["l"] = ops.fused_inbatch_ce(u2, it2, item_ids[:Bs], None, pool.detach(), 0.05)[0]
+        ms32, _ = time_op(lambda: (ce32(), res2["l"].backward()), 2, flush)
+        f32 = 6.0 * Bs * (Bs + Hc) * Dc
+        out.append({"kernel": "ce_fwd_tiles + ce_bwd_pass (exact fp32 SIMT path)", "workload": f"B={Bs} H={Hc} D={Dc} fwd+bwd",
+                    "bound": "tensor", "ms": ms32, "achieved": f32 / ms32 / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": f32 / ms32 / 1e9 / peaks["bf16_tflops"], "alg_flops": f32})
+        del u2, it2
     del u, it, pool
-    # --- C5-shaped scoring + top-100
-    Q, N, K = (1024, 200_000, 100) if quick else (4096, 1_000_000, 100)
+    torch.cuda.empty_cache()
+    # --- C5 scoring + top-100, tcgen05 filter + exact re-rank: one GPU's shard of the 10M-item corpus
+    Q, N, K = (2048, 200_000, 100) if quick else (32768, 1_250_000, 100)
     q = torch.nn.functional.normalize(torch.randn(Q, 128, device=dev), dim=1)
     e = torch.nn.functional.normalize(torch.randn(N, 128, device=dev), dim=1)
-    ms, _ = time_op(lambda: ops.score_topk(q, e, K), 2, flush)
+    prep = ops.PreparedCorpus(e)
+    ms, best = time_op(lambda: ops.score_topk(q, e, K, precision="bf16", prepared=prep), 3, flush)
     flops = 2.0 * Q * N * 128
-    out.append({"kernel": "topk_stage1 + topk_stage2 (fp32 SIMT)", "workload": f"C5 slice: Q={Q} N={N} D=128 K={K}",
-                "bound": "tensor", "ms": ms, "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": flops / ms / 1e9 / peaks["bf16_tflops"], "queries_per_s": Q / ms * 1e3, "alg_flops": flops})
+    out.append({"kernel": "topk_tc_kernel + topk_tc_stage2 (tcgen05 bf16 filter, fp64 exact re-rank, bit-exact rows)",
+                "workload": f"C5 shard: Q={Q} N={N} D=128 K={K}", "bound": "tensor", "ms": ms, "best_ms": best,
+                "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": flops / ms / 1e9 / peaks["bf16_tflops"], "queries_per_s": Q / ms * 1e3, "alg_flops": flops,
+                "fp32_fallback_queries": ops.topk_stats["unverified"]})
+    if not quick:
+        Qs = 2048
+        ms32, _ = time_op(lambda: ops.score_topk(q[:Qs], e, K), 1, flush)
+        out.append({"kernel": "topk_stage1 + topk_stage2 (exact fp32 SIMT path)", "workload": f"Q={Qs} N={N} D=128 K={K}",
+                    "bound": "tensor", "ms": ms32, "achieved": 2.0 * Qs * N * 128 / ms32 / 1e9, "peak": peaks["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": 2.0 * Qs * N * 128 / ms32 / 1e9 / peaks["bf16_tflops"],
+                    "queries_per_s": Qs / ms32 * 1e3})
     return out
 
 

@@ -25,7 +25,16 @@
 
 namespace tt {
 
-constexpr int SEG_CHUNK = 128;
+constexpr int SEG_CHUNK_MAX = 128;
+
+// Long segments are cut into `chunk` positions per lane group.  128 amortises the partial-row traffic on big
+// inputs; small inputs (an ML-1M batch is 10^4 positions) get shorter chunks so that a 30-row vocabulary still
+// spreads over the whole chip.  Depends on n only, so the summation order stays a function of the input.
+static inline int seg_chunk_for(int64_t n) {
+    int c = SEG_CHUNK_MAX;
+    while (c > 8 && n / c < 4096) c >>= 1;
+    return c;
+}
 
 __global__ void seg_build_keys(const int64_t *__restrict__ ids, int64_t n, int64_t pad, int64_t vocab,
                                uint32_t *__restrict__ keys, int32_t *__restrict__ vals) {
@@ -69,7 +78,7 @@ __global__ void seg_starts(const uint32_t *__restrict__ keys, const int32_t *__r
 
 // number of CHUNK pieces of each long segment (0 for short ones); also closes seg_start[U] = n_valid
 __global__ void seg_chunk_counts(int32_t *__restrict__ seg_start, const int32_t *__restrict__ counters,
-                                 int64_t n, int32_t *__restrict__ n_chunks) {
+                                 int64_t n, int SEG_CHUNK, int32_t *__restrict__ n_chunks) {
     const int32_t U = counters[0];
     for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < n;
          s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -131,12 +140,11 @@ template <int LPR>
 __global__ void __launch_bounds__(256)
 seg_reduce_chunks(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
                   const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
-                  int32_t total_chunks_idx, float *__restrict__ partial) {
+                  int32_t SEG_CHUNK, float *__restrict__ partial) {
     const int U = counters[0];
     if (U == 0) return;
     const int n_valid = counters[1];
     const int total = chunk_base[U - 1] + 0;  // exclusive scan value at U-1 ...
-    (void)total_chunks_idx;
     const int vpr = g.dim / 4;
     const int sub = threadIdx.x % LPR;
     const int64_t group0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
@@ -174,7 +182,7 @@ template <int LPR>
 __global__ void __launch_bounds__(256)
 seg_reduce_rows(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
                 const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
-                const float *__restrict__ partial, float scale, float *__restrict__ row_grad,
+                const float *__restrict__ partial, float scale, int SEG_CHUNK, float *__restrict__ row_grad,
                 float *__restrict__ seg_sq) {
     const int U = counters[0];
     const int n_valid = counters[1];
@@ -290,6 +298,7 @@ static inline unsigned grid_for(int64_t n, int threads) {
 struct SegPlan {
     size_t cub_sort, cub_scan, cub_bytes;
     int64_t max_chunks;
+    int chunk;
 };
 
 static SegPlan seg_plan(int64_t n) {
@@ -300,26 +309,27 @@ static SegPlan seg_plan(int64_t n) {
     cub::DeviceScan::ExclusiveSum(nullptr, p.cub_scan, static_cast<int32_t *>(nullptr),
                                   static_cast<int32_t *>(nullptr), static_cast<int>(n));
     p.cub_bytes = p.cub_sort > p.cub_scan ? p.cub_sort : p.cub_scan;
-    p.max_chunks = 2 * (n / SEG_CHUNK) + 2;  // each long segment wastes at most one partial chunk
+    p.chunk = seg_chunk_for(n);
+    p.max_chunks = 2 * (n / p.chunk) + 2;  // each long segment wastes at most one partial chunk
     return p;
 }
 
 template <int LPR>
 static int launch_reduce(const GradSrc &g, const int32_t *sorted_pos, const int32_t *seg_start,
                          const int32_t *chunk_base, const int32_t *counters, float *partial, int64_t max_chunks,
-                         float scale, float *row_grad, float *seg_sq, int64_t n, cudaStream_t st) {
+                         float scale, float *row_grad, float *seg_sq, int64_t n, int SEG_CHUNK, cudaStream_t st) {
     const int threads = 256;
     const int gpb = threads / LPR;
     if (n > SEG_CHUNK) {
         seg_reduce_chunks<LPR><<<grid_for(max_chunks * LPR, threads), threads, 0, st>>>(
-            g, sorted_pos, seg_start, chunk_base, counters, 0, partial);
+            g, sorted_pos, seg_start, chunk_base, counters, SEG_CHUNK, partial);
         TT_LAUNCH_CHECK("seg_reduce_chunks");
     }
     int64_t blocks = (n + gpb - 1) / gpb;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
     if (blocks > cap) blocks = cap;
     seg_reduce_rows<LPR><<<static_cast<unsigned>(blocks), threads, 0, st>>>(g, sorted_pos, seg_start, chunk_base,
-                                                                           counters, partial, scale, row_grad, seg_sq);
+                                                                           counters, partial, scale, SEG_CHUNK, row_grad, seg_sq);
     TT_LAUNCH_CHECK("seg_reduce_rows");
     return 0;
 }
@@ -398,7 +408,7 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
     // reuse head -> chunk counts, seg_id -> chunk bases
     int32_t *n_chunks = head;
     int32_t *chunk_base = seg_id;
-    seg_chunk_counts<<<g1, threads, 0, st>>>(seg_start, counters, n, n_chunks);
+    seg_chunk_counts<<<g1, threads, 0, st>>>(seg_start, counters, n, plan.chunk, n_chunks);
     TT_LAUNCH_CHECK("seg_chunk_counts");
     tmp = plan.cub_bytes;
     e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, n_chunks, chunk_base, static_cast<int>(n), st);
@@ -417,12 +427,12 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
         TT_LAUNCH_CHECK("seg_sq_scalar");
     } else {
         const int vpr = dim / 4;
-        if (vpr <= 1) rc = launch_reduce<1>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
-        else if (vpr <= 2) rc = launch_reduce<2>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
-        else if (vpr <= 4) rc = launch_reduce<4>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
-        else if (vpr <= 8) rc = launch_reduce<8>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
-        else if (vpr <= 16) rc = launch_reduce<16>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
-        else rc = launch_reduce<32>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, st);
+        if (vpr <= 1) rc = launch_reduce<1>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 2) rc = launch_reduce<2>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 4) rc = launch_reduce<4>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 8) rc = launch_reduce<8>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 16) rc = launch_reduce<16>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else rc = launch_reduce<32>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
         if (rc) return rc;
     }
     // *sq_norm += sum(seg_sq[0..U)), *n_unique = U
