@@ -229,6 +229,113 @@ seg_reduce_rows(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t
     }
 }
 
+// D >= 64: 8 lanes per segment, CPL float4 columns per lane (lane l owns columns l, l+8, ...: every load instruction
+// of a segment is one contiguous 128-byte line), 4 segments per warp and CPL * 2 independent 16-byte loads in flight
+// per lane.  Most segments of a 10M-row table hold one or two positions, so the kernel lives on memory-level
+// parallelism, not on the length of the inner loop.
+template <int CPL>
+__global__ void __launch_bounds__(256)
+seg_reduce_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
+                     const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
+                     const float *__restrict__ partial, float scale, int SEG_CHUNK, float *__restrict__ row_grad,
+                     float *__restrict__ seg_sq) {
+    constexpr int LPR = 8;
+    const int U = counters[0];
+    const int n_valid = counters[1];
+    const int sub = threadIdx.x % LPR;
+    const int64_t group0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+    const int64_t n_groups = static_cast<int64_t>(gridDim.x) * blockDim.x / LPR;
+    const int64_t rounds = (U + n_groups - 1) / n_groups;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t s = group0 + it * n_groups;
+        const bool ok = s < U;
+        float sq = 0.f;
+        if (ok) {
+            const int p0 = seg_start[s];
+            const int p1 = (s + 1 < U) ? seg_start[s + 1] : n_valid;
+            const int len = p1 - p0;
+            float acc[CPL][4];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+            if (len <= SEG_CHUNK) {
+                for (int i = p0; i < p1; i += 2) {
+                    float4 v[2][CPL];
+                    bool use[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        use[u] = (i + u) < p1;
+                        if (use[u]) {
+                            const int32_t p = __ldg(sorted_pos + i + u);
+                            int64_t src = p;
+                            int slot = 0;
+                            if (g.len > 1) { src = p / g.len; slot = p - static_cast<int32_t>(src) * g.len; }
+#pragma unroll
+                            for (int k = 0; k < CPL; ++k) {
+                                const int c = sub + LPR * k;
+                                v[u][k] = __ldg(reinterpret_cast<const float4 *>(g.grad_out + src * g.grad_stride + c * 4));
+                                if (g.mode == TT_POOL_MAX) {
+                                    const int4 am = __ldg(reinterpret_cast<const int4 *>(g.argmax + src * g.dim + c * 4));
+                                    if (am.x != slot) v[u][k].x = 0.f;
+                                    if (am.y != slot) v[u][k].y = 0.f;
+                                    if (am.z != slot) v[u][k].z = 0.f;
+                                    if (am.w != slot) v[u][k].w = 0.f;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (use[u]) {
+#pragma unroll
+                            for (int k = 0; k < CPL; ++k) {
+                                acc[k][0] += v[u][k].x; acc[k][1] += v[u][k].y; acc[k][2] += v[u][k].z; acc[k][3] += v[u][k].w;
+                            }
+                        }
+                }
+            } else {
+                const int nck = (len + SEG_CHUNK - 1) / SEG_CHUNK;
+                const int64_t cb = chunk_base[s];
+                for (int c2 = 0; c2 < nck; ++c2) {
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        const float4 v = *reinterpret_cast<const float4 *>(partial + (cb + c2) * g.dim + (sub + LPR * k) * 4);
+                        acc[k][0] += v.x; acc[k][1] += v.y; acc[k][2] += v.z; acc[k][3] += v.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                acc[k][0] *= scale; acc[k][1] *= scale; acc[k][2] *= scale; acc[k][3] *= scale;
+                *reinterpret_cast<float4 *>(row_grad + s * g.dim + (sub + LPR * k) * 4) =
+                    make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                sq += acc[k][0] * acc[k][0] + acc[k][1] * acc[k][1] + acc[k][2] * acc[k][2] + acc[k][3] * acc[k][3];
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (ok && sub == 0) seg_sq[s] = sq;
+    }
+}
+
+// deterministic two-level sum of x[0..n) (n on the device): SUM_BLOCKS fixed slices, then one block over the partials
+constexpr int SUM_BLOCKS = 592;
+__global__ void __launch_bounds__(256)
+seg_sum_partial(const float *__restrict__ x, const int32_t *__restrict__ n_dev, float *__restrict__ part) {
+    __shared__ float sh[256];
+    const int64_t n = *n_dev;
+    const int64_t per = (n + SUM_BLOCKS - 1) / SUM_BLOCKS;
+    const int64_t a = per * blockIdx.x, b = min(n, a + per);
+    float acc = 0.f;
+    for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) acc += x[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+
 // generic-D fallback (D % 4 != 0 or unaligned grad rows): one thread per (segment, d)
 __global__ void seg_reduce_rows_scalar(GradSrc g, const int32_t *__restrict__ sorted_pos,
                                        const int32_t *__restrict__ seg_start, const int32_t *__restrict__ counters,
@@ -285,6 +392,10 @@ sum_fixed_order(const float *__restrict__ x, const int32_t *__restrict__ n_dev, 
         *out += sh[0];
         if (n_unique_out) *n_unique_out = static_cast<int32_t>(n);
     }
+}
+
+__global__ void seg_store_count(const int32_t *__restrict__ counters, int32_t *__restrict__ n_unique) {
+    if (threadIdx.x == 0) *n_unique = counters[0];
 }
 
 static inline unsigned grid_for(int64_t n, int threads) {
@@ -427,7 +538,24 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
         TT_LAUNCH_CHECK("seg_sq_scalar");
     } else {
         const int vpr = dim / 4;
-        if (vpr <= 1) rc = launch_reduce<1>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        const int cpl = (vpr % 8 == 0) ? vpr / 8 : 0;
+        if (cpl == 2 || cpl == 3 || cpl == 4 || cpl == 6 || cpl == 8) {
+            if (n > plan.chunk) {
+                seg_reduce_chunks<8><<<grid_for(plan.max_chunks * 8, threads), threads, 0, st>>>(
+                    g, vals_out, seg_start, chunk_base, counters, plan.chunk, partial);
+                TT_LAUNCH_CHECK("seg_reduce_chunks");
+            }
+            int64_t blocks = (n + 31) / 32;
+            const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+            if (blocks > cap) blocks = cap;
+#define TT_WIDE(C) seg_reduce_rows_wide<C><<<static_cast<unsigned>(blocks), threads, 0, st>>>(                      \
+        g, vals_out, seg_start, chunk_base, counters, partial, scale, plan.chunk, row_grad, seg_sq)
+            if (cpl == 2) TT_WIDE(2); else if (cpl == 3) TT_WIDE(3); else if (cpl == 4) TT_WIDE(4);
+            else if (cpl == 6) TT_WIDE(6); else TT_WIDE(8);
+#undef TT_WIDE
+            TT_LAUNCH_CHECK("seg_reduce_rows_wide");
+        }
+        else if (vpr <= 1) rc = launch_reduce<1>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
         else if (vpr <= 2) rc = launch_reduce<2>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
         else if (vpr <= 4) rc = launch_reduce<4>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
         else if (vpr <= 8) rc = launch_reduce<8>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
@@ -437,7 +565,15 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
     }
     // *sq_norm += sum(seg_sq[0..U)), *n_unique = U
     float *sq_target = sq_norm ? sq_norm : seg_sq + (n - 1);  // dummy target when the caller does not want the norm
-    sum_fixed_order<<<1, 1024, 0, st>>>(seg_sq, counters, 0, sq_target, n_unique);
+    if (n > 65536) {
+        float *sum_part = reinterpret_cast<float *>(keys_in);   // the sort input is dead by now
+        seg_sum_partial<<<SUM_BLOCKS, 256, 0, st>>>(seg_sq, counters, sum_part);
+        TT_LAUNCH_CHECK("seg_sum_partial");
+        sum_fixed_order<<<1, 1024, 0, st>>>(sum_part, nullptr, SUM_BLOCKS, sq_target, nullptr);
+        seg_store_count<<<1, 32, 0, st>>>(counters, n_unique);
+    } else {
+        sum_fixed_order<<<1, 1024, 0, st>>>(seg_sq, counters, 0, sq_target, n_unique);
+    }
     TT_LAUNCH_CHECK("sum_fixed_order");
     return 0;
 }

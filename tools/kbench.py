@@ -62,7 +62,34 @@ def bench_topk():
     print(json.dumps({"kernel": "score_topk", "Q": Q, "N": N, "K": K, **out}))
 
 
+def bench_seg():
+    dev = "cuda"
+    peaks = load_peaks()
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush = lambda: flush_buf.fill_(1)  # noqa: E731
+    B, L, D, V = 65536, 200, 128, 10_000_001
+    gen = torch.Generator(device=dev).manual_seed(3)
+    ids = torch.randint(1, V, (B, L), device=dev, generator=gen)
+    lens = torch.randint(1, L + 1, (B,), device=dev, generator=gen)
+    ids[torch.arange(L, device=dev)[None, :] >= lens[:, None]] = 0
+    n_valid = int((ids != 0).sum().item())
+    g = torch.randn(B, D, device=dev)
+    sq = torch.zeros(1, device=dev)
+    res = {}
+
+    def seg():
+        res["r"] = ops.segment_grad(ids, ops.POOL_MEAN, 0, V, g, None, D, sq)
+    ms, best = time_op(seg, 3, flush)
+    U = int(res["r"][2].item())
+    alg = B * L * 8 + n_valid * D * 4 + U * (D * 4 + 8)
+    print(json.dumps({"kernel": "emb_segment_grad", "ms": ms, "best_ms": best, "U": U, "n_valid": n_valid,
+                      "GBps": alg / best / 1e6, "frac": alg / best / 1e6 / peaks["hbm_gbs"]}))
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "seg":
+        bench_seg()
+        sys.exit(0)
     if sys.argv[1] == "topk":
         bench_topk()
         sys.exit(0)
