@@ -359,17 +359,43 @@ class TwoTowerModel(nn.Module):
         # positives + hard-negative slabs through the item tower in one grouped pass (same numbers, 1/(1+N) of the
         # launches); False = one pass per slab, op for op like the reference
         self.group_hard_negatives = True
+        # the two towers are independent until the loss: run the item side on a second stream (forward, and therefore
+        # its autograd backward too); inside a CUDA graph this becomes two concurrent branches
+        self.parallel_towers = True
+        self._side_streams = {}
 
     def set_feature_mappings(self, user_mapping, item_mapping):
         self.user_feature_mapping = user_mapping
         self.item_feature_mapping = item_mapping
 
     def forward(self, batch_data):
+        if self.parallel_towers and torch.is_grad_enabled() and self.training:
+            return self._forward_two_streams(batch_data)
         user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping)
+        item_emb, hard_neg_emb = self._item_side(batch_data)
+        return user_emb, item_emb, hard_neg_emb
+
+    def _forward_two_streams(self, batch_data):
+        cur = torch.cuda.current_stream()
+        key = cur.device.index
+        if key not in self._side_streams:
+            self._side_streams[key] = torch.cuda.Stream(device=cur.device)
+        side = self._side_streams[key]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            item_emb, hard_neg_emb = self._item_side(batch_data)
+        user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping)
+        cur.wait_stream(side)
+        for t in (item_emb, hard_neg_emb):
+            if t is not None:
+                t.record_stream(cur)
+        return user_emb, item_emb, hard_neg_emb
+
+    def _item_side(self, batch_data):
         negs = batch_data.get("hard_negatives") or []
         if negs and self.group_hard_negatives and _same_layout(batch_data["item_tower"], negs):
             both = self.item_tower.forward_grouped([batch_data["item_tower"]] + list(negs), self.item_feature_mapping)
-            return user_emb, both[:, 0], both[:, 1:]
+            return both[:, 0], both[:, 1:]
         item_emb = self.item_tower(batch_data["item_tower"], self.item_feature_mapping)
         hard_neg_emb = None
         if "hard_negatives" in batch_data and batch_data["hard_negatives"]:
@@ -377,7 +403,7 @@ class TwoTowerModel(nn.Module):
             # statistics and running-stat update, like the reference (:54-60)
             slabs = [self.item_tower(neg, self.item_feature_mapping) for neg in batch_data["hard_negatives"]]
             hard_neg_emb = torch.stack(slabs, dim=1)
-        return user_emb, item_emb, hard_neg_emb
+        return item_emb, hard_neg_emb
 
     def predict(self, batch_data):
         user_emb, item_emb, _ = self.forward(batch_data)
