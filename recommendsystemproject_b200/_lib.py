@@ -40,7 +40,7 @@ _SIGNATURES = {
     "tt_score_topk_f32": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int64, P, P, P, P, P, c_size_t, P]),
     "tt_topk_tc_prepare_corpus": (c_int, [P, c_int64, c_int, P, P, P]),
     "tt_score_topk_tc_workspace": (c_int, [c_int64, c_int64, c_int, c_int, c_int, P]),
-    "tt_score_topk_tc": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_int, c_int64, P, P, P, P, P, P, c_size_t, P]),
+    "tt_score_topk_tc": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_int, c_int64, P, P, P, P, P, c_int, P, c_size_t, P]),
     "tt_topk_merge": (c_int, [P, P, c_int, c_int64, c_int, P, P, P]),
 }
 

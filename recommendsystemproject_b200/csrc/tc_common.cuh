@@ -278,7 +278,7 @@ struct Sched {
     int grid, max_seg;
 };
 
-inline Sched make_sched(int m_tiles, int n_tiles) {
+inline Sched make_sched(int m_tiles, int n_tiles, int max_segments = 0) {
     Sched s;
     s.m_tiles = m_tiles; s.n_tiles = n_tiles;
     s.total = static_cast<int64_t>(m_tiles) * n_tiles;
@@ -286,6 +286,8 @@ inline Sched make_sched(int m_tiles, int n_tiles) {
     if (g > sm_count()) g = sm_count();
     if (g < 1) g = 1;
     s.per_cta = (s.total + g - 1) / g;
+    // optional cap on how many CTAs share one row tile (each segment leaves a partial the epilogue must merge)
+    if (max_segments > 0 && s.per_cta * max_segments < n_tiles) s.per_cta = (n_tiles + max_segments - 1) / max_segments;
     s.grid = static_cast<int>((s.total + s.per_cta - 1) / s.per_cta);
     s.max_seg = static_cast<int>((n_tiles + s.per_cta - 2) / s.per_cta) + 1;
     return s;

@@ -45,6 +45,8 @@ struct TopkTcParams {
     int m_tiles, n_tiles;
     int64_t per_cta, total;
     int max_seg, kp;
+    int tile_stride;         // corpus tile n covers rows [n * tile_stride * 256, +256): > 1 for the sampling pass
+    const float *tau0;       // [n_query] initial thresholds from the sampling pass (NULL: start at -inf)
     const int64_t *mask_offsets, *mask_rows;
     float *cand_v;       // [n_query][2 * max_seg][KT_CAP] approximate scores
     int32_t *cand_i;     //                               corpus rows
@@ -204,7 +206,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&full[stage], W_BYTES);
                 for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(w_tiles + stage * W_BYTES + kb * WK_BYTES, &map_e, &full[stage], kb * 64, c.n * KT_BN);
+                    tma_load_2d(w_tiles + stage * W_BYTES + kb * WK_BYTES, &map_e, &full[stage], kb * 64, c.n * prm.tile_stride * KT_BN);
             }
             __syncwarp();
         }
@@ -256,7 +258,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 row_ok = q < prm.n_query;
                 const int seg = static_cast<int>(blockIdx.x) - sched_first_cta(c.m, prm.n_tiles, prm.per_cta);
                 list = q * (2 * prm.max_seg) + 2 * seg + grp;
-                tau = row_ok ? -INFINITY : INFINITY;
+                tau = row_ok ? (prm.tau0 != nullptr ? prm.tau0[q] : -INFINITY) : INFINITY;
                 cnt = 0;
                 ovf = false;
                 m_lo = m_hi = 0;
@@ -281,14 +283,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&sfree[b]);
-            const int64_t col0 = static_cast<int64_t>(c.n) * KT_BN + grp * KT_HALF;
-            // The column index inside its 32-column chunk rides in the 5 low mantissa bits of the score (a 2^-18
-            // relative perturbation, far below the bf16 error budget): one FMNMX tree then yields the best score AND
-            // where it is, so the append path needs no dynamically indexed registers and stays compact.
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq)
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[qq][j] = (r[qq][j] & 0xffffffe0u) | static_cast<uint32_t>(j);
+            const int64_t col0 = static_cast<int64_t>(c.n) * prm.tile_stride * KT_BN + grp * KT_HALF;
             if (col0 + KT_HALF > prm.n_corpus) {   // last tile: rows past the corpus were zero-filled by TMA
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq)
@@ -305,23 +300,35 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     m0 = fmaxf(m0, __uint_as_float(r[qq][j]));
                     m1 = fmaxf(m1, __uint_as_float(r[qq][j + 1]));
                 }
-                float best = fmaxf(m0, m1);
-#pragma unroll 1
-                while (best > tau) {      // expected K' ln(N / K') times per list over the whole stream
-                    const int64_t col = col0 + qq * 32 + static_cast<int>(__float_as_uint(best) & 31u);
-                    if (!(m_hi > m_lo && tk_masked(prm.mask_rows, m_lo, m_hi, col))) {
-                        if (cnt < KT_CAP) { lv[cnt] = best; li[cnt] = static_cast<int32_t>(col); ++cnt; }
-                        else ovf = true;
-                    }
-                    // next best of the chunk: strictly below `best` (packed scores of a chunk are distinct)
-                    float n0 = -INFINITY, n1 = -INFINITY;
+                if (fmaxf(m0, m1) > tau) {
+                    // Some score of this 32-column chunk beats the threshold.  Its column index goes into the 5 low
+                    // mantissa bits of every score (a 2^-18 relative perturbation, far below the bf16 error budget):
+                    // one FMNMX tree then yields the best score AND where it is, so the append path needs no
+                    // dynamically indexed registers (no local memory: L1 is ~4 KB here) and stays compact (no
+                    // instruction-cache thrash: an earlier version with 128 inlined append sites was 140 KB of SASS).
+                    float best = -INFINITY;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float x0 = __uint_as_float(r[qq][j]), x1 = __uint_as_float(r[qq][j + 1]);
-                        n0 = fmaxf(n0, x0 < best ? x0 : -INFINITY);
-                        n1 = fmaxf(n1, x1 < best ? x1 : -INFINITY);
+                    for (int j = 0; j < 32; ++j) {
+                        if (r[qq][j] != 0xff800000u) r[qq][j] = (r[qq][j] & 0xffffffe0u) | static_cast<uint32_t>(j);
+                        best = fmaxf(best, __uint_as_float(r[qq][j]));
                     }
-                    best = fmaxf(n0, n1);
+#pragma unroll 1
+                    while (best > tau) {
+                        const int64_t col = col0 + qq * 32 + static_cast<int>(__float_as_uint(best) & 31u);
+                        if (!(m_hi > m_lo && tk_masked(prm.mask_rows, m_lo, m_hi, col))) {
+                            if (cnt < KT_CAP) { lv[cnt] = best; li[cnt] = static_cast<int32_t>(col); ++cnt; }
+                            else ovf = true;
+                        }
+                        // next best of the chunk: strictly below `best` (packed scores of a chunk are distinct)
+                        float n0 = -INFINITY, n1 = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float x0 = __uint_as_float(r[qq][j]), x1 = __uint_as_float(r[qq][j + 1]);
+                            n0 = fmaxf(n0, x0 < best ? x0 : -INFINITY);
+                            n1 = fmaxf(n1, x1 < best ? x1 : -INFINITY);
+                        }
+                        best = fmaxf(n0, n1);
+                    }
                 }
             }
             const bool seg_end = (c.n == prm.n_tiles - 1 || i == n_local - 1);
@@ -442,25 +449,87 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
     }
 }
 
+// tau0[q] = the rank-th best approximate score among the query's sampling-pass candidates (one warp per query,
+// bisection on the value like tk_prune_list).  About rank * stride items of the whole corpus score above it.
+__global__ void __launch_bounds__(256)
+tk_tau0_kernel(const float *__restrict__ cand_v, const int32_t *__restrict__ cand_n, int64_t n_query, int max_seg,
+               int n_tiles, int64_t per_cta, int rank, float *__restrict__ tau0) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t q = warp; q < n_query; q += n_warps) {
+        const int mt = static_cast<int>(q / KT_BM);
+        const int n_lists = 2 * (sched_last_cta(mt, n_tiles, per_cta) - sched_first_cta(mt, n_tiles, per_cta) + 1);
+        float lo = INFINITY, hi = -INFINITY;
+        int total = 0;
+        for (int l = 0; l < n_lists; ++l) {
+            const int64_t list = q * (2 * max_seg) + l;
+            const int n = min(max(cand_n[list], 0), KT_CAP);
+            total += n;
+            for (int t = lane; t < n; t += 32) {
+                const float v = cand_v[list * KT_CAP + t];
+                lo = fminf(lo, v);
+                hi = fmaxf(hi, v);
+            }
+        }
+        lo = -warp_max(-lo);
+        hi = warp_max(hi);
+        float t0 = -INFINITY;
+        if (total >= rank) {
+            // invariant: count(v >= lo) >= rank
+            for (int it = 0; it < 30; ++it) {
+                const float mid = lo + 0.5f * (hi - lo);
+                if (!(mid > lo && mid < hi)) break;
+                int c = 0;
+                for (int l = 0; l < n_lists; ++l) {
+                    const int64_t list = q * (2 * max_seg) + l;
+                    const int n = min(max(cand_n[list], 0), KT_CAP);
+                    for (int t = lane; t < n; t += 32) c += (cand_v[list * KT_CAP + t] >= mid) ? 1 : 0;
+                }
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= rank) { lo = mid; if (c <= rank + 1) break; } else hi = mid;
+            }
+            t0 = lo;
+        }
+        if (lane == 0) tau0[q] = t0;
+    }
+}
+
+constexpr int KT_SAMPLE_STRIDE = 16;         // the sampling pass scores every 16th corpus tile
+constexpr int64_t KT_SAMPLE_MIN_ROWS = 1 << 17;
+
 struct KtPlan {
-    Sched sched;
-    int kp;
+    Sched sched, sample;
+    int kp, kp_sample;
+    bool use_sample;
+    int max_seg;
 };
 
-static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k) {
+static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k, bool sampling = true) {
     KtPlan p;
-    p.sched = make_sched(static_cast<int>((n_query + KT_BM - 1) / KT_BM), static_cast<int>((n_corpus + KT_BN - 1) / KT_BN));
+    p.sched = make_sched(static_cast<int>((n_query + KT_BM - 1) / KT_BM), static_cast<int>((n_corpus + KT_BN - 1) / KT_BN), 8);
     int margin = k / 2;
     if (margin < 32) margin = 32;
     p.kp = k + margin;
     if (p.kp > KT_MAX_KP) p.kp = KT_MAX_KP;
+    // sampling pass: every KT_SAMPLE_STRIDE-th tile, keeping the best r = 2.5 K' / stride per list.  The r-th best
+    // sampled score becomes the query's starting threshold: about 2.5 K' items of the corpus score above it (+-25 %
+    // sampling noise), few enough that a warp's 32 x 32-score chunk rarely holds one (the filter's fast path), and
+    // far more than K.  Should it still be too high, the proof obligation of stage 2 fails and the query is re-run
+    // on the fp32 path.
+    p.use_sample = sampling && n_corpus >= KT_SAMPLE_MIN_ROWS;
+    const int n_tiles = p.sched.n_tiles;
+    p.sample = make_sched(p.sched.m_tiles, (n_tiles + KT_SAMPLE_STRIDE - 1) / KT_SAMPLE_STRIDE, 8);
+    p.kp_sample = (5 * p.kp / 2 + KT_SAMPLE_STRIDE - 1) / KT_SAMPLE_STRIDE;
+    if (p.kp_sample < 8) p.kp_sample = 8;
+    p.max_seg = p.use_sample && p.sample.max_seg > p.sched.max_seg ? p.sample.max_seg : p.sched.max_seg;
     return p;
 }
 
 struct KtWs {
     __nv_bfloat16 *qb, *eb;
     unsigned int *emax;
-    float *cand_v, *cand_tau;
+    float *cand_v, *cand_tau, *tau0;
     int32_t *cand_i, *cand_n;
     bool ok;
     size_t used;
@@ -470,7 +539,7 @@ static KtWs kt_carve(void *workspace, size_t bytes, int64_t n_query, int64_t n_c
                      const KtPlan &pl) {
     Workspace ws(workspace, bytes);
     KtWs w;
-    const size_t lists = static_cast<size_t>(n_query) * 2 * pl.sched.max_seg;
+    const size_t lists = static_cast<size_t>(n_query) * 2 * pl.max_seg;
     w.qb = ws.take<__nv_bfloat16>(n_query * dim);
     w.eb = ws.take<__nv_bfloat16>(own_corpus ? n_corpus * dim : 1);
     w.emax = ws.take<unsigned int>(1);
@@ -478,6 +547,7 @@ static KtWs kt_carve(void *workspace, size_t bytes, int64_t n_query, int64_t n_c
     w.cand_i = ws.take<int32_t>(lists * KT_CAP);
     w.cand_n = ws.take<int32_t>(lists);
     w.cand_tau = ws.take<float>(lists);
+    w.tau0 = ws.take<float>(n_query);
     w.ok = ws.ok();
     w.used = ws.off;
     return w;
@@ -536,8 +606,8 @@ extern "C" int tt_score_topk_tc_workspace(int64_t n_query, int64_t n_corpus, int
 extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float *corpus, const void *corpus_bf16,
                                 const float *corpus_max_norm, int64_t n_corpus, int dim, int k, int64_t row_offset,
                                 const int64_t *mask_offsets, const int64_t *mask_rows, double *out_scores,
-                                int64_t *out_idx, int32_t *unverified, void *workspace, size_t workspace_bytes,
-                                void *stream) {
+                                int64_t *out_idx, int32_t *unverified, int use_sampling, void *workspace,
+                                size_t workspace_bytes, void *stream) {
     using namespace tt;
     TT_CHECK_ARG(query && corpus && out_scores && out_idx && unverified && workspace, "null pointer");
     TT_CHECK_ARG(n_query > 0 && n_corpus > 0 && k > 0, "non-positive size");
@@ -547,7 +617,7 @@ extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float
     if (k > KT_MAX_KP - 32) { set_error("tensor-core top-K supports k <= %d (got %d)", KT_MAX_KP - 32, k); return TT_E_UNSUPPORTED; }
     if (n_corpus >= (int64_t(1) << 31)) { set_error("corpus shard must have < 2^31 rows"); return TT_E_UNSUPPORTED; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const KtPlan pl = kt_plan(n_query, n_corpus, k);
+    const KtPlan pl = kt_plan(n_query, n_corpus, k, use_sampling != 0);
     const bool own = corpus_bf16 == nullptr;
     const KtWs w = kt_carve(workspace, workspace_bytes, n_query, n_corpus, dim, own, pl);
     if (!w.ok) { set_error("top-K (tensor core) workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
@@ -570,14 +640,26 @@ extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float
     if ((rc = make_tmap_bf16_rows(&me, eb, n_corpus, dim, KT_BN))) return rc;
     TopkTcParams prm{};
     prm.n_query = n_query; prm.n_corpus = n_corpus;
-    prm.m_tiles = pl.sched.m_tiles; prm.n_tiles = pl.sched.n_tiles;
-    prm.per_cta = pl.sched.per_cta; prm.total = pl.sched.total; prm.max_seg = pl.sched.max_seg;
-    prm.kp = pl.kp;
+    prm.max_seg = pl.max_seg;
     prm.mask_offsets = mask_offsets; prm.mask_rows = mask_rows;
     prm.cand_v = w.cand_v; prm.cand_i = w.cand_i; prm.cand_n = w.cand_n; prm.cand_tau = w.cand_tau;
+    if (pl.use_sample) {
+        // pass 1: every 16th corpus tile, small K' -> a per-query starting threshold for the full pass
+        prm.m_tiles = pl.sample.m_tiles; prm.n_tiles = pl.sample.n_tiles;
+        prm.per_cta = pl.sample.per_cta; prm.total = pl.sample.total;
+        prm.kp = pl.kp_sample; prm.tile_stride = KT_SAMPLE_STRIDE; prm.tau0 = nullptr;
+        rc = (dim == 128) ? launch_topk_tc<128>(mq, me, prm, pl.sample.grid, st) : launch_topk_tc<64>(mq, me, prm, pl.sample.grid, st);
+        if (rc) return rc;
+        tk_tau0_kernel<<<kt_grid(n_query * 32, 256), 256, 0, st>>>(w.cand_v, w.cand_n, n_query, pl.max_seg, pl.sample.n_tiles,
+                                                                  pl.sample.per_cta, pl.kp_sample, w.tau0);
+        TT_LAUNCH_CHECK("tk_tau0_kernel");
+    }
+    prm.m_tiles = pl.sched.m_tiles; prm.n_tiles = pl.sched.n_tiles;
+    prm.per_cta = pl.sched.per_cta; prm.total = pl.sched.total;
+    prm.kp = pl.kp; prm.tile_stride = 1; prm.tau0 = pl.use_sample ? w.tau0 : nullptr;
     rc = (dim == 128) ? launch_topk_tc<128>(mq, me, prm, pl.sched.grid, st) : launch_topk_tc<64>(mq, me, prm, pl.sched.grid, st);
     if (rc) return rc;
-    topk_tc_stage2<<<static_cast<unsigned>(n_query), 128, 0, st>>>(query, corpus, dim, k, pl.kp, pl.sched.max_seg,
+    topk_tc_stage2<<<static_cast<unsigned>(n_query), 128, 0, st>>>(query, corpus, dim, k, pl.kp, pl.max_seg,
                                                                    pl.sched.n_tiles, pl.sched.per_cta, row_offset, w.cand_v,
                                                                    w.cand_i, w.cand_n, w.cand_tau, emax, out_scores, out_idx,
                                                                    unverified);

@@ -287,11 +287,12 @@ class PreparedCorpus:
 
 
 # statistics of the last tensor-core top-K call (tests / bench report the fallback rate)
-topk_stats = {"queries": 0, "unverified": 0}
+topk_stats = {"queries": 0, "resampled": 0, "unverified": 0}
 TOPK_TC_QUERY_CHUNK = 32768
 
 
-def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepared: Optional["PreparedCorpus"]):
+def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepared: Optional["PreparedCorpus"],
+                   use_sampling: bool = True):
     lib = _lib.load()
     Bq, D = query.shape
     Nc = corpus.shape[0]
@@ -309,13 +310,17 @@ def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepar
         mo = None if mask_offsets is None else mask_offsets[q0:q1 + 1].contiguous()
         check(lib.tt_score_topk_tc(_p(query[q0:q1]), nq, _p(corpus), _p(None if prepared is None else prepared.bf16),
                                    _p(None if prepared is None else prepared.max_norm), Nc, D, k, row_offset, _p(mo),
-                                   _p(mask_rows), _p(scores[q0:q1]), _p(idx[q0:q1]), _p(bad[q0:q1]), _p(ws), ws.numel(),
-                                   _stream()), "tt_score_topk_tc")
+                                   _p(mask_rows), _p(scores[q0:q1]), _p(idx[q0:q1]), _p(bad[q0:q1]), 1 if use_sampling else 0,
+                                   _p(ws), ws.numel(), _stream()), "tt_score_topk_tc")
         _count(3 + own)
     # proof obligation failed for these queries (see include/tt_b200.h): exact fp32 path, one host read
     redo = torch.nonzero(bad, as_tuple=False).reshape(-1)
-    topk_stats["queries"] = Bq
-    topk_stats["unverified"] = int(redo.numel())
+    if use_sampling:
+        topk_stats["queries"] = Bq
+        topk_stats["resampled"] = int(redo.numel())
+        topk_stats["unverified"] = 0
+    else:
+        topk_stats["unverified"] = int(redo.numel())
     if redo.numel() > 0:
         sub_mo = sub_mr = None
         if mask_offsets is not None:
@@ -326,7 +331,10 @@ def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepar
             sub_mr = torch.cat(pieces) if pieces else mask_rows[:0]
             if sub_mr.numel() == 0:
                 sub_mr = torch.zeros(1, dtype=torch.int64, device=dev)
-        s2, i2 = score_topk(query[redo], corpus, k, row_offset, sub_mo, sub_mr, precision="fp32")
+        if use_sampling:   # sampled threshold too high for these: tensor-core path again, thresholds from -inf
+            s2, i2 = _score_topk_tc(query[redo].contiguous(), corpus, k, row_offset, sub_mo, sub_mr, prepared, False)
+        else:
+            s2, i2 = score_topk(query[redo], corpus, k, row_offset, sub_mo, sub_mr, precision="fp32")
         scores[redo] = s2
         idx[redo] = i2
     return scores, idx
