@@ -290,6 +290,179 @@ def kernel_rooflines(peaks, flush, quick=False):
     return out
 
 
+# ----------------------------------------------------------------------------- extra workloads: C3, C5
+def _clock_wrap(rank, local_rank):
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    return sampler
+
+
+def run_c3(args, rank, local_rank, world, dev, peaks):
+    """BASELINE configs[2], the part that sharding changes: three row-sharded tables (user id 12.5M rows per GPU,
+    history items and item ids 10M rows in total), pooled L=200 ragged history lookup, backward into the owners'
+    shards, global-norm clip, fused row-wise Adam.  Towers are data-parallel and measured by the default workload."""
+    import torch.distributed as dist
+    from recommendsystemproject_b200 import dist as tdist
+    B, L, D = 8192, 200, 128
+    V_user, V_item = 12_500_000 * world, 10_000_001
+    bags = {"user": tdist.ShardedEmbeddingBag(V_user, D, rank, world, "sum", None, dev, seed=1),
+            "hist": tdist.ShardedEmbeddingBag(V_item, D, rank, world, "mean", 0, dev, seed=2),
+            "item": tdist.ShardedEmbeddingBag(V_item, D, rank, world, "sum", None, dev, seed=3)}
+    gen = torch.Generator().manual_seed(300 + rank)
+
+    def make_host():
+        hist = torch.randint(1, V_item, (B, L), generator=gen)
+        lens = torch.randint(1, L + 1, (B, 1), generator=gen)
+        hist[torch.arange(L)[None, :] >= lens] = 0
+        return {"user": torch.randint(0, V_user, (B, 1), generator=gen).pin_memory(), "hist": hist.pin_memory(),
+                "item": torch.randint(1, V_item, (B, 1), generator=gen).pin_memory()}
+    host = [make_host() for _ in range(2)]
+    up = {k: torch.randn(B, D, device=dev) * 1e-3 for k in bags}
+    step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    n_valid = int((host[0]["hist"] != 0).sum())
+
+    def step(ids):
+        for b in bags.values():
+            b.zero_grad()
+        loss = sum((bags[k](ids[k]) * up[k]).sum() for k in bags)
+        loss.backward()
+        coef = tdist.global_clip_coef([b.sq_norm for b in bags.values()], 1.0)
+        step_dev.add_(1)
+        for b in bags.values():
+            b.step(coef, 5e-4, step_dev)
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    dev_ids = {k: v.to(dev) for k, v in host[0].items()}
+    for _ in range(args.warmup):
+        step(dev_ids)
+    sampler = _clock_wrap(rank, local_rank)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step(dev_ids)
+    b.record()
+    barrier()
+    dev_ms = a.elapsed_time(b)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    for bag in bags.values():
+        bag.a2a_bytes = 0
+    barrier()
+    a.record()
+    for s in range(args.steps):
+        ids = {k: v.to(dev, non_blocking=True) for k, v in host[s % 2].items()}
+        loss_host.copy_(step(ids))
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    n_rows = n_valid + 2 * B
+    # gathered rows read once, written once to the exchange buffer, read once by the pool; backward the same again;
+    # row-wise Adam touches 7 row-sized streams of the unique rows (<= n_rows)
+    alg = n_rows * D * 4 * (3 + 3) + n_rows * D * 4 * 7 + B * L * 8
+    a2a = sum(bag.a2a_bytes for bag in bags.values()) / args.steps
+    line = {"metric": "train samples/sec (row-sharded embedding fwd+bwd+clip+row-wise Adam)", "value": world * B * args.steps / (dev_ms / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2] embedding path: per GPU B=8192, hist L=200 ragged mean-pooled over a 10M-row "
+                                   "table + user id (12.5M rows per GPU) + item id (10M rows), D=128, tables row-sharded owner=row%W",
+                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"row-sharded tables x{world}",
+                       "l2": "working set (3 tables + Adam state, >40 GB per GPU) far exceeds L2", "peaks": peaks["source"]},
+            "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
+                    "h2d_bytes_per_step": sum(v.numel() * 8 for v in host[0].values()), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(ops_count() - 0), "roofline": {"bound": "hbm", "kernel": "gather + gather_pool + segment_grad + rowwise_adam (whole step)",
+                                                                "achieved": alg / (dev_ms / args.steps) / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                                "frac": alg / (dev_ms / args.steps) / 1e6 / peaks["hbm_gbs"], "traffic": None,
+                                                                "alg_bytes": alg},
+            "nvlink_bytes_per_step_per_gpu": a2a, "cpu_baseline": None, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+def ops_count():
+    from recommendsystemproject_b200 import ops
+    return ops.launch_counter["calls"]
+
+
+def run_c5(args, rank, local_rank, world, dev, peaks):
+    """BASELINE configs[4]: top-100 over a 10M-item corpus sharded over the GPUs (each GPU: tcgen05 filter + exact
+    re-rank over its shard), all-gather of the [Q, K] lists, global merge.  Q = 16384 queries per step."""
+    import torch.distributed as dist
+    from recommendsystemproject_b200 import dist as tdist, ops
+    N_total, Q, K, D = 10_000_000, 16384, 100, 128
+    bounds = [N_total * r // world for r in range(world + 1)]
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    shard = torch.nn.functional.normalize(torch.randn(bounds[rank + 1] - bounds[rank], D, device=dev, generator=gen), dim=1)
+    prep = ops.PreparedCorpus(shard)
+    qgen = torch.Generator().manual_seed(6)
+    host_q = torch.nn.functional.normalize(torch.randn(Q, D, generator=qgen), dim=1).pin_memory()
+    q_dev = host_q.to(dev)
+
+    def step(q):
+        return tdist.sharded_topk(q, shard, K, rank, world, bounds[:-1],
+                                  topk_fn=lambda a, e, k, off: ops.score_topk(a, e, k, off, precision="bf16", prepared=prep))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step(q_dev)
+    sampler = _clock_wrap(rank, local_rank)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step(q_dev)
+    b.record()
+    barrier()
+    dev_ms = a.elapsed_time(b)
+    out_host = torch.empty(Q, K, dtype=torch.int64).pin_memory()
+    barrier()
+    a.record()
+    for _ in range(args.steps):
+        _, idx = step(host_q.to(dev, non_blocking=True))
+        out_host.copy_(idx)
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    flops = 2.0 * Q * N_total * D / world      # per GPU per step
+    ms = dev_ms / args.steps
+    line = {"metric": "corpus top-K queries/sec (top-100, 10M-item corpus)", "value": Q * args.steps / (dev_ms / 1e3), "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 filter / f64 exact re-rank", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: 10M x 128 corpus in {world} shard(s), Q=16384 queries per step, K=100, "
+                                   "bit-exact rows (score desc, row asc)", "parallelism": f"corpus-sharded x{world}",
+                       "l2": "corpus shard (>= 320 MB bf16) exceeds L2", "peaks": peaks["source"]},
+            "e2e": {"value": Q * args.steps / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4,
+                    "d2h_bytes_per_step": Q * K * 8, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": ops_count(),
+            "roofline": {"bound": "tensor", "kernel": "topk_tc_kernel (sampling pass + full pass) + topk_tc_stage2 + topk_merge",
+                         "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": flops / ms / 1e9 / peaks["bf16_tflops"], "traffic": None, "alg_flops": flops},
+            "cpu_baseline": None, "clocks": clocks, "resampled_queries": ops.topk_stats.get("resampled"),
+            "fp32_fallback_queries": ops.topk_stats.get("unverified")}
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------- main GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -319,6 +492,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    if args.workload in ("c3", "c5"):
+        (run_c3 if args.workload == "c3" else run_c5)(args, rank, local_rank, world, dev, peaks)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     wl = workload(args.workload)
 
     torch.manual_seed(0)

@@ -142,3 +142,162 @@ def sharded_topk(query: torch.Tensor, local_corpus: torch.Tensor, k: int, rank: 
     dist.all_gather(ss, s)
     dist.all_gather(ii, i)
     return merge_fn(torch.stack(ss), torch.stack(ii))
+
+
+# ---------------------------------------------------------------------------
+# row-sharded embedding table with pooled lookup, backward and fused row-wise Adam
+# ---------------------------------------------------------------------------
+class _ShardedOps:
+    """The three device ops ShardedEmbeddingBag needs.  Production = the CUDA kernels of libtt_b200; the CPU gloo
+    tests inject oracle implementations (tests may use oracle/, the product may not)."""
+
+    @staticmethod
+    def gather(table, rows):                      # [n] -> [n, D]
+        if rows.numel() == 0:
+            return table.new_empty(0, table.shape[1], dtype=torch.float32)
+        return ops.gather_rows(table, rows.reshape(-1), None, None)
+
+    @staticmethod
+    def pool(table, idx, mode):                   # table [n+1, D] (last row = pad row), idx [B, L] -> [B, D]
+        out = torch.empty(idx.shape[0], table.shape[1], dtype=torch.float32, device=table.device)
+        oob = torch.zeros(1, dtype=torch.int32, device=table.device)
+        # the pad slot is declared as padding_idx so the kernel counts pads and adds the pad row once, exactly like
+        # the unsharded lookup does (bitwise-equal pooling)
+        ops.gather_pool_into(table, idx.contiguous(), mode, table.shape[0] - 1, out, None, oob)
+        return out
+
+    @staticmethod
+    def segment_grad(rows, vocab, grad, sq_norm):  # rows [n], grad [n, D] -> (unique_rows, row_grad, n_unique)
+        return ops.segment_grad(rows.reshape(-1, 1), ops.POOL_NONE, None, vocab, grad, None, grad.shape[1], sq_norm)
+
+    @staticmethod
+    def adam(table, m, v, rows, row_grad, n_unique, coef, lr, b1, b2, eps, step_dev):
+        ops.rowwise_adam_(table, m, v, rows, row_grad, n_unique, coef, lr, b1, b2, eps, step_dev)
+
+
+class ShardedEmbeddingBag:
+    """Embedding table row-sharded over the ranks (owner = row % W, local row = row // W) with a pooled lookup
+    (mean / sum over the L ids of a sample, pads included like GenericTower.py:153-160 does).
+
+    forward   ids [B, L]  ->  all-to-all #1: valid ids to their owners  ->  owner gathers its rows (CUDA gather kernel)
+              ->  all-to-all #2: rows back  ->  local gather+pool kernel over (returned rows, pad row)  ->  [B, D].
+              The pooling sums the L rows of a sample in position order on the sample's own rank, exactly like the
+              unsharded kernel: the result is BITWISE what one GPU holding the whole table computes.
+    backward  d pooled [B, D]  ->  per-position gradient rows in owner order  ->  all-to-all #3 to the owners  ->
+              deterministic sorted-segment reduction (tt_emb_segment_grad) on the owner  ->  (rows, row_grad, sum g^2)
+              kept for step().  No dense [V, D] gradient and no all-reduce of table gradients.
+    step      fused row-wise Adam on the touched rows of the local shard; the clip coefficient comes from the global
+              gradient norm (all-reduce of one scalar), like the unsharded optimizer.
+    The pad row (GenericTower leaves it non-zero and frozen) is replicated on every rank and never routed.
+    """
+
+    def __init__(self, vocab: int, dim: int, rank: int, world: int, mode: str = "mean", padding_idx: Optional[int] = 0,
+                 device="cuda", seed: int = 0, dev_ops=None, full_weight: Optional[torch.Tensor] = None):
+        self.vocab, self.dim, self.rank, self.world = int(vocab), int(dim), int(rank), int(world)
+        self.mode = ops.POOL_MODES[mode]
+        if self.mode not in (ops.POOL_SUM, ops.POOL_MEAN, ops.POOL_NONE):
+            raise ops.TTError("ShardedEmbeddingBag supports mean / sum pooling (and L = 1 lookups)")
+        self.padding_idx = padding_idx
+        self.ops = dev_ops or _ShardedOps
+        self.local_rows = (self.vocab - self.rank + self.world - 1) // self.world
+        if full_weight is not None:                                   # tests: shard a given table
+            self.weight = full_weight[self.rank::self.world].contiguous().to(device)
+            pad = full_weight[padding_idx].clone() if padding_idx is not None else torch.zeros(dim)
+        else:
+            gen = torch.Generator(device=device).manual_seed(seed * 1000003 + self.rank)
+            bound = (6.0 / (self.vocab + self.dim)) ** 0.5            # xavier_uniform_ over the whole table
+            self.weight = (torch.rand(self.local_rows, dim, device=device, generator=gen) * 2 - 1) * bound
+            pad = (torch.rand(dim, generator=torch.Generator().manual_seed(seed)) * 2 - 1) * bound
+        self.pad_row = pad.to(device=device, dtype=torch.float32)
+        self.exp_avg = torch.zeros_like(self.weight, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros_like(self.weight, dtype=torch.float32)
+        self.sq_norm = torch.zeros(1, dtype=torch.float32, device=device)
+        self.pending = []
+        self.a2a_bytes = 0
+        # autograd anchor: the lookup's inputs are integer ids, so something that requires grad must enter the node
+        self._anchor = torch.zeros(1, dtype=torch.float32, device=device, requires_grad=True)
+
+    # -- collectives (degenerate to local copies at W = 1)
+    def _a2a(self, send, send_counts, recv_counts):
+        self.a2a_bytes += send.numel() * send.element_size()
+        if self.world == 1:
+            return send
+        return all_to_all_rows(send, send_counts, recv_counts)
+
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        B, L = ids.shape
+        flat = ids.reshape(-1)
+        if self.padding_idx is None:
+            valid_pos = torch.arange(flat.numel(), device=flat.device)
+        else:
+            valid_pos = torch.nonzero(flat != self.padding_idx, as_tuple=False).reshape(-1)
+        vids = flat[valid_pos]
+        owner = vids % self.world
+        order = torch.argsort(owner, stable=True)
+        counts = torch.bincount(owner, minlength=self.world)
+        if self.world > 1:
+            recv_counts = exchange_counts(counts)
+            sc, rc = counts.tolist(), recv_counts.tolist()          # the one host sync of the step (NCCL split sizes)
+        else:
+            sc = rc = [int(vids.numel())]
+        send_ids = (vids // self.world)[order].contiguous()
+        recv_ids = self._a2a(send_ids, sc, rc)                                   # all-to-all #1
+        rows = self.ops.gather(self.weight, recv_ids)                            # owner-side gather
+        n_valid = int(vids.numel())
+        buf = torch.empty(n_valid + 1, self.dim, dtype=torch.float32, device=flat.device)
+        back = self._a2a(rows, rc, sc)                                           # all-to-all #2
+        buf[:n_valid] = back
+        buf[n_valid] = self.pad_row
+        idx = torch.full((B * L,), n_valid, dtype=torch.int64, device=flat.device)
+        sorted_pos = valid_pos[order]
+        idx[sorted_pos] = torch.arange(n_valid, device=flat.device)
+        pooled = self.ops.pool(buf, idx.view(B, L), self.mode if L > 1 else ops.POOL_NONE)
+        return _ShardedLookupFn.apply(pooled, self._anchor, self, sorted_pos // L, recv_ids, sc, rc, L)
+
+    __call__ = forward
+
+    def _backward(self, grad_pooled, sample_of_sorted, recv_ids, sc, rc, L):
+        scale = 1.0 / L if (self.mode == ops.POOL_MEAN and L > 1) else 1.0
+        g = (grad_pooled * scale).contiguous() if scale != 1.0 else grad_pooled.contiguous()
+        g_send = self.ops.gather(g, sample_of_sorted)                            # per-position rows, owner order
+        g_recv = self._a2a(g_send, sc, rc)                                       # all-to-all #3
+        if recv_ids.numel() == 0:
+            return
+        rows, row_grad, n_unique = self.ops.segment_grad(recv_ids, self.local_rows, g_recv, self.sq_norm)
+        self.pending.append((rows, row_grad, n_unique))
+
+    def zero_grad(self):
+        self.pending = []
+        self.sq_norm.zero_()
+
+    def step(self, clip_coef, lr, step_dev, betas=(0.9, 0.999), eps=1e-8):
+        for rows, row_grad, n_unique in self.pending:
+            self.ops.adam(self.weight, self.exp_avg, self.exp_avg_sq, rows, row_grad, n_unique, clip_coef, lr, betas[0],
+                          betas[1], eps, step_dev)
+        self.pending = []
+
+
+class _ShardedLookupFn(torch.autograd.Function):
+    """Identity on the pooled vectors in forward; routes their gradient to the owners in backward."""
+
+    @staticmethod
+    def forward(ctx, pooled, anchor, bag, sample_of_sorted, recv_ids, sc, rc, L):
+        ctx.bag, ctx.sc, ctx.rc, ctx.L = bag, sc, rc, L
+        ctx.save_for_backward(sample_of_sorted, recv_ids)
+        return pooled.view_as(pooled)
+
+    @staticmethod
+    def backward(ctx, grad):
+        sample_of_sorted, recv_ids = ctx.saved_tensors
+        ctx.bag._backward(grad, sample_of_sorted, recv_ids, ctx.sc, ctx.rc, ctx.L)
+        return (None,) * 8
+
+
+def global_clip_coef(sq_terms: List[torch.Tensor], max_norm: float = 1.0) -> torch.Tensor:
+    """min(1, max_norm / (||g||_2 + 1e-6)) over the gradients of ALL ranks' shards (+ replicated dense terms already
+    averaged): one all-reduce of a scalar (training_utils.py:53-54 semantics for row-sharded tables)."""
+    total = torch.stack([t.reshape(()) for t in sq_terms]).sum().reshape(1)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    norm = total.sqrt()
+    return torch.clamp(max_norm / (norm + 1e-6), max=1.0)

@@ -96,3 +96,85 @@ def test_sharded_lookup_two_ranks_gloo():
 
 def test_sharded_topk_two_ranks_gloo():
     assert all(_run(_topk_case).values())
+
+
+# ---------------------------------------------------------------- ShardedEmbeddingBag (host logic, gloo, oracle ops)
+class _CpuOps:
+    """Oracle stand-ins for the CUDA kernels ShardedEmbeddingBag drives (tests only)."""
+
+    @staticmethod
+    def gather(table, rows):
+        return table[rows.reshape(-1)].float()
+
+    @staticmethod
+    def pool(table, idx, mode):
+        g = table[idx]                                     # [B, L, D]
+        if mode == 0:
+            return g[:, 0]
+        return g.sum(1) if mode == 1 else g.mean(1)
+
+    @staticmethod
+    def segment_grad(rows, vocab, grad, sq_norm):
+        u, inv = torch.unique(rows.reshape(-1), sorted=True, return_inverse=True)
+        rg = torch.zeros(len(u), grad.shape[1], dtype=torch.float64).index_add_(0, inv, grad.double()).float()
+        sq_norm += rg.double().pow(2).sum().float()
+        return u, rg, torch.tensor([len(u)], dtype=torch.int32)
+
+    @staticmethod
+    def adam(table, m, v, rows, row_grad, n_unique, coef, lr, b1, b2, eps, step_dev):
+        from oracle import twotower_oracle as O
+        n = int(n_unique)
+        r = rows[:n]
+        g = row_grad[:n] * float(coef)
+        p, mm, vv = O.adam_update(table[r], g, m[r], v[r], int(step_dev), lr, b1, b2, eps)
+        table[r], m[r], v[r] = p, mm, vv
+
+
+def _sharded_bag_case(rank, world):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from recommendsystemproject_b200 import dist as tdist
+    from oracle import twotower_oracle as O
+    gen = torch.Generator().manual_seed(5)
+    V, D, L, B = 97, 8, 6, 11
+    full = torch.randn(V, D, generator=gen)
+    bag = tdist.ShardedEmbeddingBag(V, D, rank, world, "mean", 0, device="cpu", dev_ops=_CpuOps, full_weight=full)
+    g2 = torch.Generator().manual_seed(50 + rank)
+    ids = torch.randint(1, V, (B, L), generator=g2)
+    ids[torch.arange(L)[None, :] >= torch.randint(1, L + 1, (B, 1), generator=g2)] = 0
+    ids[0] = 0                                              # an all-padding sample
+    up = torch.randn(B, D, generator=g2)
+    bag.zero_grad()
+    pooled = bag(ids)
+    ok = torch.allclose(pooled, full[ids].mean(1), atol=1e-6)
+    (pooled * up).sum().backward()
+    coef = tdist.global_clip_coef([bag.sq_norm], 1.0)
+    step = torch.ones(1, dtype=torch.int64)
+    bag.step(coef, 1e-2, step)
+    # reference: dense gradient of ALL ranks' batches on the full table, clip by the global norm, dense Adam on the
+    # touched rows (first step: lazy == dense), pad row frozen
+    ids_all = [torch.empty_like(ids) for _ in range(world)]
+    up_all = [torch.empty_like(up) for _ in range(world)]
+    dist.all_gather(ids_all, ids)
+    dist.all_gather(up_all, up)
+    dense = torch.zeros(V, D, dtype=torch.float64)
+    for i_r, u_r in zip(ids_all, up_all):
+        dense.index_add_(0, i_r.reshape(-1), (u_r.double() / L).repeat_interleave(L, 0))
+    dense[0] = 0
+    c_ref = min(1.0, 1.0 / (float(dense.pow(2).sum().sqrt()) + 1e-6))
+    ok &= abs(float(coef) - c_ref) < 1e-5
+    touched = torch.nonzero(dense.abs().sum(1) > 0).reshape(-1)
+    p_ref, _, _ = O.adam_update(full[touched], (dense[touched] * c_ref).float(), torch.zeros(len(touched), D),
+                                torch.zeros(len(touched), D), 1, 1e-2)
+    mine = touched[touched % world == rank]
+    ok &= torch.allclose(bag.weight[mine // world], p_ref[touched % world == rank], atol=1e-6)
+    untouched = torch.ones(V, dtype=torch.bool)
+    untouched[touched] = False
+    mine_u = torch.nonzero(untouched).reshape(-1)
+    mine_u = mine_u[mine_u % world == rank]
+    ok &= torch.equal(bag.weight[mine_u // world], full[mine_u])
+    return bool(ok)
+
+
+def test_sharded_embedding_bag_two_ranks_gloo():
+    assert all(_run(_sharded_bag_case).values())

@@ -531,3 +531,34 @@ def test_topk_tc_equals_fp32_path_at_scale():
     _, i16 = ops.score_topk(q, e, 100, precision="bf16")
     assert torch.equal(i32, i16)
     assert ops.topk_stats["unverified"] == 0, ops.topk_stats
+
+
+def test_sharded_embedding_bag_world1_is_bitwise_the_unsharded_kernel():
+    """ShardedEmbeddingBag at W=1 (all-to-alls degenerate to local copies): the pooled vectors must be bitwise what the
+    fused gather+pool kernel gives on the whole table, the owner-side segment gradient what tt_emb_segment_grad gives
+    on the same ids, and untouched rows must not move."""
+    from recommendsystemproject_b200 import dist as tdist
+    gen = torch.Generator().manual_seed(31)
+    V, D, L, B = 5000, 64, 12, 300
+    full = torch.randn(V, D, generator=gen)
+    ids = torch.randint(1, V, (B, L), generator=gen)
+    ids[torch.arange(L)[None, :] >= torch.randint(1, L + 1, (B, 1), generator=gen)] = 0
+    bag = tdist.ShardedEmbeddingBag(V, D, 0, 1, "mean", 0, device=DEV, full_weight=full)
+    idd = ids.to(DEV)
+    ref = ops.gather_rows(full.to(DEV), idd, "mean", 0)
+    bag.zero_grad()
+    pooled = bag(idd)
+    assert torch.equal(pooled, ref)
+    up = torch.randn(B, D, generator=gen).to(DEV)
+    (pooled * up).sum().backward()
+    rows, row_grad, n_unique = bag.pending[0]
+    r_ref, g_ref, n_ref = ops.segment_grad(idd, ops.POOL_MEAN, 0, V, up, None, D)
+    n = int(n_ref.item())
+    assert int(n_unique.item()) == n and torch.equal(rows[:n], r_ref[:n])
+    assert torch.allclose(row_grad[:n], g_ref[:n], atol=1e-6, rtol=1e-5)
+    before = bag.weight.clone()
+    coef = tdist.global_clip_coef([bag.sq_norm], 1.0)
+    bag.step(coef, 1e-2, torch.ones(1, dtype=torch.int64, device=DEV))
+    touched = torch.zeros(V, dtype=torch.bool, device=DEV)
+    touched[rows[:n]] = True
+    assert torch.equal(bag.weight[~touched], before[~touched]) and not torch.equal(bag.weight[touched], before[touched])
