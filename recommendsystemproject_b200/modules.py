@@ -328,6 +328,24 @@ class GenericTower(nn.Module):
         return self.mlp(x, groups)
 
 
+def _on_cuda(obj) -> bool:
+    """True when the first tensor found in a batch tree lives on a CUDA device (CPU batches fall through to the
+    ordinary path, whose ops raise TTError: there is no CPU fallback)."""
+    if isinstance(obj, torch.Tensor):
+        return obj.is_cuda
+    if isinstance(obj, dict):
+        for v in obj.values():
+            r = _on_cuda(v)
+            if r is not None:
+                return r
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            r = _on_cuda(v)
+            if r is not None:
+                return r
+    return None
+
+
 def _same_layout(item_dict, negs) -> bool:
     """True when every hard-negative slab has the item batch's keys and shapes (so they can be stacked)."""
     def sig(d):
@@ -369,7 +387,7 @@ class TwoTowerModel(nn.Module):
         self.item_feature_mapping = item_mapping
 
     def forward(self, batch_data):
-        if self.parallel_towers and torch.is_grad_enabled() and self.training:
+        if self.parallel_towers and torch.is_grad_enabled() and self.training and _on_cuda(batch_data):
             return self._forward_two_streams(batch_data)
         user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping)
         item_emb, hard_neg_emb = self._item_side(batch_data)
