@@ -38,13 +38,17 @@ namespace tt {
 
 using namespace tt::tc;
 
-constexpr int TC_BM = 128;
-constexpr int TC_BN = 128;
-// W-tile ring depth: 1 X tile + ST W tiles of 128 x D bf16 must fit in 227 KB
-template <int D> struct TcStages { static constexpr int value = D == 128 ? 5 : 8; };
+constexpr int TC_BM = 128;   // X rows per CTA row tile (MMA M)
+constexpr int TC_BN = 256;   // W rows per tile (MMA N of the S product: a 128-wide MMA is issue-bound, tools/tc_selftest)
+constexpr int TC_HALF = 128; // columns of a W tile handled by one softmax group (thread = row, 128 logits in registers)
+// W-tile ring depth: 1 X tile + ST W tiles of 256 x D bf16 (+ 2 KB lse ring) must fit in 227 KB
+template <int D> struct TcStages { static constexpr int value = D == 128 ? 3 : 6; };
 constexpr int TC_THREADS = 320;
+constexpr int TC_SMEM_MAX = 232448;
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr uint32_t TM_S = 0, TM_G = 256, TM_OUT = 384;   // TMEM columns: S[2] x 128, G[2] x 64, Out x D
+// TMEM columns.  FWD: two 256-column S buffers.  BWD: S 256 (single buffer: the softmax groups copy it to registers
+// right away), G 128 (bf16 pairs of the 256 probabilities), Out D.
+constexpr uint32_t TM_S = 0, TM_G = 256, TM_OUT = 384;
 
 enum { MODE_FWD = 0, MODE_BWD_X = 1, MODE_BWD_Y = 2 };
 
@@ -105,13 +109,14 @@ __global__ void tc_runs(const int64_t *__restrict__ sorted_ids, int64_t n, int32
 struct CeTcParams {
     int64_t batch;       // rows of U / I
     int64_t pool_rows;   // rows of the shared pool (0 if none)
-    int tiles_item, tiles_pool;
+    int xt_split;        // X row tiles (128) below this index come from map_xa, the rest from map_xb
+    int wt_split;        // W tiles (256) below this index come from map_wa (item rows / U rows), the rest from map_wb (pool)
     int m_tiles, n_tiles;
     int64_t per_cta, total;
     int max_seg;
     float scale2;        // inv_temp * log2(e)
     const int32_t *lo, *hi;
-    const float *lse2p;      // BWD: [tiles_item * 128] lse * log2(e) in sorted order, +inf past batch
+    const float *lse2p;      // BWD: [wt_item * 256] lse * log2(e) in sorted order, +inf past batch
     float *part_m, *part_s;  // FWD: [2 * max_seg][batch]  (raw-logit max, sum of exp2)
     float *part;             // BWD: [max_seg][m_tiles * 128][D] raw fp32 accumulators
     long long *dbg;          // optional timeline of CTA 0 (tools/ce_trace.py): [event][tile] SM clock stamps
@@ -137,32 +142,41 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 template <int D, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-ce_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i,
-             const __grid_constant__ CUtensorMap map_p, const CeTcParams prm) {
+ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__ CUtensorMap map_xb,
+             const __grid_constant__ CUtensorMap map_wa, const __grid_constant__ CUtensorMap map_wb,
+             const CeTcParams prm) {
     constexpr bool BWD = MODE != MODE_FWD;
     constexpr bool TRANS = MODE == MODE_BWD_Y;
     constexpr int KB = D / 64;                       // 64-column (128-byte) K blocks
-    constexpr int TILE_BYTES = TC_BN * D * 2;        // one operand tile
-    constexpr int KBLOCK_BYTES = TC_BN * 128;        // one 64-column box of 128 rows
+    constexpr int X_BYTES = TC_BM * D * 2;
+    constexpr int W_BYTES = TC_BN * D * 2;
+    constexpr int XK_BYTES = TC_BM * 128;            // one 64-column block of the X tile
+    constexpr int WK_BYTES = TC_BN * 128;            // one 64-column block of a W tile
     constexpr int LSE_BYTES = TC_BN * 4;
-    constexpr int TC_STAGES = TcStages<D>::value;
+    constexpr int ST = TcStages<D>::value;
+    constexpr int NBUF = BWD ? 1 : 2;                // S buffers
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *x_tile = smem;
-    uint8_t *w_tiles = smem + TILE_BYTES;                           // [TC_STAGES]
-    float *lse_s = reinterpret_cast<float *>(w_tiles + TC_STAGES * TILE_BYTES);  // [TC_STAGES][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(lse_s + TC_STAGES * TC_BN);
-    uint64_t *full = bars;                   // [ST]  TMA -> MMA (and softmax, for lse_s)
-    uint64_t *empty = full + TC_STAGES;      // [ST]  MMA -> TMA
-    uint64_t *sfull = empty + TC_STAGES;     // [2]   S tile complete
-    uint64_t *sfree = sfull + 2;             // [2]   S tile copied to registers (128 arrivals)
-    uint64_t *gfull = sfree + 2;             // [2]   G tile written (128 arrivals)
-    uint64_t *gfree = gfull + 2;             // [2]   Out MMA that read G retired
-    uint64_t *xfull = gfree + 2;             // [1]   one completion per row segment
-    uint64_t *xfree = xfull + 1;             // [1]   last S MMA of the row retired
-    uint64_t *ofull = xfree + 1;             // [1]   last Out MMA of the row retired
-    uint64_t *ofree = ofull + 1;             // [1]   Out drained (256 arrivals)
+    uint8_t *w_tiles = smem + X_BYTES;                                      // [ST]
+    float *lse_s = reinterpret_cast<float *>(w_tiles + ST * W_BYTES);       // [2][256], BWD_Y only
+    uint64_t *bars = reinterpret_cast<uint64_t *>(lse_s + (TRANS ? 2 * TC_BN : 0));
+    uint64_t *full = bars;               // [ST]  TMA -> MMA
+    uint64_t *empty = full + ST;         // [ST]  MMA -> TMA
+    uint64_t *sfull = empty + ST;        // [2]   S tile complete
+    uint64_t *sfree = sfull + 2;         // [2]   S tile copied to registers (256 arrivals)
+    uint64_t *lfull = sfree + 2;         // [2]   lse ring slot landed (BWD_Y)
+    uint64_t *gfull = lfull + 2;         // [2]   a group's half of G written (128 arrivals)
+    uint64_t *gfree = gfull + 2;         // [2]   the Out MMAs that read that half retired
+    uint64_t *xfull = gfree + 2;         // [1]   one completion per row segment
+    uint64_t *xfree = xfull + 1;         // [1]   last S MMA of the row retired
+    uint64_t *ofull = xfree + 1;         // [1]   last Out MMA of the row retired
+    uint64_t *ofree = ofull + 1;         // [1]   Out drained (256 arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ofree + 1);
+    if (reinterpret_cast<uint8_t *>(tmem_slot + 2) > smem_raw + TC_SMEM_MAX) {   // needs a 1 KB-aligned dynamic smem base
+        atomicExch(&g_tc_timeout, 2);
+        __trap();
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g0 = static_cast<int64_t>(blockIdx.x) * prm.per_cta;
@@ -170,12 +184,13 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ 
     const int n_local = static_cast<int>(max(g1 - g0, static_cast<int64_t>(0)));
 
     if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&map_u);
-        prefetch_tensormap(&map_i);
-        if (prm.pool_rows > 0) prefetch_tensormap(&map_p);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        prefetch_tensormap(&map_xa);
+        prefetch_tensormap(&map_xb);
+        prefetch_tensormap(&map_wa);
+        prefetch_tensormap(&map_wb);
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&sfull[a], 1); mbar_init(&sfree[a], 128);
+            mbar_init(&sfull[a], 1); mbar_init(&sfree[a], 256); mbar_init(&lfull[a], 1);
             mbar_init(&gfull[a], 128); mbar_init(&gfree[a], 1);
         }
         mbar_init(xfull, 1);
@@ -197,29 +212,25 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ 
         for (; c.i < n_local; c.next()) {
             if (c.i == 0 || c.n == 0) {      // first tile of a row segment: (re)load X
                 if (c.r >= 1) mbar_wait(xfree, (c.r - 1) & 1);   // every S MMA of the previous row has retired
-                const bool x_item = !TRANS || c.m < prm.tiles_item;
-                const CUtensorMap *mx = !TRANS ? &map_u : (x_item ? &map_i : &map_p);
-                const int x_row0 = (x_item ? c.m : c.m - prm.tiles_item) * TC_BM;
+                const bool xa = c.m < prm.xt_split;
+                const CUtensorMap *mx = xa ? &map_xa : &map_xb;
+                const int x_row0 = (xa ? c.m : c.m - prm.xt_split) * TC_BM;
                 if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(xfull, TILE_BYTES);
-                    for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_tile + kb * KBLOCK_BYTES, mx, xfull, kb * 64, x_row0);
+                    mbar_arrive_expect_tx(xfull, X_BYTES);
+                    for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_tile + kb * XK_BYTES, mx, xfull, kb * 64, x_row0);
                 }
                 __syncwarp();
             }
-            const int stage = c.i % TC_STAGES;
-            mbar_wait(&empty[stage], ((c.i / TC_STAGES) & 1) ^ 1);
-            const CUtensorMap *mw;
-            int row0;
-            if (TRANS) { mw = &map_u; row0 = c.n * TC_BN; }
-            else if (c.n < prm.tiles_item) { mw = &map_i; row0 = c.n * TC_BN; }
-            else { mw = &map_p; row0 = (c.n - prm.tiles_item) * TC_BN; }
+            const int stage = c.i % ST;
+            mbar_wait(&empty[stage], ((c.i / ST) & 1) ^ 1);
+            const bool wa = c.n < prm.wt_split;
+            const CUtensorMap *mw = wa ? &map_wa : &map_wb;
+            const int row0 = (wa ? c.n : c.n - prm.wt_split) * TC_BN;
             if (elect_one_sync()) {
                 TT_DBG(0, c.i);
-                mbar_arrive_expect_tx(&full[stage], TILE_BYTES + (TRANS ? LSE_BYTES : 0));
+                mbar_arrive_expect_tx(&full[stage], W_BYTES);
                 for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(w_tiles + stage * TILE_BYTES + kb * KBLOCK_BYTES, mw, &full[stage], kb * 64, row0);
-                if (TRANS)
-                    bulk_load_1d(lse_s + stage * TC_BN, prm.lse2p + static_cast<int64_t>(c.n) * TC_BN, LSE_BYTES, &full[stage]);
+                    tma_load_2d(w_tiles + stage * W_BYTES + kb * WK_BYTES, mw, &full[stage], kb * 64, row0);
             }
             __syncwarp();
         }
@@ -230,78 +241,96 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ 
             constexpr uint32_t idesc_o = idesc_bf16_f32(TC_BM, D, 0, 1);   // B operand MN-major
             const uint64_t xdesc = smem_desc_k_sw128(smem_u32(x_tile));
             const uint64_t wdesc_k = smem_desc_k_sw128(smem_u32(w_tiles));
-            const uint64_t wdesc_mn = smem_desc_mn_sw128(smem_u32(w_tiles), KBLOCK_BYTES, 1024);
+            const uint64_t wdesc_mn = smem_desc_mn_sw128(smem_u32(w_tiles), WK_BYTES, 1024);
             Cursor cs, co;   // S cursor, Out cursor
             cs.init(g0, prm.n_tiles);
             co.init(g0, prm.n_tiles);
             auto issue_s = [&]() {
-                const int i = cs.i, b = i & 1, stage = i % TC_STAGES;
-                if (i >= 2) mbar_wait(&sfree[b], ((i >> 1) - 1) & 1);     // softmax(i-2) holds S[b] in registers
+                const int i = cs.i, b = BWD ? 0 : (i & 1), stage = i % ST;
+                // the softmax groups hold tile (i - NBUF) in registers: its TMEM buffer may be overwritten
+                if (i >= NBUF) mbar_wait(&sfree[b], BWD ? ((i - 1) & 1) : (((i >> 1) - 1) & 1));
                 if (i == 0 || cs.n == 0) mbar_wait(xfull, cs.r & 1);
                 TT_DBG(1, i);
-                mbar_wait(&full[stage], (i / TC_STAGES) & 1);
+                mbar_wait(&full[stage], (i / ST) & 1);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                TT_DBG(2, i);
-                // descriptors differ from the precomputed bases only in the 16-byte-unit start address field
-                const uint64_t wd = wdesc_k + static_cast<uint64_t>(stage * (TILE_BYTES >> 4));
-                const uint32_t acc = tmem_base + TM_S + b * TC_BN;
+                    TT_DBG(2, i);
+                    if (TRANS)   // this tile's 256 column statistics for the softmax groups (2-slot ring)
+                    {
+                        mbar_arrive_expect_tx(&lfull[i & 1], LSE_BYTES);
+                        bulk_load_1d(lse_s + (i & 1) * TC_BN, prm.lse2p + static_cast<int64_t>(cs.n) * TC_BN, LSE_BYTES, &lfull[i & 1]);
+                    }
+                    // descriptors differ from the precomputed bases only in the 16-byte-unit start address field
+                    const uint64_t wd = wdesc_k + static_cast<uint64_t>(stage * (W_BYTES >> 4));
+                    const uint32_t acc = tmem_base + TM_S + b * TC_BN;
 #pragma unroll
-                for (int k = 0; k < D / 16; ++k) {
-                    constexpr int dummy = 0; (void)dummy;
-                    const uint32_t off = ((k / 4) * KBLOCK_BYTES + (k % 4) * 32) >> 4;  // 16 bf16 = 32 B inside the swizzle atom
-                    if (k == 0) umma_f16_first(acc, xdesc + off, wd + off, idesc_s);
-                    else umma_f16_acc(acc, xdesc + off, wd + off, idesc_s);
-                }
-                if (!BWD) umma_commit(&empty[stage]);        // forward: the W tile is not needed again
-                umma_commit(&sfull[b]);
-                if (cs.n == prm.n_tiles - 1 || i == n_local - 1) umma_commit(xfree);
+                    for (int k = 0; k < D / 16; ++k) {
+                        const uint32_t xo = ((k / 4) * XK_BYTES + (k % 4) * 32) >> 4;   // 16 bf16 = 32 B inside the swizzle atom
+                        const uint32_t wo = ((k / 4) * WK_BYTES + (k % 4) * 32) >> 4;
+                        if (k == 0) umma_f16_first(acc, xdesc + xo, wd + wo, idesc_s);
+                        else umma_f16_acc(acc, xdesc + xo, wd + wo, idesc_s);
+                    }
+                    if (!BWD) umma_commit(&empty[stage]);        // forward: the W tile is not needed again
+                    umma_commit(&sfull[b]);
+                    if (cs.n == prm.n_tiles - 1 || i == n_local - 1) umma_commit(xfree);
                 }
                 __syncwarp();
                 cs.next();
             };
+            // Out += G W in two K = 128 halves, one per softmax group, each issued as soon as ITS group has published
+            // (the groups run out of phase: the SM's arbiter favours the higher warp ids, so one group computes while
+            // the other stalls on its tcgen05.st / barriers -- a natural ping-pong that keeps the MUFU busy)
             auto issue_out = [&]() {
-                const int i = co.i, b = i & 1, stage = i % TC_STAGES;
+                const int i = co.i, stage = i % ST;
                 const bool first = (i == 0 || co.n == 0), last = (co.n == prm.n_tiles - 1 || i == n_local - 1);
                 TT_DBG(3, i);
-                mbar_wait(&gfull[b], (i >> 1) & 1);
-                TT_DBG(4, i);
                 if (first && co.r >= 1) mbar_wait(ofree, (co.r - 1) & 1);  // previous row's Out has been drained
-                tc_fence_after();
-                if (elect_one_sync()) {
-                const uint64_t wd = wdesc_mn + static_cast<uint64_t>(stage * (TILE_BYTES >> 4));
-                const uint32_t gaddr = tmem_base + TM_G + b * (TC_BN / 2);
-                if (first) umma_f16_ts_first(tmem_base + TM_OUT, gaddr, wd, idesc_o);
-                else umma_f16_ts_acc(tmem_base + TM_OUT, gaddr, wd, idesc_o);
+                const uint64_t wd = wdesc_mn + static_cast<uint64_t>(stage * (W_BYTES >> 4));
+                bool done[2] = {false, false};
+                int n_done = 0;
+                uint32_t spins = 0;
+                while (n_done < 2) {
 #pragma unroll
-                for (int k = 1; k < TC_BN / 16; ++k)
-                    umma_f16_ts_acc(tmem_base + TM_OUT, gaddr + k * 8, wd + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o);
-                umma_commit(&empty[stage]);
-                umma_commit(&gfree[b]);
-                if (last) umma_commit(ofull);
+                    for (int h = 1; h >= 0; --h) {
+                        if (done[h] || !mbar_test(&gfull[h], i & 1)) continue;
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+                            if (h == 1) TT_DBG(4, i);
+                            const uint32_t gaddr = tmem_base + TM_G + h * (TC_HALF / 2);
+                            const uint64_t wh = wd + static_cast<uint64_t>(h * ((TC_HALF * 128) >> 4));
+#pragma unroll
+                            for (int k = 0; k < TC_HALF / 16; ++k) {
+                                if (first && n_done == 0 && k == 0) umma_f16_ts_first(tmem_base + TM_OUT, gaddr, wh, idesc_o);
+                                else umma_f16_ts_acc(tmem_base + TM_OUT, gaddr + k * 8, wh + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o);
+                            }
+                            umma_commit(&gfree[h]);
+                            if (n_done == 1) {
+                                umma_commit(&empty[stage]);
+                                if (last) umma_commit(ofull);
+                            }
+                        }
+                        __syncwarp();
+                        done[h] = true;
+                        ++n_done;
+                    }
+                    if (++spins > (1u << 26)) { atomicExch(&g_tc_timeout, 3); __trap(); }
                 }
-                __syncwarp();
                 co.next();
             };
             if (!BWD) {
                 while (cs.i < n_local) issue_s();
             } else {
-                // issue order follows the order in which the softmax groups produce their events:
-                // S(0) S(1) | S(2) | S(3) Out(0) | S(4) Out(1) | ...  (the tensor pipe retires in issue order)
+                // S(i+1) is issued as soon as the softmax groups hold S(i) in registers (early in their work on tile
+                // i), Out(i) when they have published G(i): the tensor pipe runs S(i+1) while the MUFU works on tile i
                 issue_s();
-                if (n_local > 1) issue_s();
-                for (int j = 0; j <= n_local; ++j) {
-                    // a row's last Out goes first: the softmax groups drain the row (they wait for ofull) before
-                    // they load the next S tile, which issue_s(j + 2) below waits for
-                    const bool out_first = j >= 1 && (co.n == prm.n_tiles - 1 || co.i == n_local - 1);
-                    if (out_first) issue_out();
-                    if (j + 2 < n_local) issue_s();
-                    if (j >= 1 && !out_first) issue_out();
+                for (int i = 0; i < n_local; ++i) {
+                    if (i + 1 < n_local) issue_s();
+                    issue_out();
                 }
             }
         }
     } else {
-        // ===== softmax: two groups of 4 warps alternate tiles; thread = X row =====
+        // ===== softmax: two groups of 4 warps = the two 128-column halves of every W tile; thread = X row =====
         const int quarter = warp & 3;
         const int grp = (warp - 2) >> 2;
         const int r_in_tile = quarter * 32 + lane;
@@ -316,32 +345,31 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ 
         for (; c.i < n_local; c.next()) {
             const int i = c.i;
             if (i == 0 || c.n == 0) {
-                x_item = !TRANS || c.m < prm.tiles_item;
-                p = (x_item ? c.m : c.m - prm.tiles_item) * TC_BM + r_in_tile;   // row index inside its matrix
+                x_item = !TRANS || c.m < prm.xt_split;
+                p = (c.m < prm.xt_split ? c.m : c.m - prm.xt_split) * TC_BM + r_in_tile;   // row index inside its matrix
                 lo = hi = 0;
                 if (x_item && p < prm.batch) { lo = prm.lo[p]; hi = prm.hi[p]; }
                 if (MODE == MODE_BWD_X) row_stat = (p < prm.batch) ? prm.lse2p[p] : INFINITY;
                 m_run = -INFINITY; s_run = 0.f;
             }
-            if ((i & 1) == grp) {
-                const int b = i & 1, k = i >> 1;
-                const bool w_item = TRANS || c.n < prm.tiles_item;
-                const int col0 = (w_item ? c.n : c.n - prm.tiles_item) * TC_BN;
+            {
+                const int b = BWD ? 0 : (i & 1);
+                const bool w_item = c.n < prm.wt_split;       // item columns (FWD / BWD_X) or U rows (BWD_Y)
+                const int col0 = (w_item ? c.n : c.n - prm.wt_split) * TC_BN + grp * TC_HALF;
                 const int ncol = static_cast<int>(w_item ? prm.batch : prm.pool_rows);
                 // per-element path: columns past the end (zero-filled W rows would count as logit 0; BWD_Y handles
                 // them through lse = +inf) and the collision run / diagonal of this row
-                const bool special = (!TRANS && col0 + TC_BN > ncol) || (x_item && w_item && hi > col0 && lo < col0 + TC_BN);
-                if (TRANS) mbar_wait(&full[i % TC_STAGES], (i / TC_STAGES) & 1);   // lse_s of this stage has landed
+                const bool special = (!TRANS && col0 + TC_HALF > ncol) || (x_item && w_item && hi > col0 && lo < col0 + TC_HALF);
                 if (lane == 0 && quarter == 0) TT_DBG(5, i);
-                mbar_wait(&sfull[b], k & 1);
+                mbar_wait(&sfull[b], BWD ? (i & 1) : ((i >> 1) & 1));
                 tc_fence_after();
                 if (lane == 0 && quarter == 0) TT_DBG(6, i);
                 uint32_t r[4][32];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) tmem_ld_32x32(lane_addr + TM_S + b * TC_BN + q * 32, r[q]);
+                for (int q = 0; q < 4; ++q) tmem_ld_32x32(lane_addr + TM_S + b * TC_BN + grp * TC_HALF + q * 32, r[q]);
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(&sfree[b]);          // the tensor pipe may overwrite S[b] with tile i+2 now
+                mbar_arrive(&sfree[b]);          // the tensor pipe may overwrite this S buffer now
                 if (lane == 0 && quarter == 0) TT_DBG(7, i);
                 if (MODE == MODE_FWD) {
                     if (special) {
@@ -381,7 +409,8 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ 
                         s_run += (a0 + a1) + (a2 + a3);
                     }
                 } else {
-                    const float *ls = lse_s + (i % TC_STAGES) * TC_BN;
+                    if (TRANS) mbar_wait(&lfull[i & 1], (i >> 1) & 1);   // this tile's column statistics have landed
+                    const float *ls = lse_s + (i & 1) * TC_BN + grp * TC_HALF;
                     uint32_t g[2][32];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -411,13 +440,13 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ 
                         }
                     }
                     if (lane == 0 && quarter == 0) TT_DBG(8, i);
-                    if (k >= 1) mbar_wait(&gfree[b], (k - 1) & 1);   // Out(i-2) has consumed G[b] (long ago, normally)
+                    if (i >= 1) mbar_wait(&gfree[grp], (i - 1) & 1);   // Out(i-1) has consumed this group's half of G
                     if (lane == 0 && quarter == 0) TT_DBG(9, i);
-                    tmem_st_32x32(lane_addr + TM_G + b * (TC_BN / 2), g[0]);
-                    tmem_st_32x32(lane_addr + TM_G + b * (TC_BN / 2) + 32, g[1]);
+                    tmem_st_32x32(lane_addr + TM_G + grp * (TC_HALF / 2), g[0]);
+                    tmem_st_32x32(lane_addr + TM_G + grp * (TC_HALF / 2) + 32, g[1]);
                     tmem_st_wait();
                     tc_fence_before();
-                    mbar_arrive(&gfull[b]);
+                    mbar_arrive(&gfull[grp]);
                     if (lane == 0 && quarter == 0) TT_DBG(10, i);
                 }
             }
@@ -591,19 +620,21 @@ ce_tc_reduce_rows(const float *__restrict__ part, int64_t part_rows, int n_tiles
 
 // ---------------------------------------------------------------- host side
 struct CeTcPlan {
-    int tiles_item, tiles_pool, tiles_total;
+    int xt_item, xt_pool;      // 128-row X tiles of the item (= user) rows / the pool
+    int wt_item, wt_pool;      // 256-row W tiles
     Sched fwd, bwd_x, bwd_y;
     size_t sort_bytes;
 };
 
 static CeTcPlan ce_tc_plan(int64_t batch, int64_t pool_rows) {
     CeTcPlan p;
-    p.tiles_item = static_cast<int>((batch + TC_BN - 1) / TC_BN);
-    p.tiles_pool = static_cast<int>((pool_rows + TC_BN - 1) / TC_BN);
-    p.tiles_total = p.tiles_item + p.tiles_pool;
-    p.fwd = make_sched(p.tiles_item, p.tiles_total);
+    p.xt_item = static_cast<int>((batch + TC_BM - 1) / TC_BM);
+    p.xt_pool = static_cast<int>((pool_rows + TC_BM - 1) / TC_BM);
+    p.wt_item = static_cast<int>((batch + TC_BN - 1) / TC_BN);
+    p.wt_pool = static_cast<int>((pool_rows + TC_BN - 1) / TC_BN);
+    p.fwd = make_sched(p.xt_item, p.wt_item + p.wt_pool);
     p.bwd_x = p.fwd;
-    p.bwd_y = make_sched(p.tiles_total, p.tiles_item);
+    p.bwd_y = make_sched(p.xt_item + p.xt_pool, p.wt_item);
     p.sort_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, p.sort_bytes, static_cast<int64_t *>(nullptr),
                                     static_cast<int64_t *>(nullptr), static_cast<int32_t *>(nullptr),
@@ -644,7 +675,7 @@ static CeTcWs ce_tc_carve(void *workspace, size_t bytes, int64_t batch, int64_t 
 
 struct CeBwdWs {
     float *lse2p, *extra, *part_x, *part_y;
-    int64_t rows_x, rows_y;
+    int64_t rows_x, rows_y, lse_rows;
     bool ok;
     size_t used;
 };
@@ -652,9 +683,10 @@ struct CeBwdWs {
 static CeBwdWs ce_bwd_carve(void *workspace, size_t bytes, int64_t batch, int n_rowneg, int dim, const CeTcPlan &pl) {
     Workspace ws(workspace, bytes);
     CeBwdWs w;
-    w.rows_x = static_cast<int64_t>(pl.tiles_item) * TC_BM;
-    w.rows_y = static_cast<int64_t>(pl.tiles_total) * TC_BM;
-    w.lse2p = ws.take<float>(w.rows_x);
+    w.rows_x = static_cast<int64_t>(pl.xt_item) * TC_BM;
+    w.rows_y = static_cast<int64_t>(pl.xt_item + pl.xt_pool) * TC_BM;
+    w.lse_rows = static_cast<int64_t>(pl.wt_item) * TC_BN;
+    w.lse2p = ws.take<float>(w.lse_rows);
     w.extra = ws.take<float>(n_rowneg > 0 ? batch * dim : 1);
     w.part_x = ws.take<float>(static_cast<size_t>(pl.bwd_x.max_seg) * w.rows_x * dim);
     w.part_y = ws.take<float>(static_cast<size_t>(pl.bwd_y.max_seg) * w.rows_y * dim);
@@ -664,10 +696,10 @@ static CeBwdWs ce_bwd_carve(void *workspace, size_t bytes, int64_t batch, int n_
 }
 
 template <int D, int MODE>
-static int launch_ce_tc(const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mp, const CeTcParams &prm,
-                        int grid, cudaStream_t st) {
-    constexpr int ST = TcStages<D>::value;
-    constexpr size_t smem = 1024 + static_cast<size_t>(TC_BN) * D * 2 * (1 + ST) + ST * TC_BN * 4 + 256;
+static int launch_ce_tc(const CUtensorMap &xa, const CUtensorMap &xb, const CUtensorMap &wa, const CUtensorMap &wb,
+                        const CeTcParams &prm, int grid, cudaStream_t st) {
+    // the carve-up needs up to 231.7 KB past a 1 KB-aligned base (checked in the kernel): ask for everything
+    constexpr size_t smem = TC_SMEM_MAX;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ce_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -675,15 +707,33 @@ static int launch_ce_tc(const CUtensorMap &mu, const CUtensorMap &mi, const CUte
         if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(ce_tc_kernel)");
         attr_set = true;
     }
-    ce_tc_kernel<D, MODE><<<grid, TC_THREADS, smem, st>>>(mu, mi, mp, prm);
+    ce_tc_kernel<D, MODE><<<grid, TC_THREADS, smem, st>>>(xa, xb, wa, wb, prm);
     TT_LAUNCH_CHECK("ce_tc_kernel");
     return 0;
 }
 
 template <int MODE>
-static int launch_ce_tc_dim(int dim, const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mp,
-                            const CeTcParams &prm, int grid, cudaStream_t st) {
-    return dim == 128 ? launch_ce_tc<128, MODE>(mu, mi, mp, prm, grid, st) : launch_ce_tc<64, MODE>(mu, mi, mp, prm, grid, st);
+static int launch_ce_tc_dim(int dim, const CUtensorMap &xa, const CUtensorMap &xb, const CUtensorMap &wa,
+                            const CUtensorMap &wb, const CeTcParams &prm, int grid, cudaStream_t st) {
+    return dim == 128 ? launch_ce_tc<128, MODE>(xa, xb, wa, wb, prm, grid, st)
+                      : launch_ce_tc<64, MODE>(xa, xb, wa, wb, prm, grid, st);
+}
+
+// tensor maps of the three bf16 operand matrices, with 128-row (X role) and 256-row (W role) boxes
+struct CeMaps {
+    CUtensorMap u128, i128, p128, u256, i256, p256;
+};
+static int make_ce_maps(CeMaps &m, const CeTcWs &f, int64_t batch, int64_t pool_rows, int dim) {
+    int rc;
+    const void *pb = pool_rows ? static_cast<const void *>(f.pb) : static_cast<const void *>(f.ib);
+    const int64_t pr = pool_rows ? pool_rows : batch;
+    if ((rc = make_tmap_bf16_rows(&m.u128, f.ub, batch, dim, TC_BM))) return rc;
+    if ((rc = make_tmap_bf16_rows(&m.i128, f.ib, batch, dim, TC_BM))) return rc;
+    if ((rc = make_tmap_bf16_rows(&m.p128, pb, pr, dim, TC_BM))) return rc;
+    if ((rc = make_tmap_bf16_rows(&m.u256, f.ub, batch, dim, TC_BN))) return rc;
+    if ((rc = make_tmap_bf16_rows(&m.i256, f.ib, batch, dim, TC_BN))) return rc;
+    if ((rc = make_tmap_bf16_rows(&m.p256, pb, pr, dim, TC_BN))) return rc;
+    return 0;
 }
 
 static long long *g_ce_dbg = nullptr;   // set by tt_ce_tc_debug_trace (developer tool, not part of the product path)
@@ -749,18 +799,16 @@ extern "C" int tt_ce_fwd_tc(const float *user, const float *item, const int64_t 
     if (pool) tc_convert_rows<<<tc_grid(pool_rows * 32, 256), 256, 0, st>>>(pool, nullptr, pool_rows, dim, w.pb, nan_flags, 4);
     TT_LAUNCH_CHECK("tc_convert_rows");
     // 3. tensor maps + main kernel
-    CUtensorMap mu, mi, mp;
+    CeMaps mp;
     int rc;
-    if ((rc = make_tmap_bf16_rows(&mu, w.ub, batch, dim, TC_BM))) return rc;
-    if ((rc = make_tmap_bf16_rows(&mi, w.ib, batch, dim, TC_BN))) return rc;
-    if ((rc = make_tmap_bf16_rows(&mp, pool ? w.pb : w.ib, pool ? pool_rows : batch, dim, TC_BN))) return rc;
+    if ((rc = make_ce_maps(mp, w, batch, pool_rows, dim))) return rc;
     CeTcParams prm{};
     prm.batch = batch; prm.pool_rows = pool_rows;
-    prm.tiles_item = pl.tiles_item; prm.tiles_pool = pl.tiles_pool;
+    prm.xt_split = pl.xt_item; prm.wt_split = pl.wt_item;
     fill_sched(prm, pl.fwd);
     prm.scale2 = inv_temp * LOG2E;
     prm.lo = w.lo; prm.hi = w.hi; prm.part_m = w.part_m; prm.part_s = w.part_s;
-    if ((rc = launch_ce_tc_dim<MODE_FWD>(dim, mu, mi, mp, prm, pl.fwd.grid, st))) return rc;
+    if ((rc = launch_ce_tc_dim<MODE_FWD>(dim, mp.u128, mp.u128, mp.i256, mp.p256, prm, pl.fwd.grid, st))) return rc;
     // 4. finalize
     ce_tc_finalize<<<tc_grid(batch * 32, 256), 256, 0, st>>>(w.ub, w.ib, user, hn_rows, n_rowneg, w.perm, batch, dim,
                                                             inv_temp, pl.fwd.n_tiles, pl.fwd.per_cta, w.part_m, w.part_s,
@@ -798,26 +846,25 @@ extern "C" int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowne
     if (!w.ok) { set_error("ce_tc backward workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) { set_error("ce_tc workspace must be 256-byte aligned"); return TT_E_BADARG; }
 
-    ce_tc_bwd_prep<<<tc_grid(w.rows_x, 256), 256, 0, st>>>(row_lse, f.perm, batch, w.rows_x, w.lse2p);
+    ce_tc_bwd_prep<<<tc_grid(w.lse_rows, 256), 256, 0, st>>>(row_lse, f.perm, batch, w.lse_rows, w.lse2p);
     TT_LAUNCH_CHECK("ce_tc_bwd_prep");
-    CUtensorMap mu, mi, mp;
+    CeMaps mp;
     int rc;
-    if ((rc = make_tmap_bf16_rows(&mu, f.ub, batch, dim, TC_BM))) return rc;
-    if ((rc = make_tmap_bf16_rows(&mi, f.ib, batch, dim, TC_BN))) return rc;
-    if ((rc = make_tmap_bf16_rows(&mp, pool_rows ? f.pb : f.ib, pool_rows ? pool_rows : batch, dim, TC_BN))) return rc;
+    if ((rc = make_ce_maps(mp, f, batch, pool_rows, dim))) return rc;
     CeTcParams prm{};
     prm.batch = batch; prm.pool_rows = pool_rows;
-    prm.tiles_item = pl.tiles_item; prm.tiles_pool = pl.tiles_pool;
     prm.scale2 = inv_temp * LOG2E;
     prm.lo = f.lo; prm.hi = f.hi; prm.lse2p = w.lse2p;
-    // pass 1: dU
+    // pass 1: dU   (X = U row tiles, W = [item ; pool] 256-row tiles)
     fill_sched(prm, pl.bwd_x);
+    prm.xt_split = pl.xt_item; prm.wt_split = pl.wt_item;
     prm.part = w.part_x;
-    if ((rc = launch_ce_tc_dim<MODE_BWD_X>(dim, mu, mi, mp, prm, pl.bwd_x.grid, st))) return rc;
-    // pass 2: dI, dPool
+    if ((rc = launch_ce_tc_dim<MODE_BWD_X>(dim, mp.u128, mp.u128, mp.i256, mp.p256, prm, pl.bwd_x.grid, st))) return rc;
+    // pass 2: dI, dPool   (X = [item ; pool] row tiles, W = U 256-row tiles)
     fill_sched(prm, pl.bwd_y);
+    prm.xt_split = pl.xt_item; prm.wt_split = pl.wt_item;
     prm.part = w.part_y;
-    if ((rc = launch_ce_tc_dim<MODE_BWD_Y>(dim, mu, mi, mp, prm, pl.bwd_y.grid, st))) return rc;
+    if ((rc = launch_ce_tc_dim<MODE_BWD_Y>(dim, mp.i128, mp.p128, mp.u256, mp.u256, prm, pl.bwd_y.grid, st))) return rc;
     if (hn_rows) {
         ce_tc_bwd_hn_rows<<<tc_grid(batch * 32, 256), 256, 0, st>>>(user, hn_rows, n_rowneg, batch, dim, inv_temp, row_lse,
                                                                    grad_loss, d_hn_rows, w.extra);
@@ -833,7 +880,7 @@ extern "C" int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowne
     if (pool_rows > 0)
         ce_tc_reduce_rows<<<tc_grid(pool_rows * vec, 256), 256, 0, st>>>(w.part_y, w.rows_y, pl.bwd_y.n_tiles,
                                                                         pl.bwd_y.per_cta,
-                                                                        static_cast<int64_t>(pl.tiles_item) * TC_BM,
+                                                                        static_cast<int64_t>(pl.xt_item) * TC_BM,
                                                                         pool_rows, dim, nullptr, grad_loss, scale, nullptr,
                                                                         0.f, d_pool);
     TT_LAUNCH_CHECK("ce_tc_reduce_rows");

@@ -71,6 +71,19 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// one non-blocking-ish probe of a phase (try_wait may suspend for a short, bounded time)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
