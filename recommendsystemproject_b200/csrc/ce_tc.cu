@@ -399,13 +399,15 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                     if (m_run > -INFINITY) {
                         const float neg = -m_run * prm.scale2;
                         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            a0 += ex2_approx(fmaf(__uint_as_float(r[0][j]), prm.scale2, neg));
-                            a1 += ex2_approx(fmaf(__uint_as_float(r[1][j]), prm.scale2, neg));
-                            a2 += ex2_approx(fmaf(__uint_as_float(r[2][j]), prm.scale2, neg));
-                            a3 += ex2_approx(fmaf(__uint_as_float(r[3][j]), prm.scale2, neg));
-                        }
+                        // exponentials split between the MUFU and the FMA pipe (tc_common.cuh: ex2_mixed)
+                        auto row4 = [&](auto jc) {
+                            constexpr int j = decltype(jc)::value;
+                            a0 += ex2_mixed<j>(fmaf(__uint_as_float(r[0][j]), prm.scale2, neg));
+                            a1 += ex2_mixed<j + 3>(fmaf(__uint_as_float(r[1][j]), prm.scale2, neg));
+                            a2 += ex2_mixed<j + 5>(fmaf(__uint_as_float(r[2][j]), prm.scale2, neg));
+                            a3 += ex2_mixed<j + 6>(fmaf(__uint_as_float(r[3][j]), prm.scale2, neg));
+                        };
+                        static_for<32>(row4);
                         s_run += (a0 + a1) + (a2 + a3);
                     }
                 } else {
@@ -418,15 +420,16 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                         for (int qq = 0; qq < 2; ++qq) {
                             const int q = h * 2 + qq;
                             float e[32];
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
+                            auto quad = [&](auto jc) {
+                                constexpr int j = decltype(jc)::value * 4;
                                 float4 st = make_float4(row_stat, row_stat, row_stat, row_stat);
                                 if (TRANS) st = *reinterpret_cast<const float4 *>(ls + q * 32 + j);
-                                e[j] = ex2_approx(fmaf(__uint_as_float(r[q][j]), prm.scale2, -st.x));
-                                e[j + 1] = ex2_approx(fmaf(__uint_as_float(r[q][j + 1]), prm.scale2, -st.y));
-                                e[j + 2] = ex2_approx(fmaf(__uint_as_float(r[q][j + 2]), prm.scale2, -st.z));
-                                e[j + 3] = ex2_approx(fmaf(__uint_as_float(r[q][j + 3]), prm.scale2, -st.w));
-                            }
+                                e[j] = ex2_mixed<j>(fmaf(__uint_as_float(r[q][j]), prm.scale2, -st.x));
+                                e[j + 1] = ex2_mixed<j + 1>(fmaf(__uint_as_float(r[q][j + 1]), prm.scale2, -st.y));
+                                e[j + 2] = ex2_mixed<j + 2>(fmaf(__uint_as_float(r[q][j + 2]), prm.scale2, -st.z));
+                                e[j + 3] = ex2_mixed<j + 3>(fmaf(__uint_as_float(r[q][j + 3]), prm.scale2, -st.w));
+                            };
+                            static_for<8>(quad);
                             if (special) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {

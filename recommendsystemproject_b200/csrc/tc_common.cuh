@@ -6,6 +6,8 @@
 
 #include <cuda.h>  // CUtensorMap types only; the driver entry point is fetched at run time
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tt {
@@ -209,6 +211,46 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// 2^x on the FMA pipe (Cody-Waite split + degree-4 minimax polynomial of 2^f on [0,1), relative error < 3e-6):
+// the MUFU does 4 ex2 per clock per SM sub-partition and is THE bound of the softmax epilogues, the FMA pipe is mostly
+// idle there, so a fixed fraction of the exponentials is computed here instead (same idea as FlashAttention-4).
+// Valid for x >= -126 after the clamp; x = -inf (masked logits) gives 2^-126 ~ 1e-38 instead of 0.
+__device__ __forceinline__ float ex2_poly(float x) {
+    const float xc = fmaxf(x, -126.0f);
+    float t;
+    asm("add.rm.f32 %0, %1, 0f4B400000;" : "=f"(t) : "f"(xc));      // + 1.5 * 2^23, rounded down: floor(xc) in the low mantissa bits
+    const float fl = t - 12582912.0f;
+    const float f = xc - fl;                                       // in [0, 1)
+    float p = 1.352060e-2f;                                        // weighted least-squares fit, max rel. error 2.7e-6
+    p = fmaf(p, f, 5.203743e-2f);
+    p = fmaf(p, f, 2.4142749e-1f);
+    p = fmaf(p, f, 6.9300662e-1f);
+    p = fmaf(p, f, 1.00000252f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // p * 2^floor(xc)
+}
+
+// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(integral_constant<N-1>)
+template <int N, int I = 0, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, I + 1>(f);
+    }
+}
+
+// element j of an unrolled row: which unit computes its exponential.  Bit (j & 7) of TT_POLY_MASK set = FMA pipe.
+// Measured on B200 (C4, round 1): mask 0x52 (3 of 8 on the FMA pipe) is parity-clean but NOT faster (fwd 1.69 -> 1.81 ms,
+// fwd+bwd 6.44 -> 6.84 ms): the epilogues are bound by their serial per-tile chain (barrier wake-ups, tcgen05.ld/st
+// round trips, issue slots), not by raw MUFU throughput (ncu XU pipe 46-63 %).  Default: everything on the MUFU.
+#ifndef TT_POLY_MASK
+#define TT_POLY_MASK 0x00
+#endif
+template <int J>
+__device__ __forceinline__ float ex2_mixed(float x) {
+    if constexpr (((TT_POLY_MASK >> (J & 7)) & 1) != 0) return ex2_poly(x);
+    else return ex2_approx(x);
 }
 
 // ------------------------------------------------------------------ descriptors
