@@ -3,6 +3,7 @@ reference's YAML-driven model classes).  No CPU fallback."""
 from . import _lib  # noqa: F401
 from .modules import GenericTower, MLP_Tower, SequenceEncoder, SequenceFeatureProcessor, TwoTowerModel
 from .optim import FusedTwoTowerOptimizer, GraphedTrainStep
+from .batching import GpuBatchBuilder
 
 __all__ = ["GenericTower", "MLP_Tower", "SequenceEncoder", "SequenceFeatureProcessor", "TwoTowerModel",
-           "FusedTwoTowerOptimizer", "GraphedTrainStep"]
+           "FusedTwoTowerOptimizer", "GraphedTrainStep", "GpuBatchBuilder"]

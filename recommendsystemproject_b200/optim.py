@@ -117,9 +117,55 @@ class FusedTwoTowerOptimizer:
                               self.eps, self.step_dev)
         self.sink.clear()
 
+    # checkpoint surface: the SAME dict torch.optim.Adam(model.parameters()) produces (train_twotower.py:184-195 stores
+    # optimizer.state_dict()), so checkpoints move freely between the reference's optimizer and this one
+    def _param_states(self):
+        """(param, exp_avg view, exp_avg_sq view) in model.parameters() order."""
+        flat = {id(p): (off, k) for p, off, k in self._views}
+        out = []
+        for p in self.param_groups[0]["params"]:
+            if id(p) in flat:
+                off, k = flat[id(p)]
+                out.append((p, self.flat_m[off:off + k].view_as(p), self.flat_v[off:off + k].view_as(p)))
+            else:
+                m, v = self.table_state[id(p)]
+                out.append((p, m, v))
+        return out
+
     def state_dict(self):
-        return {"step": int(self.step_dev.item()), "flat_m": self.flat_m, "flat_v": self.flat_v,
-                "tables": {k: v for k, v in self.table_state.items()}, "param_groups": [{"lr": self.lr}]}
+        step = float(self.step_dev.item())
+        state = {}
+        if step > 0:
+            for i, (_, m, v) in enumerate(self._param_states()):
+                state[i] = {"step": torch.tensor(step), "exp_avg": m.detach().clone(), "exp_avg_sq": v.detach().clone()}
+        group = {"lr": self.lr, "betas": (self.beta1, self.beta2), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.param_groups[0]["params"])))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Accepts torch.optim.Adam.state_dict() (or our own) for the same model.  Lazy-Adam tables (table_mode='sparse')
+        share one global step count, like the dense path."""
+        states = self._param_states()
+        if len(sd["param_groups"][0]["params"]) != len(states):
+            raise ValueError("optimizer state_dict does not match this model's parameter list")
+        g = sd["param_groups"][0]
+        self.lr = float(g.get("lr", self.lr))
+        self.beta1, self.beta2 = (float(b) for b in g.get("betas", (self.beta1, self.beta2)))
+        self.eps = float(g.get("eps", self.eps))
+        self.param_groups[0]["lr"] = self.lr
+        step = 0.0
+        with torch.no_grad():
+            for i, (_, m, v) in enumerate(states):
+                st = sd["state"].get(i)
+                if st is None:
+                    m.zero_()
+                    v.zero_()
+                    continue
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+                step = max(step, float(st["step"]))
+            self.step_dev.fill_(int(step))
 
 
 class GraphedTrainStep:

@@ -188,3 +188,25 @@ def _log_embedding_stats(all_item_embs, epoch):
     off = ~torch.eye(d.shape[0], dtype=torch.bool, device=d.device)
     print(f"Epoch {epoch} - item embedding std {std:.6f}, mean-norm {mean_norm:.6f}, pairwise dist "
           f"avg {d[off].mean().item():.6f} min {d[off].min().item():.6f} max {d[off].max().item():.6f}, items {n}")
+
+
+# ---------------------------------------------------------------------------- checkpoints
+def save_checkpoint(path, epoch, model, optimizer, train_loss=None, val_loss=None, metrics=None, user_mapping=None,
+                    item_mapping=None, config=None):
+    """The reference's checkpoint dict, key for key (train_twotower.py:184-195)."""
+    import os
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    torch.save({"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": optimizer.state_dict(),
+                "train_loss": train_loss, "val_loss": val_loss, "metrics": metrics, "user_mapping": user_mapping,
+                "item_mapping": item_mapping, "config": config}, path)
+
+
+def load_checkpoint(path, model, optimizer=None, map_location=None):
+    """Resume (the reference only saves): restores model weights / BatchNorm statistics and, when given, the optimizer
+    (torch.optim.Adam or FusedTwoTowerOptimizer; either kind of checkpoint loads into either kind of optimizer).
+    Returns the checkpoint dict minus the two state dicts (epoch, losses, metrics, mappings, config)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    model.load_state_dict(ckpt["model_state_dict"])
+    if optimizer is not None and ckpt.get("optimizer_state_dict") is not None:
+        optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+    return {k: v for k, v in ckpt.items() if k not in ("model_state_dict", "optimizer_state_dict")}
