@@ -208,7 +208,8 @@ def kernel_rooflines(peaks, flush, quick=False):
     alg = n_valid * D * 4 + B * L * 8 + B * D * 4  # rows actually read (pads are counted, not read) + ids + out
     out.append({"kernel": "gather_pool_kernel", "workload": f"C3 slice: B={B} L={L} ragged mean-pool D={D} fp32, V={V}",
                 "bound": "hbm", "ms": ms, "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg})
+                "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg,
+                "traffic": None if quick else 3.495e9, "traffic_source": "profiles/r1_hot_kernels_ncu.md (dram read+write, same shape)"})
     # --- sorted-segment gradient + row-wise Adam on the same ids
     g = torch.randn(B, D, device=dev)
     sq = torch.zeros(1, device=dev)
@@ -216,12 +217,12 @@ def kernel_rooflines(peaks, flush, quick=False):
 
     def seg():
         res["r"] = ops.segment_grad(ids, ops.POOL_MEAN, 0, V, g, None, D, sq)
-    ms, best = time_op(seg, 3, flush)
+    ms, best = time_op(seg, 5, flush)
     rows, row_grad, nu = res["r"]
     U = int(nu.item())
     alg = B * L * 8 + n_valid * D * 4 + U * (D * 4 + 8)
-    out.append({"kernel": "emb_segment_grad (sort + seg_reduce_rows)", "workload": f"same ids, U={U} unique rows",
-                "bound": "hbm", "ms": ms, "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    out.append({"kernel": "emb_segment_grad (keys + cub radix sort + scans + seg_reduce_rows_wide + norm)",
+                "workload": f"same ids, U={U} unique rows", "bound": "hbm", "ms": ms, "best_ms": best, "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg})
     m = torch.zeros_like(table)
     v = torch.zeros_like(table)
@@ -231,7 +232,8 @@ def kernel_rooflines(peaks, flush, quick=False):
     alg = U * (D * 4 * 7 + 8)  # grad read + 3 state reads + 3 state writes
     out.append({"kernel": "rowwise_adam_kernel", "workload": f"U={U} rows x D={D} fp32 state", "bound": "hbm", "ms": ms,
                 "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg})
+                "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg,
+                "traffic": None if quick else 17.27e9, "traffic_source": "profiles/r1_hot_kernels_ncu.md (dram read+write, same shape)"})
     del table, m, v, ids, g, rows, row_grad, res
     torch.cuda.empty_cache()
     # --- C4 fused CE, tcgen05/TMA bf16 path, forward + backward: the B x (B+H) logits live only in TMEM

@@ -131,6 +131,10 @@ def validate(model, loader, item_loader, device, epoch, k_list=[10, 20], item_id
         _log_embedding_stats(all_embs, epoch)
     meta_iter = iter(meta_data_loader) if meta_data_loader is not None else None
     kmax = max(k_list)
+    # tensor-core scoring (bf16 filter + exact fp64 re-rank: the SAME rows as the fp32 path, see include/tt_b200.h)
+    # whenever the shapes allow it; the bf16 corpus copy is made once per catalog encode
+    use_tc = all_embs.shape[1] in (64, 128) and min(kmax, all_embs.shape[0]) <= 224 and all_embs.shape[0] >= 4096
+    prepared = ops.PreparedCorpus(all_embs) if use_tc else None
     n_batches = 0
     for batch in loader:
         batch = to_device(batch, device)
@@ -162,7 +166,8 @@ def validate(model, loader, item_loader, device, epoch, k_list=[10, 20], item_id
             if flat.size:
                 mask_off = torch.from_numpy(off).to(device)
                 mask_rows = torch.from_numpy(flat).to(device)
-        _, top_rows = ops.score_topk(user_emb, all_embs, min(kmax, all_embs.shape[0]), 0, mask_off, mask_rows)
+        _, top_rows = ops.score_topk(user_emb, all_embs, min(kmax, all_embs.shape[0]), 0, mask_off, mask_rows,
+                                     precision="bf16" if use_tc else "fp32", prepared=prepared)
         valid = top_rows >= 0
         pred_ids = all_ids[top_rows.clamp(min=0)]
         match = (pred_ids == targets.view(-1, 1)) & valid
