@@ -40,18 +40,93 @@ constexpr int KT_SLACK = 32;     // a prune keeps between K' and K' + KT_SLACK e
 constexpr int KT_MAX_KP = 256;
 template <int D> struct KtStages { static constexpr int value = D == 128 ? 3 : 6; };
 
+// Tile order of one pass.  The corpus tiles are grouped into super-blocks (sbt tiles ~ 48 MB of bf16 rows); inside a
+// super-block the tiles are numbered (query tile m, corpus tile nn) and cut into one contiguous slice per CTA, and every
+// CTA walks the super-blocks in the same order.  All CTAs therefore sit in the same super-block at (roughly) the same
+// time and share its corpus tiles through L2 -- without this every query tile re-streams the whole corpus from HBM
+// (ncu r1: 16.3 GB of DRAM reads per launch for a 320 MB corpus shard).
+struct KSched {
+    int m_tiles, n_tiles;     // query tiles (128 rows), corpus tiles (256 rows) visited by this pass
+    int sbt, n_sb;            // corpus tiles per super-block, number of super-blocks
+    int64_t per_cta;          // slice of a super-block's m_tiles * sbt tiles owned by one CTA
+    int grid, max_seg;        // max_seg: CTAs that can share one (super-block, query tile) run
+    int lists;                // candidate lists per query = n_sb * max_seg * 2
+};
+__host__ __device__ __forceinline__ int ks_cnt(const KSched &s, int sb) { return min(s.sbt, s.n_tiles - sb * s.sbt); }
+__host__ __device__ __forceinline__ int ks_first_cta(const KSched &s, int sb, int m) {
+    return static_cast<int>((static_cast<int64_t>(m) * ks_cnt(s, sb)) / s.per_cta);
+}
+
+constexpr int KT_SB_TILES = 768;   // 768 tiles x 256 rows x 256 B = 50 MB of a D=128 bf16 corpus per super-block
+
+static KSched make_ksched(int m_tiles, int n_tiles, bool super_blocks) {
+    KSched s;
+    s.m_tiles = m_tiles; s.n_tiles = n_tiles;
+    s.sbt = (super_blocks && m_tiles >= 8 && n_tiles >= 2 * KT_SB_TILES) ? KT_SB_TILES : n_tiles;
+    s.n_sb = (n_tiles + s.sbt - 1) / s.sbt;
+    const int64_t sb_total = static_cast<int64_t>(m_tiles) * s.sbt;
+    int64_t g = (sb_total + 1) / 2;
+    if (g > sm_count()) g = sm_count();
+    if (g < 1) g = 1;
+    s.per_cta = (sb_total + g - 1) / g;
+    if (s.per_cta * 8 < s.sbt) s.per_cta = (s.sbt + 7) / 8;          // at most ~8 CTAs per run (each leaves 2 lists)
+    s.grid = static_cast<int>((sb_total + s.per_cta - 1) / s.per_cta);
+    s.max_seg = static_cast<int>((s.sbt + s.per_cta - 2) / s.per_cta) + 1;
+    s.lists = s.n_sb * s.max_seg * 2;
+    return s;
+}
+
+// position of a warp role inside its CTA's tiles (one slice per super-block)
+struct KCursor {
+    int i;             // local tile counter over all slices (barrier phases)
+    int sb, m, nn;     // super-block, query tile, corpus tile inside the super-block
+    int cnt;           // corpus tiles of this super-block
+    int left;          // tiles left in this super-block's slice (including the current one)
+    int r;             // local run counter (a run = consecutive tiles of one (sb, m))
+    bool first;        // current tile starts a run
+    bool done;
+    __device__ __forceinline__ void enter(const KSched &s, int cta) {   // find the next non-empty slice from `sb` on
+        for (; sb < s.n_sb; ++sb) {
+            cnt = ks_cnt(s, sb);
+            const int64_t tiles = static_cast<int64_t>(s.m_tiles) * cnt;
+            const int64_t a = static_cast<int64_t>(cta) * s.per_cta;
+            if (a >= tiles) continue;
+            const int64_t b = min(tiles, a + s.per_cta);
+            m = static_cast<int>(a / cnt);
+            nn = static_cast<int>(a - static_cast<int64_t>(m) * cnt);
+            left = static_cast<int>(b - a);
+            first = true;
+            return;
+        }
+        done = true;
+    }
+    __device__ __forceinline__ void init(const KSched &s, int cta) {
+        i = 0; r = 0; sb = 0; done = false; left = 0; m = nn = 0; cnt = 1; first = true;
+        enter(s, cta);
+    }
+    __device__ __forceinline__ void next(const KSched &s, int cta) {
+        ++i;
+        ++r;                                   // provisional: undone below when the run continues
+        if (--left == 0) { ++sb; enter(s, cta); return; }
+        if (++nn == cnt) { nn = 0; ++m; first = true; return; }
+        first = false;
+        --r;
+    }
+    __device__ __forceinline__ bool last() const { return nn == cnt - 1 || left == 1; }
+    __device__ __forceinline__ int tile(const KSched &s) const { return sb * s.sbt + nn; }
+};
+
 struct TopkTcParams {
     int64_t n_query, n_corpus;
-    int m_tiles, n_tiles;
-    int64_t per_cta, total;
-    int max_seg, kp;
+    KSched sch;
+    int kp;
     int tile_stride;         // corpus tile n covers rows [n * tile_stride * 256, +256): > 1 for the sampling pass
     const float *tau0;       // [n_query] initial thresholds from the sampling pass (NULL: start at -inf)
     const int64_t *mask_offsets, *mask_rows;
-    float *cand_v;       // [n_query][2 * max_seg][KT_CAP] approximate scores
-    int32_t *cand_i;     //                               corpus rows
-    int32_t *cand_n;     // [n_query][2 * max_seg] entries (-1: the list overflowed)
-    float *cand_tau;     // [n_query][2 * max_seg] everything left out scored <= tau
+    float *cand_v;       // [n_query][lists][KT_CAP] approximate scores
+    int32_t *cand_i;     //                          corpus rows
+    int32_t *cand_n;     // [n_query][lists] entries (-1: the list overflowed, 0: unused slot)
+    float *cand_tau;     // [n_query][lists] everything left out scored <= tau (-inf: unused slot)
 };
 
 // ---------------------------------------------------------------- prep: fp32 -> bf16 rows (+ max row norm)
@@ -140,7 +215,13 @@ __device__ __forceinline__ int tk_prune_list(float *__restrict__ lv, int32_t *__
 }
 
 // ---------------------------------------------------------------- main kernel
-template <int D>
+constexpr int KT_R = 24;   // sampling pass: scores kept per thread (registers, sorted descending)
+
+// SAMPLE = true: the sampling pass.  No candidate lists and no prunes: every thread keeps the KT_R best approximate
+// scores of its row segment in registers (bubble insertion, all indices static), its threshold is always the exact
+// KT_R-th best so far, and the survivors are written out once per run; tk_tau0_kernel then takes the KT_R-th best over a
+// query's runs as the starting threshold of the full pass.
+template <int D, bool SAMPLE>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
                const TopkTcParams prm) {
@@ -168,9 +249,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     volatile int *tau_tag = reinterpret_cast<volatile int *>(tau_sh + 2 * KT_BM);   // [8]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t g0 = static_cast<int64_t>(blockIdx.x) * prm.per_cta;
-    const int64_t g1 = min(prm.total, g0 + prm.per_cta);
-    const int n_local = static_cast<int>(max(g1 - g0, static_cast<int64_t>(0)));
+    const KSched &sch = prm.sch;
+    const int cta = static_cast<int>(blockIdx.x);
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_q);
@@ -190,10 +270,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     if (warp == 0) {
         // ===== TMA producer (whole warp in uniform control flow, one elected lane issues) =====
-        Cursor c;
-        c.init(g0, prm.n_tiles);
-        for (; c.i < n_local; c.next()) {
-            if (c.i == 0 || c.n == 0) {
+        KCursor c;
+        c.init(sch, cta);
+        for (; !c.done; c.next(sch, cta)) {
+            if (c.first) {
                 if (c.r >= 1) mbar_wait(xfree, (c.r - 1) & 1);
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(xfull, X_BYTES);
@@ -206,7 +286,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&full[stage], W_BYTES);
                 for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(w_tiles + stage * W_BYTES + kb * WK_BYTES, &map_e, &full[stage], kb * 64, c.n * prm.tile_stride * KT_BN);
+                    tma_load_2d(w_tiles + stage * W_BYTES + kb * WK_BYTES, &map_e, &full[stage], kb * 64, c.tile(sch) * prm.tile_stride * KT_BN);
             }
             __syncwarp();
         }
@@ -215,12 +295,12 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         constexpr uint32_t idesc = idesc_bf16_f32(KT_BM, KT_BN, 0, 0);
         const uint64_t xdesc = smem_desc_k_sw128(smem_u32(x_tile));
         const uint64_t wdesc = smem_desc_k_sw128(smem_u32(w_tiles));
-        Cursor c;
-        c.init(g0, prm.n_tiles);
-        for (; c.i < n_local; c.next()) {
+        KCursor c;
+        c.init(sch, cta);
+        for (; !c.done; c.next(sch, cta)) {
             const int i = c.i, b = i & 1, stage = i % ST;
             if (i >= 2) mbar_wait(&sfree[b], ((i >> 1) - 1) & 1);
-            if (i == 0 || c.n == 0) mbar_wait(xfull, c.r & 1);
+            if (c.first) mbar_wait(xfull, c.r & 1);
             mbar_wait(&full[stage], (i / ST) & 1);
             tc_fence_after();
             if (elect_one_sync()) {
@@ -235,7 +315,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 }
                 umma_commit(&empty[stage]);
                 umma_commit(&sfull[b]);
-                if (c.n == prm.n_tiles - 1 || i == n_local - 1) umma_commit(xfree);
+                if (c.last()) umma_commit(xfree);
             }
             __syncwarp();
         }
@@ -245,31 +325,36 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int grp = (warp - 2) >> 2;
         const int r_in_tile = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        Cursor c;
-        c.init(g0, prm.n_tiles);
+        KCursor c;
+        c.init(sch, cta);
         float tau = INFINITY;
         int cnt = 0;
         bool ovf = false, row_ok = false;
+        float top[SAMPLE ? KT_R : 1];
         int64_t q = 0, list = 0, m_lo = 0, m_hi = 0;
-        for (; c.i < n_local; c.next()) {
+        for (; !c.done; c.next(sch, cta)) {
             const int i = c.i, b = i & 1;
-            if (i == 0 || c.n == 0) {
+            if (c.first) {
                 q = static_cast<int64_t>(c.m) * KT_BM + r_in_tile;
                 row_ok = q < prm.n_query;
-                const int seg = static_cast<int>(blockIdx.x) - sched_first_cta(c.m, prm.n_tiles, prm.per_cta);
-                list = q * (2 * prm.max_seg) + 2 * seg + grp;
+                const int part = static_cast<int>(blockIdx.x) - ks_first_cta(sch, c.sb, c.m);
+                list = ((q * sch.n_sb + c.sb) * sch.max_seg + part) * 2 + grp;
                 tau = row_ok ? (prm.tau0 != nullptr ? prm.tau0[q] : -INFINITY) : INFINITY;
                 cnt = 0;
                 ovf = false;
+                if (SAMPLE) {
+#pragma unroll
+                    for (int t = 0; t < KT_R; ++t) top[t] = -INFINITY;
+                }
                 m_lo = m_hi = 0;
                 if (row_ok && prm.mask_offsets != nullptr) { m_lo = prm.mask_offsets[q]; m_hi = prm.mask_offsets[q + 1]; }
                 tau_sh[grp * KT_BM + r_in_tile] = -INFINITY;
                 __syncwarp();
                 __threadfence_block();
-                if (lane == 0) tau_tag[grp * 4 + quarter] = c.m;
+                if (lane == 0) tau_tag[grp * 4 + quarter] = c.sb * sch.m_tiles + c.m;
             }
             // the other group's K'-th best so far bounds the row's K'-th best from below just as well as ours does
-            if (tau_tag[(grp ^ 1) * 4 + quarter] == c.m) {
+            if (tau_tag[(grp ^ 1) * 4 + quarter] == c.sb * sch.m_tiles + c.m) {
                 const float other = *reinterpret_cast<volatile float *>(tau_sh + (grp ^ 1) * KT_BM + r_in_tile);
                 if (row_ok) tau = fmaxf(tau, other);
             }
@@ -283,7 +368,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&sfree[b]);
-            const int64_t col0 = static_cast<int64_t>(c.n) * prm.tile_stride * KT_BN + grp * KT_HALF;
+            const int64_t col0 = static_cast<int64_t>(c.tile(sch)) * prm.tile_stride * KT_BN + grp * KT_HALF;
             if (col0 + KT_HALF > prm.n_corpus) {   // last tile: rows past the corpus were zero-filled by TMA
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq)
@@ -316,7 +401,16 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     while (best > tau) {
                         const int64_t col = col0 + qq * 32 + static_cast<int>(__float_as_uint(best) & 31u);
                         if (!(m_hi > m_lo && tk_masked(prm.mask_rows, m_lo, m_hi, col))) {
-                            if (cnt < KT_CAP) { lv[cnt] = best; li[cnt] = static_cast<int32_t>(col); ++cnt; }
+                            if (SAMPLE) {
+                                float v = best;
+#pragma unroll
+                                for (int t = 0; t < KT_R; ++t) {
+                                    const float hi_v = fmaxf(top[t], v);
+                                    v = fminf(top[t], v);
+                                    top[t] = hi_v;
+                                }
+                                tau = fmaxf(tau, top[KT_R - 1]);
+                            } else if (cnt < KT_CAP) { lv[cnt] = best; li[cnt] = static_cast<int32_t>(col); ++cnt; }
                             else ovf = true;
                         }
                         // next best of the chunk: strictly below `best` (packed scores of a chunk are distinct)
@@ -331,9 +425,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     }
                 }
             }
-            const bool seg_end = (c.n == prm.n_tiles - 1 || i == n_local - 1);
+            const bool seg_end = c.last();
             // a list must have room for a whole 128-column step; at the end of the segment it is cut to ~K'
-            const bool need = row_ok && (seg_end ? cnt > prm.kp + KT_SLACK : cnt > KT_CAP - KT_HALF);
+            const bool need = !SAMPLE && row_ok && (seg_end ? cnt > prm.kp + KT_SLACK : cnt > KT_CAP - KT_HALF);
             unsigned todo = __ballot_sync(0xffffffffu, need);
             while (todo) {
                 const int src = __ffs(todo) - 1;
@@ -346,6 +440,15 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 if (lane == src) { cnt = kept; tau = fmaxf(tau, t_new); tau_sh[grp * KT_BM + r_in_tile] = tau; }
             }
             if (seg_end && row_ok) {
+                if (SAMPLE) {
+                    int n = 0;
+#pragma unroll
+                    for (int t = 0; t < KT_R; ++t) {
+                        lv[t] = top[t];
+                        n += top[t] > -INFINITY ? 1 : 0;
+                    }
+                    cnt = n;
+                }
                 prm.cand_n[list] = ovf ? -1 : cnt;
                 prm.cand_tau[list] = tau;
             }
@@ -362,8 +465,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 // ---------------------------------------------------------------- stage 2: K' best by approximate score -> exact
 // one CTA (128 threads) per query
 __global__ void __launch_bounds__(128)
-topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus, int dim, int k, int kp, int max_seg,
-               int n_tiles, int64_t per_cta, int64_t row_offset, const float *__restrict__ cand_v,
+topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus, int dim, int k, int kp, int n_lists,
+               int64_t row_offset, const float *__restrict__ cand_v,
                const int32_t *__restrict__ cand_i, const int32_t *__restrict__ cand_n,
                const float *__restrict__ cand_tau, const unsigned int *__restrict__ emax_bits,
                double *__restrict__ out_scores, int64_t *__restrict__ out_idx, int32_t *__restrict__ unverified) {
@@ -376,8 +479,6 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
     __shared__ double s_qn;
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int mt = static_cast<int>(q / KT_BM);
-    const int n_lists = 2 * (sched_last_cta(mt, n_tiles, per_cta) - sched_first_cta(mt, n_tiles, per_cta) + 1);
     if (tid == 0) { s_tau = -INFINITY; s_bad = 0; }
     __syncthreads();
     int tot = 0;   // entries in av/ai (uniform across the CTA)
@@ -395,7 +496,7 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
         __syncthreads();
     };
     for (int l = 0; l < n_lists; ++l) {
-        const int64_t list = q * (2 * max_seg) + l;
+        const int64_t list = q * n_lists + l;      // unused slots: n = 0, tau = -inf (tk_init_lists)
         const int n = cand_n[list];
         if (tid == 0) {
             s_tau = fmaxf(s_tau, cand_tau[list]);
@@ -452,18 +553,16 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
 // tau0[q] = the rank-th best approximate score among the query's sampling-pass candidates (one warp per query,
 // bisection on the value like tk_prune_list).  About rank * stride items of the whole corpus score above it.
 __global__ void __launch_bounds__(256)
-tk_tau0_kernel(const float *__restrict__ cand_v, const int32_t *__restrict__ cand_n, int64_t n_query, int max_seg,
-               int n_tiles, int64_t per_cta, int rank, float *__restrict__ tau0) {
+tk_tau0_kernel(const float *__restrict__ cand_v, const int32_t *__restrict__ cand_n, int64_t n_query, int n_lists,
+               int rank, float *__restrict__ tau0) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     for (int64_t q = warp; q < n_query; q += n_warps) {
-        const int mt = static_cast<int>(q / KT_BM);
-        const int n_lists = 2 * (sched_last_cta(mt, n_tiles, per_cta) - sched_first_cta(mt, n_tiles, per_cta) + 1);
         float lo = INFINITY, hi = -INFINITY;
         int total = 0;
         for (int l = 0; l < n_lists; ++l) {
-            const int64_t list = q * (2 * max_seg) + l;
+            const int64_t list = q * n_lists + l;
             const int n = min(max(cand_n[list], 0), KT_CAP);
             total += n;
             for (int t = lane; t < n; t += 32) {
@@ -482,7 +581,7 @@ tk_tau0_kernel(const float *__restrict__ cand_v, const int32_t *__restrict__ can
                 if (!(mid > lo && mid < hi)) break;
                 int c = 0;
                 for (int l = 0; l < n_lists; ++l) {
-                    const int64_t list = q * (2 * max_seg) + l;
+                    const int64_t list = q * n_lists + l;
                     const int n = min(max(cand_n[list], 0), KT_CAP);
                     for (int t = lane; t < n; t += 32) c += (cand_v[list * KT_CAP + t] >= mid) ? 1 : 0;
                 }
@@ -495,34 +594,44 @@ tk_tau0_kernel(const float *__restrict__ cand_v, const int32_t *__restrict__ can
     }
 }
 
-constexpr int KT_SAMPLE_STRIDE = 16;         // the sampling pass scores every 16th corpus tile
+// every pass starts from empty lists: n = 0, tau = -inf (slots no CTA writes stay that way)
+__global__ void tk_init_lists(int32_t *__restrict__ cand_n, float *__restrict__ cand_tau, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        cand_n[i] = 0;
+        cand_tau[i] = -INFINITY;
+    }
+}
+
+// The sampling pass gives every query a starting threshold (the full pass then stays on the filter's fast path): the
+// main kernel in SAMPLE mode over every 16th corpus tile keeps the KT_R = 24 best scores per row segment in registers;
+// tau_0 = the 24th best sampled score of the query, above which ~16 * 24 = 384 corpus items score (2.5 K' for K = 100,
+// +-20 % sampling noise).  A threshold that turns out too high (~1e-4 of the queries) makes the proof obligation of
+// stage 2 fail and the query is re-run without sampling.
+constexpr int KT_STRIDE_B = 16;
 constexpr int64_t KT_SAMPLE_MIN_ROWS = 1 << 17;
 
 struct KtPlan {
-    Sched sched, sample;
-    int kp, kp_sample;
+    KSched sched, sample_b;
+    int kp;
     bool use_sample;
-    int max_seg;
+    int lists;      // max over the passes
 };
 
 static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k, bool sampling = true) {
     KtPlan p;
-    p.sched = make_sched(static_cast<int>((n_query + KT_BM - 1) / KT_BM), static_cast<int>((n_corpus + KT_BN - 1) / KT_BN), 8);
+    const int m_tiles = static_cast<int>((n_query + KT_BM - 1) / KT_BM);
+    const int n_tiles = static_cast<int>((n_corpus + KT_BN - 1) / KT_BN);
+    p.sched = make_ksched(m_tiles, n_tiles, true);
     int margin = k / 2;
     if (margin < 32) margin = 32;
     p.kp = k + margin;
     if (p.kp > KT_MAX_KP) p.kp = KT_MAX_KP;
-    // sampling pass: every KT_SAMPLE_STRIDE-th tile, keeping the best r = 2.5 K' / stride per list.  The r-th best
-    // sampled score becomes the query's starting threshold: about 2.5 K' items of the corpus score above it (+-25 %
-    // sampling noise), few enough that a warp's 32 x 32-score chunk rarely holds one (the filter's fast path), and
-    // far more than K.  Should it still be too high, the proof obligation of stage 2 fails and the query is re-run
-    // on the fp32 path.
-    p.use_sample = sampling && n_corpus >= KT_SAMPLE_MIN_ROWS;
-    const int n_tiles = p.sched.n_tiles;
-    p.sample = make_sched(p.sched.m_tiles, (n_tiles + KT_SAMPLE_STRIDE - 1) / KT_SAMPLE_STRIDE, 8);
-    p.kp_sample = (5 * p.kp / 2 + KT_SAMPLE_STRIDE - 1) / KT_SAMPLE_STRIDE;
-    if (p.kp_sample < 8) p.kp_sample = 8;
-    p.max_seg = p.use_sample && p.sample.max_seg > p.sched.max_seg ? p.sample.max_seg : p.sched.max_seg;
+    // the sampled threshold must admit comfortably more than K' items: 16 * 24 = 384 >= 1.5 K'
+    p.use_sample = sampling && n_corpus >= KT_SAMPLE_MIN_ROWS && 2 * KT_STRIDE_B * KT_R >= 3 * p.kp;
+    p.sample_b = make_ksched(m_tiles, (n_tiles + KT_STRIDE_B - 1) / KT_STRIDE_B, false);
+    p.lists = p.sched.lists;
+    if (p.use_sample && p.sample_b.lists > p.lists) p.lists = p.sample_b.lists;
     return p;
 }
 
@@ -539,7 +648,7 @@ static KtWs kt_carve(void *workspace, size_t bytes, int64_t n_query, int64_t n_c
                      const KtPlan &pl) {
     Workspace ws(workspace, bytes);
     KtWs w;
-    const size_t lists = static_cast<size_t>(n_query) * 2 * pl.max_seg;
+    const size_t lists = static_cast<size_t>(n_query) * pl.lists;
     w.qb = ws.take<__nv_bfloat16>(n_query * dim);
     w.eb = ws.take<__nv_bfloat16>(own_corpus ? n_corpus * dim : 1);
     w.emax = ws.take<unsigned int>(1);
@@ -562,17 +671,17 @@ static inline unsigned kt_grid(int64_t n, int threads) {
 }
 
 // row-major bf16 [rows, dim] -> boxes of {64 columns, box_rows rows}, 128B swizzle (box_rows up to 256)
-template <int D>
+template <int D, bool SAMPLE>
 static int launch_topk_tc(const CUtensorMap &mq, const CUtensorMap &me, const TopkTcParams &prm, int grid, cudaStream_t st) {
     constexpr int ST = KtStages<D>::value;
     constexpr size_t smem = 1024 + static_cast<size_t>(KT_BM) * D * 2 + static_cast<size_t>(ST) * KT_BN * D * 2 + 256 + 2 * KT_BM * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(topk_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(topk_tc_kernel<D, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(topk_tc_kernel)");
         attr_set = true;
     }
-    topk_tc_kernel<D><<<grid, KT_THREADS, smem, st>>>(mq, me, prm);
+    topk_tc_kernel<D, SAMPLE><<<grid, KT_THREADS, smem, st>>>(mq, me, prm);
     TT_LAUNCH_CHECK("topk_tc_kernel");
     return 0;
 }
@@ -640,29 +749,27 @@ extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float
     if ((rc = make_tmap_bf16_rows(&me, eb, n_corpus, dim, KT_BN))) return rc;
     TopkTcParams prm{};
     prm.n_query = n_query; prm.n_corpus = n_corpus;
-    prm.max_seg = pl.max_seg;
     prm.mask_offsets = mask_offsets; prm.mask_rows = mask_rows;
     prm.cand_v = w.cand_v; prm.cand_i = w.cand_i; prm.cand_n = w.cand_n; prm.cand_tau = w.cand_tau;
+    auto run_pass = [&](const KSched &sc, int kp, int stride, const float *tau0, bool sample) -> int {
+        const int64_t n_lists = static_cast<int64_t>(n_query) * sc.lists;
+        tk_init_lists<<<kt_grid(n_lists, 256), 256, 0, st>>>(w.cand_n, w.cand_tau, n_lists);
+        prm.sch = sc; prm.kp = kp; prm.tile_stride = stride; prm.tau0 = tau0;
+        if (sample)
+            return (dim == 128) ? launch_topk_tc<128, true>(mq, me, prm, sc.grid, st) : launch_topk_tc<64, true>(mq, me, prm, sc.grid, st);
+        return (dim == 128) ? launch_topk_tc<128, false>(mq, me, prm, sc.grid, st) : launch_topk_tc<64, false>(mq, me, prm, sc.grid, st);
+    };
+    const float *tau_start = nullptr;
     if (pl.use_sample) {
-        // pass 1: every 16th corpus tile, small K' -> a per-query starting threshold for the full pass
-        prm.m_tiles = pl.sample.m_tiles; prm.n_tiles = pl.sample.n_tiles;
-        prm.per_cta = pl.sample.per_cta; prm.total = pl.sample.total;
-        prm.kp = pl.kp_sample; prm.tile_stride = KT_SAMPLE_STRIDE; prm.tau0 = nullptr;
-        rc = (dim == 128) ? launch_topk_tc<128>(mq, me, prm, pl.sample.grid, st) : launch_topk_tc<64>(mq, me, prm, pl.sample.grid, st);
-        if (rc) return rc;
-        tk_tau0_kernel<<<kt_grid(n_query * 32, 256), 256, 0, st>>>(w.cand_v, w.cand_n, n_query, pl.max_seg, pl.sample.n_tiles,
-                                                                  pl.sample.per_cta, pl.kp_sample, w.tau0);
+        if ((rc = run_pass(pl.sample_b, KT_R, KT_STRIDE_B, nullptr, true))) return rc;
+        tk_tau0_kernel<<<kt_grid(n_query * 32, 256), 256, 0, st>>>(w.cand_v, w.cand_n, n_query, pl.sample_b.lists, KT_R, w.tau0);
         TT_LAUNCH_CHECK("tk_tau0_kernel");
+        tau_start = w.tau0;
     }
-    prm.m_tiles = pl.sched.m_tiles; prm.n_tiles = pl.sched.n_tiles;
-    prm.per_cta = pl.sched.per_cta; prm.total = pl.sched.total;
-    prm.kp = pl.kp; prm.tile_stride = 1; prm.tau0 = pl.use_sample ? w.tau0 : nullptr;
-    rc = (dim == 128) ? launch_topk_tc<128>(mq, me, prm, pl.sched.grid, st) : launch_topk_tc<64>(mq, me, prm, pl.sched.grid, st);
-    if (rc) return rc;
-    topk_tc_stage2<<<static_cast<unsigned>(n_query), 128, 0, st>>>(query, corpus, dim, k, pl.kp, pl.max_seg,
-                                                                   pl.sched.n_tiles, pl.sched.per_cta, row_offset, w.cand_v,
-                                                                   w.cand_i, w.cand_n, w.cand_tau, emax, out_scores, out_idx,
-                                                                   unverified);
+    if ((rc = run_pass(pl.sched, pl.kp, 1, tau_start, false))) return rc;
+    topk_tc_stage2<<<static_cast<unsigned>(n_query), 128, 0, st>>>(query, corpus, dim, k, pl.kp, pl.sched.lists, row_offset,
+                                                                   w.cand_v, w.cand_i, w.cand_n, w.cand_tau, emax, out_scores,
+                                                                   out_idx, unverified);
     TT_LAUNCH_CHECK("topk_tc_stage2");
     return 0;
 }

@@ -288,7 +288,7 @@ class PreparedCorpus:
 
 # statistics of the last tensor-core top-K call (tests / bench report the fallback rate)
 topk_stats = {"queries": 0, "resampled": 0, "unverified": 0}
-TOPK_TC_QUERY_CHUNK = 32768
+TOPK_TC_QUERY_CHUNK = 16384
 
 
 def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepared: Optional["PreparedCorpus"],
