@@ -186,24 +186,30 @@ TT_API int tt_score_topk_f32(const float *query, int64_t n_query, const float *c
                       double *out_scores, int64_t *out_idx, void *workspace, size_t workspace_bytes,
                       void *stream);
 /* Tensor-core scoring path (tcgen05.mma M=128 N=256, bf16 operands, fp32 accumulate in TMEM) with the same
- * contract and the same bit-exact result: the bf16 scores only FILTER candidates (K + margin per list); the
+ * contract and the same bit-exact result: the bf16 scores only FILTER candidates (K' = K + margin per list); the
  * survivors are re-scored in fp64 from the fp32 inputs and a per-query proof obligation
- *     exact_score[K-th] > (best approximate score ever left out) + 1.02 * 2^-8 * |q| * max|e|
- * is evaluated on the device.  unverified[q] = 1 marks the (rare) queries for which it does not hold; the
- * caller must re-run those with use_sampling = 0 and, if still flagged, through tt_score_topk_f32.
- * use_sampling != 0 (corpora of >= 2^17 rows): a first pass over every 16th corpus tile gives each query a
- * starting threshold above which ~2 K' items score, which keeps the filter on its fast path; a threshold that
- * turns out too high (sampling noise, ~1e-4 of the queries) is exactly what the obligation detects.
+ *     exact_score[K-th] > tau + |q - bf16(q)| * max|bf16(e)| + |q| * max|e - bf16(e)| + 2e-5 * |q| * max|e|
+ * (tau = best approximate score ever left out; Cauchy-Schwarz on the two rounding-error vectors, the last term
+ * covers fp32 accumulation and the index bits kept in the low mantissa) is evaluated on the device.
+ * unverified[q] = 1 marks the (rare) queries for which it does not hold; the caller must re-run those with
+ * flags = TT_TOPK_WIDE and, if still flagged, through tt_score_topk_f32.
+ * flags: TT_TOPK_SAMPLING (corpora of >= 2^17 rows) -- a first pass over every 16th corpus tile gives each query
+ *   a starting threshold above which ~2.5 K' items score, which keeps the filter on its fast path; a threshold
+ *   that turns out too high (sampling noise, ~1e-4 of the queries) is exactly what the obligation detects.
+ *   TT_TOPK_WIDE -- K' = 256 whatever K (the repair pass: tolerates 2.5x more near-ties around the K-th score).
  * dim must be 64 or 128, k <= 224.
- * corpus_bf16 / corpus_max_norm (nullable, both or neither): a bf16 copy of the corpus and the largest row norm
- * prepared once with tt_topk_tc_prepare_corpus; when NULL the call converts the corpus into its workspace. */
-TT_API int tt_topk_tc_prepare_corpus(const float *corpus, int64_t n_corpus, int dim, void *corpus_bf16, float *max_norm,
+ * corpus_bf16 / corpus_bounds (nullable, both or neither): a bf16 copy of the corpus and its two bounds
+ * {max row norm of the bf16 copy, max row norm of the rounding error}, prepared once with
+ * tt_topk_tc_prepare_corpus (bounds = 2 floats); when NULL the call converts the corpus into its workspace. */
+#define TT_TOPK_SAMPLING 1
+#define TT_TOPK_WIDE 2
+TT_API int tt_topk_tc_prepare_corpus(const float *corpus, int64_t n_corpus, int dim, void *corpus_bf16, float *bounds,
                               void *stream);
 TT_API int tt_score_topk_tc_workspace(int64_t n_query, int64_t n_corpus, int dim, int k, int own_corpus, size_t *bytes_host);
 TT_API int tt_score_topk_tc(const float *query, int64_t n_query, const float *corpus, const void *corpus_bf16,
-                     const float *corpus_max_norm, int64_t n_corpus, int dim, int k, int64_t row_offset,
+                     const float *corpus_bounds, int64_t n_corpus, int dim, int k, int64_t row_offset,
                      const int64_t *mask_offsets, const int64_t *mask_rows, double *out_scores, int64_t *out_idx,
-                     int32_t *unverified, int use_sampling, void *workspace, size_t workspace_bytes, void *stream);
+                     int32_t *unverified, int flags, void *workspace, size_t workspace_bytes, void *stream);
 /* merge W per-shard lists [W, n_query, k] into the global top-k with the same tie-break */
 TT_API int tt_topk_merge(const double *scores, const int64_t *idx, int n_shards, int64_t n_query, int k,
                   double *out_scores, int64_t *out_idx, void *stream);

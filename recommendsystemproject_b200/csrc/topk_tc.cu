@@ -69,7 +69,11 @@ static KSched make_ksched(int m_tiles, int n_tiles, bool super_blocks) {
     if (g > sm_count()) g = sm_count();
     if (g < 1) g = 1;
     s.per_cta = (sb_total + g - 1) / g;
-    if (s.per_cta * 8 < s.sbt) s.per_cta = (s.sbt + 7) / 8;          // at most ~8 CTAs per run (each leaves 2 lists)
+    // at most ~8 CTAs per run (each leaves 2 lists for stage 2 to merge) -- unless there are so few query tiles that
+    // this would idle SMs (the repair pass for a handful of queries): then one run spreads over sm_count / m_tiles CTAs
+    int seg_cap = (sm_count() + m_tiles - 1) / m_tiles;
+    if (seg_cap < 8) seg_cap = 8;
+    if (s.per_cta * seg_cap < s.sbt) s.per_cta = (s.sbt + seg_cap - 1) / seg_cap;
     s.grid = static_cast<int>((sb_total + s.per_cta - 1) / s.per_cta);
     s.max_seg = static_cast<int>((s.sbt + s.per_cta - 2) / s.per_cta) + 1;
     s.lists = s.n_sb * s.max_seg * 2;
@@ -129,29 +133,38 @@ struct TopkTcParams {
     float *cand_tau;     // [n_query][lists] everything left out scored <= tau (-inf: unused slot)
 };
 
-// ---------------------------------------------------------------- prep: fp32 -> bf16 rows (+ max row norm)
+// ---------------------------------------------------------------- prep: fp32 -> bf16 rows (+ error bounds)
+// bounds[0] = max over rows of |bf16(x)|, bounds[1] = max over rows of |x - bf16(x)| (both rounded up): the two
+// corpus-side terms of stage 2's proof obligation.
 __global__ void __launch_bounds__(256)
 tk_convert_rows(const float *__restrict__ in, int64_t n, int dim, __nv_bfloat16 *__restrict__ out,
-                unsigned int *__restrict__ max_norm_bits) {
+                unsigned int *__restrict__ bounds_bits) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    float best = 0.f;
+    float best = 0.f, best_err = 0.f;
     for (int64_t p = warp; p < n; p += n_warps) {
-        float ss = 0.f;
+        float ss = 0.f, se = 0.f;
         for (int c = lane * 4; c < dim; c += 128) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(in + p * dim + c));
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
             __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
             uint2 raw;
             raw.x = *reinterpret_cast<uint32_t *>(&a);
             raw.y = *reinterpret_cast<uint32_t *>(&b);
             *reinterpret_cast<uint2 *>(out + p * dim + c) = raw;
+            const float r0 = __uint_as_float(raw.x << 16), r1 = __uint_as_float(raw.x & 0xffff0000u);
+            const float r2 = __uint_as_float(raw.y << 16), r3 = __uint_as_float(raw.y & 0xffff0000u);
+            ss += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+            const float d0 = v.x - r0, d1 = v.y - r1, d2 = v.z - r2, d3 = v.w - r3;   // exact (Sterbenz)
+            se += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
         }
         best = fmaxf(best, warp_sum(ss));
+        best_err = fmaxf(best_err, warp_sum(se));
     }
-    if (max_norm_bits != nullptr && lane == 0 && best > 0.f)
-        atomicMax(max_norm_bits, __float_as_uint(sqrtf(best) * 1.000001f));   // non-negative floats order like their bits
+    if (bounds_bits != nullptr && lane == 0) {   // non-negative floats order like their bits; 1e-5: fp32 sums above
+        if (best > 0.f) atomicMax(bounds_bits, __float_as_uint(sqrtf(best) * 1.00001f));
+        if (best_err > 0.f) atomicMax(bounds_bits + 1, __float_as_uint(sqrtf(best_err) * 1.00001f));
+    }
 }
 
 // ---------------------------------------------------------------- list prune (one warp, one list)
@@ -215,6 +228,8 @@ __device__ __forceinline__ int tk_prune_list(float *__restrict__ lv, int32_t *__
 }
 
 // ---------------------------------------------------------------- main kernel
+constexpr uint32_t KT_MASKED = 0xff7fffe0u;   // -3.4028e38 with the 5 index bits clear: stays finite once tagged
+constexpr float KT_TAU_FLOOR = -3.0e38f;      // thresholds start here ("nothing left out yet"), above KT_MASKED
 constexpr int KT_R = 24;   // sampling pass: scores kept per thread (registers, sorted descending)
 
 // SAMPLE = true: the sampling pass.  No candidate lists and no prunes: every thread keeps the KT_R best approximate
@@ -339,7 +354,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 row_ok = q < prm.n_query;
                 const int part = static_cast<int>(blockIdx.x) - ks_first_cta(sch, c.sb, c.m);
                 list = ((q * sch.n_sb + c.sb) * sch.max_seg + part) * 2 + grp;
-                tau = row_ok ? (prm.tau0 != nullptr ? prm.tau0[q] : -INFINITY) : INFINITY;
+                // never below KT_TAU_FLOOR: corpus rows past the end carry KT_MASKED, a finite value under the floor
+                tau = row_ok ? fmaxf(prm.tau0 != nullptr ? prm.tau0[q] : KT_TAU_FLOOR, KT_TAU_FLOOR) : INFINITY;
                 cnt = 0;
                 ovf = false;
                 if (SAMPLE) {
@@ -374,54 +390,62 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 for (int qq = 0; qq < 4; ++qq)
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (col0 + qq * 32 + j >= prm.n_corpus) r[qq][j] = 0xff800000u;
+                        if (col0 + qq * 32 + j >= prm.n_corpus) r[qq][j] = KT_MASKED;
             }
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
-                float m0 = fmaxf(__uint_as_float(r[qq][0]), __uint_as_float(r[qq][1]));
-                float m1 = fmaxf(__uint_as_float(r[qq][2]), __uint_as_float(r[qq][3]));
+                // fast path: four 8-score maxima (3-input max chains), one compare for the 32-column chunk
+                float sub[4];
 #pragma unroll
-                for (int j = 4; j < 32; j += 2) {
-                    m0 = fmaxf(m0, __uint_as_float(r[qq][j]));
-                    m1 = fmaxf(m1, __uint_as_float(r[qq][j + 1]));
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t *x = &r[qq][g * 8];
+                    float m = fmaxf(fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1])), __uint_as_float(x[2]));
+                    m = fmaxf(fmaxf(m, __uint_as_float(x[3])), __uint_as_float(x[4]));
+                    m = fmaxf(fmaxf(m, __uint_as_float(x[5])), __uint_as_float(x[6]));
+                    sub[g] = fmaxf(m, __uint_as_float(x[7]));
                 }
-                if (fmaxf(m0, m1) > tau) {
-                    // Some score of this 32-column chunk beats the threshold.  Its column index goes into the 5 low
-                    // mantissa bits of every score (a 2^-18 relative perturbation, far below the bf16 error budget):
-                    // one FMNMX tree then yields the best score AND where it is, so the append path needs no
-                    // dynamically indexed registers (no local memory: L1 is ~4 KB here) and stays compact (no
-                    // instruction-cache thrash: an earlier version with 128 inlined append sites was 140 KB of SASS).
-                    float best = -INFINITY;
+                if (fmaxf(fmaxf(sub[0], sub[1]), fmaxf(sub[2], sub[3])) > tau) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (r[qq][j] != 0xff800000u) r[qq][j] = (r[qq][j] & 0xffffffe0u) | static_cast<uint32_t>(j);
-                        best = fmaxf(best, __uint_as_float(r[qq][j]));
-                    }
+                    for (int g = 0; g < 4; ++g) {
+                        if (sub[g] > tau) {
+                            // Some score of these 8 columns beats the threshold.  The column index goes into the 5 low
+                            // mantissa bits of the 8 scores (a 2^-18 relative perturbation, part of the proof margin):
+                            // one max tree then yields the best score AND where it is, so the append path needs no
+                            // dynamically indexed registers (no local memory: L1 is ~4 KB here) and stays compact (an
+                            // earlier version with 128 inlined append sites was 140 KB of SASS and stalled on
+                            // instruction fetch).
+                            float best = -INFINITY;
+#pragma unroll
+                            for (int j = g * 8; j < g * 8 + 8; ++j) {
+                                r[qq][j] = (r[qq][j] & 0xffffffe0u) | static_cast<uint32_t>(j);
+                                best = fmaxf(best, __uint_as_float(r[qq][j]));
+                            }
 #pragma unroll 1
-                    while (best > tau) {
-                        const int64_t col = col0 + qq * 32 + static_cast<int>(__float_as_uint(best) & 31u);
-                        if (!(m_hi > m_lo && tk_masked(prm.mask_rows, m_lo, m_hi, col))) {
-                            if (SAMPLE) {
-                                float v = best;
+                            while (best > tau) {
+                                const int64_t col = col0 + qq * 32 + static_cast<int>(__float_as_uint(best) & 31u);
+                                if (!(m_hi > m_lo && tk_masked(prm.mask_rows, m_lo, m_hi, col))) {
+                                    if (SAMPLE) {
+                                        float v = best;
 #pragma unroll
-                                for (int t = 0; t < KT_R; ++t) {
-                                    const float hi_v = fmaxf(top[t], v);
-                                    v = fminf(top[t], v);
-                                    top[t] = hi_v;
+                                        for (int t = 0; t < KT_R; ++t) {
+                                            const float hi_v = fmaxf(top[t], v);
+                                            v = fminf(top[t], v);
+                                            top[t] = hi_v;
+                                        }
+                                        tau = fmaxf(tau, top[KT_R - 1]);
+                                    } else if (cnt < KT_CAP) { lv[cnt] = best; li[cnt] = static_cast<int32_t>(col); ++cnt; }
+                                    else ovf = true;
                                 }
-                                tau = fmaxf(tau, top[KT_R - 1]);
-                            } else if (cnt < KT_CAP) { lv[cnt] = best; li[cnt] = static_cast<int32_t>(col); ++cnt; }
-                            else ovf = true;
-                        }
-                        // next best of the chunk: strictly below `best` (packed scores of a chunk are distinct)
-                        float n0 = -INFINITY, n1 = -INFINITY;
+                                // next best of the 8: strictly below `best` (packed scores are distinct)
+                                float nb = -INFINITY;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float x0 = __uint_as_float(r[qq][j]), x1 = __uint_as_float(r[qq][j + 1]);
-                            n0 = fmaxf(n0, x0 < best ? x0 : -INFINITY);
-                            n1 = fmaxf(n1, x1 < best ? x1 : -INFINITY);
+                                for (int j = g * 8; j < g * 8 + 8; ++j) {
+                                    const float x0 = __uint_as_float(r[qq][j]);
+                                    nb = fmaxf(nb, x0 < best ? x0 : -INFINITY);
+                                }
+                                best = nb;
+                            }
                         }
-                        best = fmaxf(n0, n1);
                     }
                 }
             }
@@ -468,7 +492,7 @@ __global__ void __launch_bounds__(128)
 topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus, int dim, int k, int kp, int n_lists,
                int64_t row_offset, const float *__restrict__ cand_v,
                const int32_t *__restrict__ cand_i, const int32_t *__restrict__ cand_n,
-               const float *__restrict__ cand_tau, const unsigned int *__restrict__ emax_bits,
+               const float *__restrict__ cand_tau, const unsigned int *__restrict__ ebounds_bits,
                double *__restrict__ out_scores, int64_t *__restrict__ out_idx, int32_t *__restrict__ unverified) {
     __shared__ float av[TK_STAGE2_MAX];
     __shared__ int32_t ai[TK_STAGE2_MAX];
@@ -476,7 +500,7 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
     __shared__ int32_t ei[KT_MAX_KP];
     __shared__ float s_tau;
     __shared__ int s_bad;
-    __shared__ double s_qn;
+    __shared__ double s_qn, s_qd;
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_tau = -INFINITY; s_bad = 0; }
@@ -519,12 +543,20 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
         if (lane == 0) { ev[c] = d; ei[c] = ai[c]; }
     }
-    if (warp == 0) {
-        double n2 = 0.0;
-        for (int t = lane; t < dim; t += 32) n2 = fma(static_cast<double>(qv[t]), static_cast<double>(qv[t]), n2);
+    if (warp == 0) {   // |q| and |q - bf16(q)| for the proof obligation
+        double n2 = 0.0, d2 = 0.0;
+        for (int t = lane; t < dim; t += 32) {
+            const double x = static_cast<double>(qv[t]);
+            const double dx = x - static_cast<double>(__bfloat162float(__float2bfloat16_rn(qv[t])));
+            n2 = fma(x, x, n2);
+            d2 = fma(dx, dx, d2);
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-        if (lane == 0) s_qn = sqrt(n2);
+        for (int o = 16; o > 0; o >>= 1) {
+            n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        if (lane == 0) { s_qn = sqrt(n2); s_qd = sqrt(d2); }
     }
     int np2 = 32;
     while (np2 < tot) np2 <<= 1;
@@ -539,11 +571,17 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
         out_idx[q * k + t] = ok ? static_cast<int64_t>(ei[t]) + row_offset : -1;
     }
     if (tid == 0) {
-        // nothing was ever left out (tau = -inf): exact by construction.  Otherwise the K-th exact score must clear
-        // the best score anything left out could have.
+        // nothing was ever left out (tau still at its floor): exact by construction.  Otherwise the K-th exact score
+        // must clear the best exact score anything left out could have.  For a left-out row e with bf16 copies q~, e~:
+        //   q.e - q~.e~ = (q - q~).e~ + q.(e - e~)  =>  q.e <= q~.e~ + |q - q~| max|e~| + |q| max|e - e~|
+        // (Cauchy-Schwarz; |q - q~| is this query's own rounding error, the two corpus bounds come from
+        // tk_convert_rows), and the filter's value of q~.e~ is below tau + 2e-5 |q~| |e~|: fp32 accumulation of 128
+        // products in the tensor core (<= 1.6e-5) plus the 5 index bits written over the low mantissa (2^-18).
         bool good = s_bad == 0;
-        if (good && s_tau > -INFINITY) {
-            const double eps = (1.02 * 0.00390625 + 1.6e-5) * s_qn * static_cast<double>(__uint_as_float(*emax_bits)) + 1e-30;
+        if (good && s_tau > KT_TAU_FLOOR) {
+            const double e_norm = static_cast<double>(__uint_as_float(ebounds_bits[0]));
+            const double e_err = static_cast<double>(__uint_as_float(ebounds_bits[1]));
+            const double eps = s_qd * e_norm + s_qn * e_err + 2.0e-5 * (s_qn + s_qd) * e_norm + 1e-30;
             good = (tot >= k) && (ev[k - 1] > static_cast<double>(s_tau) + eps);
         }
         unverified[q] = good ? 0 : 1;
@@ -618,7 +656,7 @@ struct KtPlan {
     int lists;      // max over the passes
 };
 
-static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k, bool sampling = true) {
+static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k, bool sampling = true, bool wide = false) {
     KtPlan p;
     const int m_tiles = static_cast<int>((n_query + KT_BM - 1) / KT_BM);
     const int n_tiles = static_cast<int>((n_corpus + KT_BN - 1) / KT_BN);
@@ -626,7 +664,7 @@ static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k, bool sampling = 
     int margin = k / 2;
     if (margin < 32) margin = 32;
     p.kp = k + margin;
-    if (p.kp > KT_MAX_KP) p.kp = KT_MAX_KP;
+    if (wide || p.kp > KT_MAX_KP) p.kp = KT_MAX_KP;   // wide: the repair pass for queries whose proof failed
     // the sampled threshold must admit comfortably more than K' items: 16 * 24 = 384 >= 1.5 K'
     p.use_sample = sampling && n_corpus >= KT_SAMPLE_MIN_ROWS && 2 * KT_STRIDE_B * KT_R >= 3 * p.kp;
     p.sample_b = make_ksched(m_tiles, (n_tiles + KT_STRIDE_B - 1) / KT_STRIDE_B, false);
@@ -651,7 +689,7 @@ static KtWs kt_carve(void *workspace, size_t bytes, int64_t n_query, int64_t n_c
     const size_t lists = static_cast<size_t>(n_query) * pl.lists;
     w.qb = ws.take<__nv_bfloat16>(n_query * dim);
     w.eb = ws.take<__nv_bfloat16>(own_corpus ? n_corpus * dim : 1);
-    w.emax = ws.take<unsigned int>(1);
+    w.emax = ws.take<unsigned int>(2);
     w.cand_v = ws.take<float>(lists * KT_CAP);
     w.cand_i = ws.take<int32_t>(lists * KT_CAP);
     w.cand_n = ws.take<int32_t>(lists);
@@ -689,15 +727,15 @@ static int launch_topk_tc(const CUtensorMap &mq, const CUtensorMap &me, const To
 }  // namespace tt
 
 extern "C" int tt_topk_tc_prepare_corpus(const float *corpus, int64_t n_corpus, int dim, void *corpus_bf16,
-                                         float *max_norm, void *stream) {
+                                         float *bounds, void *stream) {
     using namespace tt;
-    TT_CHECK_ARG(corpus && corpus_bf16 && max_norm && n_corpus > 0, "null pointer / empty corpus");
+    TT_CHECK_ARG(corpus && corpus_bf16 && bounds && n_corpus > 0, "null pointer / empty corpus");
     if (dim != 64 && dim != 128) { set_error("tensor-core top-K supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(max_norm, 0, sizeof(float), st);
-    if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(max_norm)");
+    cudaError_t e = cudaMemsetAsync(bounds, 0, 2 * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(bounds)");
     tk_convert_rows<<<kt_grid(n_corpus * 32, 256), 256, 0, st>>>(corpus, n_corpus, dim, static_cast<__nv_bfloat16 *>(corpus_bf16),
-                                                                reinterpret_cast<unsigned int *>(max_norm));
+                                                                reinterpret_cast<unsigned int *>(bounds));
     TT_LAUNCH_CHECK("tk_convert_rows");
     return 0;
 }
@@ -713,20 +751,20 @@ extern "C" int tt_score_topk_tc_workspace(int64_t n_query, int64_t n_corpus, int
 }
 
 extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float *corpus, const void *corpus_bf16,
-                                const float *corpus_max_norm, int64_t n_corpus, int dim, int k, int64_t row_offset,
+                                const float *corpus_bounds, int64_t n_corpus, int dim, int k, int64_t row_offset,
                                 const int64_t *mask_offsets, const int64_t *mask_rows, double *out_scores,
-                                int64_t *out_idx, int32_t *unverified, int use_sampling, void *workspace,
+                                int64_t *out_idx, int32_t *unverified, int flags, void *workspace,
                                 size_t workspace_bytes, void *stream) {
     using namespace tt;
     TT_CHECK_ARG(query && corpus && out_scores && out_idx && unverified && workspace, "null pointer");
     TT_CHECK_ARG(n_query > 0 && n_corpus > 0 && k > 0, "non-positive size");
     TT_CHECK_ARG((mask_offsets == nullptr) == (mask_rows == nullptr), "mask_offsets / mask_rows mismatch");
-    TT_CHECK_ARG((corpus_bf16 == nullptr) == (corpus_max_norm == nullptr), "corpus_bf16 / corpus_max_norm mismatch");
+    TT_CHECK_ARG((corpus_bf16 == nullptr) == (corpus_bounds == nullptr), "corpus_bf16 / corpus_bounds mismatch");
     if (dim != 64 && dim != 128) { set_error("tensor-core top-K supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
     if (k > KT_MAX_KP - 32) { set_error("tensor-core top-K supports k <= %d (got %d)", KT_MAX_KP - 32, k); return TT_E_UNSUPPORTED; }
     if (n_corpus >= (int64_t(1) << 31)) { set_error("corpus shard must have < 2^31 rows"); return TT_E_UNSUPPORTED; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const KtPlan pl = kt_plan(n_query, n_corpus, k, use_sampling != 0);
+    const KtPlan pl = kt_plan(n_query, n_corpus, k, (flags & TT_TOPK_SAMPLING) != 0, (flags & TT_TOPK_WIDE) != 0);
     const bool own = corpus_bf16 == nullptr;
     const KtWs w = kt_carve(workspace, workspace_bytes, n_query, n_corpus, dim, own, pl);
     if (!w.ok) { set_error("top-K (tensor core) workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
@@ -734,9 +772,9 @@ extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float
 
     tk_convert_rows<<<kt_grid(n_query * 32, 256), 256, 0, st>>>(query, n_query, dim, w.qb, nullptr);
     const __nv_bfloat16 *eb = static_cast<const __nv_bfloat16 *>(corpus_bf16);
-    const unsigned int *emax = reinterpret_cast<const unsigned int *>(corpus_max_norm);
+    const unsigned int *emax = reinterpret_cast<const unsigned int *>(corpus_bounds);
     if (own) {
-        cudaError_t e = cudaMemsetAsync(w.emax, 0, sizeof(unsigned int), st);
+        cudaError_t e = cudaMemsetAsync(w.emax, 0, 2 * sizeof(unsigned int), st);
         if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(emax)");
         tk_convert_rows<<<kt_grid(n_corpus * 32, 256), 256, 0, st>>>(corpus, n_corpus, dim, w.eb, w.emax);
         eb = w.eb;

@@ -271,8 +271,8 @@ def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, tempera
 # 4. corpus scoring + top-K
 # --------------------------------------------------------------------------
 class PreparedCorpus:
-    """bf16 copy of a corpus shard + its largest row norm for the tensor-core top-K path (built once per
-    catalog encode, reused for every query batch)."""
+    """bf16 copy of a corpus shard + its two proof bounds (largest row norm of the copy, largest row norm of the
+    rounding error) for the tensor-core top-K path (built once per catalog encode, reused for every query batch)."""
 
     def __init__(self, corpus: torch.Tensor):
         _need_cuda(corpus)
@@ -280,8 +280,8 @@ class PreparedCorpus:
         self.corpus = corpus.contiguous().float()
         n, d = self.corpus.shape
         self.bf16 = torch.empty(n, d, dtype=torch.bfloat16, device=corpus.device)
-        self.max_norm = torch.zeros(1, dtype=torch.float32, device=corpus.device)
-        check(lib.tt_topk_tc_prepare_corpus(_p(self.corpus), n, d, _p(self.bf16), _p(self.max_norm), _stream()),
+        self.bounds = torch.zeros(2, dtype=torch.float32, device=corpus.device)
+        check(lib.tt_topk_tc_prepare_corpus(_p(self.corpus), n, d, _p(self.bf16), _p(self.bounds), _stream()),
               "tt_topk_tc_prepare_corpus")
         _count()
 
@@ -291,8 +291,13 @@ topk_stats = {"queries": 0, "resampled": 0, "unverified": 0}
 TOPK_TC_QUERY_CHUNK = 16384
 
 
+TOPK_SAMPLING, TOPK_WIDE = 1, 2   # include/tt_b200.h
+
+
 def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepared: Optional["PreparedCorpus"],
-                   use_sampling: bool = True):
+                   flags: int = TOPK_SAMPLING):
+    """Tensor-core top-K with its repair ladder: sampled thresholds, K' = K + margin  ->  (flagged queries only)
+    thresholds from -inf, K' = 256  ->  (never observed) the exact fp32 path."""
     lib = _lib.load()
     Bq, D = query.shape
     Nc = corpus.shape[0]
@@ -309,13 +314,14 @@ def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepar
         ws = _ws(nbytes.value, dev)
         mo = None if mask_offsets is None else mask_offsets[q0:q1 + 1].contiguous()
         check(lib.tt_score_topk_tc(_p(query[q0:q1]), nq, _p(corpus), _p(None if prepared is None else prepared.bf16),
-                                   _p(None if prepared is None else prepared.max_norm), Nc, D, k, row_offset, _p(mo),
-                                   _p(mask_rows), _p(scores[q0:q1]), _p(idx[q0:q1]), _p(bad[q0:q1]), 1 if use_sampling else 0,
+                                   _p(None if prepared is None else prepared.bounds), Nc, D, k, row_offset, _p(mo),
+                                   _p(mask_rows), _p(scores[q0:q1]), _p(idx[q0:q1]), _p(bad[q0:q1]), int(flags),
                                    _p(ws), ws.numel(), _stream()), "tt_score_topk_tc")
         _count(3 + own)
-    # proof obligation failed for these queries (see include/tt_b200.h): exact fp32 path, one host read
+    # proof obligation failed for these queries (see include/tt_b200.h): one host read
     redo = torch.nonzero(bad, as_tuple=False).reshape(-1)
-    if use_sampling:
+    first_rung = (flags & TOPK_WIDE) == 0
+    if first_rung:
         topk_stats["queries"] = Bq
         topk_stats["resampled"] = int(redo.numel())
         topk_stats["unverified"] = 0
@@ -331,8 +337,8 @@ def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepar
             sub_mr = torch.cat(pieces) if pieces else mask_rows[:0]
             if sub_mr.numel() == 0:
                 sub_mr = torch.zeros(1, dtype=torch.int64, device=dev)
-        if use_sampling:   # sampled threshold too high for these: tensor-core path again, thresholds from -inf
-            s2, i2 = _score_topk_tc(query[redo].contiguous(), corpus, k, row_offset, sub_mo, sub_mr, prepared, False)
+        if first_rung:   # sampled threshold too high, or too many near-ties around the K-th score for K'
+            s2, i2 = _score_topk_tc(query[redo].contiguous(), corpus, k, row_offset, sub_mo, sub_mr, prepared, TOPK_WIDE)
         else:
             s2, i2 = score_topk(query[redo], corpus, k, row_offset, sub_mo, sub_mr, precision="fp32")
         scores[redo] = s2

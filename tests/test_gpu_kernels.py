@@ -533,6 +533,38 @@ def test_topk_tc_equals_fp32_path_at_scale():
     assert ops.topk_stats["unverified"] == 0, ops.topk_stats
 
 
+def test_topk_tc_proof_obligation_holds_against_worst_case_bf16_rounding():
+    """Adversarial corpus for the bf16 filter: the true top-K rows (family B) sit just below a bf16 rounding midpoint
+    in the very dimensions where the query does too, so both roundings go the same way and their approximate score
+    (32.0) is 0.78 % under the exact one (32.2495); 10 + 100 decoy rows with exactly representable values score
+    32.2109 / 32.0078 on the other half of the dimensions.  By approximate score the decoys win and B falls out of
+    every candidate list; a proof margin that assumed half-ulp 2^-9 per operand (0.18 here) would accept the decoys.
+    The data-dependent Cauchy-Schwarz margin (0.30) flags the query, the K'=256 repair pass finds B."""
+    D, N, K = 64, 3000, 10
+    h = D // 2
+    below_mid = float(np.float32(1.0 + 2.0 ** -8 - 2.0 ** -16))     # rounds DOWN to 1.0 in bf16
+    gen = torch.Generator().manual_seed(77)
+    e = torch.randn(N, D, generator=gen) * 0.01                      # filler: scores ~ 0
+    perm = torch.randperm(N, generator=gen)
+    b_rows, a1_rows, a2_rows = perm[:10], perm[10:20], perm[20:120]
+    e[b_rows] = 0.0
+    e[b_rows, h:] = below_mid
+    a1 = torch.zeros(D); a1[:h] = 1.0; a1[:27] = 1.0078125            # sum 32.2109, exact in bf16
+    a2 = torch.zeros(D); a2[:h] = 1.0; a2[0] = 1.0078125              # sum 32.0078
+    e[a1_rows] = a1
+    e[a2_rows] = a2
+    q_adv = torch.ones(D); q_adv[h:] = below_mid
+    q = torch.randn(6, D, generator=gen)
+    q[1] = q_adv
+    q[4] = q_adv
+    vals_ref, idx_ref = O.score_topk(q.numpy(), e.numpy(), K)
+    assert set(idx_ref[1].tolist()) == set(b_rows.tolist())           # the construction does what it says
+    s, idx = ops.score_topk(q.to(DEV), e.to(DEV), K, precision="bf16")
+    assert ops.topk_stats["resampled"] >= 2, ops.topk_stats           # the first rung must NOT have believed the decoys
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+    assert np.allclose(s.cpu().numpy(), vals_ref, atol=1e-12)
+
+
 def test_sharded_embedding_bag_world1_is_bitwise_the_unsharded_kernel():
     """ShardedEmbeddingBag at W=1 (all-to-alls degenerate to local copies): the pooled vectors must be bitwise what the
     fused gather+pool kernel gives on the whole table, the owner-side segment gradient what tt_emb_segment_grad gives
