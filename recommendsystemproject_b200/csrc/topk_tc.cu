@@ -125,7 +125,11 @@ struct TopkTcParams {
     KSched sch;
     int kp;
     int tile_stride;         // corpus tile n covers rows [n * tile_stride * 256, +256): > 1 for the sampling pass
-    const float *tau0;       // [n_query] initial thresholds from the sampling pass (NULL: start at -inf)
+    const float *tau0;       // [n_query] initial thresholds from the sampling pass (NULL: start at the floor)
+    float *raw_v;            // full pass: [grid][256][KT_RAW_CAP][8] raw score groups of the filter threads
+    int32_t *raw_c;          //            [grid][256][KT_RAW_CAP]    corpus row of each group's first score
+    float *blk_max;          // sampling pass only: [m_tiles][n_blk][128] block maxima (see topk_tc_kernel)
+    int blk_tiles, n_blk;    // sampled tiles per block; blocks per query = ceil(sampled tiles / blk_tiles) * 2
     const int64_t *mask_offsets, *mask_rows;
     float *cand_v;       // [n_query][lists][KT_CAP] approximate scores
     int32_t *cand_i;     //                          corpus rows
@@ -228,14 +232,32 @@ __device__ __forceinline__ int tk_prune_list(float *__restrict__ lv, int32_t *__
 }
 
 // ---------------------------------------------------------------- main kernel
+constexpr int KT_RAW_CAP = 64;                // raw 8-score groups a filter thread can hold before they are drained
 constexpr uint32_t KT_MASKED = 0xff7fffe0u;   // -3.4028e38 with the 5 index bits clear: stays finite once tagged
 constexpr float KT_TAU_FLOOR = -3.0e38f;      // thresholds start here ("nothing left out yet"), above KT_MASKED
-constexpr int KT_R = 24;   // sampling pass: scores kept per thread (registers, sorted descending)
 
-// SAMPLE = true: the sampling pass.  No candidate lists and no prunes: every thread keeps the KT_R best approximate
-// scores of its row segment in registers (bubble insertion, all indices static), its threshold is always the exact
-// KT_R-th best so far, and the survivors are written out once per run; tk_tau0_kernel then takes the KT_R-th best over a
-// query's runs as the starting threshold of the full pass.
+__device__ __forceinline__ void st_global_v4_pred(float *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
+                 :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(static_cast<uint32_t>(pred)) : "memory");
+}
+__device__ __forceinline__ void st_global_u32_pred(int32_t *p, uint32_t v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}"
+                 :: "l"(p), "r"(v), "r"(static_cast<uint32_t>(pred)) : "memory");
+}
+
+// float max through integer atomics (the slot starts at -inf): non-negative floats order like ints, negative ones
+// like unsigned ints reversed
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// SAMPLE = true: the sampling pass over every KT_STRIDE_B-th corpus tile.  No candidate lists, no append path at all:
+// a filter thread only keeps the maximum of its row over a BLOCK of blk_tiles consecutive sampled half tiles (the
+// 3-input-max chain the filter runs anyway) and folds it into blk_max[query tile][block][row].  tk_tau0_kernel turns
+// the ~600 block maxima of a query into its starting threshold: with p = P(score > t), a block of b scores has
+// P(max > t) = 1 - exp(-b p), so the r-th largest block maximum estimates the score above which C corpus items
+// lie for r = n_blk * (1 - exp(-b C / N)).
 template <int D, bool SAMPLE>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
@@ -343,25 +365,82 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         KCursor c;
         c.init(sch, cta);
         float tau = INFINITY;
-        int cnt = 0;
+        int cnt = 0;        // entries of this thread's candidate list
+        int rcnt = 0;       // 8-score groups waiting in this thread's raw buffer
         bool ovf = false, row_ok = false;
-        float top[SAMPLE ? KT_R : 1];
+        float run_max = -INFINITY;   // SAMPLE: maximum of the current block
         int64_t q = 0, list = 0, m_lo = 0, m_hi = 0;
+        // raw buffer of this thread: KT_RAW_CAP groups of 8 scores + the corpus row of each group's first score
+        const int64_t raw_slot = static_cast<int64_t>(blockIdx.x) * (KT_THREADS - 64) + (threadIdx.x - 64);
+        float *raw_v = SAMPLE ? nullptr : prm.raw_v + raw_slot * (KT_RAW_CAP * 8);
+        int32_t *raw_c = SAMPLE ? nullptr : prm.raw_c + raw_slot * KT_RAW_CAP;
+
+        // Every lane moves its own raw groups into its own candidate list, keeping the scores above its threshold that
+        // its history mask does not exclude (all 32 lanes at once: the trip counts are similar, ~Poisson around the
+        // same mean).  A lane whose list runs full stops; those lists are pruned by the whole warp (threshold rises)
+        // and the lanes carry on against the new threshold.
+        auto drain = [&]() {
+            float *lv = prm.cand_v + list * KT_CAP;
+            int32_t *li = prm.cand_i + list * KT_CAP;
+            int g = 0;
+            const int n_g = row_ok ? rcnt : 0;
+            while (true) {
+                float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+                int32_t nc = 0;
+                if (g < n_g) {
+                    na = *reinterpret_cast<const float4 *>(raw_v + g * 8);
+                    nb = *reinterpret_cast<const float4 *>(raw_v + g * 8 + 4);
+                    nc = raw_c[g];
+                }
+                while (g < n_g && cnt <= KT_CAP - 8) {
+                    const float xs[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+                    const int32_t col = nc;
+                    ++g;
+                    if (g < n_g) {   // next group's loads fly while this one is appended
+                        na = *reinterpret_cast<const float4 *>(raw_v + g * 8);
+                        nb = *reinterpret_cast<const float4 *>(raw_v + g * 8 + 4);
+                        nc = raw_c[g];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        bool keep = xs[j] > tau;
+                        if (keep && m_hi > m_lo) keep = !tk_masked(prm.mask_rows, m_lo, m_hi, static_cast<int64_t>(col + j));
+                        if (keep) { lv[cnt] = xs[j]; li[cnt] = col + j; ++cnt; }
+                    }
+                }
+                unsigned full = __ballot_sync(0xffffffffu, g < n_g);
+                if (!full) break;
+                while (full) {
+                    const int src = __ffs(full) - 1;
+                    full &= full - 1;
+                    const int64_t l2 = __shfl_sync(0xffffffffu, list, src);
+                    const int n2 = __shfl_sync(0xffffffffu, cnt, src);
+                    float t_new;
+                    __syncwarp();
+                    const int kept = tk_prune_list(prm.cand_v + l2 * KT_CAP, prm.cand_i + l2 * KT_CAP, n2, prm.kp, lane, &t_new);
+                    if (lane == src) {
+                        cnt = kept;
+                        if (t_new > tau) { tau = t_new; tau_sh[grp * KT_BM + r_in_tile] = tau; }
+                        if (kept > KT_CAP - 8) { ovf = true; g = n_g; }   // only if > 500 scores tie
+                    }
+                }
+            }
+            rcnt = 0;
+        };
+
         for (; !c.done; c.next(sch, cta)) {
             const int i = c.i, b = i & 1;
             if (c.first) {
                 q = static_cast<int64_t>(c.m) * KT_BM + r_in_tile;
                 row_ok = q < prm.n_query;
                 const int part = static_cast<int>(blockIdx.x) - ks_first_cta(sch, c.sb, c.m);
-                list = ((q * sch.n_sb + c.sb) * sch.max_seg + part) * 2 + grp;
+                list = (q * sch.lists) + (c.sb * sch.max_seg + part) * 2 + grp;
                 // never below KT_TAU_FLOOR: corpus rows past the end carry KT_MASKED, a finite value under the floor
                 tau = row_ok ? fmaxf(prm.tau0 != nullptr ? prm.tau0[q] : KT_TAU_FLOOR, KT_TAU_FLOOR) : INFINITY;
                 cnt = 0;
+                rcnt = 0;
                 ovf = false;
-                if (SAMPLE) {
-#pragma unroll
-                    for (int t = 0; t < KT_R; ++t) top[t] = -INFINITY;
-                }
+                run_max = -INFINITY;
                 m_lo = m_hi = 0;
                 if (row_ok && prm.mask_offsets != nullptr) { m_lo = prm.mask_offsets[q]; m_hi = prm.mask_offsets[q + 1]; }
                 tau_sh[grp * KT_BM + r_in_tile] = -INFINITY;
@@ -370,12 +449,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 if (lane == 0) tau_tag[grp * 4 + quarter] = c.sb * sch.m_tiles + c.m;
             }
             // the other group's K'-th best so far bounds the row's K'-th best from below just as well as ours does
-            if (tau_tag[(grp ^ 1) * 4 + quarter] == c.sb * sch.m_tiles + c.m) {
+            if (!SAMPLE && tau_tag[(grp ^ 1) * 4 + quarter] == c.sb * sch.m_tiles + c.m) {
                 const float other = *reinterpret_cast<volatile float *>(tau_sh + (grp ^ 1) * KT_BM + r_in_tile);
                 if (row_ok) tau = fmaxf(tau, other);
             }
-            float *lv = prm.cand_v + list * KT_CAP;
-            int32_t *li = prm.cand_i + list * KT_CAP;
             mbar_wait(&sfull[b], (i >> 1) & 1);
             tc_fence_after();
             uint32_t r[4][32];
@@ -392,89 +469,63 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     for (int j = 0; j < 32; ++j)
                         if (col0 + qq * 32 + j >= prm.n_corpus) r[qq][j] = KT_MASKED;
             }
+            float tile_max = -INFINITY;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
-                // fast path: four 8-score maxima (3-input max chains), one compare for the 32-column chunk
-                float sub[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
+                    // maximum of 8 scores (3-input max chain); a group that beats the threshold is copied RAW into the
+                    // thread's buffer by predicated 16-byte stores: no branch, no divergence, no dependent chain.
+                    // (Finding and appending the individual scores right here cost the warp ~350 cycles of latency per
+                    // hit -- 2.3 ms of a 6.6 ms pass -- whichever way it was coded: tag + max tree + loop, or 8
+                    // predicated appends.)
                     const uint32_t *x = &r[qq][g * 8];
                     float m = fmaxf(fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1])), __uint_as_float(x[2]));
                     m = fmaxf(fmaxf(m, __uint_as_float(x[3])), __uint_as_float(x[4]));
                     m = fmaxf(fmaxf(m, __uint_as_float(x[5])), __uint_as_float(x[6]));
-                    sub[g] = fmaxf(m, __uint_as_float(x[7]));
-                }
-                if (fmaxf(fmaxf(sub[0], sub[1]), fmaxf(sub[2], sub[3])) > tau) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (sub[g] > tau) {
-                            // Some score of these 8 columns beats the threshold.  The column index goes into the 5 low
-                            // mantissa bits of the 8 scores (a 2^-18 relative perturbation, part of the proof margin):
-                            // one max tree then yields the best score AND where it is, so the append path needs no
-                            // dynamically indexed registers (no local memory: L1 is ~4 KB here) and stays compact (an
-                            // earlier version with 128 inlined append sites was 140 KB of SASS and stalled on
-                            // instruction fetch).
-                            float best = -INFINITY;
-#pragma unroll
-                            for (int j = g * 8; j < g * 8 + 8; ++j) {
-                                r[qq][j] = (r[qq][j] & 0xffffffe0u) | static_cast<uint32_t>(j);
-                                best = fmaxf(best, __uint_as_float(r[qq][j]));
-                            }
-#pragma unroll 1
-                            while (best > tau) {
-                                const int64_t col = col0 + qq * 32 + static_cast<int>(__float_as_uint(best) & 31u);
-                                if (!(m_hi > m_lo && tk_masked(prm.mask_rows, m_lo, m_hi, col))) {
-                                    if (SAMPLE) {
-                                        float v = best;
-#pragma unroll
-                                        for (int t = 0; t < KT_R; ++t) {
-                                            const float hi_v = fmaxf(top[t], v);
-                                            v = fminf(top[t], v);
-                                            top[t] = hi_v;
-                                        }
-                                        tau = fmaxf(tau, top[KT_R - 1]);
-                                    } else if (cnt < KT_CAP) { lv[cnt] = best; li[cnt] = static_cast<int32_t>(col); ++cnt; }
-                                    else ovf = true;
-                                }
-                                // next best of the 8: strictly below `best` (packed scores are distinct)
-                                float nb = -INFINITY;
-#pragma unroll
-                                for (int j = g * 8; j < g * 8 + 8; ++j) {
-                                    const float x0 = __uint_as_float(r[qq][j]);
-                                    nb = fmaxf(nb, x0 < best ? x0 : -INFINITY);
-                                }
-                                best = nb;
-                            }
-                        }
+                    m = fmaxf(m, __uint_as_float(x[7]));
+                    if (SAMPLE) {
+                        tile_max = fmaxf(tile_max, m);
+                    } else {
+                        const bool hit = m > tau;
+                        st_global_v4_pred(raw_v + rcnt * 8, x[0], x[1], x[2], x[3], hit);
+                        st_global_v4_pred(raw_v + rcnt * 8 + 4, x[4], x[5], x[6], x[7], hit);
+                        st_global_u32_pred(raw_c + rcnt, static_cast<uint32_t>(col0 + qq * 32 + g * 8), hit);
+                        rcnt += hit ? 1 : 0;
                     }
                 }
             }
             const bool seg_end = c.last();
-            // a list must have room for a whole 128-column step; at the end of the segment it is cut to ~K'
-            const bool need = !SAMPLE && row_ok && (seg_end ? cnt > prm.kp + KT_SLACK : cnt > KT_CAP - KT_HALF);
-            unsigned todo = __ballot_sync(0xffffffffu, need);
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int64_t l2 = __shfl_sync(0xffffffffu, list, src);
-                const int n2 = __shfl_sync(0xffffffffu, cnt, src);
-                float t_new;
-                __syncwarp();
-                const int kept = tk_prune_list(prm.cand_v + l2 * KT_CAP, prm.cand_i + l2 * KT_CAP, n2, prm.kp, lane, &t_new);
-                if (lane == src) { cnt = kept; tau = fmaxf(tau, t_new); tau_sh[grp * KT_BM + r_in_tile] = tau; }
-            }
-            if (seg_end && row_ok) {
-                if (SAMPLE) {
-                    int n = 0;
-#pragma unroll
-                    for (int t = 0; t < KT_R; ++t) {
-                        lv[t] = top[t];
-                        n += top[t] > -INFINITY ? 1 : 0;
-                    }
-                    cnt = n;
+            if (SAMPLE) {
+                run_max = fmaxf(run_max, tile_max);
+                const int st = c.tile(sch);
+                if ((st + 1) % prm.blk_tiles == 0 || seg_end) {
+                    if (row_ok)
+                        atomic_max_float(prm.blk_max + (static_cast<int64_t>(c.m) * prm.n_blk + (st / prm.blk_tiles) * 2 + grp) * KT_BM + r_in_tile,
+                                         run_max);
+                    run_max = -INFINITY;
                 }
-                prm.cand_n[list] = ovf ? -1 : cnt;
-                prm.cand_tau[list] = tau;
+            } else {
+                // the raw buffer must have room for the 16 groups of one more tile
+                if (__any_sync(0xffffffffu, row_ok && (seg_end ? rcnt > 0 : rcnt > KT_RAW_CAP - 16))) drain();
+                if (seg_end) {
+                    // the list is cut to ~K' before it is handed to stage 2
+                    unsigned cut = __ballot_sync(0xffffffffu, row_ok && cnt > prm.kp + KT_SLACK);
+                    while (cut) {
+                        const int src = __ffs(cut) - 1;
+                        cut &= cut - 1;
+                        const int64_t l2 = __shfl_sync(0xffffffffu, list, src);
+                        const int n2 = __shfl_sync(0xffffffffu, cnt, src);
+                        float t_new;
+                        __syncwarp();
+                        const int kept = tk_prune_list(prm.cand_v + l2 * KT_CAP, prm.cand_i + l2 * KT_CAP, n2, prm.kp, lane, &t_new);
+                        if (lane == src) { cnt = kept; tau = fmaxf(tau, t_new); }
+                    }
+                    if (row_ok) {
+                        prm.cand_n[list] = ovf ? -1 : cnt;
+                        prm.cand_tau[list] = tau;
+                    }
+                }
             }
         }
     }
@@ -588,48 +639,60 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
     }
 }
 
-// tau0[q] = the rank-th best approximate score among the query's sampling-pass candidates (one warp per query,
-// bisection on the value like tk_prune_list).  About rank * stride items of the whole corpus score above it.
+// tau0[q] = the rank-th largest of the query's block maxima (one warp per query, values in registers, bisection on
+// the value; the result may sit a little below the exact order statistic, which only admits more candidates).
+// Rows the query masks out can be among those maxima: the rank is pushed down by the number of its masked rows that
+// lie in sampled tiles.
+constexpr int KT_MAX_BLK = 640;
 __global__ void __launch_bounds__(256)
-tk_tau0_kernel(const float *__restrict__ cand_v, const int32_t *__restrict__ cand_n, int64_t n_query, int n_lists,
-               int rank, float *__restrict__ tau0) {
+tk_tau0_kernel(const float *__restrict__ blk_max, int64_t n_query, int n_blk, int rank, int tile_stride,
+               const int64_t *__restrict__ mask_offsets, const int64_t *__restrict__ mask_rows,
+               float *__restrict__ tau0) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     for (int64_t q = warp; q < n_query; q += n_warps) {
+        const float *src = blk_max + (q / KT_BM) * static_cast<int64_t>(n_blk) * KT_BM + (q % KT_BM);
+        float v[KT_MAX_BLK / 32];
         float lo = INFINITY, hi = -INFINITY;
-        int total = 0;
-        for (int l = 0; l < n_lists; ++l) {
-            const int64_t list = q * n_lists + l;
-            const int n = min(max(cand_n[list], 0), KT_CAP);
-            total += n;
-            for (int t = lane; t < n; t += 32) {
-                const float v = cand_v[list * KT_CAP + t];
-                lo = fminf(lo, v);
-                hi = fmaxf(hi, v);
-            }
+#pragma unroll
+        for (int t = 0; t < KT_MAX_BLK / 32; ++t) {
+            const int bI = t * 32 + lane;
+            v[t] = bI < n_blk ? src[static_cast<int64_t>(bI) * KT_BM] : -INFINITY;
+            if (bI < n_blk) lo = fminf(lo, v[t]);
+            hi = fmaxf(hi, v[t]);
         }
         lo = -warp_max(-lo);
         hi = warp_max(hi);
+        int want = rank;
+        if (mask_offsets != nullptr) {
+            int hidden = 0;
+            for (int64_t t = mask_offsets[q] + lane; t < mask_offsets[q + 1]; t += 32)
+                hidden += ((mask_rows[t] / KT_BN) % tile_stride == 0) ? 1 : 0;
+            want += __reduce_add_sync(0xffffffffu, hidden);
+        }
         float t0 = -INFINITY;
-        if (total >= rank) {
-            // invariant: count(v >= lo) >= rank
+        if (want <= n_blk && hi > -INFINITY) {
+            // invariant: count(v >= lo) >= want
             for (int it = 0; it < 30; ++it) {
                 const float mid = lo + 0.5f * (hi - lo);
                 if (!(mid > lo && mid < hi)) break;
                 int c = 0;
-                for (int l = 0; l < n_lists; ++l) {
-                    const int64_t list = q * n_lists + l;
-                    const int n = min(max(cand_n[list], 0), KT_CAP);
-                    for (int t = lane; t < n; t += 32) c += (cand_v[list * KT_CAP + t] >= mid) ? 1 : 0;
-                }
+#pragma unroll
+                for (int t = 0; t < KT_MAX_BLK / 32; ++t) c += (v[t] >= mid) ? 1 : 0;
                 c = __reduce_add_sync(0xffffffffu, c);
-                if (c >= rank) { lo = mid; if (c <= rank + 1) break; } else hi = mid;
+                if (c >= want) { lo = mid; if (c <= want + 1) break; } else hi = mid;
             }
             t0 = lo;
         }
         if (lane == 0) tau0[q] = t0;
     }
+}
+
+__global__ void tk_fill(float *__restrict__ p, int64_t n, float v) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        p[i] = v;
 }
 
 // every pass starts from empty lists: n = 0, tau = -inf (slots no CTA writes stay that way)
@@ -642,10 +705,11 @@ __global__ void tk_init_lists(int32_t *__restrict__ cand_n, float *__restrict__ 
 }
 
 // The sampling pass gives every query a starting threshold (the full pass then stays on the filter's fast path): the
-// main kernel in SAMPLE mode over every 16th corpus tile keeps the KT_R = 24 best scores per row segment in registers;
-// tau_0 = the 24th best sampled score of the query, above which ~16 * 24 = 384 corpus items score (2.5 K' for K = 100,
-// +-20 % sampling noise).  A threshold that turns out too high (~1e-4 of the queries) makes the proof obligation of
-// stage 2 fail and the query is re-run without sampling.
+// main kernel in SAMPLE mode over every 16th corpus tile leaves ~600 block maxima per query, tk_tau0_kernel picks the
+// rank-th largest.  The number of corpus items above that threshold is ~ stride * Gamma(rank): the rank is the smallest
+// one for which fewer than 1.25 K' items (what the proof obligation needs with the usual crowd of near-ties around the
+// K-th score) has probability < 1e-4 -- rank 26, ~420 items, for K = 100.  A threshold that still turns out too high
+// makes the proof obligation of stage 2 fail and the query goes to the repair pass.
 constexpr int KT_STRIDE_B = 16;
 constexpr int64_t KT_SAMPLE_MIN_ROWS = 1 << 17;
 
@@ -653,8 +717,20 @@ struct KtPlan {
     KSched sched, sample_b;
     int kp;
     bool use_sample;
-    int lists;      // max over the passes
+    int rank, blk_tiles, n_blk;   // sampling pass
+    int lists;
 };
+
+// smallest r with P(Gamma(r) < x) = P(Poisson(x) >= r) < 1e-4
+static int kt_rank_for(double x) {
+    double term = exp(-x), below = 0.0;   // below = P(Poisson(x) < r)
+    for (int r = 0; r < 4096; ++r) {
+        if (1.0 - below < 1e-4) return r < 4 ? 4 : r;
+        below += term;
+        term *= x / (r + 1);
+    }
+    return 4096;
+}
 
 static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k, bool sampling = true, bool wide = false) {
     KtPlan p;
@@ -665,18 +741,26 @@ static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k, bool sampling = 
     if (margin < 32) margin = 32;
     p.kp = k + margin;
     if (wide || p.kp > KT_MAX_KP) p.kp = KT_MAX_KP;   // wide: the repair pass for queries whose proof failed
-    // the sampled threshold must admit comfortably more than K' items: 16 * 24 = 384 >= 1.5 K'
-    p.use_sample = sampling && n_corpus >= KT_SAMPLE_MIN_ROWS && 2 * KT_STRIDE_B * KT_R >= 3 * p.kp;
-    p.sample_b = make_ksched(m_tiles, (n_tiles + KT_STRIDE_B - 1) / KT_STRIDE_B, false);
+    const int s_tiles = (n_tiles + KT_STRIDE_B - 1) / KT_STRIDE_B;
+    p.sample_b = make_ksched(m_tiles, s_tiles, false);
+    p.blk_tiles = (s_tiles + KT_MAX_BLK / 2 - 1) / (KT_MAX_BLK / 2);
+    p.n_blk = (s_tiles + p.blk_tiles - 1) / p.blk_tiles * 2;
+    // items wanted above the threshold: C = stride * rank; as a rank among block maxima: n_blk * (1 - exp(-b C / N))
+    const double want = static_cast<double>(KT_STRIDE_B) * kt_rank_for(1.25 * p.kp / KT_STRIDE_B);
+    const double b = static_cast<double>(p.blk_tiles) * KT_HALF;
+    p.rank = static_cast<int>(ceil(p.n_blk * (1.0 - exp(-b * want / static_cast<double>(n_corpus)))));
+    if (p.rank < 4) p.rank = 4;
+    // a meaningful order statistic needs the rank well inside the blocks (small corpora: scan without thresholds)
+    p.use_sample = sampling && n_corpus >= KT_SAMPLE_MIN_ROWS && 4 * p.rank <= p.n_blk;
     p.lists = p.sched.lists;
-    if (p.use_sample && p.sample_b.lists > p.lists) p.lists = p.sample_b.lists;
     return p;
 }
 
 struct KtWs {
     __nv_bfloat16 *qb, *eb;
     unsigned int *emax;
-    float *cand_v, *cand_tau, *tau0;
+    float *cand_v, *cand_tau, *tau0, *blk_max, *raw_v;
+    int32_t *raw_c;
     int32_t *cand_i, *cand_n;
     bool ok;
     size_t used;
@@ -695,6 +779,9 @@ static KtWs kt_carve(void *workspace, size_t bytes, int64_t n_query, int64_t n_c
     w.cand_n = ws.take<int32_t>(lists);
     w.cand_tau = ws.take<float>(lists);
     w.tau0 = ws.take<float>(n_query);
+    w.raw_v = ws.take<float>(static_cast<size_t>(pl.sched.grid) * (KT_THREADS - 64) * KT_RAW_CAP * 8);
+    w.raw_c = ws.take<int32_t>(static_cast<size_t>(pl.sched.grid) * (KT_THREADS - 64) * KT_RAW_CAP);
+    w.blk_max = ws.take<float>(static_cast<size_t>((n_query + KT_BM - 1) / KT_BM) * pl.n_blk * KT_BM);
     w.ok = ws.ok();
     w.used = ws.off;
     return w;
@@ -789,22 +876,32 @@ extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float
     prm.n_query = n_query; prm.n_corpus = n_corpus;
     prm.mask_offsets = mask_offsets; prm.mask_rows = mask_rows;
     prm.cand_v = w.cand_v; prm.cand_i = w.cand_i; prm.cand_n = w.cand_n; prm.cand_tau = w.cand_tau;
-    auto run_pass = [&](const KSched &sc, int kp, int stride, const float *tau0, bool sample) -> int {
-        const int64_t n_lists = static_cast<int64_t>(n_query) * sc.lists;
-        tk_init_lists<<<kt_grid(n_lists, 256), 256, 0, st>>>(w.cand_n, w.cand_tau, n_lists);
-        prm.sch = sc; prm.kp = kp; prm.tile_stride = stride; prm.tau0 = tau0;
-        if (sample)
-            return (dim == 128) ? launch_topk_tc<128, true>(mq, me, prm, sc.grid, st) : launch_topk_tc<64, true>(mq, me, prm, sc.grid, st);
-        return (dim == 128) ? launch_topk_tc<128, false>(mq, me, prm, sc.grid, st) : launch_topk_tc<64, false>(mq, me, prm, sc.grid, st);
-    };
     const float *tau_start = nullptr;
     if (pl.use_sample) {
-        if ((rc = run_pass(pl.sample_b, KT_R, KT_STRIDE_B, nullptr, true))) return rc;
-        tk_tau0_kernel<<<kt_grid(n_query * 32, 256), 256, 0, st>>>(w.cand_v, w.cand_n, n_query, pl.sample_b.lists, KT_R, w.tau0);
+        const int64_t n_max = (n_query + KT_BM - 1) / KT_BM * pl.n_blk * KT_BM;
+        tk_fill<<<kt_grid(n_max, 256), 256, 0, st>>>(w.blk_max, n_max, -INFINITY);
+        TT_LAUNCH_CHECK("tk_fill");
+        prm.sch = pl.sample_b; prm.kp = pl.kp; prm.tile_stride = KT_STRIDE_B; prm.tau0 = nullptr;
+        prm.blk_max = w.blk_max; prm.blk_tiles = pl.blk_tiles; prm.n_blk = pl.n_blk;
+        rc = (dim == 128) ? launch_topk_tc<128, true>(mq, me, prm, pl.sample_b.grid, st)
+                          : launch_topk_tc<64, true>(mq, me, prm, pl.sample_b.grid, st);
+        if (rc) return rc;
+        tk_tau0_kernel<<<kt_grid(n_query * 32, 256), 256, 0, st>>>(w.blk_max, n_query, pl.n_blk, pl.rank, KT_STRIDE_B,
+                                                                    mask_offsets, mask_rows, w.tau0);
         TT_LAUNCH_CHECK("tk_tau0_kernel");
         tau_start = w.tau0;
     }
-    if ((rc = run_pass(pl.sched, pl.kp, 1, tau_start, false))) return rc;
+    {
+        const int64_t n_lists = static_cast<int64_t>(n_query) * pl.sched.lists;
+        tk_init_lists<<<kt_grid(n_lists, 256), 256, 0, st>>>(w.cand_n, w.cand_tau, n_lists);
+        TT_LAUNCH_CHECK("tk_init_lists");
+        prm.sch = pl.sched; prm.kp = pl.kp; prm.tile_stride = 1; prm.tau0 = tau_start;
+        prm.blk_max = nullptr; prm.blk_tiles = 1; prm.n_blk = 0;
+        prm.raw_v = w.raw_v; prm.raw_c = w.raw_c;
+        rc = (dim == 128) ? launch_topk_tc<128, false>(mq, me, prm, pl.sched.grid, st)
+                          : launch_topk_tc<64, false>(mq, me, prm, pl.sched.grid, st);
+        if (rc) return rc;
+    }
     topk_tc_stage2<<<static_cast<unsigned>(n_query), 128, 0, st>>>(query, corpus, dim, k, pl.kp, pl.sched.lists, row_offset,
                                                                    w.cand_v, w.cand_i, w.cand_n, w.cand_tau, emax, out_scores,
                                                                    out_idx, unverified);
