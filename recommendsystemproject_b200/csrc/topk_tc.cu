@@ -232,6 +232,7 @@ __device__ __forceinline__ int tk_prune_list(float *__restrict__ lv, int32_t *__
 }
 
 // ---------------------------------------------------------------- main kernel
+constexpr int KT_S2_LISTS = 512;              // stage 2 gathers up to this many lists per query in one step
 constexpr int KT_RAW_CAP = 64;                // raw 8-score groups a filter thread can hold before they are drained
 constexpr uint32_t KT_MASKED = 0xff7fffe0u;   // -3.4028e38 with the 5 index bits clear: stays finite once tagged
 constexpr float KT_TAU_FLOOR = -3.0e38f;      // thresholds start here ("nothing left out yet"), above KT_MASKED
@@ -570,29 +571,111 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
         }
         __syncthreads();
     };
-    for (int l = 0; l < n_lists; ++l) {
-        const int64_t list = q * n_lists + l;      // unused slots: n = 0, tau = -inf (tk_init_lists)
-        const int n = cand_n[list];
-        if (tid == 0) {
-            s_tau = fmaxf(s_tau, cand_tau[list]);
-            if (n < 0) s_bad = 1;
+    // gather the query's lists.  Fast path (the usual case: a few hundred candidates in a few dozen lists): counts and
+    // thresholds of all lists at once, prefix sums in shared memory, then one flat copy with every load independent.
+    __shared__ int s_off[KT_S2_LISTS + 1];
+    __shared__ int s_wsum[4];
+    __shared__ float s_wtau[4];
+    bool gathered = false;
+    if (n_lists <= KT_S2_LISTS) {
+        constexpr int PER = KT_S2_LISTS / 128;
+        int take[PER];
+        int mine = 0, bad = 0;
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int l = tid * PER + u;
+            take[u] = 0;
+            if (l < n_lists) {
+                const int n = cand_n[q * n_lists + l];      // unused slots: n = 0, tau = -inf (tk_init_lists)
+                tmax = fmaxf(tmax, cand_tau[q * n_lists + l]);
+                bad |= n < 0 ? 1 : 0;
+                take[u] = n < 0 ? KT_CAP : n;
+            }
+            mine += take[u];
         }
-        const int take = n < 0 ? KT_CAP : n;
-        if (tot + take > TK_STAGE2_MAX) reduce_to_kp();
-        for (int t = tid; t < take; t += blockDim.x) { av[tot + t] = cand_v[list * KT_CAP + t]; ai[tot + t] = cand_i[list * KT_CAP + t]; }
-        tot += take;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        tmax = warp_max(tmax);
+        bad = __any_sync(0xffffffffu, bad != 0) ? 1 : 0;
+        if (lane == 31) s_wsum[warp] = incl;
+        if (lane == 0) { s_wtau[warp] = tmax; if (bad) s_bad = 1; }
         __syncthreads();
+        int base = incl - mine;
+        for (int w = 0; w < warp; ++w) base += s_wsum[w];
+        const int total = s_wsum[0] + s_wsum[1] + s_wsum[2] + s_wsum[3];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int l = tid * PER + u;
+            if (l < n_lists) s_off[l] = base;
+            base += take[u];
+        }
+        if (tid == 0) {
+            s_off[n_lists] = total;
+            s_tau = fmaxf(fmaxf(s_wtau[0], s_wtau[1]), fmaxf(s_wtau[2], s_wtau[3]));
+        }
+        __syncthreads();
+        if (total <= TK_STAGE2_MAX) {
+            for (int pI = tid; pI < total; pI += blockDim.x) {
+                int lo = 0, hi = n_lists;            // last list with s_off[l] <= pI
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[mid] <= pI) lo = mid; else hi = mid;
+                }
+                const int64_t src = (q * n_lists + lo) * KT_CAP + (pI - s_off[lo]);
+                av[pI] = cand_v[src];
+                ai[pI] = cand_i[src];
+            }
+            tot = total;
+            gathered = true;
+            __syncthreads();
+        }
+    }
+    if (!gathered) {
+        for (int l = 0; l < n_lists; ++l) {
+            const int64_t list = q * n_lists + l;
+            const int n = cand_n[list];
+            if (tid == 0) {
+                s_tau = fmaxf(s_tau, cand_tau[list]);
+                if (n < 0) s_bad = 1;
+            }
+            const int take = n < 0 ? KT_CAP : n;
+            if (tot + take > TK_STAGE2_MAX) reduce_to_kp();
+            for (int t = tid; t < take; t += blockDim.x) { av[tot + t] = cand_v[list * KT_CAP + t]; ai[tot + t] = cand_i[list * KT_CAP + t]; }
+            tot += take;
+            __syncthreads();
+        }
     }
     reduce_to_kp();
-    // exact fp64 re-score of the survivors (fixed summation order: lane-strided, then xor tree)
+    // exact fp64 re-score of the survivors (fixed summation order: lane-strided, then xor tree); four candidates per
+    // warp step so that their row loads are in flight together
     const float *qv = query + q * dim;
-    for (int c = warp; c < tot; c += 4) {
-        const float *e = corpus + static_cast<int64_t>(ai[c]) * dim;
-        double d = 0.0;
-        for (int t = lane; t < dim; t += 32) d = fma(static_cast<double>(qv[t]), static_cast<double>(e[t]), d);
+    for (int c0 = warp * 4; c0 < tot; c0 += 16) {
+        double d[4] = {0.0, 0.0, 0.0, 0.0};
+        const float *e[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (lane == 0) { ev[c] = d; ei[c] = ai[c]; }
+        for (int u = 0; u < 4; ++u) e[u] = corpus + static_cast<int64_t>(ai[min(c0 + u, tot - 1)]) * dim;
+        for (int t = lane; t < dim; t += 32) {
+            const double qt = static_cast<double>(qv[t]);
+            float x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = __ldg(e[u] + t);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) d[u] = fma(qt, static_cast<double>(x[u]), d[u]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c0 + u < tot) { ev[c0 + u] = d[u]; ei[c0 + u] = ai[c0 + u]; }
+        }
     }
     if (warp == 0) {   // |q| and |q - bf16(q)| for the proof obligation
         double n2 = 0.0, d2 = 0.0;
