@@ -46,10 +46,12 @@ template <int D> struct KtStages { static constexpr int value = D == 128 ? 3 : 6
 // time and share its corpus tiles through L2 -- without this every query tile re-streams the whole corpus from HBM
 // (ncu r1: 16.3 GB of DRAM reads per launch for a 320 MB corpus shard).
 struct KSched {
-    int m_tiles, n_tiles;     // query tiles (128 rows), corpus tiles (256 rows) visited by this pass
+    int cl;                   // CTAs per cluster: the CTAs of a cluster take `cl` consecutive query tiles through the SAME
+                              // corpus tiles, each loading 1/cl of every corpus tile and multicasting it to the others
+    int m_tiles, n_tiles;     // query tile GROUPS (cl x 128 rows), corpus tiles (256 rows) visited by this pass
     int sbt, n_sb;            // corpus tiles per super-block, number of super-blocks
-    int64_t per_cta;          // slice of a super-block's m_tiles * sbt tiles owned by one CTA
-    int grid, max_seg;        // max_seg: CTAs that can share one (super-block, query tile) run
+    int64_t per_cta;          // slice of a super-block's m_tiles * sbt tiles owned by one cluster
+    int grid, max_seg;        // clusters launched; max_seg: clusters that can share one (super-block, query group) run
     int lists;                // candidate lists per query = n_sb * max_seg * 2
 };
 __host__ __device__ __forceinline__ int ks_cnt(const KSched &s, int sb) { return min(s.sbt, s.n_tiles - sb * s.sbt); }
@@ -59,19 +61,22 @@ __host__ __device__ __forceinline__ int ks_first_cta(const KSched &s, int sb, in
 
 constexpr int KT_SB_TILES = 768;   // 768 tiles x 256 rows x 256 B = 50 MB of a D=128 bf16 corpus per super-block
 
-static KSched make_ksched(int m_tiles, int n_tiles, bool super_blocks) {
+static KSched make_ksched(int q_tiles, int n_tiles, bool super_blocks, int cl) {
     KSched s;
+    const int m_tiles = (q_tiles + cl - 1) / cl;
+    const int n_sm = sm_count() / cl;
+    s.cl = cl;
     s.m_tiles = m_tiles; s.n_tiles = n_tiles;
     s.sbt = (super_blocks && m_tiles >= 8 && n_tiles >= 2 * KT_SB_TILES) ? KT_SB_TILES : n_tiles;
     s.n_sb = (n_tiles + s.sbt - 1) / s.sbt;
     const int64_t sb_total = static_cast<int64_t>(m_tiles) * s.sbt;
     int64_t g = (sb_total + 1) / 2;
-    if (g > sm_count()) g = sm_count();
+    if (g > n_sm) g = n_sm;
     if (g < 1) g = 1;
     s.per_cta = (sb_total + g - 1) / g;
     // at most ~8 CTAs per run (each leaves 2 lists for stage 2 to merge) -- unless there are so few query tiles that
     // this would idle SMs (the repair pass for a handful of queries): then one run spreads over sm_count / m_tiles CTAs
-    int seg_cap = (sm_count() + m_tiles - 1) / m_tiles;
+    int seg_cap = (n_sm + m_tiles - 1) / m_tiles;
     if (seg_cap < 8) seg_cap = 8;
     if (s.per_cta * seg_cap < s.sbt) s.per_cta = (s.sbt + seg_cap - 1) / seg_cap;
     s.grid = static_cast<int>((sb_total + s.per_cta - 1) / s.per_cta);
@@ -259,7 +264,7 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
 // the ~600 block maxima of a query into its starting threshold: with p = P(score > t), a block of b scores has
 // P(max > t) = 1 - exp(-b p), so the r-th largest block maximum estimates the score above which C corpus items
 // lie for r = n_blk * (1 - exp(-b C / N)).
-template <int D, bool SAMPLE>
+template <int D, bool SAMPLE, int CL>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
                const TopkTcParams prm) {
@@ -288,12 +293,16 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const KSched &sch = prm.sch;
-    const int cta = static_cast<int>(blockIdx.x);
+    // cluster c = CTAs [c * CL, (c + 1) * CL): same tile sequence, query tile = group * CL + rank
+    const int cta = static_cast<int>(blockIdx.x) / CL;
+    const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_q);
         prefetch_tensormap(&map_e);
-        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // a stage is free again once EVERY CTA of the cluster has consumed it (the others multicast into it)
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(&sfull[a], 1); mbar_init(&sfree[a], 256); }
         mbar_init(xfull, 1);
         mbar_init(xfree, 1);
@@ -303,6 +312,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // the peers' barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -315,7 +325,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 if (c.r >= 1) mbar_wait(xfree, (c.r - 1) & 1);
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(xfull, X_BYTES);
-                    for (int kb = 0; kb < KB; ++kb) tma_load_2d(x_tile + kb * XK_BYTES, &map_q, xfull, kb * 64, c.m * KT_BM);
+                    for (int kb = 0; kb < KB; ++kb)
+                        tma_load_2d(x_tile + kb * XK_BYTES, &map_q, xfull, kb * 64, (c.m * CL + rank) * KT_BM);
                 }
                 __syncwarp();
             }
@@ -323,8 +334,16 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             mbar_wait(&empty[stage], ((c.i / ST) & 1) ^ 1);
             if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&full[stage], W_BYTES);
-                for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(w_tiles + stage * W_BYTES + kb * WK_BYTES, &map_e, &full[stage], kb * 64, c.tile(sch) * prm.tile_stride * KT_BN);
+                const int row0 = c.tile(sch) * prm.tile_stride * KT_BN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (CL == 1) {
+                        tma_load_2d(w_tiles + stage * W_BYTES + kb * WK_BYTES, &map_e, &full[stage], kb * 64, row0);
+                    } else {   // this CTA's 1/CL of the rows, into every CTA of the cluster
+                        constexpr int PART = KT_BN / CL;
+                        tma_load_2d_multicast(w_tiles + stage * W_BYTES + kb * WK_BYTES + rank * PART * 128, &map_e,
+                                              &full[stage], kb * 64, row0 + rank * PART, CL_MASK);
+                    }
+                }
             }
             __syncwarp();
         }
@@ -351,7 +370,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     if (k == 0) umma_f16_first(acc, xdesc + xo, wd + wo, idesc);
                     else umma_f16_acc(acc, xdesc + xo, wd + wo, idesc);
                 }
-                umma_commit(&empty[stage]);
+                if (CL == 1) umma_commit(&empty[stage]); else umma_commit_multicast(&empty[stage], CL_MASK);
                 umma_commit(&sfull[b]);
                 if (c.last()) umma_commit(xfree);
             }
@@ -432,9 +451,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (; !c.done; c.next(sch, cta)) {
             const int i = c.i, b = i & 1;
             if (c.first) {
-                q = static_cast<int64_t>(c.m) * KT_BM + r_in_tile;
+                q = static_cast<int64_t>(c.m * CL + rank) * KT_BM + r_in_tile;
                 row_ok = q < prm.n_query;
-                const int part = static_cast<int>(blockIdx.x) - ks_first_cta(sch, c.sb, c.m);
+                const int part = cta - ks_first_cta(sch, c.sb, c.m);
                 list = (q * sch.lists) + (c.sb * sch.max_seg + part) * 2 + grp;
                 // never below KT_TAU_FLOOR: corpus rows past the end carry KT_MASKED, a finite value under the floor
                 tau = row_ok ? fmaxf(prm.tau0 != nullptr ? prm.tau0[q] : KT_TAU_FLOOR, KT_TAU_FLOOR) : INFINITY;
@@ -473,22 +492,29 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             float tile_max = -INFINITY;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
+                // four 8-score maxima (3-input max chains) and ONE compare + branch per 32-column chunk: two chunks in
+                // three have no score above the threshold
+                float sub[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    // maximum of 8 scores (3-input max chain); a group that beats the threshold is copied RAW into the
-                    // thread's buffer by predicated 16-byte stores: no branch, no divergence, no dependent chain.
-                    // (Finding and appending the individual scores right here cost the warp ~350 cycles of latency per
-                    // hit -- 2.3 ms of a 6.6 ms pass -- whichever way it was coded: tag + max tree + loop, or 8
-                    // predicated appends.)
                     const uint32_t *x = &r[qq][g * 8];
                     float m = fmaxf(fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1])), __uint_as_float(x[2]));
                     m = fmaxf(fmaxf(m, __uint_as_float(x[3])), __uint_as_float(x[4]));
                     m = fmaxf(fmaxf(m, __uint_as_float(x[5])), __uint_as_float(x[6]));
-                    m = fmaxf(m, __uint_as_float(x[7]));
-                    if (SAMPLE) {
-                        tile_max = fmaxf(tile_max, m);
-                    } else {
-                        const bool hit = m > tau;
+                    sub[g] = fmaxf(m, __uint_as_float(x[7]));
+                }
+                const float chunk_max = fmaxf(fmaxf(sub[0], sub[1]), fmaxf(sub[2], sub[3]));
+                if (SAMPLE) {
+                    tile_max = fmaxf(tile_max, chunk_max);
+                } else if (chunk_max > tau) {
+                    // A group that beats the threshold is copied RAW into the thread's buffer by predicated 16-byte
+                    // stores: no search for "which score", no loop, no dependent chain.  (Finding and appending the
+                    // individual scores right here cost the warp ~350 cycles of latency per hit -- 2.3 ms of a 6.6 ms
+                    // pass -- whichever way it was coded: tag + max tree + loop, or 8 predicated appends.)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t *x = &r[qq][g * 8];
+                        const bool hit = sub[g] > tau;
                         st_global_v4_pred(raw_v + rcnt * 8, x[0], x[1], x[2], x[3], hit);
                         st_global_v4_pred(raw_v + rcnt * 8 + 4, x[4], x[5], x[6], x[7], hit);
                         st_global_u32_pred(raw_c + rcnt, static_cast<uint32_t>(col0 + qq * 32 + g * 8), hit);
@@ -502,7 +528,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const int st = c.tile(sch);
                 if ((st + 1) % prm.blk_tiles == 0 || seg_end) {
                     if (row_ok)
-                        atomic_max_float(prm.blk_max + (static_cast<int64_t>(c.m) * prm.n_blk + (st / prm.blk_tiles) * 2 + grp) * KT_BM + r_in_tile,
+                        atomic_max_float(prm.blk_max + (static_cast<int64_t>(c.m * CL + rank) * prm.n_blk + (st / prm.blk_tiles) * 2 + grp) * KT_BM + r_in_tile,
                                          run_max);
                     run_max = -INFINITY;
                 }
@@ -532,6 +558,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc<512>(tmem_base);
@@ -801,6 +828,7 @@ struct KtPlan {
     int kp;
     bool use_sample;
     int rank, blk_tiles, n_blk;   // sampling pass
+    int cl;                       // CTAs per cluster (both passes)
     int lists;
 };
 
@@ -819,13 +847,17 @@ static KtPlan kt_plan(int64_t n_query, int64_t n_corpus, int k, bool sampling = 
     KtPlan p;
     const int m_tiles = static_cast<int>((n_query + KT_BM - 1) / KT_BM);
     const int n_tiles = static_cast<int>((n_corpus + KT_BN - 1) / KT_BN);
-    p.sched = make_ksched(m_tiles, n_tiles, true);
+    // pairs of CTAs share every corpus tile (each loads half and multicasts it): the pass is bound by the L2 -> SM
+    // stream of corpus tiles (64 KB per 128 x 256 scores: 148 SMs at the tensor rate would need 17 TB/s), so halving
+    // that stream is what buys speed.  With only a few query tiles the second CTA of a pair would mostly idle.
+    p.cl = m_tiles >= 8 ? 2 : 1;
+    p.sched = make_ksched(m_tiles, n_tiles, true, p.cl);
     int margin = k / 2;
     if (margin < 32) margin = 32;
     p.kp = k + margin;
     if (wide || p.kp > KT_MAX_KP) p.kp = KT_MAX_KP;   // wide: the repair pass for queries whose proof failed
     const int s_tiles = (n_tiles + KT_STRIDE_B - 1) / KT_STRIDE_B;
-    p.sample_b = make_ksched(m_tiles, s_tiles, false);
+    p.sample_b = make_ksched(m_tiles, s_tiles, false, p.cl);
     p.blk_tiles = (s_tiles + KT_MAX_BLK / 2 - 1) / (KT_MAX_BLK / 2);
     p.n_blk = (s_tiles + p.blk_tiles - 1) / p.blk_tiles * 2;
     // items wanted above the threshold: C = stride * rank; as a rank among block maxima: n_blk * (1 - exp(-b C / N))
@@ -862,8 +894,8 @@ static KtWs kt_carve(void *workspace, size_t bytes, int64_t n_query, int64_t n_c
     w.cand_n = ws.take<int32_t>(lists);
     w.cand_tau = ws.take<float>(lists);
     w.tau0 = ws.take<float>(n_query);
-    w.raw_v = ws.take<float>(static_cast<size_t>(pl.sched.grid) * (KT_THREADS - 64) * KT_RAW_CAP * 8);
-    w.raw_c = ws.take<int32_t>(static_cast<size_t>(pl.sched.grid) * (KT_THREADS - 64) * KT_RAW_CAP);
+    w.raw_v = ws.take<float>(static_cast<size_t>(pl.sched.grid) * pl.cl * (KT_THREADS - 64) * KT_RAW_CAP * 8);
+    w.raw_c = ws.take<int32_t>(static_cast<size_t>(pl.sched.grid) * pl.cl * (KT_THREADS - 64) * KT_RAW_CAP);
     w.blk_max = ws.take<float>(static_cast<size_t>((n_query + KT_BM - 1) / KT_BM) * pl.n_blk * KT_BM);
     w.ok = ws.ok();
     w.used = ws.off;
@@ -879,19 +911,40 @@ static inline unsigned kt_grid(int64_t n, int threads) {
 }
 
 // row-major bf16 [rows, dim] -> boxes of {64 columns, box_rows rows}, 128B swizzle (box_rows up to 256)
-template <int D, bool SAMPLE>
-static int launch_topk_tc(const CUtensorMap &mq, const CUtensorMap &me, const TopkTcParams &prm, int grid, cudaStream_t st) {
+template <int D, bool SAMPLE, int CL>
+static int launch_topk_tc_cl(const CUtensorMap &mq, const CUtensorMap &me, const TopkTcParams &prm, cudaStream_t st) {
     constexpr int ST = KtStages<D>::value;
     constexpr size_t smem = 1024 + static_cast<size_t>(KT_BM) * D * 2 + static_cast<size_t>(ST) * KT_BN * D * 2 + 256 + 2 * KT_BM * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(topk_tc_kernel<D, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(topk_tc_kernel<D, SAMPLE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(topk_tc_kernel)");
         attr_set = true;
     }
-    topk_tc_kernel<D, SAMPLE><<<grid, KT_THREADS, smem, st>>>(mq, me, prm);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(prm.sch.grid * CL));
+    cfg.blockDim = dim3(KT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, topk_tc_kernel<D, SAMPLE, CL>, mq, me, prm);
+    if (e != cudaSuccess) return cuda_status(e, "cudaLaunchKernelEx(topk_tc_kernel)");
     TT_LAUNCH_CHECK("topk_tc_kernel");
     return 0;
+}
+
+// `me` must have been built with box rows = KT_BN / prm.sch.cl
+template <bool SAMPLE>
+static int launch_topk_tc(int dim, const CUtensorMap &mq, const CUtensorMap &me, const TopkTcParams &prm, cudaStream_t st) {
+    if (prm.sch.cl == 2)
+        return dim == 128 ? launch_topk_tc_cl<128, SAMPLE, 2>(mq, me, prm, st) : launch_topk_tc_cl<64, SAMPLE, 2>(mq, me, prm, st);
+    return dim == 128 ? launch_topk_tc_cl<128, SAMPLE, 1>(mq, me, prm, st) : launch_topk_tc_cl<64, SAMPLE, 1>(mq, me, prm, st);
 }
 
 }  // namespace tt
@@ -954,7 +1007,7 @@ extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float
     CUtensorMap mq, me;
     int rc;
     if ((rc = make_tmap_bf16_rows(&mq, w.qb, n_query, dim, KT_BM))) return rc;
-    if ((rc = make_tmap_bf16_rows(&me, eb, n_corpus, dim, KT_BN))) return rc;
+    if ((rc = make_tmap_bf16_rows(&me, eb, n_corpus, dim, KT_BN / pl.cl))) return rc;
     TopkTcParams prm{};
     prm.n_query = n_query; prm.n_corpus = n_corpus;
     prm.mask_offsets = mask_offsets; prm.mask_rows = mask_rows;
@@ -966,9 +1019,7 @@ extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float
         TT_LAUNCH_CHECK("tk_fill");
         prm.sch = pl.sample_b; prm.kp = pl.kp; prm.tile_stride = KT_STRIDE_B; prm.tau0 = nullptr;
         prm.blk_max = w.blk_max; prm.blk_tiles = pl.blk_tiles; prm.n_blk = pl.n_blk;
-        rc = (dim == 128) ? launch_topk_tc<128, true>(mq, me, prm, pl.sample_b.grid, st)
-                          : launch_topk_tc<64, true>(mq, me, prm, pl.sample_b.grid, st);
-        if (rc) return rc;
+        if ((rc = launch_topk_tc<true>(dim, mq, me, prm, st))) return rc;
         tk_tau0_kernel<<<kt_grid(n_query * 32, 256), 256, 0, st>>>(w.blk_max, n_query, pl.n_blk, pl.rank, KT_STRIDE_B,
                                                                     mask_offsets, mask_rows, w.tau0);
         TT_LAUNCH_CHECK("tk_tau0_kernel");
@@ -981,9 +1032,7 @@ extern "C" int tt_score_topk_tc(const float *query, int64_t n_query, const float
         prm.sch = pl.sched; prm.kp = pl.kp; prm.tile_stride = 1; prm.tau0 = tau_start;
         prm.blk_max = nullptr; prm.blk_tiles = 1; prm.n_blk = 0;
         prm.raw_v = w.raw_v; prm.raw_c = w.raw_c;
-        rc = (dim == 128) ? launch_topk_tc<128, false>(mq, me, prm, pl.sched.grid, st)
-                          : launch_topk_tc<64, false>(mq, me, prm, pl.sched.grid, st);
-        if (rc) return rc;
+        if ((rc = launch_topk_tc<false>(dim, mq, me, prm, st))) return rc;
     }
     topk_tc_stage2<<<static_cast<unsigned>(n_query), 128, 0, st>>>(query, corpus, dim, k, pl.kp, pl.sched.lists, row_offset,
                                                                    w.cand_v, w.cand_i, w.cand_n, w.cand_tau, emax, out_scores,
