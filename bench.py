@@ -637,4 +637,9 @@ def step_roofline(model, wl, dev, peaks, flush):
 
 
 if __name__ == "__main__":
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner under NCCL_DEBUG, torchrun helpers)
+    # write to fd 1 too: send fd 1 to stderr while the benchmark runs and hand the real stdout back to print().
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w", buffering=1)
     main()
