@@ -171,6 +171,17 @@ class _ShardedOps:
         return ops.segment_grad(rows.reshape(-1, 1), ops.POOL_NONE, None, vocab, grad, None, grad.shape[1], sq_norm)
 
     @staticmethod
+    def pool_sum(table, idx, null_row):           # table [n+1, D] (row null_row = zeros), idx [R, L] -> [R, D] sums
+        out = torch.empty(idx.shape[0], table.shape[1], dtype=torch.float32, device=table.device)
+        oob = torch.zeros(1, dtype=torch.int32, device=table.device)
+        ops.gather_pool_into(table, idx.contiguous(), ops.POOL_SUM, null_row, out, None, oob)
+        return out
+
+    @staticmethod
+    def segment_grad_pooled(idx, null_row, grad, sq_norm):   # idx [R, L] (null_row = not mine), grad [R, D] per sample
+        return ops.segment_grad(idx.contiguous(), ops.POOL_SUM, null_row, null_row, grad, None, grad.shape[1], sq_norm)
+
+    @staticmethod
     def adam(table, m, v, rows, row_grad, n_unique, coef, lr, b1, b2, eps, step_dev):
         ops.rowwise_adam_(table, m, v, rows, row_grad, n_unique, coef, lr, b1, b2, eps, step_dev)
 
@@ -189,24 +200,41 @@ class ShardedEmbeddingBag:
     step      fused row-wise Adam on the touched rows of the local shard; the clip coefficient comes from the global
               gradient norm (all-reduce of one scalar), like the unsharded optimizer.
     The pad row (GenericTower leaves it non-zero and frozen) is replicated on every rank and never routed.
+
+    exchange="pooled" (default for sum / mean): the owners pool.  Every rank sends each owner the [B, L] id matrix with
+    the ids that owner does not hold blanked out (equal-sized all-to-all: no counts to exchange, NO host sync), the owner
+    runs the fused gather+pool kernel over its shard -> a partial sum per (sample, owner), one [B, D] block travels
+    back per peer and the partials are added in rank order (+ pads x pad row, / L for mean).  Backward: all-gather of
+    the [B, D] upstream gradients, tt_emb_segment_grad on the owner expands them over the ids it already holds.
+    Per GPU and step this moves B*L*8 + 2*B*D*4 bytes per peer instead of the ~n_valid*D*8 bytes of whole rows
+    (C3 shapes: 15 MB instead of 867 MB).  The sum is regrouped by owner, so the result equals the single-GPU one
+    to rounding (1e-6), not bitwise; exchange="rows" keeps the bitwise path above.
     """
 
     def __init__(self, vocab: int, dim: int, rank: int, world: int, mode: str = "mean", padding_idx: Optional[int] = 0,
-                 device="cuda", seed: int = 0, dev_ops=None, full_weight: Optional[torch.Tensor] = None):
+                 device="cuda", seed: int = 0, dev_ops=None, full_weight: Optional[torch.Tensor] = None,
+                 exchange: str = "pooled"):
         self.vocab, self.dim, self.rank, self.world = int(vocab), int(dim), int(rank), int(world)
         self.mode = ops.POOL_MODES[mode]
         if self.mode not in (ops.POOL_SUM, ops.POOL_MEAN, ops.POOL_NONE):
             raise ops.TTError("ShardedEmbeddingBag supports mean / sum pooling (and L = 1 lookups)")
         self.padding_idx = padding_idx
         self.ops = dev_ops or _ShardedOps
+        if exchange not in ("pooled", "rows"):
+            raise ops.TTError(f"unknown exchange '{exchange}' (use 'pooled' or 'rows')")
+        self.exchange = exchange
         self.local_rows = (self.vocab - self.rank + self.world - 1) // self.world
+        # shard + one all-zero "null" row behind it (index local_rows): what an id held by another rank points at
+        # when this rank pools; never touched by the optimizer
+        self._weight_ext = torch.zeros(self.local_rows + 1, dim, dtype=torch.float32, device=device)
+        self.weight = self._weight_ext[:self.local_rows]
         if full_weight is not None:                                   # tests: shard a given table
-            self.weight = full_weight[self.rank::self.world].contiguous().to(device)
+            self.weight.copy_(full_weight[self.rank::self.world])
             pad = full_weight[padding_idx].clone() if padding_idx is not None else torch.zeros(dim)
         else:
             gen = torch.Generator(device=device).manual_seed(seed * 1000003 + self.rank)
             bound = (6.0 / (self.vocab + self.dim)) ** 0.5            # xavier_uniform_ over the whole table
-            self.weight = (torch.rand(self.local_rows, dim, device=device, generator=gen) * 2 - 1) * bound
+            self.weight.copy_((torch.rand(self.local_rows, dim, device=device, generator=gen) * 2 - 1) * bound)
             pad = (torch.rand(dim, generator=torch.Generator().manual_seed(seed)) * 2 - 1) * bound
         self.pad_row = pad.to(device=device, dtype=torch.float32)
         self.exp_avg = torch.zeros_like(self.weight, dtype=torch.float32)
@@ -214,6 +242,9 @@ class ShardedEmbeddingBag:
         self.sq_norm = torch.zeros(1, dtype=torch.float32, device=device)
         self.pending = []
         self.a2a_bytes = 0
+        # null row index of every rank's shard (shards differ in length by at most one row)
+        self._null_rows = torch.tensor([(self.vocab - r + self.world - 1) // self.world for r in range(self.world)],
+                                       dtype=torch.int64, device=device)
         # autograd anchor: the lookup's inputs are integer ids, so something that requires grad must enter the node
         self._anchor = torch.zeros(1, dtype=torch.float32, device=device, requires_grad=True)
 
@@ -224,7 +255,53 @@ class ShardedEmbeddingBag:
             return send
         return all_to_all_rows(send, send_counts, recv_counts)
 
+    def _forward_pooled(self, ids: torch.Tensor) -> torch.Tensor:
+        B, L = ids.shape
+        W = self.world
+        is_pad = (ids == self.padding_idx) if self.padding_idx is not None else torch.zeros_like(ids, dtype=torch.bool)
+        owner = ids % W
+        local = ids // W
+        ranks = torch.arange(W, device=ids.device).view(W, 1, 1)
+        # [W, B, L]: block w = what owner w pools for my samples (its local row, or its null row)
+        send = torch.where((owner.unsqueeze(0) == ranks) & ~is_pad.unsqueeze(0), local.unsqueeze(0),
+                           self._null_rows.view(W, 1, 1)).contiguous()
+        recv = self._a2a_equal(send)                                             # all-to-all #1 (equal splits)
+        partial = self.ops.pool_sum(self._weight_ext, recv.view(W * B, L), self.local_rows)
+        back = self._a2a_equal(partial.view(W, B, self.dim))                     # all-to-all #2: [owner, B, D]
+        pooled = back[0]
+        for w in range(1, W):                                                    # fixed order
+            pooled = pooled + back[w]
+        if self.padding_idx is not None:
+            pooled = pooled + is_pad.sum(1, keepdim=True).to(torch.float32) * self.pad_row
+        if self.mode == ops.POOL_MEAN and L > 1:
+            pooled = pooled * (1.0 / L)
+        return _ShardedPooledFn.apply(pooled, self._anchor, self, recv, L)
+
+    def _backward_pooled(self, grad_pooled, recv, L):
+        W = self.world
+        scale = 1.0 / L if (self.mode == ops.POOL_MEAN and L > 1) else 1.0
+        g = (grad_pooled * scale).contiguous() if scale != 1.0 else grad_pooled.contiguous()
+        self.a2a_bytes += g.numel() * g.element_size() * (W - 1)
+        if W > 1:
+            g_all = torch.empty((W,) + tuple(g.shape), dtype=g.dtype, device=g.device)
+            dist.all_gather(list(g_all.unbind(0)), g)                            # every owner needs every rank's rows
+        else:
+            g_all = g.unsqueeze(0)
+        rows, row_grad, n_unique = self.ops.segment_grad_pooled(recv.view(W * g.shape[0], L), self.local_rows,
+                                                                g_all.view(W * g.shape[0], self.dim), self.sq_norm)
+        self.pending.append((rows, row_grad, n_unique))
+
+    def _a2a_equal(self, send):
+        self.a2a_bytes += send.numel() * send.element_size() * (self.world - 1) // self.world
+        if self.world == 1:
+            return send
+        out = torch.empty_like(send)
+        dist.all_to_all_single(out, send)
+        return out
+
     def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        if self.exchange == "pooled":
+            return self._forward_pooled(ids)
         B, L = ids.shape
         flat = ids.reshape(-1)
         if self.padding_idx is None:
@@ -291,6 +368,22 @@ class _ShardedLookupFn(torch.autograd.Function):
         sample_of_sorted, recv_ids = ctx.saved_tensors
         ctx.bag._backward(grad, sample_of_sorted, recv_ids, ctx.sc, ctx.rc, ctx.L)
         return (None,) * 8
+
+
+class _ShardedPooledFn(torch.autograd.Function):
+    """Identity on the pooled vectors in forward; sends their gradient to every owner in backward."""
+
+    @staticmethod
+    def forward(ctx, pooled, anchor, bag, recv, L):
+        ctx.bag, ctx.L = bag, L
+        ctx.save_for_backward(recv)
+        return pooled.view_as(pooled)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (recv,) = ctx.saved_tensors
+        ctx.bag._backward_pooled(grad, recv, ctx.L)
+        return (None,) * 5
 
 
 def global_clip_coef(sq_terms: List[torch.Tensor], max_norm: float = 1.0) -> torch.Tensor:

@@ -121,6 +121,17 @@ class _CpuOps:
         return u, rg, torch.tensor([len(u)], dtype=torch.int32)
 
     @staticmethod
+    def pool_sum(table, idx, null_row):
+        return table[idx].sum(1)
+
+    @staticmethod
+    def segment_grad_pooled(idx, null_row, grad, sq_norm):
+        flat = idx.reshape(-1)
+        g = grad.repeat_interleave(idx.shape[1], 0)
+        keep = flat != null_row
+        return _CpuOps.segment_grad(flat[keep], null_row, g[keep], sq_norm)
+
+    @staticmethod
     def adam(table, m, v, rows, row_grad, n_unique, coef, lr, b1, b2, eps, step_dev):
         from oracle import twotower_oracle as O
         n = int(n_unique)
@@ -130,7 +141,7 @@ class _CpuOps:
         table[r], m[r], v[r] = p, mm, vv
 
 
-def _sharded_bag_case(rank, world):
+def _sharded_bag_case(rank, world, exchange="rows"):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from recommendsystemproject_b200 import dist as tdist
@@ -138,7 +149,8 @@ def _sharded_bag_case(rank, world):
     gen = torch.Generator().manual_seed(5)
     V, D, L, B = 97, 8, 6, 11
     full = torch.randn(V, D, generator=gen)
-    bag = tdist.ShardedEmbeddingBag(V, D, rank, world, "mean", 0, device="cpu", dev_ops=_CpuOps, full_weight=full)
+    bag = tdist.ShardedEmbeddingBag(V, D, rank, world, "mean", 0, device="cpu", dev_ops=_CpuOps, full_weight=full,
+                                    exchange=exchange)
     g2 = torch.Generator().manual_seed(50 + rank)
     ids = torch.randint(1, V, (B, L), generator=g2)
     ids[torch.arange(L)[None, :] >= torch.randint(1, L + 1, (B, 1), generator=g2)] = 0
@@ -178,3 +190,12 @@ def _sharded_bag_case(rank, world):
 
 def test_sharded_embedding_bag_two_ranks_gloo():
     assert all(_run(_sharded_bag_case).values())
+
+
+def _sharded_bag_pooled_case(rank, world):
+    return _sharded_bag_case(rank, world, exchange="pooled")
+
+
+def test_sharded_embedding_bag_owner_side_pooling_two_ranks_gloo():
+    """exchange='pooled': the owners pool and only [B, D] partial sums travel; same lookup, same update."""
+    assert all(_run(_sharded_bag_pooled_case).values())

@@ -575,7 +575,7 @@ def test_sharded_embedding_bag_world1_is_bitwise_the_unsharded_kernel():
     full = torch.randn(V, D, generator=gen)
     ids = torch.randint(1, V, (B, L), generator=gen)
     ids[torch.arange(L)[None, :] >= torch.randint(1, L + 1, (B, 1), generator=gen)] = 0
-    bag = tdist.ShardedEmbeddingBag(V, D, 0, 1, "mean", 0, device=DEV, full_weight=full)
+    bag = tdist.ShardedEmbeddingBag(V, D, 0, 1, "mean", 0, device=DEV, full_weight=full, exchange="rows")
     idd = ids.to(DEV)
     ref = ops.gather_rows(full.to(DEV), idd, "mean", 0)
     bag.zero_grad()
@@ -594,3 +594,31 @@ def test_sharded_embedding_bag_world1_is_bitwise_the_unsharded_kernel():
     touched = torch.zeros(V, dtype=torch.bool, device=DEV)
     touched[rows[:n]] = True
     assert torch.equal(bag.weight[~touched], before[~touched]) and not torch.equal(bag.weight[touched], before[touched])
+
+
+def test_sharded_embedding_bag_owner_side_pooling_world1():
+    """exchange='pooled' at W=1: the owner-side partial sums (fused gather+pool over shard + null row, pads added as
+    count x pad row) equal the unsharded lookup to rounding, and the segment gradient the owner builds from the [B, D]
+    upstream rows equals tt_emb_segment_grad on the same ids."""
+    from recommendsystemproject_b200 import dist as tdist
+    gen = torch.Generator().manual_seed(32)
+    V, D, L, B = 5000, 64, 12, 300
+    full = torch.randn(V, D, generator=gen)
+    ids = torch.randint(1, V, (B, L), generator=gen)
+    ids[torch.arange(L)[None, :] >= torch.randint(1, L + 1, (B, 1), generator=gen)] = 0
+    ids[3] = 0
+    for mode in ("mean", "sum"):
+        bag = tdist.ShardedEmbeddingBag(V, D, 0, 1, mode, 0, device=DEV, full_weight=full, exchange="pooled")
+        idd = ids.to(DEV)
+        ref = ops.gather_rows(full.to(DEV), idd, mode, 0)
+        bag.zero_grad()
+        pooled = bag(idd)
+        assert torch.allclose(pooled, ref, atol=1e-5, rtol=1e-5), mode
+        up = torch.randn(B, D, generator=gen).to(DEV)
+        (pooled * up).sum().backward()
+        rows, row_grad, n_unique = bag.pending[0]
+        r_ref, g_ref, n_ref = ops.segment_grad(idd, ops.POOL_MODES[mode], 0, V, up, None, D)
+        n = int(n_ref.item())
+        assert int(n_unique.item()) == n and torch.equal(rows[:n], r_ref[:n])
+        assert torch.allclose(row_grad[:n], g_ref[:n], atol=1e-6, rtol=1e-5)
+        assert float(bag._weight_ext[-1].abs().max()) == 0.0     # the null row stays zero

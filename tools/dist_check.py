@@ -61,28 +61,39 @@ dist.all_reduce(lo, op=dist.ReduceOp.MIN)
 dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 t3 = bool(torch.equal(lo, hi)) and bool(torch.isfinite(loss))
 ok &= t3
-# 4. ShardedEmbeddingBag: pooled lookup bitwise == unsharded kernel on the full table; untouched rows do not move
+# 4. ShardedEmbeddingBag: exchange="rows": pooled lookup bitwise == unsharded kernel on the full table; exchange="pooled"
+#    (owner-side partial sums): equal to rounding, and both exchanges leave the SAME updated shard (to rounding);
+#    untouched rows do not move
 Vb, Db, Lb, Bb = 200003, 128, 50, 1000
 fullw = torch.randn(Vb, Db, device=dev, generator=torch.Generator(device=dev).manual_seed(77))
-bag = tdist.ShardedEmbeddingBag(Vb, Db, rank, world, "mean", 0, device=dev, full_weight=fullw)
 g4 = torch.Generator(device=dev).manual_seed(400 + rank)
 idb = torch.randint(1, Vb, (Bb, Lb), device=dev, generator=g4)
 idb[torch.arange(Lb, device=dev)[None, :] >= torch.randint(1, Lb + 1, (Bb, 1), device=dev, generator=g4)] = 0
-bag.zero_grad()
-pooled = bag(idb)
-t4 = bool(torch.equal(pooled, ops.gather_rows(fullw, idb, "mean", 0)))
 upb = torch.randn(Bb, Db, device=dev, generator=g4)
-(pooled * upb).sum().backward()
-coef = tdist.global_clip_coef([bag.sq_norm], 1.0)
-before = bag.weight.clone()
-bag.step(coef, 1e-2, torch.ones(1, dtype=torch.int64, device=dev))
+ref_pool = ops.gather_rows(fullw, idb, "mean", 0)
 all_ids = [torch.empty_like(idb) for _ in range(world)]
 dist.all_gather(all_ids, idb)
 touched = torch.zeros(Vb, dtype=torch.bool, device=dev)
 touched[torch.cat(all_ids).reshape(-1)] = True
 touched[0] = False
 mine = touched[rank::world]
-t4 &= bool(torch.equal(bag.weight[~mine], before[~mine])) and bool((bag.weight[mine] != before[mine]).any(dim=1).all())
+t4 = True
+shards = {}
+for exch in ("rows", "pooled"):
+    bag = tdist.ShardedEmbeddingBag(Vb, Db, rank, world, "mean", 0, device=dev, full_weight=fullw, exchange=exch)
+    bag.zero_grad()
+    pooled = bag(idb)
+    t4 &= bool(torch.equal(pooled, ref_pool)) if exch == "rows" else bool(torch.allclose(pooled, ref_pool, atol=1e-6, rtol=1e-5))
+    (pooled * upb).sum().backward()
+    coef = tdist.global_clip_coef([bag.sq_norm], 1.0)
+    before = bag.weight.clone()
+    bag.step(coef, 1e-2, torch.ones(1, dtype=torch.int64, device=dev))
+    t4 &= bool(torch.equal(bag.weight[~mine], before[~mine])) and bool((bag.weight[mine] != before[mine]).any(dim=1).all())
+    shards[exch] = (bag.weight.clone(), float(coef))
+t4 &= abs(shards["rows"][1] - shards["pooled"][1]) < 1e-6 * max(1.0, abs(shards["rows"][1]))
+# first Adam step moves every touched element by ~lr * sign(g): compare where the gradient is not vanishing
+diff = (shards["rows"][0] - shards["pooled"][0]).abs()
+t4 &= bool((diff > 1e-4).float().mean() < 1e-3)
 ok &= t4
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
