@@ -192,7 +192,7 @@ TT_API int tt_score_topk_f32(const float *query, int64_t n_query, const float *c
  * (tau = best approximate score ever left out; Cauchy-Schwarz on the two rounding-error vectors, the last term
  * covers fp32 accumulation and the index bits kept in the low mantissa) is evaluated on the device.
  * unverified[q] = 1 marks the (rare) queries for which it does not hold; the caller must re-run those with
- * flags = TT_TOPK_WIDE and, if still flagged, through tt_score_topk_f32.
+ * flags = TT_TOPK_SAMPLING | TT_TOPK_WIDE, then TT_TOPK_WIDE and, if still flagged, through tt_score_topk_f32.
  * flags: TT_TOPK_SAMPLING (corpora of >= 2^17 rows) -- a first pass over every 16th corpus tile gives each query
  *   a starting threshold above which ~2.5 K' items score, which keeps the filter on its fast path; a threshold
  *   that turns out too high (sampling noise, ~1e-4 of the queries) is exactly what the obligation detects.

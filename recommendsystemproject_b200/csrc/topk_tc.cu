@@ -237,6 +237,7 @@ __device__ __forceinline__ int tk_prune_list(float *__restrict__ lv, int32_t *__
 }
 
 // ---------------------------------------------------------------- main kernel
+constexpr int KT_S2_CAP = 1024;               // stage 2 holds this many candidates at once (>= K' + one full list)
 constexpr int KT_S2_LISTS = 512;              // stage 2 gathers up to this many lists per query in one step
 constexpr int KT_RAW_CAP = 64;                // raw 8-score groups a filter thread can hold before they are drained
 constexpr uint32_t KT_MASKED = 0xff7fffe0u;   // -3.4028e38 with the 5 index bits clear: stays finite once tagged
@@ -573,8 +574,7 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
                const int32_t *__restrict__ cand_i, const int32_t *__restrict__ cand_n,
                const float *__restrict__ cand_tau, const unsigned int *__restrict__ ebounds_bits,
                double *__restrict__ out_scores, int64_t *__restrict__ out_idx, int32_t *__restrict__ unverified) {
-    __shared__ float av[TK_STAGE2_MAX];
-    __shared__ int32_t ai[TK_STAGE2_MAX];
+    __shared__ uint64_t ak[KT_S2_CAP];   // (approximate score, row) keys, see tk_pack_key
     __shared__ double ev[KT_MAX_KP];
     __shared__ int32_t ei[KT_MAX_KP];
     __shared__ float s_tau;
@@ -589,11 +589,11 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
         int np2 = 32;
         while (np2 < tot) np2 <<= 1;
         for (int t = tid; t < np2; t += blockDim.x)
-            if (t >= tot) { av[t] = -INFINITY; ai[t] = 0x7fffffff; }
+            if (t >= tot) ak[t] = 0;          // below every real key
         __syncthreads();
-        tk_bitonic(av, ai, np2, tid, static_cast<int>(blockDim.x), [] { __syncthreads(); });
+        tk_bitonic_keys_desc(ak, np2, tid, static_cast<int>(blockDim.x), [] { __syncthreads(); });
         if (tot > kp) {
-            if (tid == 0) s_tau = fmaxf(s_tau, av[kp]);
+            if (tid == 0) s_tau = fmaxf(s_tau, tk_key_score(ak[kp]));
             tot = kp;
         }
         __syncthreads();
@@ -646,7 +646,7 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
             s_tau = fmaxf(fmaxf(s_wtau[0], s_wtau[1]), fmaxf(s_wtau[2], s_wtau[3]));
         }
         __syncthreads();
-        if (total <= TK_STAGE2_MAX) {
+        if (total <= KT_S2_CAP) {
             for (int pI = tid; pI < total; pI += blockDim.x) {
                 int lo = 0, hi = n_lists;            // last list with s_off[l] <= pI
                 while (hi - lo > 1) {
@@ -654,8 +654,7 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
                     if (s_off[mid] <= pI) lo = mid; else hi = mid;
                 }
                 const int64_t src = (q * n_lists + lo) * KT_CAP + (pI - s_off[lo]);
-                av[pI] = cand_v[src];
-                ai[pI] = cand_i[src];
+                ak[pI] = tk_pack_key(cand_v[src], cand_i[src]);
             }
             tot = total;
             gathered = true;
@@ -671,8 +670,8 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
                 if (n < 0) s_bad = 1;
             }
             const int take = n < 0 ? KT_CAP : n;
-            if (tot + take > TK_STAGE2_MAX) reduce_to_kp();
-            for (int t = tid; t < take; t += blockDim.x) { av[tot + t] = cand_v[list * KT_CAP + t]; ai[tot + t] = cand_i[list * KT_CAP + t]; }
+            if (tot + take > KT_S2_CAP) reduce_to_kp();
+            for (int t = tid; t < take; t += blockDim.x) ak[tot + t] = tk_pack_key(cand_v[list * KT_CAP + t], cand_i[list * KT_CAP + t]);
             tot += take;
             __syncthreads();
         }
@@ -685,7 +684,7 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
         double d[4] = {0.0, 0.0, 0.0, 0.0};
         const float *e[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) e[u] = corpus + static_cast<int64_t>(ai[min(c0 + u, tot - 1)]) * dim;
+        for (int u = 0; u < 4; ++u) e[u] = corpus + static_cast<int64_t>(tk_key_row(ak[min(c0 + u, tot - 1)])) * dim;
         for (int t = lane; t < dim; t += 32) {
             const double qt = static_cast<double>(qv[t]);
             float x[4];
@@ -701,7 +700,7 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
         if (lane == 0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (c0 + u < tot) { ev[c0 + u] = d[u]; ei[c0 + u] = ai[c0 + u]; }
+                if (c0 + u < tot) { ev[c0 + u] = d[u]; ei[c0 + u] = tk_key_row(ak[c0 + u]); }
         }
     }
     if (warp == 0) {   // |q| and |q - bf16(q)| for the proof obligation

@@ -296,8 +296,9 @@ TOPK_SAMPLING, TOPK_WIDE = 1, 2   # include/tt_b200.h
 
 def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepared: Optional["PreparedCorpus"],
                    flags: int = TOPK_SAMPLING):
-    """Tensor-core top-K with its repair ladder: sampled thresholds, K' = K + margin  ->  (flagged queries only)
-    thresholds from -inf, K' = 256  ->  (never observed) the exact fp32 path."""
+    """Tensor-core top-K with its repair ladder (flagged queries only move on): sampled thresholds, K' = K + margin
+    ->  sampled thresholds at a lower rank, K' = 256  ->  thresholds from the floor, K' = 256  ->  (never observed)
+    the exact fp32 path."""
     lib = _lib.load()
     Bq, D = query.shape
     Nc = corpus.shape[0]
@@ -320,12 +321,13 @@ def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepar
         _count(3 + own)
     # proof obligation failed for these queries (see include/tt_b200.h): one host read
     redo = torch.nonzero(bad, as_tuple=False).reshape(-1)
-    first_rung = (flags & TOPK_WIDE) == 0
+    first_rung = flags == TOPK_SAMPLING
+    next_flags = {TOPK_SAMPLING: TOPK_SAMPLING | TOPK_WIDE, TOPK_SAMPLING | TOPK_WIDE: TOPK_WIDE}.get(flags)
     if first_rung:
         topk_stats["queries"] = Bq
         topk_stats["resampled"] = int(redo.numel())
         topk_stats["unverified"] = 0
-    else:
+    elif next_flags is None:
         topk_stats["unverified"] = int(redo.numel())
     if redo.numel() > 0:
         sub_mo = sub_mr = None
@@ -337,8 +339,8 @@ def _score_topk_tc(query, corpus, k, row_offset, mask_offsets, mask_rows, prepar
             sub_mr = torch.cat(pieces) if pieces else mask_rows[:0]
             if sub_mr.numel() == 0:
                 sub_mr = torch.zeros(1, dtype=torch.int64, device=dev)
-        if first_rung:   # sampled threshold too high, or too many near-ties around the K-th score for K'
-            s2, i2 = _score_topk_tc(query[redo].contiguous(), corpus, k, row_offset, sub_mo, sub_mr, prepared, TOPK_WIDE)
+        if next_flags is not None:   # sampled threshold too high, or too many near-ties around the K-th score for K'
+            s2, i2 = _score_topk_tc(query[redo].contiguous(), corpus, k, row_offset, sub_mo, sub_mr, prepared, next_flags)
         else:
             s2, i2 = score_topk(query[redo], corpus, k, row_offset, sub_mo, sub_mr, precision="fp32")
         scores[redo] = s2
