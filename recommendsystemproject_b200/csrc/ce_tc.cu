@@ -364,14 +364,14 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                 mbar_wait(&sfull[b], BWD ? (i & 1) : ((i >> 1) & 1));
                 tc_fence_after();
                 if (lane == 0 && quarter == 0) TT_DBG(6, i);
-                uint32_t r[4][32];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) tmem_ld_32x32(lane_addr + TM_S + b * TC_BN + grp * TC_HALF + q * 32, r[q]);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&sfree[b]);          // the tensor pipe may overwrite this S buffer now
-                if (lane == 0 && quarter == 0) TT_DBG(7, i);
                 if (MODE == MODE_FWD) {
+                    uint32_t r[4][32];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tmem_ld_32x32(lane_addr + TM_S + b * TC_BN + grp * TC_HALF + q * 32, r[q]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(&sfree[b]);          // the tensor pipe may overwrite this S buffer now
+                    if (lane == 0 && quarter == 0) TT_DBG(7, i);
                     if (special) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
@@ -413,40 +413,85 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                 } else {
                     if (TRANS) mbar_wait(&lfull[i & 1], (i >> 1) & 1);   // this tile's column statistics have landed
                     const float *ls = lse_s + (i & 1) * TC_BN + grp * TC_HALF;
-                    uint32_t g[2][32];
+                    // Register budget of a 320-thread CTA: 200.  128 logits + 64 packed words + 32 exponentials at once
+                    // overflowed it: ptxas spilled inside this loop and, with 224 KB of shared memory configured, L1 is
+                    // ~4 KB, so every spill reload was an L2 round trip (4650 cycles per tile).  Two code paths instead,
+                    // chosen per WARP (uniform branch, so the compiler cannot fold the per-element checks of the rare
+                    // path into the common one):
+                    if (!__any_sync(0xffffffffu, special)) {
+                        // common tile: all 128 logits at once (S is released early, the tensor pipe starts S(i+1) right
+                        // away); exponentials are packed four at a time, G goes out in two 64-column sub-steps
+                        uint32_t r[4][32];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                        for (int q = 0; q < 4; ++q) tmem_ld_32x32(lane_addr + TM_S + grp * TC_HALF + q * 32, r[q]);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        mbar_arrive(&sfree[b]);          // the tensor pipe may overwrite the S buffer now
+                        if (lane == 0 && quarter == 0) TT_DBG(7, i);
 #pragma unroll
-                        for (int qq = 0; qq < 2; ++qq) {
-                            const int q = h * 2 + qq;
-                            float e[32];
-                            auto quad = [&](auto jc) {
-                                constexpr int j = decltype(jc)::value * 4;
-                                float4 st = make_float4(row_stat, row_stat, row_stat, row_stat);
-                                if (TRANS) st = *reinterpret_cast<const float4 *>(ls + q * 32 + j);
-                                e[j] = ex2_mixed<j>(fmaf(__uint_as_float(r[q][j]), prm.scale2, -st.x));
-                                e[j + 1] = ex2_mixed<j + 1>(fmaf(__uint_as_float(r[q][j + 1]), prm.scale2, -st.y));
-                                e[j + 2] = ex2_mixed<j + 2>(fmaf(__uint_as_float(r[q][j + 2]), prm.scale2, -st.z));
-                                e[j + 3] = ex2_mixed<j + 3>(fmaf(__uint_as_float(r[q][j + 3]), prm.scale2, -st.w));
-                            };
-                            static_for<8>(quad);
-                            if (special) {
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t g[32];
+#pragma unroll
+                            for (int qq = 0; qq < 2; ++qq) {
+                                const int q = h * 2 + qq;
+                                auto quad = [&](auto jc) {
+                                    constexpr int j = decltype(jc)::value * 4;
+                                    float4 st = make_float4(row_stat, row_stat, row_stat, row_stat);
+                                    if (TRANS) st = *reinterpret_cast<const float4 *>(ls + q * 32 + j);
+                                    const float e0 = ex2_mixed<j>(fmaf(__uint_as_float(r[q][j]), prm.scale2, -st.x));
+                                    const float e1 = ex2_mixed<j + 1>(fmaf(__uint_as_float(r[q][j + 1]), prm.scale2, -st.y));
+                                    const float e2 = ex2_mixed<j + 2>(fmaf(__uint_as_float(r[q][j + 2]), prm.scale2, -st.z));
+                                    const float e3 = ex2_mixed<j + 3>(fmaf(__uint_as_float(r[q][j + 3]), prm.scale2, -st.w));
+                                    g[qq * 16 + j / 2] = pack_bf16x2(e0, e1);
+                                    g[qq * 16 + j / 2 + 1] = pack_bf16x2(e2, e3);
+                                };
+                                static_for<8>(quad);
+                            }
+                            if (h == 0) {
+                                if (lane == 0 && quarter == 0) TT_DBG(8, i);
+                                if (i >= 1) mbar_wait(&gfree[grp], (i - 1) & 1);   // Out(i-1) has consumed this group's half of G
+                                if (lane == 0 && quarter == 0) TT_DBG(9, i);
+                            }
+                            tmem_st_32x32(lane_addr + TM_G + grp * (TC_HALF / 2) + h * 32, g);
+                        }
+                    } else {
+                        // tile with the diagonal / a collision run / columns past the end (one or two per row of
+                        // tiles): 64 columns at a time with the per-element fix-ups
+#pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t r[2][32];
+                            tmem_ld_32x32(lane_addr + TM_S + grp * TC_HALF + h * 64, r[0]);
+                            tmem_ld_32x32(lane_addr + TM_S + grp * TC_HALF + h * 64 + 32, r[1]);
+                            tmem_ld_wait();
+                            if (h == 1) {
+                                tc_fence_before();
+                                mbar_arrive(&sfree[b]);
+                                if (lane == 0 && quarter == 0) TT_DBG(7, i);
+                            }
+                            uint32_t g[32];
+#pragma unroll
+                            for (int qq = 0; qq < 2; ++qq) {
+                                const int q = h * 2 + qq;
+                                float e[32];
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
+                                    const float st = TRANS ? ls[q * 32 + j] : row_stat;
+                                    e[j] = ex2_approx(fmaf(__uint_as_float(r[qq][j]), prm.scale2, -st));
                                     const int col = col0 + q * 32 + j;
                                     if (col >= ncol) e[j] = 0.f;
                                     else if (x_item && w_item && col >= lo && col < hi) e[j] = (col == p) ? e[j] - 1.0f : 0.f;
                                 }
-                            }
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) g[h][qq * 16 + j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+                                for (int j = 0; j < 16; ++j) g[qq * 16 + j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+                            }
+                            if (h == 0) {
+                                if (lane == 0 && quarter == 0) TT_DBG(8, i);
+                                if (i >= 1) mbar_wait(&gfree[grp], (i - 1) & 1);
+                                if (lane == 0 && quarter == 0) TT_DBG(9, i);
+                            }
+                            tmem_st_32x32(lane_addr + TM_G + grp * (TC_HALF / 2) + h * 32, g);
                         }
                     }
-                    if (lane == 0 && quarter == 0) TT_DBG(8, i);
-                    if (i >= 1) mbar_wait(&gfree[grp], (i - 1) & 1);   // Out(i-1) has consumed this group's half of G
-                    if (lane == 0 && quarter == 0) TT_DBG(9, i);
-                    tmem_st_32x32(lane_addr + TM_G + grp * (TC_HALF / 2), g[0]);
-                    tmem_st_32x32(lane_addr + TM_G + grp * (TC_HALF / 2) + 32, g[1]);
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&gfull[grp]);

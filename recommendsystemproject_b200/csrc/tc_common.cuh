@@ -276,6 +276,9 @@ __device__ __forceinline__ void static_for(F &&f) {
 #endif
 template <int J>
 __device__ __forceinline__ float ex2_mixed(float x) {
+#ifdef TT_EXPERIMENT_NO_EXP   // developer experiment only (wrong results): how much do the exponentials cost the tile?
+    return x * 0.5f;
+#endif
     if constexpr (((TT_POLY_MASK >> (J & 7)) & 1) != 0) return ex2_poly(x);
     else return ex2_approx(x);
 }
