@@ -382,14 +382,17 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                                 if (dead) r[q][j] = 0xff800000u;   // -inf
                             }
                     }
-                    float c0 = __uint_as_float(r[0][0]), c1 = __uint_as_float(r[1][0]);
-                    float c2 = __uint_as_float(r[2][0]), c3 = __uint_as_float(r[3][0]);
+                    // 3-input max chains (FMNMX3): two logits per ALU instruction
+                    float c0 = fmaxf(__uint_as_float(r[0][0]), __uint_as_float(r[0][1]));
+                    float c1 = fmaxf(__uint_as_float(r[1][0]), __uint_as_float(r[1][1]));
+                    float c2 = fmaxf(__uint_as_float(r[2][0]), __uint_as_float(r[2][1]));
+                    float c3 = fmaxf(__uint_as_float(r[3][0]), __uint_as_float(r[3][1]));
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) {
-                        c0 = fmaxf(c0, __uint_as_float(r[0][j]));
-                        c1 = fmaxf(c1, __uint_as_float(r[1][j]));
-                        c2 = fmaxf(c2, __uint_as_float(r[2][j]));
-                        c3 = fmaxf(c3, __uint_as_float(r[3][j]));
+                    for (int j = 2; j < 32; j += 2) {
+                        c0 = fmaxf(fmaxf(c0, __uint_as_float(r[0][j])), __uint_as_float(r[0][j + 1]));
+                        c1 = fmaxf(fmaxf(c1, __uint_as_float(r[1][j])), __uint_as_float(r[1][j + 1]));
+                        c2 = fmaxf(fmaxf(c2, __uint_as_float(r[2][j])), __uint_as_float(r[2][j + 1]));
+                        c3 = fmaxf(fmaxf(c3, __uint_as_float(r[3][j])), __uint_as_float(r[3][j + 1]));
                     }
                     const float cmax = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
                     if (cmax > m_run) {
