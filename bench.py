@@ -575,6 +575,39 @@ def main():
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
     h2d = tree_bytes(host_batches[0])
 
+    # ---- secondary number: the same step with TF32 tensor-core GEMMs in the towers (BASELINE quotes this config in
+    # bf16; TF32 keeps fp32 range and 10 mantissa bits).  The headline `value` above stays fp32, the precision every
+    # parity test checks; tolerance of the TF32 step (loss 1e-3, gradient 2.1e-2 relative): tests/test_gpu_model.py::test_tf32_tower_step_within_tolerance.
+    tf32 = None
+    if world == 1:
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+            torch.manual_seed(0)
+            model_t = tt.TwoTowerModel(tt.GenericTower(wl["cfg"], "user_tower"), tt.GenericTower(wl["cfg"], "item_tower"),
+                                       *wl["maps"]).to(dev).train()
+            opt_t = tt.FusedTwoTowerOptimizer(model_t, lr=wl["lr"], max_grad_norm=1.0, table_mode="dense")
+            step_t = tt.GraphedTrainStep(model_t, opt_t, dev_batch, wl["T"])
+            for _ in range(args.warmup):
+                step_t()
+            torch.cuda.synchronize()
+            evs_t = []
+            for _ in range(args.steps):
+                flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                step_t()
+                b.record()
+                evs_t.append((a, b))
+            torch.cuda.synchronize()
+            ms_t = sum(a.elapsed_time(b) for a, b in evs_t) / args.steps
+            tf32 = {"value": B * 1e3 / ms_t, "unit": "samples/s", "ms_per_step": ms_t,
+                    "note": "tower / encoder GEMMs in TF32 (torch.backends.cuda.matmul.allow_tf32), everything else as in `value`"}
+            del step_t, opt_t, model_t
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+
     kernels = []
     if not args.no_kernels:
         try:
@@ -595,7 +628,7 @@ def main():
     line = {
         "metric": "train samples/sec (fwd+bwd+clip+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "tf32_towers": tf32,
         "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "flushed between steps by an untimed 256 MiB write; step = one CUDA-graph replay",
