@@ -175,7 +175,8 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------- kernel rooflines
 def time_op(fn, reps, flush):
     """Mean CUDA-event duration (ms) of fn() on the current stream, L2 flushed before each rep."""
-    fn()  # untimed warm-up: first-launch costs (function attributes, lazy module load) stay out of the mean
+    for _ in range(3):  # untimed warm-up: first-launch costs (function attributes, lazy module load) and the caching
+        fn()            # allocator's first cudaMalloc of each output / workspace block stay out of the mean
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
