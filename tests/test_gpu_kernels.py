@@ -521,6 +521,38 @@ def test_topk_tc_history_mask_and_merge():
     assert np.array_equal(mi.cpu().numpy(), full_idx)
 
 
+@pytest.mark.parametrize("Bq", [70, 1100])
+def test_topk_tc_history_mask_with_sampled_thresholds(Bq):
+    """Corpus large enough for the sampling pass (>= 2^17 rows); every query masks its own best items plus random ones,
+    so masked rows sit among the block maxima the starting threshold is derived from (the rank is pushed down by the
+    number of masked rows in sampled tiles) and the drains have to drop masked candidates.  Bq = 70: one query tile,
+    single-CTA clusters; Bq = 1100: CTA pairs with multicast corpus tiles."""
+    gen = torch.Generator().manual_seed(23 + Bq)
+    Nc, D, K = 140_000, 128, 50
+    q = torch.nn.functional.normalize(torch.randn(Bq, D, generator=gen), dim=1)
+    e = torch.nn.functional.normalize(torch.randn(Nc, D, generator=gen), dim=1)
+    qd, ed = q.to(DEV), e.to(DEV)
+    _, full_idx = ops.score_topk(qd, ed, 40)                     # fp32 path (oracle-checked above) picks the rows to mask
+    full_idx = full_idx.cpu().numpy()
+    rs = np.random.RandomState(5)
+    hist = [np.unique(np.concatenate([rs.choice(Nc, size=(r % 5) * 40, replace=False), full_idx[r, :(r % 3) * 20]]))
+            for r in range(Bq)]
+    off = np.zeros(Bq + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(h) for h in hist])
+    flat = np.concatenate(hist).astype(np.int64) if off[-1] else np.zeros(1, dtype=np.int64)
+    offd, flatd = torch.from_numpy(off).to(DEV), torch.from_numpy(flat).to(DEV)
+    s_, idx = ops.score_topk(qd, ed, K, 0, offd, flatd, precision="bf16")
+    assert ops.topk_stats["unverified"] == 0, ops.topk_stats
+    if Bq <= 128:    # the CPU oracle on this corpus takes seconds per 100 queries
+        vals_ref, idx_ref = O.score_topk(q.numpy(), e.numpy(), K, hist_mask=hist)
+        assert np.array_equal(idx.cpu().numpy(), idx_ref)
+        assert np.allclose(s_.cpu().numpy(), vals_ref, atol=1e-12)
+    else:            # against this library's exact fp32 path, itself oracle-checked with masks above
+        s32, i32 = ops.score_topk(qd, ed, K, 0, offd, flatd)
+        assert torch.equal(idx, i32)
+        assert torch.allclose(s_, s32, atol=1e-12)
+
+
 def test_topk_tc_equals_fp32_path_at_scale():
     """Q=2048 x N=400k (an 3.3 GB score matrix if materialised): the tensor-core path and the fp32 SIMT path of this
     library must return identical rows (both claim the oracle's answer; the fp32 path is oracle-checked above)."""
