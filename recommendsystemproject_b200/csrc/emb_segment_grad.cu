@@ -233,8 +233,10 @@ seg_reduce_rows(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t
 // of a segment is one contiguous 128-byte line), 4 segments per warp and CPL * 2 independent 16-byte loads in flight
 // per lane.  Most segments of a 10M-row table hold one or two positions, so the kernel lives on memory-level
 // parallelism, not on the length of the inner loop.
+// <= 64 registers at D <= 128: 4 blocks = 32 warps per SM (ncu: long_scoreboard-bound at the 2 blocks per SM that 86
+// registers allowed)
 template <int CPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2)
 seg_reduce_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
                      const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
                      const float *__restrict__ partial, float scale, int SEG_CHUNK, float *__restrict__ row_grad,
@@ -258,11 +260,12 @@ seg_reduce_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const in
 #pragma unroll
             for (int k = 0; k < CPL; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
             if (len <= SEG_CHUNK) {
-                for (int i = p0; i < p1; i += 2) {
-                    float4 v[2][CPL];
-                    bool use[2];
+                constexpr int UN = (CPL <= 2) ? 2 : 1;   // positions in flight per lane (register budget: 64)
+                for (int i = p0; i < p1; i += UN) {
+                    float4 v[UN][CPL];
+                    bool use[UN];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < UN; ++u) {
                         use[u] = (i + u) < p1;
                         if (use[u]) {
                             const int32_t p = __ldg(sorted_pos + i + u);
@@ -284,7 +287,7 @@ seg_reduce_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const in
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u)
+                    for (int u = 0; u < UN; ++u)
                         if (use[u]) {
 #pragma unroll
                             for (int k = 0; k < CPL; ++k) {
