@@ -465,6 +465,55 @@ def test_ce_tc_backward_large_properties():
         assert rel < 3e-2, f"{name}: bf16 tensor-core path differs from the fp32 path by {rel:.3e} (relative Frobenius)"
 
 
+def test_c4_full_size_fused_ce_properties():
+    """BASELINE configs[3] at full size (B=65536 rows + 4096 shared hard negatives, D=128, T=0.05: a 18 GB logit matrix
+    if it were materialised) through the tcgen05 fwd+bwd.  Checked against fp64 torch on the bf16-rounded inputs for
+    SAMPLED rows / columns (what the kernel is meant to compute; tolerances = bf16 probabilities, fp32 accumulation):
+      * row log-sum-exp and loss terms of 512 sampled rows;
+      * dU of those rows (needs only their own softmax rows);
+      * dI of 256 sampled item columns and dPool of 128 pool rows (need the kernel's lse of ALL rows, checked above on
+        the sample) -- plus the identity sum_j G[b, j] = 0 that every softmax gradient row obeys."""
+    gen = torch.Generator(device=DEV).manual_seed(404)
+    B, H, D, T = 65536, 4096, 128, 0.05
+    u = torch.nn.functional.normalize(torch.randn(B, D, device=DEV, generator=gen), dim=1)
+    it = torch.nn.functional.normalize(torch.randn(B, D, device=DEV, generator=gen), dim=1)
+    pool = torch.nn.functional.normalize(torch.randn(H, D, device=DEV, generator=gen), dim=1)
+    ids = torch.randint(1, B // 3, (B,), device=DEV, generator=gen)        # ~3 rows share an item id: collision masks
+    ud, idv, pd = (t.clone().requires_grad_(True) for t in (u, it, pool))
+    loss, lse, flags = ops.fused_inbatch_ce(ud, idv, ids, None, pd, T, precision="bf16")
+    loss.backward()
+    assert int(flags.item()) == 0 and bool(torch.isfinite(loss))
+    ub, ib, pb = (t.bfloat16().double() for t in (u, it, pool))
+    rows = torch.randperm(B, device=DEV, generator=gen)[:512]
+    z = torch.cat([ub[rows] @ ib.t(), ub[rows] @ pb.t()], dim=1) / T                       # [512, B + H]
+    coll = (ids[rows, None] == ids[None, :]) & (rows[:, None] != torch.arange(B, device=DEV)[None, :])
+    z[:, :B] = z[:, :B].masked_fill(coll, -1e9)
+    lse_ref = torch.logsumexp(z, dim=1)
+    assert torch.allclose(lse[rows].double(), lse_ref, atol=2e-3), float((lse[rows].double() - lse_ref).abs().max())
+    p = torch.exp(z - lse_ref[:, None])
+    assert float((p.sum(1) - 1).abs().max()) < 1e-9
+    g = p.clone()
+    g[torch.arange(512, device=DEV), rows] -= 1.0                                          # dL/dz * B
+    du_ref = (g[:, :B] @ ib + g[:, B:] @ pb) / (T * B)
+    rel = float((ud.grad[rows].double() - du_ref).norm() / du_ref.norm())
+    assert rel < 2e-2, f"dU rel {rel:.3e}"
+    # columns: G[:, j] for all rows needs every row's lse -> use the kernel's (sample-checked) lse
+    cols = torch.randperm(B, device=DEV, generator=gen)[:256]
+    zc = (ub @ ib[cols].t()) / T                                                           # [B, 256]
+    collc = (ids[:, None] == ids[None, cols]) & (torch.arange(B, device=DEV)[:, None] != cols[None, :])
+    zc = zc.masked_fill(collc, -1e9)
+    gc = torch.exp(zc - lse.double()[:, None])
+    gc[cols, torch.arange(256, device=DEV)] -= 1.0
+    di_ref = (gc.t() @ ub) / (T * B)
+    rel = float((idv.grad[cols].double() - di_ref).norm() / di_ref.norm())
+    assert rel < 2e-2, f"dI rel {rel:.3e}"
+    pc = torch.randperm(H, device=DEV, generator=gen)[:128]
+    gp = torch.exp((ub @ pb[pc].t()) / T - lse.double()[:, None])
+    dp_ref = (gp.t() @ ub) / (T * B)
+    rel = float((pd.grad[pc].double() - dp_ref).norm() / dp_ref.norm())
+    assert rel < 2e-2, f"dPool rel {rel:.3e}"
+
+
 # ---------------------------------------------------------------- scoring + top-K, tcgen05 (bf16 filter + exact re-rank)
 @pytest.mark.parametrize("Bq,Nc,D,K", [(1, 50, 64, 5), (33, 1000, 64, 10), (64, 3416, 128, 50), (100, 20000, 128, 100),
                                        (5, 130, 128, 128), (300, 70000, 128, 100), (129, 257, 64, 20)])
@@ -654,3 +703,88 @@ def test_sharded_embedding_bag_owner_side_pooling_world1():
         assert int(n_unique.item()) == n and torch.equal(rows[:n], r_ref[:n])
         assert torch.allclose(row_grad[:n], g_ref[:n], atol=1e-6, rtol=1e-5)
         assert float(bag._weight_ext[-1].abs().max()) == 0.0     # the null row stays zero
+
+
+def test_c3_full_size_embedding_path_properties():
+    """BASELINE configs[2] slice at full size (B=65536 samples x L=200 ragged ids over a 10M-row D=128 table: 13.1M
+    positions, far beyond what the CPU oracle can chew), checked through size-independent identities computed by
+    independent torch ops in fp64:
+      * sum-pooling is linear:  sum_b pooled[b] == sum_rows count[row] * table[row]  (count from torch.bincount);
+      * the segment gradient's unique rows are exactly torch.unique of the valid ids (bit-exact, ascending), and its
+        checksum  sum_rows row_grad == sum_b n_valid[b] * g[b]  ("checksum of checksums");
+      * row-wise Adam moves every touched row (by at most ~lr per element on the first step) and no other row."""
+    gen = torch.Generator(device=DEV).manual_seed(303)
+    B, L, D, V = 65536, 200, 128, 10_000_001
+    table = torch.empty(V, D, device=DEV).uniform_(-0.05, 0.05, generator=gen)
+    ids = torch.randint(1, V, (B, L), device=DEV, generator=gen)
+    lens = torch.randint(1, L + 1, (B,), device=DEV, generator=gen)
+    ids[torch.arange(L, device=DEV)[None, :] >= lens[:, None]] = 0
+    pooled = torch.empty(B, D, device=DEV)
+    oob = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.gather_pool_into(table, ids, ops.POOL_SUM, 0, pooled, None, oob)
+    assert int(oob.item()) == 0
+    count = torch.bincount(ids.reshape(-1), minlength=V)                 # pads counted at row 0 (pooled over, like the reference)
+    nz = torch.nonzero(count).reshape(-1)
+    ref_sum = (count[nz, None].double() * table[nz].double()).sum(0)
+    got_sum = pooled.double().sum(0)
+    assert torch.allclose(got_sum, ref_sum, rtol=1e-6, atol=1e-3), float((got_sum - ref_sum).abs().max())
+    del pooled
+    g = torch.randn(B, D, device=DEV, generator=gen)
+    sq = torch.zeros(1, device=DEV)
+    rows, rg, nu = ops.segment_grad(ids, ops.POOL_SUM, 0, V, g, None, D, sq)
+    U = int(nu.item())
+    uniq = torch.unique(ids[ids != 0])
+    assert U == uniq.numel() and torch.equal(rows[:U], uniq)
+    ref_chk = (lens[:, None].double() * g.double()).sum(0)
+    got_chk = rg[:U].double().sum(0)
+    assert torch.allclose(got_chk, ref_chk, rtol=1e-6, atol=1e-2), float((got_chk - ref_chk).abs().max())
+    assert abs(float(sq.item()) - float(rg[:U].double().pow(2).sum())) < 1e-4 * float(sq.item())
+    m, v = torch.zeros_like(table), torch.zeros_like(table)
+    probe = torch.cat([uniq[:1000], uniq[-1000:]])
+    before_touched = table[probe].clone()
+    untouched = torch.ones(V, dtype=torch.bool, device=DEV)
+    untouched[uniq] = False
+    probe_u = torch.nonzero(untouched).reshape(-1)[:2000]
+    before_untouched = table[probe_u].clone()
+    ops.rowwise_adam_(table, m, v, rows, rg, nu, torch.ones(1, device=DEV), 1e-3, 0.9, 0.999, 1e-8,
+                      torch.ones(1, dtype=torch.int64, device=DEV))
+    moved = (table[probe] - before_touched).abs()
+    assert float(moved.max()) <= 1e-3 * 1.001 and bool((moved.max(dim=1).values > 0).all())
+    assert torch.equal(table[probe_u], before_untouched)
+    assert int((m != 0).any(dim=1).sum()) == U
+
+
+def test_c5_full_size_topk_properties():
+    """BASELINE configs[4] at full size on one GPU: top-100 over a 10M x 128 corpus (tensor-core filter + exact re-rank).
+      * 48 sampled queries against a chunked fp64 torch scan of the whole corpus: same rows, same order, same scores;
+      * every returned list is sorted (score desc, row asc), rows are distinct and in range, scores are the exact fp64
+        dot products of the rows returned;
+      * idempotence: a second run returns the identical tensors; no query needed the fp32 fallback."""
+    gen = torch.Generator(device=DEV).manual_seed(505)
+    N, D, Q, K = 10_000_000, 128, 4096, 100
+    e = torch.nn.functional.normalize(torch.randn(N, D, device=DEV, generator=gen), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(Q, D, device=DEV, generator=gen), dim=1)
+    prep = ops.PreparedCorpus(e)
+    s, idx = ops.score_topk(q, e, K, precision="bf16", prepared=prep)
+    assert ops.topk_stats["unverified"] == 0, ops.topk_stats
+    s2, idx2 = ops.score_topk(q, e, K, precision="bf16", prepared=prep)
+    assert torch.equal(idx, idx2) and torch.equal(s, s2)
+    assert bool((idx >= 0).all()) and bool((idx < N).all())
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+    tie = s[:, 1:] == s[:, :-1]
+    assert bool((idx[:, 1:][tie] > idx[:, :-1][tie]).all())
+    assert int((torch.sort(idx, dim=1).values[:, 1:] == torch.sort(idx, dim=1).values[:, :-1]).sum()) == 0
+    sub = torch.arange(0, Q, Q // 48, device=DEV)[:48]
+    exact_of_returned = torch.einsum("qkd,qd->qk", e[idx[sub]].double(), q[sub].double())
+    assert torch.allclose(s[sub], exact_of_returned, atol=1e-12)
+    best_v = torch.full((48, K), -float("inf"), dtype=torch.float64, device=DEV)
+    best_i = torch.zeros(48, K, dtype=torch.int64, device=DEV)
+    qd = q[sub].double()
+    for a in range(0, N, 1_000_000):
+        sc = qd @ e[a:a + 1_000_000].double().t()
+        v, i = sc.topk(K, dim=1)
+        cat_v, cat_i = torch.cat([best_v, v], 1), torch.cat([best_i, i + a], 1)
+        order = torch.argsort(cat_v, dim=1, descending=True, stable=True)[:, :K]    # earlier (smaller) rows win ties
+        best_v, best_i = torch.gather(cat_v, 1, order), torch.gather(cat_i, 1, order)
+    assert torch.equal(idx[sub], best_i)
+    assert torch.allclose(s[sub], best_v, atol=1e-12)
