@@ -214,6 +214,35 @@ TT_API int tt_score_topk_tc(const float *query, int64_t n_query, const float *co
 TT_API int tt_topk_merge(const double *scores, const int64_t *idx, int n_shards, int64_t n_query, int k,
                   double *out_scores, int64_t *out_idx, void *stream);
 
+/* ------------------------------------------------------------------------
+ * 5. Small-sequence Transformer behaviour encoder, the non-GEMM parts.
+ * Replaces, inside nn.TransformerEncoderLayer as the reference builds it (SequenceEncoder.py:13-21: batch_first,
+ * post-norm, ReLU; called at SequenceEncoder.py:60 with src_key_padding_mask): scaled-dot-product attention with
+ * key padding mask and attention dropout, and  norm(x + dropout(sublayer(x))).  fp32 throughout.
+ * Dropout masks are a counter-based hash of (*seed_dev, call_id, element index); the backward rebuilds them, so the
+ * caller passes the same three values to both and changes *seed_dev between steps (it lives in device memory: a
+ * CUDA-graph replay sees the new value).  dropout_p = 0 or seed_dev = NULL: no dropout.
+ *   tt_attn_small_*: qkv [batch, len, 3*heads*head_dim] packed as the in_proj GEMM leaves it (q | k | v, head h =
+ *     columns [h*head_dim, (h+1)*head_dim) of each third); key_pad_mask [batch, len] bytes, 1 = ignore this key
+ *     (nullable); out / grad_out [batch, len, heads*head_dim].  len <= 32, head_dim in {8, 16, 32}.
+ *   tt_add_dropout_ln_*: y = LayerNorm(x + dropout(z)) over rows of `dim` (= 32k <= 256, biased variance, eps as
+ *     given); xhat [rows, dim] and rstd [rows] are saved for the backward, which returns grad_x, grad_z and the full
+ *     grad_gamma / grad_beta (per-CTA partials in `workspace`, added in fixed order: deterministic).
+ * ---------------------------------------------------------------------- */
+TT_API int tt_attn_small_fwd(const float *qkv, const uint8_t *key_pad_mask, int64_t batch, int len, int heads, int head_dim,
+                      float dropout_p, const int64_t *seed_dev, int64_t call_id, float *out, void *stream);
+TT_API int tt_attn_small_bwd(const float *qkv, const uint8_t *key_pad_mask, const float *grad_out, int64_t batch, int len,
+                      int heads, int head_dim, float dropout_p, const int64_t *seed_dev, int64_t call_id,
+                      float *grad_qkv, void *stream);
+TT_API int tt_add_dropout_ln_fwd(const float *x, const float *z, int64_t rows, int dim, const float *gamma, const float *beta,
+                          float eps, float dropout_p, const int64_t *seed_dev, int64_t call_id, float *y, float *xhat,
+                          float *rstd, void *stream);
+TT_API int tt_add_dropout_ln_bwd_workspace(int64_t rows, int dim, size_t *bytes_host);
+TT_API int tt_add_dropout_ln_bwd(const float *grad_y, const float *xhat, const float *rstd, const float *gamma, int64_t rows,
+                          int dim, float dropout_p, const int64_t *seed_dev, int64_t call_id, float *grad_x,
+                          float *grad_z, float *grad_gamma, float *grad_beta, void *workspace, size_t workspace_bytes,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

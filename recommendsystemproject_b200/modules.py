@@ -159,6 +159,46 @@ class SequenceEncoder(nn.Module):
         layer = nn.TransformerEncoderLayer(d_model=model_dim, nhead=n_head, dim_feedforward=dim_feedforward,
                                            dropout=dropout, batch_first=True)
         self.transformer_backbone = nn.TransformerEncoder(layer, num_layers=n_layers, enable_nested_tensor=False)
+        # The layers keep torch's parameter names (checkpoints of the reference load unchanged) but, on the GPU, run
+        # through two fused kernels + cuBLAS GEMMs instead of torch's ~55 launches per layer (`fused_layers`).
+        self.fused_layers = True
+        self.dropout_p = float(dropout)
+        self.n_head = int(n_head)
+        # dropout seed of the fused kernels: lives on the device and is bumped once per training forward, so a CUDA
+        # graph replay draws new masks every step; reproducible under torch.manual_seed
+        # (own generator seeded from torch.initial_seed(): the global stream the reference's init consumes is untouched)
+        gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 63))
+        self.register_buffer("_drop_seed", torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, generator=gen), persistent=False)
+
+    def _fused_ok(self, x):
+        d = x.shape[-1]
+        dh = d // self.n_head
+        first = self.transformer_backbone.layers[0]
+        return (self.fused_layers and x.is_cuda and x.dtype == torch.float32 and x.shape[1] <= 32 and dh in (8, 16, 32)
+                and d % 32 == 0 and d <= 256 and not first.norm_first and self.transformer_backbone.norm is None
+                and first.activation_relu_or_gelu == 1)
+
+    def _fused_backbone(self, x, padding_mask):
+        """nn.TransformerEncoder.forward(src, src_key_padding_mask) for post-norm ReLU layers (SequenceEncoder.py:60):
+        x = norm1(x + dropout1(out_proj(attn(in_proj(x)))));  x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))."""
+        p = self.dropout_p if self.training else 0.0
+        seed = None
+        if p > 0.0:
+            self._drop_seed.add_(1)
+            seed = self._drop_seed
+        pad = padding_mask.to(torch.uint8).contiguous()
+        for li, layer in enumerate(self.transformer_backbone.layers):
+            sa = layer.self_attn
+            qkv = F.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+            a = ops.attn_small(qkv, pad, sa.num_heads, p, seed, 3 * li)
+            a = F.linear(a, sa.out_proj.weight, sa.out_proj.bias)
+            x = ops.add_dropout_layer_norm(x, a, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p, seed, 3 * li + 1)
+            f = F.relu(F.linear(x, layer.linear1.weight, layer.linear1.bias))
+            if p > 0.0:
+                f = F.dropout(f, p, True)
+            f = F.linear(f, layer.linear2.weight, layer.linear2.bias)
+            x = ops.add_dropout_layer_norm(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p, seed, 3 * li + 2)
+        return x
 
     def forward(self, input_dict):
         main = self.feature_embedder.feature_config_list[0]
@@ -170,7 +210,10 @@ class SequenceEncoder(nn.Module):
         padding_mask = padding_mask.clone()
         padding_mask[:, -1] &= ~all_pad
         seq_emb = self.feature_embedder(input_dict)
-        ctx = self.transformer_backbone(src=seq_emb, src_key_padding_mask=padding_mask)
+        if self._fused_ok(seq_emb):
+            ctx = self._fused_backbone(seq_emb, padding_mask)
+        else:
+            ctx = self.transformer_backbone(src=seq_emb, src_key_padding_mask=padding_mask)
         return self._gather_last_valid(ctx, padding_mask)
 
     def _gather_last_valid(self, seq_output, padding_mask):

@@ -268,6 +268,92 @@ def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, tempera
 
 
 # --------------------------------------------------------------------------
+# 3b. small-sequence Transformer encoder: attention core and add + dropout + LayerNorm
+# --------------------------------------------------------------------------
+class AttnSmall(torch.autograd.Function):
+    """softmax(q k^T / sqrt(dh) + key padding mask) -> dropout -> . v for L <= 32, straight from the packed in_proj
+    output (what nn.MultiheadAttention computes between in_proj and out_proj, SequenceEncoder.py:13-21,60)."""
+
+    @staticmethod
+    def forward(ctx, qkv, key_pad_u8, heads, dropout_p, seed_dev, call_id):
+        _need_cuda(qkv)
+        lib = _lib.load()
+        qkv = qkv.contiguous()
+        B, L, three_d = qkv.shape
+        d = three_d // 3
+        out = torch.empty(B, L, d, dtype=torch.float32, device=qkv.device)
+        check(lib.tt_attn_small_fwd(_p(qkv), _p(key_pad_u8), B, L, heads, d // heads, float(dropout_p), _p(seed_dev),
+                                    int(call_id), _p(out), _stream()), "tt_attn_small_fwd")
+        _count()
+        ctx.save_for_backward(qkv, key_pad_u8, seed_dev)
+        ctx.cfg = (heads, float(dropout_p), int(call_id))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        qkv, key_pad_u8, seed_dev = ctx.saved_tensors
+        heads, p, call_id = ctx.cfg
+        lib = _lib.load()
+        B, L, three_d = qkv.shape
+        grad_qkv = torch.empty_like(qkv)
+        check(lib.tt_attn_small_bwd(_p(qkv), _p(key_pad_u8), _p(grad_out.contiguous()), B, L, heads, three_d // 3 // heads, p,
+                                    _p(seed_dev), call_id, _p(grad_qkv), _stream()), "tt_attn_small_bwd")
+        _count()
+        return grad_qkv, None, None, None, None, None
+
+
+class AddDropoutLayerNorm(torch.autograd.Function):
+    """y = LayerNorm(x + dropout(z)): the post-norm residual step of nn.TransformerEncoderLayer (twice per layer)."""
+
+    @staticmethod
+    def forward(ctx, x, z, gamma, beta, eps, dropout_p, seed_dev, call_id):
+        _need_cuda(x, z)
+        lib = _lib.load()
+        x = x.contiguous()
+        z = z.contiguous()
+        dim = x.shape[-1]
+        rows = x.numel() // dim
+        y = torch.empty_like(x)
+        xhat = torch.empty_like(x)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        check(lib.tt_add_dropout_ln_fwd(_p(x), _p(z), rows, dim, _p(gamma), _p(beta), float(eps), float(dropout_p),
+                                        _p(seed_dev), int(call_id), _p(y), _p(xhat), _p(rstd), _stream()),
+              "tt_add_dropout_ln_fwd")
+        _count()
+        ctx.save_for_backward(xhat, rstd, gamma, seed_dev)
+        ctx.cfg = (float(dropout_p), int(call_id))
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        xhat, rstd, gamma, seed_dev = ctx.saved_tensors
+        p, call_id = ctx.cfg
+        lib = _lib.load()
+        dim = xhat.shape[-1]
+        rows = xhat.numel() // dim
+        nbytes = ctypes.c_size_t(0)
+        check(lib.tt_add_dropout_ln_bwd_workspace(rows, dim, ctypes.byref(nbytes)), "tt_add_dropout_ln_bwd_workspace")
+        ws = _ws(nbytes.value, xhat.device)
+        gx = torch.empty_like(xhat)
+        gz = torch.empty_like(xhat)
+        gg = torch.empty_like(gamma)
+        gb = torch.empty_like(gamma)
+        check(lib.tt_add_dropout_ln_bwd(_p(grad_y.contiguous()), _p(xhat), _p(rstd), _p(gamma), rows, dim, p, _p(seed_dev),
+                                        call_id, _p(gx), _p(gz), _p(gg), _p(gb), _p(ws), ws.numel(), _stream()),
+              "tt_add_dropout_ln_bwd")
+        _count(2)
+        return gx, gz, gg, gb, None, None, None, None
+
+
+def attn_small(qkv, key_pad_u8, heads, dropout_p=0.0, seed_dev=None, call_id=0):
+    return AttnSmall.apply(qkv, key_pad_u8, heads, dropout_p, seed_dev, call_id)
+
+
+def add_dropout_layer_norm(x, z, gamma, beta, eps=1e-5, dropout_p=0.0, seed_dev=None, call_id=0):
+    return AddDropoutLayerNorm.apply(x, z, gamma, beta, eps, dropout_p, seed_dev, call_id)
+
+
+# --------------------------------------------------------------------------
 # 4. corpus scoring + top-K
 # --------------------------------------------------------------------------
 class PreparedCorpus:

@@ -788,3 +788,81 @@ def test_c5_full_size_topk_properties():
         best_v, best_i = torch.gather(cat_v, 1, order), torch.gather(cat_i, 1, order)
     assert torch.equal(idx[sub], best_i)
     assert torch.allclose(s[sub], best_v, atol=1e-12)
+
+
+# ---------------------------------------------------------------- small-sequence encoder pieces
+@pytest.mark.parametrize("B,L,H,dh", [(7, 20, 4, 16), (33, 32, 2, 32), (5, 1, 4, 8), (64, 13, 8, 16)])
+def test_attn_small_matches_torch_attention(B, L, H, dh):
+    """No dropout: forward and backward against torch's scaled_dot_product_attention with the same key padding mask
+    (what nn.MultiheadAttention runs between in_proj and out_proj)."""
+    gen = torch.Generator().manual_seed(B * 100 + L)
+    d = H * dh
+    qkv = torch.randn(B, L, 3 * d, generator=gen)
+    lens = torch.randint(1, L + 1, (B,), generator=gen)
+    pad = torch.arange(L)[None, :] >= lens[:, None]                       # True = padding key
+    up = torch.randn(B, L, d, generator=gen)
+    ref_in = qkv.clone().requires_grad_(True)
+    q, k, v = (t.view(B, L, H, dh).transpose(1, 2) for t in ref_in.split(d, dim=2))
+    mask = torch.zeros(B, 1, 1, L).masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(B, L, d)
+    (ref * up).sum().backward()
+    x = qkv.to(DEV).requires_grad_(True)
+    out = ops.attn_small(x, pad.to(torch.uint8).to(DEV), H)
+    (out * up.to(DEV)).sum().backward()
+    assert torch.allclose(out.detach().cpu(), ref.detach(), atol=2e-6, rtol=1e-5)
+    assert torch.allclose(x.grad.cpu(), ref_in.grad, atol=5e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("rows,dim", [(37, 64), (1000, 32), (513, 256), (9, 96)])
+def test_add_dropout_layer_norm_matches_torch(rows, dim):
+    gen = torch.Generator().manual_seed(rows + dim)
+    x, z, up = (torch.randn(rows, dim, generator=gen) for _ in range(3))
+    gamma, beta = torch.randn(dim, generator=gen), torch.randn(dim, generator=gen)
+    refs = [t.clone().requires_grad_(True) for t in (x, z, gamma, beta)]
+    ref = torch.nn.functional.layer_norm(refs[0] + refs[1], (dim,), refs[2], refs[3], 1e-5)
+    (ref * up).sum().backward()
+    mine = [t.to(DEV).requires_grad_(True) for t in (x, z, gamma, beta)]
+    y = ops.add_dropout_layer_norm(mine[0], mine[1], mine[2], mine[3], 1e-5)
+    (y * up.to(DEV)).sum().backward()
+    assert torch.allclose(y.detach().cpu(), ref.detach(), atol=5e-6, rtol=1e-5)
+    for a, b, name in zip(mine, refs, ("dx", "dz", "dgamma", "dbeta")):
+        assert torch.allclose(a.grad.cpu(), b.grad, atol=2e-5 * (rows ** 0.5 if name in ("dgamma", "dbeta") else 1), rtol=1e-4), name
+
+
+def test_fused_encoder_dropout_is_consistent_and_deterministic():
+    """Dropout inside the fused kernels: the keep rate is 1 - p, the same (seed, call site) gives the same mask, another
+    seed or call site a different one, and the backward uses the mask of the forward (directional derivative)."""
+    gen = torch.Generator().manual_seed(7)
+    p = 0.3
+    seed = torch.tensor([12345], dtype=torch.int64, device=DEV)
+    rows, dim = 4096, 64
+    zeros, ones = torch.zeros(rows, dim, device=DEV), torch.ones(rows, dim, device=DEV)
+    g1, b0 = torch.ones(dim, device=DEV), torch.zeros(dim, device=DEV)
+    y = ops.add_dropout_layer_norm(zeros, ones, g1, b0, 1e-5, p, seed, 1)
+    keep = (y > 0).float().mean().item()                                  # kept entries sit above the row mean
+    assert abs(keep - (1 - p)) < 4 * (p * (1 - p) / (rows * dim)) ** 0.5
+    assert torch.equal(y, ops.add_dropout_layer_norm(zeros, ones, g1, b0, 1e-5, p, seed, 1))
+    assert not torch.equal(y, ops.add_dropout_layer_norm(zeros, ones, g1, b0, 1e-5, p, seed, 2))
+    assert not torch.equal(y, ops.add_dropout_layer_norm(zeros, ones, g1, b0, 1e-5, p, seed + 1, 1))
+    # directional derivatives (fp64 accumulation of fp32 outputs, central differences)
+    B, L, H, dh = 16, 20, 4, 16
+    qkv = torch.randn(B, L, 3 * H * dh, generator=gen).to(DEV)
+    pad = (torch.arange(L)[None, :] >= torch.randint(1, L + 1, (B, 1), generator=gen)).to(torch.uint8).to(DEV)
+    w = torch.randn(B, L, H * dh, generator=gen).to(DEV)
+    v = torch.randn(B, L, 3 * H * dh, generator=gen).to(DEV)
+    xq = qkv.clone().requires_grad_(True)
+    (ops.attn_small(xq, pad, H, p, seed, 5) * w).sum().backward()
+    eps = 1e-2
+    f = lambda t: float((ops.attn_small(t, pad, H, p, seed, 5).double() * w.double()).sum())
+    num = (f(qkv + eps * v) - f(qkv - eps * v)) / (2 * eps)
+    ana = float((xq.grad.double() * v.double()).sum())
+    assert abs(num - ana) < 2e-2 * max(1.0, abs(ana)), (num, ana)
+    x0, z0 = torch.randn(rows, dim, generator=gen).to(DEV), torch.randn(rows, dim, generator=gen).to(DEV)
+    gam, bet = torch.randn(dim, generator=gen).to(DEV), torch.randn(dim, generator=gen).to(DEV)
+    wl, vz = torch.randn(rows, dim, generator=gen).to(DEV), torch.randn(rows, dim, generator=gen).to(DEV)
+    zz = z0.clone().requires_grad_(True)
+    (ops.add_dropout_layer_norm(x0, zz, gam, bet, 1e-5, p, seed, 9) * wl).sum().backward()
+    f2 = lambda t: float((ops.add_dropout_layer_norm(x0, t, gam, bet, 1e-5, p, seed, 9).double() * wl.double()).sum())
+    num = (f2(z0 + eps * vz) - f2(z0 - eps * vz)) / (2 * eps)
+    ana = float((zz.grad.double() * vz.double()).sum())
+    assert abs(num - ana) < 2e-2 * max(1.0, abs(ana)), (num, ana)
