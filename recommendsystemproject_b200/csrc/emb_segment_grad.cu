@@ -92,6 +92,113 @@ __global__ void seg_chunk_counts(int32_t *__restrict__ seg_start, const int32_t 
     }
 }
 
+// ---- small problems (an ML-1M batch: 10^2..10^4 positions per table, vocabularies of 10..10^4 rows) ----
+// keys -> sort -> heads -> scan -> starts -> chunk counts -> scan are nine launches of the general path; here ONE CTA
+// does all of it in shared memory: (row << pos_bits | position) packed into one 32-bit key, cub::BlockRadixSort over
+// the significant bits only, block scans for the segment numbers and the chunk bases.  Same outputs as the general
+// path (sorted positions ascending inside a segment => same summation order), for n <= 1024 * ITEMS positions with
+// bits(vocab) + bits(n) <= 32.
+template <int ITEMS>
+__global__ void __launch_bounds__(1024, 1)
+seg_small_prep(const int64_t *__restrict__ ids, int n, int64_t pad, int64_t vocab, int pos_bits, int end_bit, int SEG_CHUNK,
+               int32_t *__restrict__ sorted_pos, int32_t *__restrict__ seg_start, int64_t *__restrict__ unique_rows,
+               int32_t *__restrict__ chunk_base, int32_t *__restrict__ counters) {
+    using Sort = cub::BlockRadixSort<uint32_t, 1024, ITEMS>;
+    using Scan = cub::BlockScan<int, 1024>;
+    extern __shared__ unsigned char seg_small_smem[];
+    auto &sort_tmp = *reinterpret_cast<typename Sort::TempStorage *>(seg_small_smem);
+    auto &scan_tmp = *reinterpret_cast<typename Scan::TempStorage *>(seg_small_smem);
+    __shared__ uint32_t last_key[1024];
+    __shared__ int s_U, s_valid;
+    const int t = threadIdx.x;
+    const uint32_t SENT = 0xffffffffu;
+    uint32_t key[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int p = t * ITEMS + k;
+        key[k] = SENT;
+        if (p < n) {
+            const int64_t id = ids[p];
+            if (!(id == pad || id < 0 || id >= vocab)) key[k] = (static_cast<uint32_t>(id) << pos_bits) | static_cast<uint32_t>(p);
+        }
+    }
+    Sort(sort_tmp).Sort(key, 0, end_bit);     // dropped positions carry all-ones in the sorted bits: they end up last
+    __syncthreads();
+    last_key[t] = key[ITEMS - 1];
+    __syncthreads();
+    // heads and the number of valid positions
+    int heads = 0, valid = 0;
+    uint32_t prev = (t == 0) ? SENT : last_key[t - 1];
+    uint32_t head_mask = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const bool ok = key[k] != SENT;
+        const bool hd = ok && (prev == SENT || (prev >> pos_bits) != (key[k] >> pos_bits) || (t == 0 && k == 0));
+        prev = key[k];
+        head_mask |= (hd ? 1u : 0u) << k;
+        valid += ok ? 1 : 0;
+    }
+    heads = __popc(head_mask);
+    int seg_base, total_heads;
+    Scan(scan_tmp).ExclusiveSum(heads, seg_base, total_heads);
+    __syncthreads();
+    int valid_base, total_valid;
+    Scan(scan_tmp).ExclusiveSum(valid, valid_base, total_valid);
+    __syncthreads();
+    if (t == 0) { s_U = total_heads; s_valid = total_valid; counters[0] = total_heads; counters[1] = total_valid; }
+    int seg = seg_base;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int idx = t * ITEMS + k;
+        if (key[k] != SENT) {
+            sorted_pos[idx] = static_cast<int32_t>(key[k] & ((1u << pos_bits) - 1u));
+            if ((head_mask >> k) & 1u) {
+                seg_start[seg] = idx;
+                unique_rows[seg] = static_cast<int64_t>(key[k] >> pos_bits);
+                ++seg;
+            }
+        }
+    }
+    __syncthreads();   // seg_start[] of this CTA is visible to this CTA (global writes + barrier)
+    const int U = s_U, n_valid = s_valid;
+    // chunk bases: exclusive sum over segments of ceil(len / CHUNK) for the long ones
+    auto chunks_of = [&](int sg) {
+        if (sg >= U) return 0;
+        const int end = (sg + 1 < U) ? seg_start[sg + 1] : n_valid;
+        const int len = end - seg_start[sg];
+        return len > SEG_CHUNK ? (len + SEG_CHUNK - 1) / SEG_CHUNK : 0;
+    };
+    int mine = 0;
+    for (int k = 0; k < ITEMS; ++k) mine += chunks_of(t * ITEMS + k);
+    int cb;
+    Scan(scan_tmp).ExclusiveSum(mine, cb);
+    for (int k = 0; k < ITEMS; ++k) {
+        const int sg = t * ITEMS + k;
+        if (sg < U) chunk_base[sg] = cb;
+        cb += chunks_of(sg);
+    }
+}
+
+template <int ITEMS>
+static int launch_seg_small(const int64_t *ids, int n, int64_t pad, int64_t vocab, int pos_bits, int end_bit, int chunk,
+                            int32_t *sorted_pos, int32_t *seg_start, int64_t *unique_rows, int32_t *chunk_base,
+                            int32_t *counters, cudaStream_t st) {
+    using Sort = cub::BlockRadixSort<uint32_t, 1024, ITEMS>;
+    using Scan = cub::BlockScan<int, 1024>;
+    constexpr size_t smem = sizeof(typename Sort::TempStorage) > sizeof(typename Scan::TempStorage)
+                                ? sizeof(typename Sort::TempStorage) : sizeof(typename Scan::TempStorage);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(seg_small_prep<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(seg_small_prep)");
+        attr_set = true;
+    }
+    seg_small_prep<ITEMS><<<1, 1024, smem, st>>>(ids, n, pad, vocab, pos_bits, end_bit, chunk, sorted_pos, seg_start,
+                                                  unique_rows, chunk_base, counters);
+    TT_LAUNCH_CHECK("seg_small_prep");
+    return 0;
+}
+
 struct GradSrc {
     const float *grad_out;
     int64_t grad_stride;
@@ -503,6 +610,21 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
 
     const int threads = 256;
     const unsigned g1 = grid_for(n, threads);
+    int32_t *n_chunks = head;       // the general path reuses head -> chunk counts, seg_id -> chunk bases
+    int32_t *chunk_base = seg_id;
+    // small problem: one CTA prepares everything (see seg_small_prep)
+    int pos_bits = 1, id_bits = 1;
+    while ((int64_t(1) << pos_bits) < n) ++pos_bits;
+    while ((int64_t(1) << id_bits) < vocab) ++id_bits;
+    const bool small = n <= 32768 && pos_bits + id_bits <= 32;
+    if (small) {
+        const int nn = static_cast<int>(n);
+        int rc2;
+        if (nn <= 4096) rc2 = launch_seg_small<4>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
+        else if (nn <= 16384) rc2 = launch_seg_small<16>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
+        else rc2 = launch_seg_small<32>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
+        if (rc2) return rc2;
+    } else {
     seg_build_keys<<<g1, threads, 0, st>>>(ids, n, padding_idx, vocab, keys_in, vals_in);
     TT_LAUNCH_CHECK("seg_build_keys");
     int end_bit = 1;
@@ -519,14 +641,12 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
     if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum");
     seg_starts<<<g1, threads, 0, st>>>(keys_out, head, seg_id, n, sentinel, seg_start, unique_rows, counters);
     TT_LAUNCH_CHECK("seg_starts");
-    // reuse head -> chunk counts, seg_id -> chunk bases
-    int32_t *n_chunks = head;
-    int32_t *chunk_base = seg_id;
     seg_chunk_counts<<<g1, threads, 0, st>>>(seg_start, counters, n, plan.chunk, n_chunks);
     TT_LAUNCH_CHECK("seg_chunk_counts");
     tmp = plan.cub_bytes;
     e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, n_chunks, chunk_base, static_cast<int>(n), st);
     if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum(chunks)");
+    }   // general path
 
     GradSrc g{grad_out, grad_stride, argmax, len, mode, dim};
     const float scale = (mode == TT_POOL_MEAN) ? 1.0f / static_cast<float>(len) : 1.0f;
