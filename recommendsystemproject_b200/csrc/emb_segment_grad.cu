@@ -97,7 +97,7 @@ __global__ void seg_chunk_counts(int32_t *__restrict__ seg_start, const int32_t 
 // does all of it in shared memory: (row << pos_bits | position) packed into one 32-bit key, cub::BlockRadixSort over
 // the significant bits only, block scans for the segment numbers and the chunk bases.  Same outputs as the general
 // path (sorted positions ascending inside a segment => same summation order), for n <= 1024 * ITEMS positions with
-// bits(vocab) + bits(n) <= 32.
+// bits(vocab) + bits(n) <= 32; used up to 8192 positions.
 template <int ITEMS>
 __global__ void __launch_bounds__(1024, 1)
 seg_small_prep(const int64_t *__restrict__ ids, int n, int64_t pad, int64_t vocab, int pos_bits, int end_bit, int SEG_CHUNK,
@@ -616,13 +616,14 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
     int pos_bits = 1, id_bits = 1;
     while ((int64_t(1) << pos_bits) < n) ++pos_bits;
     while ((int64_t(1) << id_bits) < vocab) ++id_bits;
-    const bool small = n <= 32768 && pos_bits + id_bits <= 32;
+    // (measured on the C2 step: 17 us for <= 4096 positions against ~35 us of launches; at 16 / 32 keys per thread the
+    // single CTA is no faster than the general path -- 41 / 90 us -- so those sizes stay there)
+    const bool small = n <= 8192 && pos_bits + id_bits <= 32;
     if (small) {
         const int nn = static_cast<int>(n);
         int rc2;
         if (nn <= 4096) rc2 = launch_seg_small<4>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
-        else if (nn <= 16384) rc2 = launch_seg_small<16>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
-        else rc2 = launch_seg_small<32>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
+        else rc2 = launch_seg_small<8>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
         if (rc2) return rc2;
     } else {
     seg_build_keys<<<g1, threads, 0, st>>>(ids, n, padding_idx, vocab, keys_in, vals_in);

@@ -125,15 +125,16 @@ __global__ void __launch_bounds__(WARPS * 32)
 attn_small_bwd_kernel(AttnArgs a, const float *__restrict__ grad_out, float *__restrict__ grad_qkv) {
     extern __shared__ float smem_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per warp: K, V, Q (scaled), dO: [32][DH] each; Pd, dS: [32][33]
-    constexpr int PER_WARP = 4 * AT_MAXL * DH + 2 * AT_MAXL * (AT_MAXL + 1);
-    float *mine = smem_dyn + warp * PER_WARP;
+    // per warp: K, V, Q (scaled), dO: [L][DH] each; Pd, dS: [L][L + 1]  (sized by the actual L: more warps per SM)
+    const int LS = a.len + 1;
+    const int per_warp = 4 * a.len * DH + 2 * a.len * LS;
+    float *mine = smem_dyn + warp * per_warp;
     float (*Ks)[DH] = reinterpret_cast<float (*)[DH]>(mine);
-    float (*Vs)[DH] = reinterpret_cast<float (*)[DH]>(mine + AT_MAXL * DH);
-    float (*Qs)[DH] = reinterpret_cast<float (*)[DH]>(mine + 2 * AT_MAXL * DH);
-    float (*Gs)[DH] = reinterpret_cast<float (*)[DH]>(mine + 3 * AT_MAXL * DH);
-    float (*Pd)[AT_MAXL + 1] = reinterpret_cast<float (*)[AT_MAXL + 1]>(mine + 4 * AT_MAXL * DH);
-    float (*dS)[AT_MAXL + 1] = reinterpret_cast<float (*)[AT_MAXL + 1]>(mine + 4 * AT_MAXL * DH + AT_MAXL * (AT_MAXL + 1));
+    float (*Vs)[DH] = reinterpret_cast<float (*)[DH]>(mine + a.len * DH);
+    float (*Qs)[DH] = reinterpret_cast<float (*)[DH]>(mine + 2 * a.len * DH);
+    float (*Gs)[DH] = reinterpret_cast<float (*)[DH]>(mine + 3 * a.len * DH);
+    float *Pd = mine + 4 * a.len * DH;
+    float *dS = Pd + a.len * LS;
     __shared__ uint8_t Pad[WARPS][AT_MAXL];
     const int64_t w = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
     if (w >= a.batch * a.heads) return;
@@ -172,7 +173,7 @@ attn_small_bwd_kernel(AttnArgs a, const float *__restrict__ grad_out, float *__r
                 for (int c = 0; c < DH; ++c) x = fmaf(go[c], Vs[j][c], x);      // d(dropped prob)
                 float keep = 1.0f;
                 if (a.thresh) keep = drop_keep(seed, a.call, (w * L + i) * L + j, a.thresh) ? a.keep_scale : 0.f;
-                Pd[i][j] = p[j] * keep;
+                Pd[i * LS + j] = p[j] * keep;
                 dp[j] = x * keep;                                               // d(prob)
                 dot = fmaf(p[j], dp[j], dot);
             }
@@ -184,7 +185,7 @@ attn_small_bwd_kernel(AttnArgs a, const float *__restrict__ grad_out, float *__r
         for (int j = 0; j < AT_MAXL; ++j) {
             if (j < L) {
                 const float ds = p[j] * (dp[j] - dot);
-                dS[i][j] = ds;
+                dS[i * LS + j] = ds;
 #pragma unroll
                 for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, Ks[j][c], dq[c]);
             }
@@ -200,7 +201,7 @@ attn_small_bwd_kernel(AttnArgs a, const float *__restrict__ grad_out, float *__r
 #pragma unroll
         for (int c = 0; c < DH; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
         for (int i = 0; i < L; ++i) {
-            const float ds = dS[i][j], pd = Pd[i][j];
+            const float ds = dS[i * LS + j], pd = Pd[i * LS + j];
 #pragma unroll
             for (int c = 0; c < DH; ++c) {
                 dk[c] = fmaf(ds, Qs[i][c], dk[c]);
@@ -325,14 +326,19 @@ add_dropout_ln_bwd_kernel(LnArgs a, const float *__restrict__ gy, const float *_
     }
 }
 
-__global__ void ln_reduce_partials(const float *__restrict__ partial, int n_cta, int dim, float *__restrict__ ggamma,
-                                   float *__restrict__ gbeta) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output column (dgamma[c] or dbeta[c]): lanes stride over the CTAs' partials, fixed-order tree
+__global__ void __launch_bounds__(256)
+ln_reduce_partials(const float *__restrict__ partial, int n_cta, int dim, float *__restrict__ ggamma,
+                   float *__restrict__ gbeta) {
+    const int lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= 2 * dim) return;
     const int which = t / dim, c = t % dim;
     float s = 0.f;
-    for (int k = 0; k < n_cta; ++k) s += partial[(static_cast<int64_t>(k) * 2 + which) * dim + c];
-    (which == 0 ? ggamma : gbeta)[c] = s;
+    for (int k = lane; k < n_cta; k += 32) s += partial[(static_cast<int64_t>(k) * 2 + which) * dim + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) (which == 0 ? ggamma : gbeta)[c] = s;
 }
 
 static int ln_grid(int64_t rows) {
@@ -379,11 +385,12 @@ extern "C" int tt_attn_small_fwd(const float *qkv, const uint8_t *key_pad_mask, 
 namespace tt {
 template <int DH, int WARPS>
 static int launch_attn_bwd(const AttnArgs &a, const float *grad_out, float *grad_qkv, cudaStream_t st) {
-    constexpr size_t smem = static_cast<size_t>(WARPS) * (4 * AT_MAXL * DH + 2 * AT_MAXL * (AT_MAXL + 1)) * sizeof(float);
+    constexpr size_t smem_max = static_cast<size_t>(WARPS) * (4 * AT_MAXL * DH + 2 * AT_MAXL * (AT_MAXL + 1)) * sizeof(float);
+    const size_t smem = static_cast<size_t>(WARPS) * (4 * a.len * DH + 2 * a.len * (a.len + 1)) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_small_bwd_kernel<DH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
+                                             static_cast<int>(smem_max));
         if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(attn_small_bwd_kernel)");
         attr_set = true;
     }
@@ -403,8 +410,8 @@ extern "C" int tt_attn_small_bwd(const float *qkv, const uint8_t *key_pad_mask, 
     if (len > AT_MAXL) { set_error("attn_small supports sequence length <= %d (got %d)", AT_MAXL, len); return TT_E_UNSUPPORTED; }
     const AttnArgs a = make_attn(qkv, key_pad_mask, batch, len, heads, head_dim, dropout_p, seed_dev, call_id);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (head_dim == 8) return launch_attn_bwd<8, 4>(a, grad_out, grad_qkv, st);
-    if (head_dim == 16) return launch_attn_bwd<16, 4>(a, grad_out, grad_qkv, st);
+    if (head_dim == 8) return launch_attn_bwd<8, 8>(a, grad_out, grad_qkv, st);
+    if (head_dim == 16) return launch_attn_bwd<16, 8>(a, grad_out, grad_qkv, st);
     if (head_dim == 32) return launch_attn_bwd<32, 4>(a, grad_out, grad_qkv, st);
     set_error("attn_small supports head_dim 8, 16 or 32 (got %d)", head_dim);
     return TT_E_UNSUPPORTED;
@@ -462,7 +469,7 @@ extern "C" int tt_add_dropout_ln_bwd(const float *grad_y, const float *xhat, con
     }
 #undef TT_LN_BWD
     TT_LAUNCH_CHECK("add_dropout_ln_bwd_kernel");
-    ln_reduce_partials<<<(2 * dim + 127) / 128, 128, 0, st>>>(partial, grid, dim, grad_gamma, grad_beta);
+    ln_reduce_partials<<<(2 * dim * 32 + 255) / 256, 256, 0, st>>>(partial, grid, dim, grad_gamma, grad_beta);
     TT_LAUNCH_CHECK("ln_reduce_partials");
     return 0;
 }

@@ -67,6 +67,16 @@ def grouped_batch_norm(bn: nn.BatchNorm1d, x: torch.Tensor, groups: int) -> torc
     return y.view(rows, C)
 
 
+class TTLinear(nn.Linear):
+    """nn.Linear (same parameters, same init, same checkpoint keys) whose backward computes dW and db in one pass over
+    the rows with the library kernel (ops.LinearFn) instead of cuBLAS' no-split-K "nt" GEMM + a bias reduction."""
+
+    def forward(self, x):
+        if x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled():
+            return ops.linear(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)
+
+
 class MLP_Tower(nn.Module):
     """[Linear -> BatchNorm1d -> ReLU -> Dropout] x len(hidden) -> Linear -> L2 normalise
     (Tower.py:9-41)."""
@@ -76,9 +86,9 @@ class MLP_Tower(nn.Module):
         layers = []
         curr = input_dim
         for h in hidden_dims:
-            layers += [nn.Linear(curr, h), nn.BatchNorm1d(h), nn.ReLU(), nn.Dropout(dropout)]
+            layers += [TTLinear(curr, h), nn.BatchNorm1d(h), nn.ReLU(), nn.Dropout(dropout)]
             curr = h
-        layers.append(nn.Linear(curr, output_dim))
+        layers.append(TTLinear(curr, output_dim))
         self.mlp = nn.Sequential(*layers)
         self.apply(self._init_weights)
 
@@ -114,7 +124,7 @@ class SequenceFeatureProcessor(nn.Module):
             self.embeddings[feat["name"]] = nn.Embedding(feat["vocab_size"], feat["embedding_dim"],
                                                          padding_idx=feat.get("padding_index", 0))
             total += feat["embedding_dim"]
-        self.feature_projection = nn.Sequential(nn.Linear(total, target_dim), nn.Dropout(dropout))
+        self.feature_projection = nn.Sequential(TTLinear(total, target_dim), nn.Dropout(dropout))
         self.pos_emb = nn.Embedding(max_seq_len, target_dim)
         self.sparse_sink: Optional[ops.SparseGradSink] = None
 
@@ -189,14 +199,15 @@ class SequenceEncoder(nn.Module):
         pad = padding_mask.to(torch.uint8).contiguous()
         for li, layer in enumerate(self.transformer_backbone.layers):
             sa = layer.self_attn
-            qkv = F.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+            lin = ops.linear if torch.is_grad_enabled() else F.linear
+            qkv = lin(x, sa.in_proj_weight, sa.in_proj_bias)
             a = ops.attn_small(qkv, pad, sa.num_heads, p, seed, 3 * li)
-            a = F.linear(a, sa.out_proj.weight, sa.out_proj.bias)
+            a = lin(a, sa.out_proj.weight, sa.out_proj.bias)
             x = ops.add_dropout_layer_norm(x, a, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p, seed, 3 * li + 1)
-            f = F.relu(F.linear(x, layer.linear1.weight, layer.linear1.bias))
+            f = F.relu(lin(x, layer.linear1.weight, layer.linear1.bias))
             if p > 0.0:
                 f = F.dropout(f, p, True)
-            f = F.linear(f, layer.linear2.weight, layer.linear2.bias)
+            f = lin(f, layer.linear2.weight, layer.linear2.bias)
             x = ops.add_dropout_layer_norm(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p, seed, 3 * li + 2)
         return x
 
@@ -265,7 +276,7 @@ class GenericTower(nn.Module):
                     missing = [k for k in ("name", "dim", "embedding_dim") if k not in field]
                     if missing:
                         raise ValueError(f"Dense feature config missing keys {missing}: {field}, tower initializing failed")
-                self.embeddings[feat["name"]] = nn.Sequential(nn.Linear(feat["dim"], feat["embedding_dim"]))
+                self.embeddings[feat["name"]] = nn.Sequential(TTLinear(feat["dim"], feat["embedding_dim"]))
                 dense_total += feat["embedding_dim"]
         seq_total = 0
         # the reference leaves self.seq_encoder undefined for `sequence_features: []`

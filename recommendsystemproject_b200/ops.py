@@ -10,6 +10,7 @@ import ctypes
 from typing import List, Optional, Sequence, Tuple
 
 import torch
+import torch.nn.functional as F
 
 from . import _lib
 from ._lib import TTError, check
@@ -270,6 +271,45 @@ def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, tempera
 # --------------------------------------------------------------------------
 # 3b. small-sequence Transformer encoder: attention core and add + dropout + LayerNorm
 # --------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b with the library's one-pass weight + bias gradient (linear_grad.cu) in the backward; the forward
+    and the input gradient are plain cuBLAS GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x, weight)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        lib = _lib.load()
+        n_out, n_in = weight.shape
+        g2 = grad_out.reshape(-1, n_out).contiguous()
+        x2 = x.reshape(-1, n_in).contiguous()
+        rows = g2.shape[0]
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = (g2 @ weight).reshape(x.shape)
+        gw = gb = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            nbytes = ctypes.c_size_t(0)
+            check(lib.tt_linear_wgrad_workspace(rows, n_out, n_in, ctypes.byref(nbytes)), "tt_linear_wgrad_workspace")
+            ws = _ws(nbytes.value, g2.device)
+            gw = torch.empty_like(weight)
+            gb = torch.empty(n_out, dtype=torch.float32, device=g2.device) if ctx.has_bias else None
+            check(lib.tt_linear_wgrad(_p(g2), _p(x2), rows, n_out, n_in, _p(gw), _p(gb), _p(ws), ws.numel(), _stream()),
+                  "tt_linear_wgrad")
+            _count(2)
+        return gx, gw, gb
+
+
+def linear(x, weight, bias=None):
+    return LinearFn.apply(x, weight, bias)
+
+
 class AttnSmall(torch.autograd.Function):
     """softmax(q k^T / sqrt(dh) + key padding mask) -> dropout -> . v for L <= 32, straight from the packed in_proj
     output (what nn.MultiheadAttention computes between in_proj and out_proj, SequenceEncoder.py:13-21,60)."""

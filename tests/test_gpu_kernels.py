@@ -866,3 +866,26 @@ def test_fused_encoder_dropout_is_consistent_and_deterministic():
     num = (f2(z0 + eps * vz) - f2(z0 - eps * vz)) / (2 * eps)
     ana = float((zz.grad.double() * vz.double()).sum())
     assert abs(num - ana) < 2e-2 * max(1.0, abs(ana)), (num, ana)
+
+
+@pytest.mark.parametrize("rows,n_out,n_in", [(5632, 256, 64), (10240, 192, 64), (512, 64, 200), (33, 7, 5), (1000, 130, 66)])
+def test_linear_weight_and_bias_gradient_match_torch(rows, n_out, n_in):
+    gen = torch.Generator().manual_seed(rows + n_out)
+    x = torch.randn(rows, n_in, generator=gen)
+    w = torch.randn(n_out, n_in, generator=gen) * 0.1
+    b = torch.randn(n_out, generator=gen)
+    up = torch.randn(rows, n_out, generator=gen)
+    ref = [t.clone().double().requires_grad_(True) for t in (x, w, b)]
+    (torch.nn.functional.linear(*ref) * up.double()).sum().backward()
+    mine = [t.to(DEV).requires_grad_(True) for t in (x, w, b)]
+    y = ops.linear(*mine)
+    (y * up.to(DEV)).sum().backward()
+    assert torch.allclose(y.detach().cpu().double(), torch.nn.functional.linear(x, w, b).double(), atol=1e-5)
+    scale = rows ** 0.5
+    assert torch.allclose(mine[1].grad.cpu().double(), ref[1].grad, atol=2e-6 * scale * 4, rtol=1e-5)
+    assert torch.allclose(mine[2].grad.cpu().double(), ref[2].grad, atol=2e-6 * scale * 4, rtol=1e-5)
+    assert torch.allclose(mine[0].grad.cpu().double(), ref[0].grad, atol=1e-5, rtol=1e-5)
+    # deterministic: a second backward gives the same bits
+    mine2 = [t.to(DEV).requires_grad_(True) for t in (x, w, b)]
+    (ops.linear(*mine2) * up.to(DEV)).sum().backward()
+    assert torch.equal(mine2[1].grad, mine[1].grad) and torch.equal(mine2[2].grad, mine[2].grad)
