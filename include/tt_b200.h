@@ -240,18 +240,20 @@ TT_API int tt_add_dropout_ln_fwd(const float *x, const float *z, int64_t rows, i
 TT_API int tt_add_dropout_ln_bwd_workspace(int64_t rows, int dim, size_t *bytes_host);
 TT_API int tt_add_dropout_ln_bwd(const float *grad_y, const float *xhat, const float *rstd, const float *gamma, int64_t rows,
                           int dim, float dropout_p, const int64_t *seed_dev, int64_t call_id, float *grad_x,
-                          float *grad_z, float *grad_gamma, float *grad_beta, void *workspace, size_t workspace_bytes,
-                          void *stream);
+                          float *grad_z, float *grad_gamma, float *grad_beta, int accumulate, void *workspace,
+                          size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * 6. Linear-layer weight + bias gradient in one pass (backward of every nn.Linear of the towers and the sequence
  * encoder: Tower.py:17-24, SequenceFeatureProcessor.py:30, SequenceEncoder.py:13-21):
  *   grad_weight[n_out, n_in] = grad_out[rows, n_out]^T . input[rows, n_in],  grad_bias[n_out] = column sums of grad_out
  * (grad_bias nullable).  The row dimension is split over the whole chip, partials are added in fixed order.
+ * accumulate != 0: the results are ADDED to grad_weight / grad_bias (a parameter's .grad buffer) instead of stored;
+ * tt_add_dropout_ln_bwd's grad_gamma / grad_beta take the same flag.
  * ---------------------------------------------------------------------- */
 TT_API int tt_linear_wgrad_workspace(int64_t rows, int n_out, int n_in, size_t *bytes_host);
 TT_API int tt_linear_wgrad(const float *grad_out, const float *input, int64_t rows, int n_out, int n_in, float *grad_weight,
-                    float *grad_bias, void *workspace, size_t workspace_bytes, void *stream);
+                    float *grad_bias, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -43,12 +43,12 @@ _SIGNATURES = {
     "tt_score_topk_tc": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_int, c_int64, P, P, P, P, P, c_int, P, c_size_t, P]),
     "tt_topk_merge": (c_int, [P, P, c_int, c_int64, c_int, P, P, P]),
     "tt_linear_wgrad_workspace": (c_int, [c_int64, c_int, c_int, P]),
-    "tt_linear_wgrad": (c_int, [P, P, c_int64, c_int, c_int, P, P, P, c_size_t, P]),
+    "tt_linear_wgrad": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int, P, c_size_t, P]),
     "tt_attn_small_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_float, P, c_int64, P, P]),
     "tt_attn_small_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_float, P, c_int64, P, P]),
     "tt_add_dropout_ln_fwd": (c_int, [P, P, c_int64, c_int, P, P, c_float, c_float, P, c_int64, P, P, P, P]),
     "tt_add_dropout_ln_bwd_workspace": (c_int, [c_int64, c_int, P]),
-    "tt_add_dropout_ln_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_float, P, c_int64, P, P, P, P, P, c_size_t, P]),
+    "tt_add_dropout_ln_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_float, P, c_int64, P, P, P, P, c_int, P, c_size_t, P]),
 }
 
 _lib = None

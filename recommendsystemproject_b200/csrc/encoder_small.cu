@@ -328,7 +328,7 @@ add_dropout_ln_bwd_kernel(LnArgs a, const float *__restrict__ gy, const float *_
 
 // one warp per output column (dgamma[c] or dbeta[c]): lanes stride over the CTAs' partials, fixed-order tree
 __global__ void __launch_bounds__(256)
-ln_reduce_partials(const float *__restrict__ partial, int n_cta, int dim, float *__restrict__ ggamma,
+ln_reduce_partials(const float *__restrict__ partial, int n_cta, int dim, int accumulate, float *__restrict__ ggamma,
                    float *__restrict__ gbeta) {
     const int lane = threadIdx.x & 31;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -338,7 +338,10 @@ ln_reduce_partials(const float *__restrict__ partial, int n_cta, int dim, float 
     for (int k = lane; k < n_cta; k += 32) s += partial[(static_cast<int64_t>(k) * 2 + which) * dim + c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) (which == 0 ? ggamma : gbeta)[c] = s;
+    if (lane == 0) {
+        float *dst = (which == 0 ? ggamma : gbeta) + c;
+        *dst = accumulate ? *dst + s : s;
+    }
 }
 
 static int ln_grid(int64_t rows) {
@@ -446,8 +449,8 @@ extern "C" int tt_add_dropout_ln_bwd_workspace(int64_t rows, int dim, size_t *by
 
 extern "C" int tt_add_dropout_ln_bwd(const float *grad_y, const float *xhat, const float *rstd, const float *gamma,
                                      int64_t rows, int dim, float dropout_p, const int64_t *seed_dev, int64_t call_id,
-                                     float *grad_x, float *grad_z, float *grad_gamma, float *grad_beta, void *workspace,
-                                     size_t workspace_bytes, void *stream) {
+                                     float *grad_x, float *grad_z, float *grad_gamma, float *grad_beta, int accumulate,
+                                     void *workspace, size_t workspace_bytes, void *stream) {
     using namespace tt;
     TT_CHECK_ARG(grad_y && xhat && rstd && gamma && grad_x && grad_z && grad_gamma && grad_beta && workspace && rows > 0,
                  "null pointer / empty input");
@@ -469,7 +472,7 @@ extern "C" int tt_add_dropout_ln_bwd(const float *grad_y, const float *xhat, con
     }
 #undef TT_LN_BWD
     TT_LAUNCH_CHECK("add_dropout_ln_bwd_kernel");
-    ln_reduce_partials<<<(2 * dim * 32 + 255) / 256, 256, 0, st>>>(partial, grid, dim, grad_gamma, grad_beta);
+    ln_reduce_partials<<<(2 * dim * 32 + 255) / 256, 256, 0, st>>>(partial, grid, dim, accumulate, grad_gamma, grad_beta);
     TT_LAUNCH_CHECK("ln_reduce_partials");
     return 0;
 }

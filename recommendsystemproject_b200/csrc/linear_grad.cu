@@ -79,17 +79,17 @@ linear_wgrad_partial(const float *__restrict__ dy, const float *__restrict__ x, 
 
 __global__ void __launch_bounds__(256)
 linear_wgrad_reduce(const float *__restrict__ part_w, const float *__restrict__ part_b, int n_chunks, int64_t n_w,
-                    int n_out, float *__restrict__ dw, float *__restrict__ db) {
+                    int n_out, int accumulate, float *__restrict__ dw, float *__restrict__ db) {
     const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e < n_w) {
         float s = 0.f;
         for (int c = 0; c < n_chunks; ++c) s += part_w[static_cast<int64_t>(c) * n_w + e];
-        dw[e] = s;
+        dw[e] = accumulate ? dw[e] + s : s;
     } else if (e < n_w + n_out && db != nullptr) {
         const int o = static_cast<int>(e - n_w);
         float s = 0.f;
         for (int c = 0; c < n_chunks; ++c) s += part_b[static_cast<int64_t>(c) * n_out + o];
-        db[o] = s;
+        db[o] = accumulate ? db[o] + s : s;
     }
 }
 
@@ -118,8 +118,8 @@ extern "C" int tt_linear_wgrad_workspace(int64_t rows, int n_out, int n_in, size
 }
 
 extern "C" int tt_linear_wgrad(const float *grad_out, const float *input, int64_t rows, int n_out, int n_in,
-                               float *grad_weight, float *grad_bias, void *workspace, size_t workspace_bytes,
-                               void *stream) {
+                               float *grad_weight, float *grad_bias, int accumulate, void *workspace,
+                               size_t workspace_bytes, void *stream) {
     using namespace tt;
     TT_CHECK_ARG(grad_out && input && grad_weight && workspace && rows > 0 && n_out > 0 && n_in > 0, "null pointer / empty input");
     TT_CHECK_ARG(reinterpret_cast<uintptr_t>(grad_out) % 16 == 0 && reinterpret_cast<uintptr_t>(input) % 16 == 0,
@@ -137,7 +137,7 @@ extern "C" int tt_linear_wgrad(const float *grad_out, const float *input, int64_
     TT_LAUNCH_CHECK("linear_wgrad_partial");
     const int64_t total = static_cast<int64_t>(n_w) + (grad_bias ? n_out : 0);
     linear_wgrad_reduce<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(part_w, part_b, p.chunks,
-                                                                                    static_cast<int64_t>(n_w), n_out, grad_weight, grad_bias);
+                                                                                    static_cast<int64_t>(n_w), n_out, accumulate, grad_weight, grad_bias);
     TT_LAUNCH_CHECK("linear_wgrad_reduce");
     return 0;
 }

@@ -271,6 +271,12 @@ def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, tempera
 # --------------------------------------------------------------------------
 # 3b. small-sequence Transformer encoder: attention core and add + dropout + LayerNorm
 # --------------------------------------------------------------------------
+def _direct_grad(p) -> bool:
+    """True for a leaf parameter whose optimizer (optim.FusedTwoTowerOptimizer) preallocated a .grad view of its flat
+    gradient buffer and allows the library's backward kernels to add into it directly."""
+    return getattr(p, "_tt_grad_direct", False) and p.grad is not None and p.grad.is_contiguous()
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b with the library's one-pass weight + bias gradient (linear_grad.cu) in the backward; the forward
     and the input gradient are plain cuBLAS GEMMs."""
@@ -280,6 +286,7 @@ class LinearFn(torch.autograd.Function):
         _need_cuda(x, weight)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         return F.linear(x, weight, bias)
 
     @staticmethod
@@ -298,10 +305,17 @@ class LinearFn(torch.autograd.Function):
             nbytes = ctypes.c_size_t(0)
             check(lib.tt_linear_wgrad_workspace(rows, n_out, n_in, ctypes.byref(nbytes)), "tt_linear_wgrad_workspace")
             ws = _ws(nbytes.value, g2.device)
-            gw = torch.empty_like(weight)
-            gb = torch.empty(n_out, dtype=torch.float32, device=g2.device) if ctx.has_bias else None
-            check(lib.tt_linear_wgrad(_p(g2), _p(x2), rows, n_out, n_in, _p(gw), _p(gb), _p(ws), ws.numel(), _stream()),
-                  "tt_linear_wgrad")
+            bias = ctx.bias_ref
+            if _direct_grad(weight) and (bias is None or _direct_grad(bias)):
+                # the optimizer owns preallocated .grad buffers: add into them here and hand autograd nothing
+                # (saves one accumulate kernel per parameter and step)
+                check(lib.tt_linear_wgrad(_p(g2), _p(x2), rows, n_out, n_in, _p(weight.grad), _p(None if bias is None else bias.grad),
+                                          1, _p(ws), ws.numel(), _stream()), "tt_linear_wgrad")
+            else:
+                gw = torch.empty_like(weight)
+                gb = torch.empty(n_out, dtype=torch.float32, device=g2.device) if ctx.has_bias else None
+                check(lib.tt_linear_wgrad(_p(g2), _p(x2), rows, n_out, n_in, _p(gw), _p(gb), 0, _p(ws), ws.numel(), _stream()),
+                      "tt_linear_wgrad")
             _count(2)
         return gx, gw, gb
 
@@ -362,6 +376,7 @@ class AddDropoutLayerNorm(torch.autograd.Function):
         _count()
         ctx.save_for_backward(xhat, rstd, gamma, seed_dev)
         ctx.cfg = (float(dropout_p), int(call_id))
+        ctx.beta_ref = beta
         return y
 
     @staticmethod
@@ -376,11 +391,18 @@ class AddDropoutLayerNorm(torch.autograd.Function):
         ws = _ws(nbytes.value, xhat.device)
         gx = torch.empty_like(xhat)
         gz = torch.empty_like(xhat)
-        gg = torch.empty_like(gamma)
-        gb = torch.empty_like(gamma)
-        check(lib.tt_add_dropout_ln_bwd(_p(grad_y.contiguous()), _p(xhat), _p(rstd), _p(gamma), rows, dim, p, _p(seed_dev),
-                                        call_id, _p(gx), _p(gz), _p(gg), _p(gb), _p(ws), ws.numel(), _stream()),
-              "tt_add_dropout_ln_bwd")
+        beta = ctx.beta_ref
+        if _direct_grad(gamma) and _direct_grad(beta):
+            gg = gb = None
+            check(lib.tt_add_dropout_ln_bwd(_p(grad_y.contiguous()), _p(xhat), _p(rstd), _p(gamma), rows, dim, p, _p(seed_dev),
+                                            call_id, _p(gx), _p(gz), _p(gamma.grad), _p(beta.grad), 1, _p(ws), ws.numel(),
+                                            _stream()), "tt_add_dropout_ln_bwd")
+        else:
+            gg = torch.empty_like(gamma)
+            gb = torch.empty_like(gamma)
+            check(lib.tt_add_dropout_ln_bwd(_p(grad_y.contiguous()), _p(xhat), _p(rstd), _p(gamma), rows, dim, p, _p(seed_dev),
+                                            call_id, _p(gx), _p(gz), _p(gg), _p(gb), 0, _p(ws), ws.numel(), _stream()),
+                  "tt_add_dropout_ln_bwd")
         _count(2)
         return gx, gz, gg, gb, None, None, None, None
 

@@ -73,6 +73,7 @@ class FusedTwoTowerOptimizer:
             self.flat_p[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + k].view_as(p)
             p.grad = self.flat_g[off:off + k].view_as(p)
+            p._tt_grad_direct = True      # ops.LinearFn / AddDropoutLayerNorm add into the flat buffer themselves
             self._views.append((p, off, k))
             off += k
         self.flat_params = flat_params
