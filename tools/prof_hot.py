@@ -37,7 +37,7 @@ for _ in range(2):
     loss = ops.fused_inbatch_ce(u, it, iid, None, pool, 0.05, precision="bf16")[0]
     loss.backward()
 torch.cuda.synchronize()
-q = torch.nn.functional.normalize(torch.randn(8192, D, device=dev), dim=1)
+q = torch.nn.functional.normalize(torch.randn(16384, D, device=dev), dim=1)
 e = torch.nn.functional.normalize(torch.randn(1_250_000, D, device=dev), dim=1)
 prep = ops.PreparedCorpus(e)
 for _ in range(2):
