@@ -5,7 +5,7 @@
 // launches: an fp32 SIMT GEMM "nt" whose reduction dimension is the ROW count (5632 item rows, 10240 sequence
 // positions) over a 64..256-wide output -- cuBLAS picks a 64x64 tile without split-K, i.e. 1..16 CTAs on 148 SMs,
 // 27 us each -- and a separate reduce_kernel for the bias (15 us each): together a quarter of the kernel time of a
-// C2 training step (profiles/r1_c2_step_launches_fused.md).  Here the rows are split over ~4 waves of CTAs, each
+// C2 training step (profiles/r1_c2_step_launches_fused.md).  Here the rows are split over ~2 waves of CTAs, each
 // writes a partial tile (and, for the first column tile, the partial column sums of dY it has in shared memory
 // anyway), and a second kernel adds the partials in fixed order: deterministic, fp32 FMA.
 #include "common.cuh"
@@ -77,19 +77,28 @@ linear_wgrad_partial(const float *__restrict__ dy, const float *__restrict__ x, 
     }
 }
 
+// 64 outputs per CTA, 4 threads per output: thread g of an output adds chunks g, g+4, ... and the four sums are
+// combined in fixed order (deterministic; 4x shorter dependent chains than one thread per output)
 __global__ void __launch_bounds__(256)
 linear_wgrad_reduce(const float *__restrict__ part_w, const float *__restrict__ part_b, int n_chunks, int64_t n_w,
                     int n_out, int accumulate, float *__restrict__ dw, float *__restrict__ db) {
-    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    __shared__ float red[4][64];
+    const int el = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * 64 + el;
+    const int64_t total = n_w + (db != nullptr ? n_out : 0);
+    float s = 0.f;
     if (e < n_w) {
-        float s = 0.f;
-        for (int c = 0; c < n_chunks; ++c) s += part_w[static_cast<int64_t>(c) * n_w + e];
-        dw[e] = accumulate ? dw[e] + s : s;
-    } else if (e < n_w + n_out && db != nullptr) {
+        for (int c = grp; c < n_chunks; c += 4) s += part_w[static_cast<int64_t>(c) * n_w + e];
+    } else if (e < total) {
         const int o = static_cast<int>(e - n_w);
-        float s = 0.f;
-        for (int c = 0; c < n_chunks; ++c) s += part_b[static_cast<int64_t>(c) * n_out + o];
-        db[o] = accumulate ? db[o] + s : s;
+        for (int c = grp; c < n_chunks; c += 4) s += part_b[static_cast<int64_t>(c) * n_out + o];
+    }
+    red[grp][el] = s;
+    __syncthreads();
+    if (grp == 0 && e < total) {
+        const float v = ((red[0][el] + red[1][el]) + red[2][el]) + red[3][el];
+        float *dst = e < n_w ? dw + e : db + (e - n_w);
+        *dst = accumulate ? *dst + v : v;
     }
 }
 
@@ -99,7 +108,7 @@ static LgPlan lg_plan(int64_t rows, int n_out, int n_in) {
     p.tiles_o = (n_out + LG_T - 1) / LG_T;
     p.tiles_i = (n_in + LG_T - 1) / LG_T;
     const int tiles = p.tiles_o * p.tiles_i;
-    int64_t want = (static_cast<int64_t>(sm_count()) * 4 + tiles - 1) / tiles;
+    int64_t want = (static_cast<int64_t>(sm_count()) * 2 + tiles - 1) / tiles;    // ~2 waves of CTAs
     const int64_t most = (rows + 4 * LG_K - 1) / (4 * LG_K);     // at least 64 rows per chunk
     if (want > most) want = most;
     if (want < 1) want = 1;
@@ -136,7 +145,7 @@ extern "C" int tt_linear_wgrad(const float *grad_out, const float *input, int64_
                                                grad_bias ? part_b : nullptr);
     TT_LAUNCH_CHECK("linear_wgrad_partial");
     const int64_t total = static_cast<int64_t>(n_w) + (grad_bias ? n_out : 0);
-    linear_wgrad_reduce<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(part_w, part_b, p.chunks,
+    linear_wgrad_reduce<<<static_cast<unsigned>((total + 63) / 64), 256, 0, st>>>(part_w, part_b, p.chunks,
                                                                                     static_cast<int64_t>(n_w), n_out, accumulate, grad_weight, grad_bias);
     TT_LAUNCH_CHECK("linear_wgrad_reduce");
     return 0;
