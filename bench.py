@@ -615,8 +615,8 @@ def main():
             kernels = kernel_rooflines(peaks, flush, quick=args.quick)
         except torch.cuda.OutOfMemoryError as ex:  # report, never hide
             kernels = [{"error": f"kernel roofline section skipped: {ex}"}]
-    # dominant kernel of the C2 step = the fused-CE backward pass (see profiles/); its standalone roofline
-    roof = step_roofline(model, wl, dev, peaks, flush)
+    # dominant hand-written kernel of the C2 step (see profiles/r1_c2_step_launches_fused.md); its standalone roofline
+    roof = step_roofline(model, wl, dev, peaks, flush, dev_batch)
 
     cpu = None
     try:
@@ -646,28 +646,48 @@ def main():
         dist.destroy_process_group()
 
 
-def step_roofline(model, wl, dev, peaks, flush):
-    """Roofline of the dominant hand-written kernel inside the C2 step: the fused-CE backward passes
-    (ce_bwd_pass) at the step's own shape, timed standalone with CUDA events."""
+def step_roofline(model, wl, dev, peaks, flush, batch):
+    """Roofline of the dominant hand-written kernel inside the C2 step (profiles/r1_c2_step_launches_fused.md): the
+    one-pass Linear weight + bias gradient (linear_wgrad_partial + linear_wgrad_reduce, 16 Linear layers per step).
+    Its shapes are recorded from one eager backward of this very model and batch, then every call is timed standalone
+    with CUDA events (L2 flushed before each).  HBM-bound by construction (each operand is read once):
+    algorithmic bytes = (rows * (n_out + n_in) + n_out * n_in + n_out) * 4 per call."""
     from recommendsystemproject_b200 import ops
-    B = wl["B"]
-    D = wl["cfg"]["two_tower"]["user_tower"]["output_dims"]
-    N = 10 if "hard" in wl["desc"] else 0
-    u = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1).requires_grad_(True)
-    it = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1).requires_grad_(True)
-    hn = torch.nn.functional.normalize(torch.randn(B, N, D, device=dev), dim=2).requires_grad_(True) if N else None
-    ids = torch.randint(1, 3500, (B,), device=dev)
-    res = {}
+    import ctypes
+    ops.wgrad_shapes = []
+    try:
+        model.zero_grad(set_to_none=False)
+        u, i, hn = model(batch)
+        ids = batch["item_tower"]["sparse"][:, 0]
+        model.compute_loss(u, i, item_ids=ids, hard_neg_emb=hn, temperature=wl["T"]).backward()
+        torch.cuda.synchronize()
+        shapes = list(ops.wgrad_shapes)
+    finally:
+        ops.wgrad_shapes = None
+    lib = ops._lib.load()
+    total_ms, total_bytes, total_flops = 0.0, 0, 0.0
+    for rows, n_out, n_in in shapes:
+        g = torch.randn(rows, n_out, device=dev)
+        x = torch.randn(rows, n_in, device=dev)
+        gw, gb = torch.empty(n_out, n_in, device=dev), torch.empty(n_out, device=dev)
+        nb = ctypes.c_size_t(0)
+        ops.check(lib.tt_linear_wgrad_workspace(rows, n_out, n_in, ctypes.byref(nb)), "tt_linear_wgrad_workspace")
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
 
-    def fwd():
-        res["l"] = ops.fused_inbatch_ce(u, it, ids, hn, None, wl["T"])[0]
-    ms_f, _ = time_op(fwd, 10, flush)
-    ms_fb, _ = time_op(lambda: (fwd(), res["l"].backward()), 10, flush)
-    flops = 6.0 * B * (B + N) * D
-    return {"bound": "tensor", "kernel": "fused in-batch CE fwd+bwd (ce_fwd_tiles, ce_bwd_pass; fp32 SIMT path)",
-            "achieved": flops / ms_fb / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": flops / ms_fb / 1e9 / peaks["bf16_tflops"], "traffic": None, "ms": ms_fb, "ms_fwd": ms_f,
-            "alg_flops": flops, "note": "B=512: launch/latency-bound; see `kernels` for BASELINE-scale shapes"}
+        def call():
+            ops.check(lib.tt_linear_wgrad(ops._p(g), ops._p(x), rows, n_out, n_in, ops._p(gw), ops._p(gb), 0, ops._p(ws),
+                                          ws.numel(), ops._stream()), "tt_linear_wgrad")
+        ms, _ = time_op(call, 5, flush)
+        total_ms += ms
+        total_bytes += (rows * (n_out + n_in) + n_out * n_in + n_out) * 4
+        total_flops += 2.0 * rows * n_out * n_in
+    gbs = total_bytes / total_ms / 1e6
+    return {"bound": "hbm", "kernel": f"linear_wgrad_partial + linear_wgrad_reduce (weight + bias gradient of the step's {len(shapes)} Linear layers)",
+            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+            "ms": total_ms, "launches": 2 * len(shapes), "alg_bytes": total_bytes, "alg_flops": total_flops,
+            "shapes": sorted(set(shapes)),
+            "note": "B=512 step: every kernel of it is launch/latency-bound (6-12 us per launch for ~10 MB of operands); "
+                    "see `kernels` for the hot-path kernels at BASELINE-scale shapes"}
 
 
 if __name__ == "__main__":

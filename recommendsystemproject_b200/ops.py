@@ -271,6 +271,11 @@ def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, tempera
 # --------------------------------------------------------------------------
 # 3b. small-sequence Transformer encoder: attention core and add + dropout + LayerNorm
 # --------------------------------------------------------------------------
+# when set to a list, LinearFn.backward appends (rows, n_out, n_in) of every weight-gradient call (bench.py uses it to
+# time the step's dominant hand-written kernel at the step's own shapes)
+wgrad_shapes = None
+
+
 def _direct_grad(p) -> bool:
     """True for a leaf parameter whose optimizer (optim.FusedTwoTowerOptimizer) preallocated a .grad view of its flat
     gradient buffer and allows the library's backward kernels to add into it directly."""
@@ -302,6 +307,8 @@ class LinearFn(torch.autograd.Function):
             gx = (g2 @ weight).reshape(x.shape)
         gw = gb = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            if wgrad_shapes is not None:
+                wgrad_shapes.append((rows, n_out, n_in))
             nbytes = ctypes.c_size_t(0)
             check(lib.tt_linear_wgrad_workspace(rows, n_out, n_in, ctypes.byref(nbytes)), "tt_linear_wgrad_workspace")
             ws = _ws(nbytes.value, g2.device)
