@@ -29,9 +29,10 @@ linear_wgrad_partial(const float *__restrict__ dy, const float *__restrict__ x, 
     float acc[4][4] = {};
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
     const bool vec_y = (n_out % 4 == 0), vec_x = (n_in % 4 == 0);
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += LG_K) {
+    auto load_stage = [&](int64_t r0, float4 &vy, float4 &vx) {
         const int64_t r = r0 + lr;
-        float4 vy = make_float4(0.f, 0.f, 0.f, 0.f), vx = vy;
+        vy = make_float4(0.f, 0.f, 0.f, 0.f);
+        vx = vy;
         if (r < r_end) {
             if (vec_y && o0 + lc + 3 < n_out) vy = *reinterpret_cast<const float4 *>(dy + r * n_out + o0 + lc);
             else {
@@ -46,10 +47,15 @@ linear_wgrad_partial(const float *__restrict__ dy, const float *__restrict__ x, 
                 vx = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
             }
         }
+    };
+    float4 vy, vx;
+    if (r_begin < r_end) load_stage(r_begin, vy, vx);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += LG_K) {
         __syncthreads();
         *reinterpret_cast<float4 *>(&ys[lr][lc]) = vy;
         *reinterpret_cast<float4 *>(&xs[lr][lc]) = vx;
         __syncthreads();
+        if (r0 + LG_K < r_end) load_stage(r0 + LG_K, vy, vx);     // next stage's rows fly while this one is multiplied
 #pragma unroll
         for (int k = 0; k < LG_K; ++k) {
             const float4 a = *reinterpret_cast<const float4 *>(&ys[k][ty * 4]);
