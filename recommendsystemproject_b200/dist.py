@@ -9,6 +9,8 @@ kind), so everything here is new:
                           identical on every rank.
   * shard helpers       -- row-sharded embedding routing (owner = row % W) and
                           corpus-sharded top-K + global merge.
+  * global_inbatch_ce   -- in-batch softmax over the global batch: all-gather of
+                          item embeddings with a gradient-carrying backward.
 Host-side routing logic is plain index arithmetic on tensors of either device
 so that it can be exercised with gloo on CPU (tests/test_dist_cpu.py); the
 kernels it feeds are CUDA-only.
@@ -384,6 +386,45 @@ class _ShardedPooledFn(torch.autograd.Function):
         (recv,) = ctx.saved_tensors
         ctx.bag._backward_pooled(grad, recv, ctx.L)
         return (None,) * 5
+
+
+class _AllGatherWithGrad(torch.autograd.Function):
+    """[B, D] -> [W, B, D] (all ranks' blocks); backward: every rank holds a gradient for every block, the owner of a
+    block receives their SUM (all-reduce + own slice: gloo has no reduce-scatter; the tensors are a few hundred KB)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        world = dist.get_world_size()
+        out = torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        dist.all_gather(list(out.unbind(0)), x.contiguous())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dist.all_reduce(g)
+        return g[dist.get_rank()]
+
+
+def global_inbatch_ce(user, item, item_ids, pool, temperature, precision: str = "fp32", ce_fn=None):
+    """SURVEY 8e, "towers + loss": the in-batch softmax over the GLOBAL batch of W*B items while every rank keeps only
+    its own B rows.  item embeddings are all-gathered; on rank r the other ranks' items enter the fused CE kernel as
+    extra shared negatives (its pool argument), so the [B, W*B + H] logit slab never exists in HBM either; their
+    gradients flow back to the owners through the all-gather's backward (sum), the dense-gradient all-reduce (AVG) of
+    DataParallelStep then yields exactly d(mean of the W rank losses) = d(global-batch loss).
+    Returns this rank's mean loss over its B rows (global loss = mean over ranks).  False-negative masking
+    (TwoTowerModel.py:101-104) covers the rank's own B x B block, like the single-process code at batch B; an item id
+    repeated on ANOTHER rank counts as a negative.  `ce_fn(user, item, item_ids, pool, temperature)` overrides the CUDA
+    kernel (CPU gloo tests inject the oracle)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world > 1:
+        rank = dist.get_rank()
+        blocks = _AllGatherWithGrad.apply(item)
+        others = torch.cat([blocks[r] for r in range(world) if r != rank], dim=0)
+        pool = others if pool is None else torch.cat([others, pool], dim=0)
+    if ce_fn is not None:
+        return ce_fn(user, item, item_ids, pool, temperature)
+    return ops.fused_inbatch_ce(user, item, item_ids, None, pool, temperature, precision=precision)[0]
 
 
 def global_clip_coef(sq_terms: List[torch.Tensor], max_norm: float = 1.0) -> torch.Tensor:

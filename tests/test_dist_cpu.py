@@ -199,3 +199,40 @@ def _sharded_bag_pooled_case(rank, world):
 def test_sharded_embedding_bag_owner_side_pooling_two_ranks_gloo():
     """exchange='pooled': the owners pool and only [B, D] partial sums travel; same lookup, same update."""
     assert all(_run(_sharded_bag_pooled_case).values())
+
+
+# ---------------------------------------------------------------- global-batch in-batch softmax (host logic, gloo, oracle CE)
+def _global_ce_case(rank, world):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from recommendsystemproject_b200 import dist as tdist
+    from oracle import twotower_oracle as O
+    gen = torch.Generator().manual_seed(77)
+    B, D, H, T = 6, 8, 5, 0.2
+    U = torch.nn.functional.normalize(torch.randn(world * B, D, generator=gen), dim=1)
+    I = torch.nn.functional.normalize(torch.randn(world * B, D, generator=gen), dim=1)
+    pool = torch.nn.functional.normalize(torch.randn(H, D, generator=gen), dim=1)
+    ids = torch.arange(1, world * B + 1)                        # unique ids: no cross-rank collisions
+    sl = slice(rank * B, (rank + 1) * B)
+    u, i, pl = U[sl].clone().requires_grad_(True), I[sl].clone().requires_grad_(True), pool.clone().requires_grad_(True)
+    ce = lambda uu, ii, idd, pp, tt: O.compute_loss(uu, ii, idd, None, tt, hn_pool=pp)
+    loss = tdist.global_inbatch_ce(u, i, ids[sl], pl, T, ce_fn=ce)
+    loss.backward()
+    # single-process reference on the global batch
+    Ug, Ig, Pg = U.clone().requires_grad_(True), I.clone().requires_grad_(True), pool.clone().requires_grad_(True)
+    ref = O.compute_loss(Ug, Ig, ids, None, T, hn_pool=Pg)
+    ref.backward()
+    tot = loss.detach().clone()
+    dist.all_reduce(tot)
+    ok = abs(float(tot) / world - float(ref)) < 1e-6
+    # rank losses are each a mean over B rows and the global loss their mean: d(global)/dx = (1/W) d(sum of rank losses)/dx
+    ok &= torch.allclose(u.grad / world, Ug.grad[sl], atol=1e-6)
+    ok &= torch.allclose(i.grad / world, Ig.grad[sl], atol=1e-6)
+    gp = pl.grad.clone()
+    dist.all_reduce(gp)
+    ok &= torch.allclose(gp / world, Pg.grad, atol=1e-6)
+    return bool(ok)
+
+
+def test_global_inbatch_ce_equals_single_process_global_batch_gloo():
+    assert all(_run(_global_ce_case).values())

@@ -95,9 +95,33 @@ t4 &= abs(shards["rows"][1] - shards["pooled"][1]) < 1e-6 * max(1.0, abs(shards[
 diff = (shards["rows"][0] - shards["pooled"][0]).abs()
 t4 &= bool((diff > 1e-4).float().mean() < 1e-3)
 ok &= t4
+# 5. global-batch in-batch softmax: all-gather of item embeddings + gradient return == the fused CE kernel run by
+#    one GPU on the whole global batch (unique item ids: no cross-rank collisions)
+Bg, Dg, Hg, Tg = 1024, 128, 256, 0.05
+gg = torch.Generator(device=dev).manual_seed(909)
+Ug = torch.nn.functional.normalize(torch.randn(world * Bg, Dg, device=dev, generator=gg), dim=1)
+Ig = torch.nn.functional.normalize(torch.randn(world * Bg, Dg, device=dev, generator=gg), dim=1)
+Pg = torch.nn.functional.normalize(torch.randn(Hg, Dg, device=dev, generator=gg), dim=1)
+idg = torch.arange(1, world * Bg + 1, device=dev)
+slg = slice(rank * Bg, (rank + 1) * Bg)
+ul, il, pl = (t.clone().requires_grad_(True) for t in (Ug[slg], Ig[slg], Pg))
+lossg = tdist.global_inbatch_ce(ul, il, idg[slg], pl, Tg)
+lossg.backward()
+ur, ir, pr = (t.clone().requires_grad_(True) for t in (Ug, Ig, Pg))
+ref = ops.fused_inbatch_ce(ur, ir, idg, None, pr, Tg)[0]
+ref.backward()
+tot = lossg.detach().clone()
+dist.all_reduce(tot)
+t5 = abs(float(tot) / world - float(ref)) < 1e-5
+t5 &= bool(torch.allclose(ul.grad / world, ur.grad[slg], atol=1e-7, rtol=1e-4))
+t5 &= bool(torch.allclose(il.grad / world, ir.grad[slg], atol=1e-7, rtol=1e-4))
+gp = pl.grad.clone()
+dist.all_reduce(gp)
+t5 &= bool(torch.allclose(gp / world, pr.grad, atol=1e-7, rtol=1e-4))
+ok &= t5
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"dist_check world={world}: sharded_topk={t1} sharded_lookup={t2} dp_replicas_identical={t3} sharded_bag={t4} all_ranks_ok={bool(flag.item())}")
+    print(f"dist_check world={world}: sharded_topk={t1} sharded_lookup={t2} dp_replicas_identical={t3} sharded_bag={t4} global_inbatch_ce={t5} all_ranks_ok={bool(flag.item())}")
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)
