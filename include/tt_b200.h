@@ -190,7 +190,7 @@ TT_API int tt_score_topk_f32(const float *query, int64_t n_query, const float *c
  * survivors are re-scored in fp64 from the fp32 inputs and a per-query proof obligation
  *     exact_score[K-th] > tau + |q - bf16(q)| * max|bf16(e)| + |q| * max|e - bf16(e)| + 2e-5 * |q| * max|e|
  * (tau = best approximate score ever left out; Cauchy-Schwarz on the two rounding-error vectors, the last term
- * covers fp32 accumulation and the index bits kept in the low mantissa) is evaluated on the device.
+ * covers fp32 accumulation in the tensor core) is evaluated on the device.
  * unverified[q] = 1 marks the (rare) queries for which it does not hold; the caller must re-run those with
  * flags = TT_TOPK_SAMPLING | TT_TOPK_WIDE, then TT_TOPK_WIDE and, if still flagged, through tt_score_topk_f32.
  * flags: TT_TOPK_SAMPLING (corpora of >= 2^17 rows) -- a first pass over every 16th corpus tile gives each query

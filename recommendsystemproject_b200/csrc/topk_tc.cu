@@ -240,7 +240,7 @@ __device__ __forceinline__ int tk_prune_list(float *__restrict__ lv, int32_t *__
 constexpr int KT_S2_CAP = 1024;               // stage 2 holds this many candidates at once (>= K' + one full list)
 constexpr int KT_S2_LISTS = 512;              // stage 2 gathers up to this many lists per query in one step
 constexpr int KT_RAW_CAP = 64;                // raw 8-score groups a filter thread can hold before they are drained
-constexpr uint32_t KT_MASKED = 0xff7fffe0u;   // -3.4028e38 with the 5 index bits clear: stays finite once tagged
+constexpr uint32_t KT_MASKED = 0xff7fffe0u;   // -3.4028e38: the score of a corpus row past the end (finite, below every threshold)
 constexpr float KT_TAU_FLOOR = -3.0e38f;      // thresholds start here ("nothing left out yet"), above KT_MASKED
 
 __device__ __forceinline__ void st_global_v4_pred(float *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool pred) {
@@ -736,7 +736,7 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
         //   q.e - q~.e~ = (q - q~).e~ + q.(e - e~)  =>  q.e <= q~.e~ + |q - q~| max|e~| + |q| max|e - e~|
         // (Cauchy-Schwarz; |q - q~| is this query's own rounding error, the two corpus bounds come from
         // tk_convert_rows), and the filter's value of q~.e~ is below tau + 2e-5 |q~| |e~|: fp32 accumulation of 128
-        // products in the tensor core (<= 1.6e-5) plus the 5 index bits written over the low mantissa (2^-18).
+        // products in the tensor core (<= 1.6e-5, with slack).
         bool good = s_bad == 0;
         if (good && s_tau > KT_TAU_FLOOR) {
             const double e_norm = static_cast<double>(__uint_as_float(ebounds_bits[0]));
