@@ -251,6 +251,12 @@ TT_API int tt_add_dropout_ln_bwd(const float *grad_y, const float *xhat, const f
  * accumulate != 0: the results are ADDED to grad_weight / grad_bias (a parameter's .grad buffer) instead of stored;
  * tt_add_dropout_ln_bwd's grad_gamma / grad_beta take the same flag.
  * ---------------------------------------------------------------------- */
+/* out[rows, n_out] = input[rows, n_in] . weight[n_out, n_in]^T + bias (nullable), optional ReLU; and the input gradient
+ * grad_input[rows, n_in] = grad_out[rows, n_out] . weight.  One launch each (fp32 FMA, k loop in order: deterministic). */
+TT_API int tt_linear_fwd(const float *input, const float *weight, const float *bias, int64_t rows, int n_out, int n_in,
+                  int relu, float *out, void *stream);
+TT_API int tt_linear_dgrad(const float *grad_out, const float *weight, int64_t rows, int n_out, int n_in, float *grad_input,
+                    void *stream);
 TT_API int tt_linear_wgrad_workspace(int64_t rows, int n_out, int n_in, size_t *bytes_host);
 TT_API int tt_linear_wgrad(const float *grad_out, const float *input, int64_t rows, int n_out, int n_in, float *grad_weight,
                     float *grad_bias, int accumulate, void *workspace, size_t workspace_bytes, void *stream);

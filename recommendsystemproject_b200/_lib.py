@@ -42,6 +42,8 @@ _SIGNATURES = {
     "tt_score_topk_tc_workspace": (c_int, [c_int64, c_int64, c_int, c_int, c_int, P]),
     "tt_score_topk_tc": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_int, c_int64, P, P, P, P, P, c_int, P, c_size_t, P]),
     "tt_topk_merge": (c_int, [P, P, c_int, c_int64, c_int, P, P, P]),
+    "tt_linear_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, P, P]),
+    "tt_linear_dgrad": (c_int, [P, P, c_int64, c_int, c_int, P, P]),
     "tt_linear_wgrad_workspace": (c_int, [c_int64, c_int, c_int, P]),
     "tt_linear_wgrad": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int, P, c_size_t, P]),
     "tt_attn_small_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_float, P, c_int64, P, P]),

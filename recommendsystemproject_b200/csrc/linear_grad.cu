@@ -156,3 +156,129 @@ extern "C" int tt_linear_wgrad(const float *grad_out, const float *input, int64_
     TT_LAUNCH_CHECK("linear_wgrad_reduce");
     return 0;
 }
+
+// ---------------------------------------------------------------- forward and input gradient
+// y[R, N] = x[R, K] . W[N, K]^T + b   (B_TRANS = true,  B = W)          -- nn.Linear forward
+// dx[R, K'] = dy[R, N'] . W[N', K']   (B_TRANS = false, B = W, no bias)  -- its input gradient
+// One launch each.  cuBLASLt runs these skinny fp32 products (R = 512..10240 rows, 8..256 columns) as a split-K SIMT
+// GEMM + a split-K reduce + a bias epilogue kernel: three launches per Linear and direction in a step that is
+// launch-bound (profiles/r1_c2_step_launches_fused.md).  64 x 64 tile, 16-wide k stages, 4 x 4 outputs per thread,
+// next stage prefetched into registers; the k loop runs in order => deterministic.
+namespace tt {
+
+template <bool B_TRANS>
+__global__ void __launch_bounds__(256)
+linear_gemm64(const float *__restrict__ A, const float *__restrict__ B, const float *__restrict__ bias,
+              float *__restrict__ C, int64_t R, int N, int K, int relu) {
+    __shared__ __align__(16) float As[LG_K][LG_T + 4];
+    __shared__ __align__(16) float Bs[LG_K][LG_T + 4];
+    const int t = threadIdx.x, ty = t / 16, tx = t % 16;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * LG_T;
+    const int n0 = blockIdx.x * LG_T;
+    const bool vecA = (K % 4 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
+    const bool vecB = (B_TRANS ? (K % 4 == 0) : (N % 4 == 0)) && (reinterpret_cast<uintptr_t>(B) % 16 == 0);
+    float acc[4][4] = {};
+    float ra[4], rb[4];
+    auto load_stage = [&](int k0) {
+        {   // A tile: row = t / 4, four consecutive k
+            const int64_t r = r0 + t / 4;
+            const int kq = k0 + (t % 4) * 4;
+            ra[0] = ra[1] = ra[2] = ra[3] = 0.f;
+            if (r < R) {
+                if (vecA && kq + 3 < K) {
+                    const float4 v = *reinterpret_cast<const float4 *>(A + r * K + kq);
+                    ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; ra[3] = v.w;
+                } else {
+                    for (int j = 0; j < 4; ++j) if (kq + j < K) ra[j] = A[r * K + kq + j];
+                }
+            }
+        }
+        rb[0] = rb[1] = rb[2] = rb[3] = 0.f;
+        if (B_TRANS) {   // B[n, k]: row n = t / 4, four consecutive k
+            const int n = n0 + t / 4;
+            const int kq = k0 + (t % 4) * 4;
+            if (n < N) {
+                if (vecB && kq + 3 < K) {
+                    const float4 v = *reinterpret_cast<const float4 *>(B + static_cast<int64_t>(n) * K + kq);
+                    rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w;
+                } else {
+                    for (int j = 0; j < 4; ++j) if (kq + j < K) rb[j] = B[static_cast<int64_t>(n) * K + kq + j];
+                }
+            }
+        } else {         // B[k, n]: k = t / 16, four consecutive n
+            const int k = k0 + t / 16;
+            const int nq = n0 + (t % 16) * 4;
+            if (k < K) {
+                if (vecB && nq + 3 < N) {
+                    const float4 v = *reinterpret_cast<const float4 *>(B + static_cast<int64_t>(k) * N + nq);
+                    rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w;
+                } else {
+                    for (int j = 0; j < 4; ++j) if (nq + j < N) rb[j] = B[static_cast<int64_t>(k) * N + nq + j];
+                }
+            }
+        }
+    };
+    load_stage(0);
+    for (int k0 = 0; k0 < K; k0 += LG_K) {
+        __syncthreads();
+        {
+            const int row = t / 4, kq = (t % 4) * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[kq + j][row] = ra[j];
+            if (B_TRANS) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Bs[kq + j][row] = rb[j];
+            } else {
+                *reinterpret_cast<float4 *>(&Bs[t / 16][(t % 16) * 4]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+            }
+        }
+        __syncthreads();
+        if (k0 + LG_K < K) load_stage(k0 + LG_K);
+#pragma unroll
+        for (int k = 0; k < LG_K; ++k) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int64_t r = r0 + ty * 4 + p;
+        if (r >= R) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int n = n0 + tx * 4 + q;
+            if (n >= N) continue;
+            float v = acc[p][q] + (bias != nullptr ? bias[n] : 0.f);
+            if (relu) v = fmaxf(v, 0.f);
+            C[r * N + n] = v;
+        }
+    }
+}
+
+}  // namespace tt
+
+extern "C" int tt_linear_fwd(const float *input, const float *weight, const float *bias, int64_t rows, int n_out, int n_in,
+                             int relu, float *out, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(input && weight && out && rows > 0 && n_out > 0 && n_in > 0, "null pointer / empty input");
+    dim3 grid(static_cast<unsigned>((n_out + LG_T - 1) / LG_T), static_cast<unsigned>((rows + LG_T - 1) / LG_T));
+    linear_gemm64<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(input, weight, bias, out, rows, n_out, n_in, relu);
+    TT_LAUNCH_CHECK("linear_gemm64<fwd>");
+    return 0;
+}
+
+extern "C" int tt_linear_dgrad(const float *grad_out, const float *weight, int64_t rows, int n_out, int n_in,
+                               float *grad_input, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(grad_out && weight && grad_input && rows > 0 && n_out > 0 && n_in > 0, "null pointer / empty input");
+    dim3 grid(static_cast<unsigned>((n_in + LG_T - 1) / LG_T), static_cast<unsigned>((rows + LG_T - 1) / LG_T));
+    // dx[R, n_in] = dy[R, n_out] . W[n_out, n_in]: A = dy (K = n_out), B = W as [K, N = n_in]
+    linear_gemm64<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, weight, nullptr, grad_input, rows, n_in, n_out, 0);
+    TT_LAUNCH_CHECK("linear_gemm64<dgrad>");
+    return 0;
+}

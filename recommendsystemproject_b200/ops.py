@@ -283,8 +283,8 @@ def _direct_grad(p) -> bool:
 
 
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b with the library's one-pass weight + bias gradient (linear_grad.cu) in the backward; the forward
-    and the input gradient are plain cuBLAS GEMMs."""
+    """y = x W^T + b: forward, input gradient and the one-pass weight + bias gradient are library kernels
+    (linear_grad.cu), one launch each (two for the weight gradient)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -292,7 +292,16 @@ class LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.bias_ref = bias
-        return F.linear(x, weight, bias)
+        ctx.tf32 = bool(torch.backends.cuda.matmul.allow_tf32)
+        if ctx.tf32:     # the caller asked for TF32 tensor-core products: cuBLAS has them, the fp32 FMA kernels below do not
+            return F.linear(x, weight, bias)
+        lib = _lib.load()
+        n_out, n_in = weight.shape
+        x2 = x.reshape(-1, n_in).contiguous()
+        out = torch.empty(x2.shape[0], n_out, dtype=torch.float32, device=x.device)
+        check(lib.tt_linear_fwd(_p(x2), _p(weight), _p(bias), x2.shape[0], n_out, n_in, 0, _p(out), _stream()), "tt_linear_fwd")
+        _count()
+        return out.reshape(*x.shape[:-1], n_out)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -303,8 +312,13 @@ class LinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, n_in).contiguous()
         rows = g2.shape[0]
         gx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and ctx.tf32:
             gx = (g2 @ weight).reshape(x.shape)
+        elif ctx.needs_input_grad[0]:
+            gx = torch.empty(rows, n_in, dtype=torch.float32, device=g2.device)
+            check(lib.tt_linear_dgrad(_p(g2), _p(weight), rows, n_out, n_in, _p(gx), _stream()), "tt_linear_dgrad")
+            _count()
+            gx = gx.reshape(x.shape)
         gw = gb = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             if wgrad_shapes is not None:
