@@ -159,6 +159,11 @@ class MultiGatherPool(torch.autograd.Function):
             if sparse_grad and ctx.sink is not None:
                 ctx.sink.entries.append((table, rows, row_grad, n_unique))
                 grads.append(None)
+            elif _direct_grad(table) and table.grad.shape == table.shape:
+                # the optimizer owns a preallocated, zeroed .grad view: scatter-add into it (no dense temporary, no
+                # fill, no accumulate kernel)
+                scatter_rows_(table.grad, rows, row_grad, n_unique)
+                grads.append(None)
             else:
                 dense = torch.zeros(V, D, dtype=torch.float32, device=g.device)
                 scatter_rows_(dense, rows, row_grad, n_unique)
