@@ -585,17 +585,100 @@ topk_tc_stage2(const float *__restrict__ query, const float *__restrict__ corpus
     if (tid == 0) { s_tau = -INFINITY; s_bad = 0; }
     __syncthreads();
     int tot = 0;   // entries in av/ai (uniform across the CTA)
-    auto reduce_to_kp = [&]() {   // keep the kp best by approximate score; what falls out bounds tau from below
-        int np2 = 32;
-        while (np2 < tot) np2 <<= 1;
-        for (int t = tid; t < np2; t += blockDim.x)
-            if (t >= tot) ak[t] = 0;          // below every real key
-        __syncthreads();
-        tk_bitonic_keys_desc(ak, np2, tid, static_cast<int>(blockDim.x), [] { __syncthreads(); });
-        if (tot > kp) {
-            if (tid == 0) s_tau = fmaxf(s_tau, tk_key_score(ak[kp]));
-            tot = kp;
+    // keep the kp largest keys (= best approximate scores, ties by row); what falls out bounds tau from below.
+    // MSB-first radix SELECT over the 64-bit keys, 8 bits per pass, stopping as soon as the boundary bin is taken
+    // whole (4 passes for distinct scores): ~10x fewer instructions than sorting the 512 / 1024 keys, which was 40 %
+    // of this kernel.
+    __shared__ int s_hist[256];
+    __shared__ int s_sel[3];                  // boundary bin, keys above it, keys in it
+    __shared__ unsigned long long s_wmax[4];
+    __shared__ int s_wcnt[4];
+    auto reduce_to_kp = [&]() {
+        if (tot <= kp) return;                // uniform
+        constexpr int PER_T = KT_S2_CAP / 128;
+        uint64_t mine[PER_T];
+#pragma unroll
+        for (int j = 0; j < PER_T; ++j) mine[j] = (tid + 128 * j < tot) ? ak[tid + 128 * j] : 0ull;   // 0 = below every key
+        uint64_t prefix = 0;
+        int fixed_bits = 0, remaining = kp;
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            for (int t = tid; t < 256; t += blockDim.x) s_hist[t] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < PER_T; ++j) {
+                if (tid + 128 * j < tot && (fixed_bits == 0 || (mine[j] >> (shift + 8)) == prefix))
+                    atomicAdd(&s_hist[static_cast<int>((mine[j] >> shift) & 255u)], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // bins from high to low: lane l owns bins 255 - 8l .. 248 - 8l
+                int c[8], lane_sum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { c[k] = s_hist[255 - (lane * 8 + k)]; lane_sum += c[k]; }
+                int incl = lane_sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += x;
+                }
+                int above = incl - lane_sum;              // keys in bins higher than this lane's
+                if (above < remaining && incl >= remaining) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (above < remaining && above + c[k] >= remaining) {
+                            s_sel[0] = 255 - (lane * 8 + k); s_sel[1] = above; s_sel[2] = c[k];
+                            above = remaining;            // stop
+                        } else if (above < remaining) above += c[k];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | static_cast<uint64_t>(s_sel[0]);
+            fixed_bits += 8;
+            remaining -= s_sel[1];
+            const int in_bin = s_sel[2];
+            __syncthreads();
+            if (in_bin == remaining) break;               // the whole boundary bin is kept
         }
+        // keep keys whose fixed high bits are >= prefix; the largest dropped key bounds tau
+        const int fs = 64 - fixed_bits;
+        uint64_t dropped_max = 0;
+        int n_keep = 0;
+        bool keep[PER_T];
+#pragma unroll
+        for (int j = 0; j < PER_T; ++j) {
+            const bool valid = tid + 128 * j < tot;
+            const uint64_t hi = (fs >= 64) ? 0ull : (mine[j] >> fs);
+            keep[j] = valid && hi >= prefix;
+            if (valid && !keep[j] && mine[j] > dropped_max) dropped_max = mine[j];
+            n_keep += keep[j] ? 1 : 0;
+        }
+        int incl = n_keep;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t x = __shfl_xor_sync(0xffffffffu, dropped_max, o);
+            if (x > dropped_max) dropped_max = x;
+        }
+        if (lane == 31) s_wcnt[warp] = incl;
+        if (lane == 0) s_wmax[warp] = dropped_max;
+        __syncthreads();
+        int pos = incl - n_keep;
+        for (int w2 = 0; w2 < warp; ++w2) pos += s_wcnt[w2];
+#pragma unroll
+        for (int j = 0; j < PER_T; ++j)
+            if (keep[j]) ak[pos++] = mine[j];
+        if (tid == 0) {
+            uint64_t dm = s_wmax[0];
+            for (int w2 = 1; w2 < 4; ++w2) if (s_wmax[w2] > dm) dm = s_wmax[w2];
+            if (dm != 0ull) s_tau = fmaxf(s_tau, tk_key_score(dm));
+        }
+        tot = s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
         __syncthreads();
     };
     // gather the query's lists.  Fast path (the usual case: a few hundred candidates in a few dozen lists): counts and
