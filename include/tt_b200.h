@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TT_ABI_VERSION 1
+#define TT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TT_API __attribute__((visibility("default")))
@@ -96,13 +96,23 @@ TT_API int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, int 
                         int dim, int64_t *unique_rows, float *row_grad, int32_t *n_unique, float *sq_norm,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* List form of tt_emb_segment_grad (owner side of the row-sharded exchange, section 7): position p = piece * piece_len + e
+ * holds local row rows[piece * piece_stride + e] (negative or >= vocab: dropped) and reads gradient row
+ * q = pos_src ? pos_src[p] : p, stored at grad[(q / grad_piece_rows) * grad_piece_stride + (q % grad_piece_rows) * dim].
+ * Same outputs and the same determinism (stable sort => ascending positions inside a segment). */
+TT_API int tt_emb_segment_grad_lists(const int32_t *rows, int64_t n_pieces, int64_t piece_len, int64_t piece_stride,
+                              const int32_t *pos_src, int64_t vocab, const float *grad, int64_t grad_piece_rows,
+                              int64_t grad_piece_stride, int dim, int64_t *unique_rows, float *row_grad,
+                              int32_t *n_unique, float *sq_norm, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Adam on the touched rows only ("lazy" Adam; equals dense Adam the first
  * time a row is touched).  g = row_grad * (*clip_coef) (NULL -> 1).  The step
- * count t is read from *step_dev (so CUDA graphs can replay). */
+ * count t is read from *step_dev (so CUDA graphs can replay); lr_dev (nullable,
+ * device double) overrides `lr`, so an LR scheduler reaches a captured graph. */
 TT_API int tt_emb_rowwise_adam(void *table, int table_dtype, float *exp_avg, float *exp_avg_sq, int dim,
                         const int64_t *unique_rows, const float *row_grad, const int32_t *n_unique,
                         int64_t max_rows, const float *clip_coef, double lr, double beta1, double beta2, double eps,
-                        const int64_t *step_dev, void *stream);
+                        const int64_t *step_dev, const double *lr_dev, void *stream);
 
 /* dense[rows[u], :] += row_grad[u, :]  -- builds the dense .grad the drop-in
  * modules expose to an unmodified torch.optim.Adam. */
@@ -119,7 +129,7 @@ TT_API int tt_clip_coef(const float *sq_terms, int n_terms, float max_norm, floa
 /* flat dense Adam over n contiguous floats, g scaled by *clip_coef */
 TT_API int tt_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
                  const float *clip_coef, double lr, double beta1, double beta2, double eps,
-                 const int64_t *step_dev, void *stream);
+                 const int64_t *step_dev, const double *lr_dev, void *stream);
 
 /* ------------------------------------------------------------------------
  * 3. Fused in-batch (+ hard-negative) softmax cross-entropy.
@@ -260,6 +270,42 @@ TT_API int tt_linear_dgrad(const float *grad_out, const float *weight, int64_t r
 TT_API int tt_linear_wgrad_workspace(int64_t rows, int n_out, int n_in, size_t *bytes_host);
 TT_API int tt_linear_wgrad(const float *grad_out, const float *input, int64_t rows, int n_out, int n_in, float *grad_weight,
                     float *grad_bias, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 7. Row-sharded embedding tables (owner = row % world, local row = row / world): device side of the exchange.
+ * New (the reference is single-process); it is what GenericTower.py:141-183 becomes when a table of BASELINE
+ * configs[2] (100M users / 10M items x 128) is spread over the GPUs of one NVSwitch box.
+ * Every rank sends every owner one int32 block [block_ints] and receives one fp32 block [block_floats] back; both have
+ * fixed sizes (capacities), so no size ever crosses the host and the step can be one CUDA graph.  Per table a block holds
+ *   off [n_rows + 1] at off_base : exclusive offsets, the entries of sample b for this owner are [off[b], off[b+1])
+ *   rows[cap]        at rows_base: the owner's LOCAL rows in (sample, position) order, unused slots = -1
+ * and the float block holds, at vec_base, [n_rows][dim] partial sums (len > 1) or [cap][dim] rows (len == 1).
+ *   tt_shard_route        source: buckets ids [n_rows, len] by owner into send[world][block_ints] (count, scan, fill:
+ *                         ballots only, order preserved); n_pad[n_rows] (nullable) = pads per sample;
+ *                         *flags |= 1 (id outside [0, vocab)), |= 2 (an owner's entries exceed cap: dropped)
+ *   tt_shard_owner_gather owner: pooled != 0: out[s][vec_base + b*dim] = sum of table rows of (source s, sample b) and
+ *                         pos_src[s*cap + e] = s*n_rows + b (nullable; feeds tt_emb_segment_grad_lists);
+ *                         pooled == 0: out[s][vec_base + e*dim] = table[rows[s][e]]
+ *   tt_shard_combine      source: out[b] = sum_w recv_vec[w][b] in rank order + n_pad[b] * pad_row, / len for MEAN
+ *                         (len > 1), or recv_vec[owner(b)][slot(b)] (len == 1; pad id -> pad_row)
+ *   tt_shard_grad_pack    source, backward: grad_out[b] (x 1/len for MEAN) into every owner's block (len > 1) or into
+ *                         the owner's slot (len == 1), the layout tt_shard_owner_gather produced
+ * ---------------------------------------------------------------------- */
+TT_API int tt_shard_route(const int64_t *ids, int64_t n_rows, int len, int64_t padding_idx, int64_t vocab, int world,
+                   int32_t *send, int64_t block_ints, int64_t off_base, int64_t rows_base, int64_t cap, int32_t *n_pad,
+                   int *flags, void *stream);
+TT_API int tt_shard_owner_gather(const void *table, int table_dtype, int64_t local_rows, int dim, int world,
+                          const int32_t *recv, int64_t block_ints, int64_t off_base, int64_t rows_base, int64_t cap,
+                          int64_t n_rows, int pooled, float *out, int64_t block_floats, int64_t vec_base,
+                          int32_t *pos_src, void *stream);
+TT_API int tt_shard_combine(const float *recv_vec, int64_t block_floats, int64_t vec_base, int world, const int64_t *ids,
+                     int64_t n_rows, int len, int64_t padding_idx, int64_t vocab, int mode, const int32_t *send,
+                     int64_t block_ints, int64_t off_base, int64_t cap, const int32_t *n_pad, const float *pad_row,
+                     int dim, float *out, int64_t out_stride, void *stream);
+TT_API int tt_shard_grad_pack(const float *grad_out, int64_t grad_stride, int64_t n_rows, int len, int mode, int dim,
+                       int world, const int64_t *ids, int64_t padding_idx, int64_t vocab, const int32_t *send,
+                       int64_t block_ints, int64_t off_base, int64_t cap, float *send_vec, int64_t block_floats,
+                       int64_t vec_base, void *stream);
 
 #ifdef __cplusplus
 }

@@ -23,11 +23,20 @@ _SIGNATURES = {
     "tt_emb_segment_grad_workspace": (c_int, [c_int64, c_int, P]),
     "tt_emb_segment_grad": (c_int, [P, c_int64, c_int, c_int, c_int64, c_int64, P, c_int64, P, c_int, P, P, P, P, P,
                                     c_size_t, P]),
-    "tt_emb_rowwise_adam": (c_int, [P, c_int, P, P, c_int, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, P, P]),
+    "tt_emb_segment_grad_lists": (c_int, [P, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, c_int, P, P, P, P, P,
+                                          c_size_t, P]),
+    "tt_shard_route": (c_int, [P, c_int64, c_int, c_int64, c_int64, c_int, P, c_int64, c_int64, c_int64, c_int64, P, P, P]),
+    "tt_shard_owner_gather": (c_int, [P, c_int, c_int64, c_int, c_int, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
+                                      P, c_int64, c_int64, P, P]),
+    "tt_shard_combine": (c_int, [P, c_int64, c_int64, c_int, P, c_int64, c_int, c_int64, c_int64, c_int, P, c_int64, c_int64,
+                                 c_int64, P, P, c_int, P, c_int64, P]),
+    "tt_shard_grad_pack": (c_int, [P, c_int64, c_int64, c_int, c_int, c_int, c_int, P, c_int64, c_int64, P, c_int64, c_int64,
+                                   c_int64, P, c_int64, c_int64, P]),
+    "tt_emb_rowwise_adam": (c_int, [P, c_int, P, P, c_int, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, P, P, P]),
     "tt_emb_scatter_rows": (c_int, [P, c_int, P, P, P, c_int64, P]),
     "tt_sq_norm_accum": (c_int, [P, c_int64, P, P, c_size_t, P]),
     "tt_clip_coef": (c_int, [P, c_int, c_float, P, P, P]),
-    "tt_adam_flat": (c_int, [P, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, P, P]),
+    "tt_adam_flat": (c_int, [P, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, P, P, P]),
     "tt_ce_workspace": (c_int, [c_int64, c_int64, c_int, c_int, P]),
     "tt_ce_fwd_f32": (c_int, [P, P, P, P, c_int, P, c_int64, c_int64, c_int, c_float, P, P, P, P, P, c_size_t, P]),
     "tt_ce_bwd_f32": (c_int, [P, P, P, P, c_int, P, c_int64, c_int64, c_int, c_float, P, P, P, P, P, P, P, c_size_t, P]),
@@ -81,7 +90,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.tt_abi_version() != 1:
+    if lib.tt_abi_version() != 2:
         raise TTError("libtt_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -84,7 +84,9 @@ class GpuBatchBuilder:
         out = {"user_tower": _take(self.user, idx), "item_tower": _take(self.item, idx)}
         if self.hard_neg_ids is not None:
             neg = self.hard_neg_ids.index_select(0, idx)                       # [B, n_neg] item ids
-            rows = self.id_to_row[neg.clamp(max=self.id_to_row.numel() - 1)]   # unknown ids -> "no negative"
+            n_map = self.id_to_row.numel()                                     # ids outside [0, max catalog id] and ids the
+            known = (neg >= 0) & (neg < n_map)                                 # catalog does not hold -> row 0 ("no negative")
+            rows = torch.where(known, self.id_to_row[neg.clamp(0, n_map - 1)], torch.zeros_like(neg))
             out["hard_negatives"] = [_take(self.catalog, rows[:, n].contiguous()) for n in range(rows.shape[1])]
         return out
 

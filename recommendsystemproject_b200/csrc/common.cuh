@@ -56,11 +56,12 @@ struct Workspace {
 // corrections in double) plus the fp32 constants the element loop uses.
 struct AdamHyper {
     double lr, beta1, beta2;
+    const double *lr_dev;   // when not NULL the learning rate is read from device memory (schedulers + CUDA graphs)
     float b1, omb1, b2, omb2, eps;
 };
-inline AdamHyper make_adam(double lr, double beta1, double beta2, double eps) {
+inline AdamHyper make_adam(double lr, double beta1, double beta2, double eps, const double *lr_dev = nullptr) {
     AdamHyper h;
-    h.lr = lr; h.beta1 = beta1; h.beta2 = beta2;
+    h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.lr_dev = lr_dev;
     h.b1 = static_cast<float>(beta1); h.omb1 = static_cast<float>(1.0 - beta1);
     h.b2 = static_cast<float>(beta2); h.omb2 = static_cast<float>(1.0 - beta2);
     h.eps = static_cast<float>(eps);
@@ -69,7 +70,8 @@ inline AdamHyper make_adam(double lr, double beta1, double beta2, double eps) {
 __device__ __forceinline__ void adam_step_consts(const AdamHyper &h, const int64_t *step_dev, float &step_size,
                                                  float &bc2_sqrt) {
     const double t = static_cast<double>(*step_dev);
-    step_size = static_cast<float>(h.lr / (1.0 - pow(h.beta1, t)));
+    const double lr = h.lr_dev ? *h.lr_dev : h.lr;
+    step_size = static_cast<float>(lr / (1.0 - pow(h.beta1, t)));
     bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(h.beta2, t)));
 }
 __device__ __forceinline__ void adam_elem(const AdamHyper &h, float step_size, float bc2_sqrt, float g, float &p,

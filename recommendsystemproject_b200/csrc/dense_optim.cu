@@ -107,14 +107,14 @@ extern "C" int tt_clip_coef(const float *sq_terms, int n_terms, float max_norm, 
 
 extern "C" int tt_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
                             const float *clip_coef, double lr, double beta1, double beta2, double eps,
-                            const int64_t *step_dev, void *stream) {
+                            const int64_t *step_dev, const double *lr_dev, void *stream) {
     TT_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_dev && n >= 0, "bad argument");
     if (n == 0) return 0;
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = static_cast<int64_t>(tt::sm_count()) * 16;
     if (blocks > cap) blocks = cap;
     tt::adam_flat_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        param, grad, exp_avg, exp_avg_sq, n, clip_coef, tt::make_adam(lr, beta1, beta2, eps), step_dev);
+        param, grad, exp_avg, exp_avg_sq, n, clip_coef, tt::make_adam(lr, beta1, beta2, eps, lr_dev), step_dev);
     TT_LAUNCH_CHECK("adam_flat_kernel");
     return 0;
 }

@@ -206,10 +206,31 @@ struct GradSrc {
     int len;
     int mode;
     int dim;
+    // list form (tt_emb_segment_grad_lists): position p reads gradient row q = pos_src ? pos_src[p] : p, which lives in
+    // piece q / piece_rows of a buffer cut into pieces `piece_stride` floats apart (the per-source blocks of the
+    // row-sharded exchange); piece_rows == 0: the flat [n, grad_stride] form above
+    const int32_t *pos_src;
+    int64_t piece_rows;
+    int64_t piece_stride;
 };
 
+// gradient row (and pooling slot) of sorted position p
+template <bool LISTS>
+__device__ __forceinline__ const float *seg_grad_row(const GradSrc &g, int32_t p, int &slot, int64_t &src) {
+    slot = 0;
+    if (LISTS) {
+        const int64_t q = g.pos_src ? static_cast<int64_t>(__ldg(g.pos_src + p)) : static_cast<int64_t>(p);
+        src = q;
+        const int64_t piece = q / g.piece_rows;
+        return g.grad_out + piece * g.piece_stride + (q - piece * g.piece_rows) * g.grad_stride;
+    }
+    src = p;
+    if (g.len > 1) { src = p / g.len; slot = p - static_cast<int32_t>(src) * g.len; }
+    return g.grad_out + src * g.grad_stride;
+}
+
 // accumulate positions [p0, p1) of the sorted order into acc (LPR lanes per row, 4 floats per lane)
-template <int LPR>
+template <int LPR, bool LISTS = false>
 __device__ __forceinline__ void seg_accumulate(const GradSrc &g, const int32_t *__restrict__ sorted_pos, int p0,
                                                int p1, int c, bool col_ok, float (&acc)[4]) {
     constexpr int UNROLL = 4;
@@ -223,10 +244,10 @@ __device__ __forceinline__ void seg_accumulate(const GradSrc &g, const int32_t *
             slot[u] = 0;
             if (use[u]) {
                 const int32_t p = __ldg(sorted_pos + i + u);
-                int64_t src = p;
-                if (g.len > 1) { src = p / g.len; slot[u] = p - static_cast<int32_t>(src) * g.len; }
-                v[u] = __ldg(reinterpret_cast<const float4 *>(g.grad_out + src * g.grad_stride + c * 4));
-                if (g.mode == TT_POOL_MAX) {
+                int64_t src;
+                const float *grow = seg_grad_row<LISTS>(g, p, slot[u], src);
+                v[u] = __ldg(reinterpret_cast<const float4 *>(grow + c * 4));
+                if (!LISTS && g.mode == TT_POOL_MAX) {
                     const int4 am = __ldg(reinterpret_cast<const int4 *>(g.argmax + src * g.dim + c * 4));
                     if (am.x != slot[u]) v[u].x = 0.f;
                     if (am.y != slot[u]) v[u].y = 0.f;
@@ -243,7 +264,7 @@ __device__ __forceinline__ void seg_accumulate(const GradSrc &g, const int32_t *
 }
 
 // one LPR-lane group per CHUNK piece of a long segment -> partial[c, D]
-template <int LPR>
+template <int LPR, bool LISTS = false>
 __global__ void __launch_bounds__(256)
 seg_reduce_chunks(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
                   const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
@@ -277,7 +298,7 @@ seg_reduce_chunks(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32
             const int c = c0 + sub;
             const bool col_ok = c < vpr;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            seg_accumulate<LPR>(g, sorted_pos, p0, p1, c, col_ok, acc);
+            seg_accumulate<LPR, LISTS>(g, sorted_pos, p0, p1, c, col_ok, acc);
             if (col_ok)
                 *reinterpret_cast<float4 *>(partial + ck * g.dim + c * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
@@ -285,7 +306,7 @@ seg_reduce_chunks(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32
 }
 
 // one LPR-lane group per segment -> row_grad[s, D], sq[s]
-template <int LPR>
+template <int LPR, bool LISTS = false>
 __global__ void __launch_bounds__(256)
 seg_reduce_rows(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
                 const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
@@ -313,7 +334,7 @@ seg_reduce_rows(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t
                 const bool col_ok = c < vpr;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 if (len <= SEG_CHUNK) {
-                    seg_accumulate<LPR>(g, sorted_pos, p0, p1, c, col_ok, acc);
+                    seg_accumulate<LPR, LISTS>(g, sorted_pos, p0, p1, c, col_ok, acc);
                 } else if (col_ok) {
                     const int nck = (len + SEG_CHUNK - 1) / SEG_CHUNK;
                     const int64_t cb = chunk_base[s];
@@ -342,7 +363,7 @@ seg_reduce_rows(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t
 // parallelism, not on the length of the inner loop.
 // <= 64 registers at D <= 128: 4 blocks = 32 warps per SM (ncu: long_scoreboard-bound at the 2 blocks per SM that 86
 // registers allowed)
-template <int CPL>
+template <int CPL, bool LISTS = false>
 __global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2)
 seg_reduce_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
                      const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
@@ -376,14 +397,14 @@ seg_reduce_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const in
                         use[u] = (i + u) < p1;
                         if (use[u]) {
                             const int32_t p = __ldg(sorted_pos + i + u);
-                            int64_t src = p;
-                            int slot = 0;
-                            if (g.len > 1) { src = p / g.len; slot = p - static_cast<int32_t>(src) * g.len; }
+                            int64_t src;
+                            int slot;
+                            const float *grow = seg_grad_row<LISTS>(g, p, slot, src);
 #pragma unroll
                             for (int k = 0; k < CPL; ++k) {
                                 const int c = sub + LPR * k;
-                                v[u][k] = __ldg(reinterpret_cast<const float4 *>(g.grad_out + src * g.grad_stride + c * 4));
-                                if (g.mode == TT_POOL_MAX) {
+                                v[u][k] = __ldg(reinterpret_cast<const float4 *>(grow + c * 4));
+                                if (!LISTS && g.mode == TT_POOL_MAX) {
                                     const int4 am = __ldg(reinterpret_cast<const int4 *>(g.argmax + src * g.dim + c * 4));
                                     if (am.x != slot) v[u][k].x = 0.f;
                                     if (am.y != slot) v[u][k].y = 0.f;
@@ -461,11 +482,11 @@ __global__ void seg_reduce_rows_scalar(GradSrc g, const int32_t *__restrict__ so
         float acc = 0.f;
         for (int i = seg_start[s]; i < p1; ++i) {
             const int32_t p = sorted_pos[i];
-            int64_t src = p;
-            int slot = 0;
-            if (g.len > 1) { src = p / g.len; slot = p - static_cast<int32_t>(src) * g.len; }
-            float v = g.grad_out[src * g.grad_stride + d];
-            if (g.mode == TT_POOL_MAX && g.argmax[src * g.dim + d] != slot) v = 0.f;
+            int64_t src;
+            int slot;
+            const float *grow = g.piece_rows > 0 ? seg_grad_row<true>(g, p, slot, src) : seg_grad_row<false>(g, p, slot, src);
+            float v = grow[d];
+            if (g.piece_rows == 0 && g.mode == TT_POOL_MAX && g.argmax[src * g.dim + d] != slot) v = 0.f;
             acc += v;
         }
         row_grad[t] = acc * scale;
@@ -535,21 +556,21 @@ static SegPlan seg_plan(int64_t n) {
     return p;
 }
 
-template <int LPR>
+template <int LPR, bool LISTS = false>
 static int launch_reduce(const GradSrc &g, const int32_t *sorted_pos, const int32_t *seg_start,
                          const int32_t *chunk_base, const int32_t *counters, float *partial, int64_t max_chunks,
                          float scale, float *row_grad, float *seg_sq, int64_t n, int SEG_CHUNK, cudaStream_t st) {
     const int threads = 256;
     const int gpb = threads / LPR;
     if (n > SEG_CHUNK) {
-        seg_reduce_chunks<LPR><<<grid_for(max_chunks * LPR, threads), threads, 0, st>>>(
+        seg_reduce_chunks<LPR, LISTS><<<grid_for(max_chunks * LPR, threads), threads, 0, st>>>(
             g, sorted_pos, seg_start, chunk_base, counters, SEG_CHUNK, partial);
         TT_LAUNCH_CHECK("seg_reduce_chunks");
     }
     int64_t blocks = (n + gpb - 1) / gpb;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
     if (blocks > cap) blocks = cap;
-    seg_reduce_rows<LPR><<<static_cast<unsigned>(blocks), threads, 0, st>>>(g, sorted_pos, seg_start, chunk_base,
+    seg_reduce_rows<LPR, LISTS><<<static_cast<unsigned>(blocks), threads, 0, st>>>(g, sorted_pos, seg_start, chunk_base,
                                                                            counters, partial, scale, SEG_CHUNK, row_grad, seg_sq);
     TT_LAUNCH_CHECK("seg_reduce_rows");
     return 0;
@@ -578,20 +599,32 @@ extern "C" int tt_emb_segment_grad_workspace(int64_t n_pos, int dim, size_t *byt
     return 0;
 }
 
-extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, int mode, int64_t padding_idx,
-                                   int64_t vocab, const float *grad_out, int64_t grad_stride, const int32_t *argmax,
-                                   int dim, int64_t *unique_rows, float *row_grad, int32_t *n_unique,
-                                   float *sq_norm, void *workspace, size_t workspace_bytes, void *stream) {
-    using namespace tt;
-    TT_CHECK_ARG(ids && grad_out && unique_rows && row_grad && n_unique && workspace, "null pointer");
-    TT_CHECK_ARG(n_rows > 0 && len > 0 && dim > 0 && vocab > 0, "non-positive size");
-    TT_CHECK_ARG(mode >= TT_POOL_NONE && mode <= TT_POOL_MAX, "unknown pooling mode");
-    TT_CHECK_ARG(mode != TT_POOL_MAX || argmax, "TT_POOL_MAX needs argmax");
-    TT_CHECK_ARG(mode != TT_POOL_NONE || len == 1, "TT_POOL_NONE needs len == 1");
-    TT_CHECK_ARG(vocab < (int64_t(1) << 31) - 1, "vocab must fit 31 bits");
-    const int64_t n = n_rows * len;
-    TT_CHECK_ARG(n < (int64_t(1) << 31) - 2, "more than 2^31 positions per call");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+namespace tt {
+
+// keys of the list form: key[p] = rows[(p / piece_len) * piece_stride + p % piece_len] (negative / >= vocab: dropped)
+__global__ void seg_build_keys_lists(const int32_t *__restrict__ rows, int64_t n, int64_t piece_len, int64_t piece_stride,
+                                     int64_t vocab, uint32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n;
+         p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t piece = p / piece_len;
+        const int32_t r = __ldg(rows + piece * piece_stride + (p - piece * piece_len));
+        keys[p] = (r < 0 || r >= vocab) ? static_cast<uint32_t>(vocab) : static_cast<uint32_t>(r);
+        vals[p] = static_cast<int32_t>(p);
+    }
+}
+
+struct KeySrc {
+    const int64_t *ids;       // flat form: ids[n], pad dropped
+    int64_t pad;
+    const int32_t *rows;      // list form (ids == nullptr)
+    int64_t piece_len, piece_stride;
+};
+
+template <bool LISTS>
+static int segment_grad_run(const KeySrc &ks, const GradSrc &g, int64_t n, int64_t vocab, float scale,
+                            int64_t *unique_rows, float *row_grad, int32_t *n_unique, float *sq_norm, void *workspace,
+                            size_t workspace_bytes, cudaStream_t st) {
+    const int dim = g.dim;
     const SegPlan plan = seg_plan(n);
 
     Workspace ws(workspace, workspace_bytes);
@@ -618,41 +651,40 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
     while ((int64_t(1) << id_bits) < vocab) ++id_bits;
     // (measured on the C2 step: 17 us for <= 4096 positions against ~35 us of launches; at 16 / 32 keys per thread the
     // single CTA is no faster than the general path -- 41 / 90 us -- so those sizes stay there)
-    const bool small = n <= 8192 && pos_bits + id_bits <= 32;
+    const bool small = !LISTS && n <= 8192 && pos_bits + id_bits <= 32;
     if (small) {
         const int nn = static_cast<int>(n);
         int rc2;
-        if (nn <= 4096) rc2 = launch_seg_small<4>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
-        else rc2 = launch_seg_small<8>(ids, nn, padding_idx, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
+        if (nn <= 4096) rc2 = launch_seg_small<4>(ks.ids, nn, ks.pad, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
+        else rc2 = launch_seg_small<8>(ks.ids, nn, ks.pad, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
         if (rc2) return rc2;
     } else {
-    seg_build_keys<<<g1, threads, 0, st>>>(ids, n, padding_idx, vocab, keys_in, vals_in);
-    TT_LAUNCH_CHECK("seg_build_keys");
-    int end_bit = 1;
-    while ((int64_t(1) << end_bit) <= vocab) ++end_bit;  // keys are in [0, vocab]
-    size_t tmp = plan.cub_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, keys_in, keys_out, vals_in, vals_out,
-                                                    static_cast<int>(n), 0, end_bit, st);
-    if (e != cudaSuccess) return cuda_status(e, "cub SortPairs");
-    const uint32_t sentinel = static_cast<uint32_t>(vocab);
-    seg_heads<<<g1, threads, 0, st>>>(keys_out, n, sentinel, head);
-    TT_LAUNCH_CHECK("seg_heads");
-    tmp = plan.cub_bytes;
-    e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, head, seg_id, static_cast<int>(n), st);
-    if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum");
-    seg_starts<<<g1, threads, 0, st>>>(keys_out, head, seg_id, n, sentinel, seg_start, unique_rows, counters);
-    TT_LAUNCH_CHECK("seg_starts");
-    seg_chunk_counts<<<g1, threads, 0, st>>>(seg_start, counters, n, plan.chunk, n_chunks);
-    TT_LAUNCH_CHECK("seg_chunk_counts");
-    tmp = plan.cub_bytes;
-    e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, n_chunks, chunk_base, static_cast<int>(n), st);
-    if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum(chunks)");
+        if (LISTS) seg_build_keys_lists<<<g1, threads, 0, st>>>(ks.rows, n, ks.piece_len, ks.piece_stride, vocab, keys_in, vals_in);
+        else seg_build_keys<<<g1, threads, 0, st>>>(ks.ids, n, ks.pad, vocab, keys_in, vals_in);
+        TT_LAUNCH_CHECK("seg_build_keys");
+        int end_bit = 1;
+        while ((int64_t(1) << end_bit) <= vocab) ++end_bit;  // keys are in [0, vocab]
+        size_t tmp = plan.cub_bytes;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, keys_in, keys_out, vals_in, vals_out,
+                                                        static_cast<int>(n), 0, end_bit, st);
+        if (e != cudaSuccess) return cuda_status(e, "cub SortPairs");
+        const uint32_t sentinel = static_cast<uint32_t>(vocab);
+        seg_heads<<<g1, threads, 0, st>>>(keys_out, n, sentinel, head);
+        TT_LAUNCH_CHECK("seg_heads");
+        tmp = plan.cub_bytes;
+        e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, head, seg_id, static_cast<int>(n), st);
+        if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum");
+        seg_starts<<<g1, threads, 0, st>>>(keys_out, head, seg_id, n, sentinel, seg_start, unique_rows, counters);
+        TT_LAUNCH_CHECK("seg_starts");
+        seg_chunk_counts<<<g1, threads, 0, st>>>(seg_start, counters, n, plan.chunk, n_chunks);
+        TT_LAUNCH_CHECK("seg_chunk_counts");
+        tmp = plan.cub_bytes;
+        e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, n_chunks, chunk_base, static_cast<int>(n), st);
+        if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum(chunks)");
     }   // general path
 
-    GradSrc g{grad_out, grad_stride, argmax, len, mode, dim};
-    const float scale = (mode == TT_POOL_MEAN) ? 1.0f / static_cast<float>(len) : 1.0f;
-    const bool vec = (dim % 4 == 0) && (grad_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(grad_out) % 16 == 0) &&
-                     (reinterpret_cast<uintptr_t>(row_grad) % 16 == 0);
+    const bool vec = (dim % 4 == 0) && (g.grad_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(g.grad_out) % 16 == 0) &&
+                     (reinterpret_cast<uintptr_t>(row_grad) % 16 == 0) && (g.piece_stride % 4 == 0);
     int rc = 0;
     if (!vec) {
         seg_reduce_rows_scalar<<<grid_for(n * dim, threads), threads, 0, st>>>(g, vals_out, seg_start, counters, scale,
@@ -665,26 +697,26 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
         const int cpl = (vpr % 8 == 0) ? vpr / 8 : 0;
         if (cpl == 2 || cpl == 3 || cpl == 4 || cpl == 6 || cpl == 8) {
             if (n > plan.chunk) {
-                seg_reduce_chunks<8><<<grid_for(plan.max_chunks * 8, threads), threads, 0, st>>>(
+                seg_reduce_chunks<8, LISTS><<<grid_for(plan.max_chunks * 8, threads), threads, 0, st>>>(
                     g, vals_out, seg_start, chunk_base, counters, plan.chunk, partial);
                 TT_LAUNCH_CHECK("seg_reduce_chunks");
             }
             int64_t blocks = (n + 31) / 32;
             const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
             if (blocks > cap) blocks = cap;
-#define TT_WIDE(C) seg_reduce_rows_wide<C><<<static_cast<unsigned>(blocks), threads, 0, st>>>(                      \
+#define TT_WIDE(C) seg_reduce_rows_wide<C, LISTS><<<static_cast<unsigned>(blocks), threads, 0, st>>>(               \
         g, vals_out, seg_start, chunk_base, counters, partial, scale, plan.chunk, row_grad, seg_sq)
             if (cpl == 2) TT_WIDE(2); else if (cpl == 3) TT_WIDE(3); else if (cpl == 4) TT_WIDE(4);
             else if (cpl == 6) TT_WIDE(6); else TT_WIDE(8);
 #undef TT_WIDE
             TT_LAUNCH_CHECK("seg_reduce_rows_wide");
         }
-        else if (vpr <= 1) rc = launch_reduce<1>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
-        else if (vpr <= 2) rc = launch_reduce<2>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
-        else if (vpr <= 4) rc = launch_reduce<4>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
-        else if (vpr <= 8) rc = launch_reduce<8>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
-        else if (vpr <= 16) rc = launch_reduce<16>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
-        else rc = launch_reduce<32>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 1) rc = launch_reduce<1, LISTS>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 2) rc = launch_reduce<2, LISTS>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 4) rc = launch_reduce<4, LISTS>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 8) rc = launch_reduce<8, LISTS>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else if (vpr <= 16) rc = launch_reduce<16, LISTS>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
+        else rc = launch_reduce<32, LISTS>(g, vals_out, seg_start, chunk_base, counters, partial, plan.max_chunks, scale, row_grad, seg_sq, n, plan.chunk, st);
         if (rc) return rc;
     }
     // *sq_norm += sum(seg_sq[0..U)), *n_unique = U
@@ -700,6 +732,46 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
     }
     TT_LAUNCH_CHECK("sum_fixed_order");
     return 0;
+}
+
+}  // namespace tt
+
+extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, int mode, int64_t padding_idx,
+                                   int64_t vocab, const float *grad_out, int64_t grad_stride, const int32_t *argmax,
+                                   int dim, int64_t *unique_rows, float *row_grad, int32_t *n_unique,
+                                   float *sq_norm, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(ids && grad_out && unique_rows && row_grad && n_unique && workspace, "null pointer");
+    TT_CHECK_ARG(n_rows > 0 && len > 0 && dim > 0 && vocab > 0, "non-positive size");
+    TT_CHECK_ARG(mode >= TT_POOL_NONE && mode <= TT_POOL_MAX, "unknown pooling mode");
+    TT_CHECK_ARG(mode != TT_POOL_MAX || argmax, "TT_POOL_MAX needs argmax");
+    TT_CHECK_ARG(mode != TT_POOL_NONE || len == 1, "TT_POOL_NONE needs len == 1");
+    TT_CHECK_ARG(vocab < (int64_t(1) << 31) - 1, "vocab must fit 31 bits");
+    const int64_t n = n_rows * len;
+    TT_CHECK_ARG(n < (int64_t(1) << 31) - 2, "more than 2^31 positions per call");
+    const KeySrc ks{ids, padding_idx, nullptr, 0, 0};
+    const GradSrc g{grad_out, grad_stride, argmax, len, mode, dim, nullptr, 0, 0};
+    const float scale = (mode == TT_POOL_MEAN) ? 1.0f / static_cast<float>(len) : 1.0f;
+    return segment_grad_run<false>(ks, g, n, vocab, scale, unique_rows, row_grad, n_unique, sq_norm, workspace,
+                                   workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tt_emb_segment_grad_lists(const int32_t *rows, int64_t n_pieces, int64_t piece_len, int64_t piece_stride,
+                                         const int32_t *pos_src, int64_t vocab, const float *grad, int64_t grad_piece_rows,
+                                         int64_t grad_piece_stride, int dim, int64_t *unique_rows, float *row_grad,
+                                         int32_t *n_unique, float *sq_norm, void *workspace, size_t workspace_bytes,
+                                         void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(rows && grad && unique_rows && row_grad && n_unique && workspace, "null pointer");
+    TT_CHECK_ARG(n_pieces > 0 && piece_len > 0 && piece_stride >= piece_len && dim > 0 && vocab > 0, "bad size");
+    TT_CHECK_ARG(grad_piece_rows > 0 && grad_piece_stride >= grad_piece_rows * dim, "bad gradient piece layout");
+    TT_CHECK_ARG(vocab < (int64_t(1) << 31) - 1, "vocab must fit 31 bits");
+    const int64_t n = n_pieces * piece_len;
+    TT_CHECK_ARG(n < (int64_t(1) << 31) - 2, "more than 2^31 positions per call");
+    const KeySrc ks{nullptr, -1, rows, piece_len, piece_stride};
+    const GradSrc g{grad, dim, nullptr, 1, TT_POOL_SUM, dim, pos_src, grad_piece_rows, grad_piece_stride};
+    return segment_grad_run<true>(ks, g, n, vocab, 1.0f, unique_rows, row_grad, n_unique, sq_norm, workspace,
+                                  workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 namespace tt {
@@ -773,7 +845,7 @@ scatter_rows_kernel(float *__restrict__ dense, int dim, const int64_t *__restric
 extern "C" int tt_emb_rowwise_adam(void *table, int table_dtype, float *exp_avg, float *exp_avg_sq, int dim,
                                    const int64_t *unique_rows, const float *row_grad, const int32_t *n_unique,
                                    int64_t max_rows, const float *clip_coef, double lr, double beta1, double beta2,
-                                   double eps, const int64_t *step_dev, void *stream) {
+                                   double eps, const int64_t *step_dev, const double *lr_dev, void *stream) {
     using namespace tt;
     TT_CHECK_ARG(table && exp_avg && exp_avg_sq && unique_rows && row_grad && n_unique && step_dev, "null pointer");
     TT_CHECK_ARG(dim > 0 && dim % 4 == 0, "row-wise Adam needs dim % 4 == 0");
@@ -783,7 +855,7 @@ extern "C" int tt_emb_rowwise_adam(void *table, int table_dtype, float *exp_avg,
     const int vpr = dim / 4;
     const int lpr = vpr >= 32 ? 32 : (vpr >= 16 ? 16 : (vpr >= 8 ? 8 : (vpr >= 4 ? 4 : (vpr >= 2 ? 2 : 1))));
     const unsigned grid = grid_for(max_rows * lpr, 256);
-    const AdamHyper hyper = make_adam(lr, beta1, beta2, eps);
+    const AdamHyper hyper = make_adam(lr, beta1, beta2, eps, lr_dev);
 #define TT_ADAM(T, L)                                                                                              \
     rowwise_adam_kernel<T, L><<<grid, 256, 0, st>>>(static_cast<T *>(table), exp_avg, exp_avg_sq, dim, unique_rows, \
                                                    row_grad, n_unique, clip_coef, hyper, step_dev)

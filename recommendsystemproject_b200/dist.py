@@ -84,6 +84,7 @@ class DataParallelStep:
     def __call__(self, batch=None):
         if batch is not None:
             self.load_batch(batch)
+        self.opt.sync_lr()
         self.g_fb.replay()
         self._reduce()
         self.g_opt.replay()

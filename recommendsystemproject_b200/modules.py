@@ -127,11 +127,15 @@ class SequenceFeatureProcessor(nn.Module):
         self.feature_projection = nn.Sequential(TTLinear(total, target_dim), nn.Dropout(dropout))
         self.pos_emb = nn.Embedding(max_seq_len, target_dim)
         self.sparse_sink: Optional[ops.SparseGradSink] = None
+        # one device flag word per feature: the gather kernel ORs 1 into it when it meets an id outside [0, vocab)
+        # (read at TwoTowerModel.check_nan_flags: the reference raises IndexError there, SURVEY 8b "errors")
+        self._oob_names = [(f["name"], f["vocab_size"]) for f in feature_config_list]
+        self.register_buffer("_oob_flags", torch.zeros(max(1, len(feature_config_list)), dtype=torch.int32), persistent=False)
 
     def forward(self, input_dict):
         specs, tables = [], []
         shape = None
-        for feat in self.feature_config_list:
+        for fi, feat in enumerate(self.feature_config_list):
             name = feat["name"]
             if name not in input_dict:
                 print(f"Configuration Error: Unable to find {name} in the input dictionary, {name} has skipped")
@@ -149,7 +153,7 @@ class SequenceFeatureProcessor(nn.Module):
             else:
                 raise ValueError(f"sequence feature {name}: expected [B, L] or [B, L, Tags] ids")
             shape = x.shape[:2]
-            specs.append((ids.contiguous(), mode, pad, False))
+            specs.append((ids.contiguous(), mode, pad, False, self._oob_flags[fi:fi + 1]))
             tables.append(self.embeddings[name].weight)
         if not specs:
             raise ValueError("Configuration Error: No valid features were processed!")
@@ -195,7 +199,9 @@ class SequenceEncoder(nn.Module):
         seed = None
         if p > 0.0:
             self._drop_seed.add_(1)
-            seed = self._drop_seed
+            # a private copy per forward: the kernels' backward re-reads it, and a second forward before that backward
+            # (hard-negative slabs one pass at a time) must neither change it nor trip autograd's version check
+            seed = self._drop_seed.clone()
         pad = padding_mask.to(torch.uint8).contiguous()
         for li, layer in enumerate(self.transformer_backbone.layers):
             sa = layer.self_attn
@@ -293,6 +299,8 @@ class GenericTower(nn.Module):
                                                max_seq_len=tp.get("max_seq_len", 20), n_head=n_head,
                                                n_layers=tp.get("n_layers", 1), dropout=tp.get("dropout", 0.1))
             seq_total = model_dim
+        self._oob_names = [(f["name"], f["vocab_size"]) for f in (self.sparse_features or [])]
+        self.register_buffer("_oob_flags", torch.zeros(max(1, len(self._oob_names)), dtype=torch.int32), persistent=False)
         self.total_embed_dim = sparse_total + dense_total + seq_total
         self.feature_bn = nn.BatchNorm1d(self.total_embed_dim)
         self.mlp = MLP_Tower(input_dim=self.total_embed_dim, hidden_dims=hidden, output_dim=out_dims, dropout=dropout)
@@ -302,7 +310,7 @@ class GenericTower(nn.Module):
         specs, tables = [], []
         sparse_matrix = input_dict["sparse"]
         seq_dict = input_dict.get("sequence", {})
-        for feat in self.sparse_features:
+        for fi, feat in enumerate(self.sparse_features):
             name = feat["name"]
             pad = feat.get("padding_idx", 0)
             if "pooling" in feat:
@@ -328,7 +336,7 @@ class GenericTower(nn.Module):
                 ids = sparse_matrix[:, col].unsqueeze(1)
                 mode = ops.POOL_NONE
             _need_cuda(ids, "GenericTower")
-            specs.append((ids.contiguous().long(), mode, pad, name in self.sparse_grad_tables))
+            specs.append((ids.contiguous().long(), mode, pad, name in self.sparse_grad_tables, self._oob_flags[fi:fi + 1]))
             tables.append(self.embeddings[name].weight)
         return specs, tables
 
@@ -485,10 +493,21 @@ class TwoTowerModel(nn.Module):
         return self.item_tower(item_inputs, self.item_feature_mapping)
 
     def check_nan_flags(self):
-        """Raise the reference's RuntimeErrors from the device flag word (one host sync)."""
+        """Raise the reference's RuntimeErrors from the device flag word, and IndexError for ids outside a table
+        (nn.Embedding raises it on the CPU; here the gather kernels set a per-feature flag): one host sync."""
         if self.last_nan_flags is None:
             return
-        flags = int(self.last_nan_flags.item())
+        owners = [m for m in self.modules() if isinstance(getattr(m, "_oob_flags", None), torch.Tensor) and m._oob_flags.is_cuda]
+        words = torch.cat([self.last_nan_flags.reshape(-1)] + [m._oob_flags for m in owners]).tolist()
+        flags = int(words[0])
+        pos = 1
+        for m in owners:
+            for k, (name, vocab) in enumerate(m._oob_names):
+                if words[pos + k]:
+                    m._oob_flags.zero_()
+                    raise IndexError(f"index out of range in feature '{name}': ids must lie in [0, {vocab - 1}] "
+                                     f"(vocab_size {vocab})")
+            pos += m._oob_flags.numel()
         if flags & 1:
             raise RuntimeError("Found NaN in User Embedding")
         if flags & 2:

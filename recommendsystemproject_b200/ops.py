@@ -94,24 +94,40 @@ def scatter_rows_(dense: torch.Tensor, rows: torch.Tensor, row_grad: torch.Tenso
 
 def rowwise_adam_(table: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, rows: torch.Tensor,
                   row_grad: torch.Tensor, n_unique: torch.Tensor, clip_coef: Optional[torch.Tensor], lr: float,
-                  beta1: float, beta2: float, eps: float, step_dev: torch.Tensor):
+                  beta1: float, beta2: float, eps: float, step_dev: torch.Tensor, lr_dev: Optional[torch.Tensor] = None):
+    """lr_dev (float64 [1] on the device) overrides lr: what a scheduler changes between CUDA-graph replays."""
     lib = _lib.load()
     check(lib.tt_emb_rowwise_adam(_p(table), _DTYPES[table.dtype], _p(exp_avg), _p(exp_avg_sq), table.shape[1],
                                   _p(rows), _p(row_grad), _p(n_unique), rows.numel(), _p(clip_coef), lr, beta1, beta2,
-                                  eps, _p(step_dev), _stream()), "tt_emb_rowwise_adam")
+                                  eps, _p(step_dev), _p(lr_dev), _stream()), "tt_emb_rowwise_adam")
     _count()
 
 
 class SparseGradSink:
     """Collects (table, rows, row_grad, n_unique) produced by backward when a
-    table runs in sparse-gradient mode (consumed by optim.FusedTwoTowerOptimizer)."""
+    table runs in sparse-gradient mode (consumed by optim.FusedTwoTowerOptimizer).
+
+    Every entry gets its OWN slot of ``sq_terms`` for its sum of squared gradients: the two towers' backward passes
+    run on different streams (TwoTowerModel.parallel_towers), so two segment-gradient calls must never
+    read-modify-write the same float.  tt_clip_coef adds the slots in index order (double accumulator)."""
+
+    MAX_ENTRIES = 64
 
     def __init__(self):
-        self.entries: List[Tuple[torch.nn.Parameter, torch.Tensor, torch.Tensor, torch.Tensor]] = []
-        self.sq_norm: Optional[torch.Tensor] = None
+        self.entries: List[Tuple[torch.nn.Parameter, torch.Tensor, torch.Tensor, torch.Tensor, int]] = []
+        self.sq_terms: Optional[torch.Tensor] = None     # [1 + MAX_ENTRIES]: slot 0 = dense parameters
+        self.sq_norm: Optional[torch.Tensor] = None      # legacy single slot (callers that own exactly one stream)
 
     def clear(self):
         self.entries = []
+
+    def next_slot(self) -> Tuple[Optional[torch.Tensor], int]:
+        if self.sq_terms is None:
+            return self.sq_norm, -1
+        k = 1 + len(self.entries)
+        if k >= self.sq_terms.numel():
+            raise TTError(f"more than {self.MAX_ENTRIES} sparse-gradient entries in one step")
+        return self.sq_terms[k:k + 1], k
 
 
 class _GatherSpec:
@@ -125,18 +141,24 @@ class MultiGatherPool(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, specs: Sequence[tuple], sink: Optional[SparseGradSink], *tables: torch.Tensor):
-        # specs[i] = (ids [B, L] int64, mode, padding_idx, sparse_grad: bool)
+        # specs[i] = (ids [B, L] int64, mode, padding_idx, sparse_grad: bool[, oob flag word int32 [1]])
         dev = tables[0].device
         B = specs[0][0].shape[0]
         width = sum(t.shape[1] for t in tables)
         out = torch.empty(B, width, dtype=torch.float32, device=dev)
-        oob = torch.zeros(1, dtype=torch.int32, device=dev)
+        oob = None
         col = 0
         saved = []
-        for (ids, mode, pad, sparse_grad), table in zip(specs, tables):
+        for spec, table in zip(specs, tables):
+            ids, mode, pad, sparse_grad = spec[:4]
+            flag = spec[4] if len(spec) > 4 and spec[4] is not None else None
+            if flag is None:     # callers without a flag word of their own (tests read ctx.oob)
+                if oob is None:
+                    oob = torch.zeros(1, dtype=torch.int32, device=dev)
+                flag = oob
             D = table.shape[1]
             argmax = torch.empty(B, D, dtype=torch.int32, device=dev) if mode == POOL_MAX else None
-            gather_pool_into(table.detach(), ids, mode, pad, out[:, col:col + D], argmax, oob)
+            gather_pool_into(table.detach(), ids, mode, pad, out[:, col:col + D], argmax, flag)
             saved.append((ids, mode, pad, sparse_grad, col, D, table.shape[0], argmax))
             col += D
         ctx.saved_specs = saved
@@ -154,10 +176,10 @@ class MultiGatherPool(torch.autograd.Function):
                 grads.append(None)
                 continue
             g = grad_out[:, col:col + D]
-            sq = ctx.sink.sq_norm if (sparse_grad and ctx.sink is not None) else None
+            sq, slot = ctx.sink.next_slot() if (sparse_grad and ctx.sink is not None) else (None, -1)
             rows, row_grad, n_unique = segment_grad(ids, mode, pad, V, g, argmax, D, sq)
             if sparse_grad and ctx.sink is not None:
-                ctx.sink.entries.append((table, rows, row_grad, n_unique))
+                ctx.sink.entries.append((table, rows, row_grad, n_unique, slot))
                 grads.append(None)
             elif _direct_grad(table) and table.grad.shape == table.shape:
                 # the optimizer owns a preallocated, zeroed .grad view: scatter-add into it (no dense temporary, no
@@ -585,8 +607,8 @@ def clip_coef_(sq_terms: torch.Tensor, max_norm: float, coef: torch.Tensor, tota
     _count()
 
 
-def adam_flat_(param, grad, exp_avg, exp_avg_sq, clip_coef, lr, beta1, beta2, eps, step_dev):
+def adam_flat_(param, grad, exp_avg, exp_avg_sq, clip_coef, lr, beta1, beta2, eps, step_dev, lr_dev=None):
     lib = _lib.load()
     check(lib.tt_adam_flat(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), _p(clip_coef), lr, beta1,
-                           beta2, eps, _p(step_dev), _stream()), "tt_adam_flat")
+                           beta2, eps, _p(step_dev), _p(lr_dev), _stream()), "tt_adam_flat")
     _count()

@@ -82,8 +82,13 @@ class FusedTwoTowerOptimizer:
         self.sink = ops.SparseGradSink()
         self.table_state = {id(p): (torch.zeros_like(p, dtype=torch.float32), torch.zeros_like(p, dtype=torch.float32))
                             for p in self.sparse_tables}
-        self.sq_terms = torch.zeros(2, dtype=torch.float32, device=dev)  # [dense, sparse rows]
-        self.sink.sq_norm = self.sq_terms[1:2]
+        # [0] dense parameters, [1..] one slot per sparse-gradient entry of the step (never shared: the two towers'
+        # backward passes run on different streams)
+        self.sq_terms = torch.zeros(1 + ops.SparseGradSink.MAX_ENTRIES, dtype=torch.float32, device=dev)
+        self.sink.sq_terms = self.sq_terms
+        # learning rate on the device: the Adam kernels read it there, so a scheduler that edits
+        # param_groups[0]["lr"] reaches a captured CUDA graph too (refreshed by step() / GraphedTrainStep.__call__)
+        self.lr_dev = torch.full((1,), self.lr, dtype=torch.float64, device=dev)
         self.coef = torch.ones(1, dtype=torch.float32, device=dev)
         self.total_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -103,7 +108,45 @@ class FusedTwoTowerOptimizer:
         self.sq_terms.zero_()
         self.sink.clear()
 
+    def sync_lr(self):
+        """Copy param_groups[0]['lr'] (what torch LR schedulers edit) to the device scalar the kernels read.  Call
+        outside CUDA-graph capture; step() does it when not capturing, GraphedTrainStep before every replay."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self.lr:
+            self.lr = lr
+            self.lr_dev.fill_(lr)
+
+    def _merged_entries(self):
+        """One (table, rows, row_grad, n_unique) per table.  A table that met several backward calls in this step (the
+        item tower run once per hard-negative slab, group_hard_negatives=False) gets its entries merged by one more
+        sorted-segment reduction over (rows, row gradients): Adam then sees sum_i g_i once -- what autograd's
+        accumulation into .grad gives the reference -- and the norm term is ||sum_i g_i||^2."""
+        by_table: Dict[int, list] = {}
+        for e in self.sink.entries:
+            by_table.setdefault(id(e[0]), []).append(e)
+        out = []
+        for group in by_table.values():
+            if len(group) == 1:
+                out.append(group[0][:4])
+                continue
+            table = group[0][0]
+            rows_all, grads_all = [], []
+            for _, rows, row_grad, n_unique, slot in group:
+                live = torch.arange(rows.numel(), device=rows.device) < n_unique
+                rows_all.append(torch.where(live, rows, torch.full_like(rows, -1)))   # id -1: dropped by the kernel
+                grads_all.append(row_grad)
+                self.sq_terms[slot].zero_()
+            slot = group[0][4]
+            rows, row_grad, n_unique = ops.segment_grad(torch.cat(rows_all).view(-1, 1), ops.POOL_NONE, None,
+                                                        table.shape[0], torch.cat(grads_all), None, table.shape[1],
+                                                        self.sq_terms[slot:slot + 1])
+            out.append((table, rows, row_grad, n_unique))
+        return out
+
     def step(self):
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        entries = self._merged_entries()
         ops.sq_norm_accum_(self.flat_g, self.sq_terms[0:1], self._ws)
         coef = None
         if self.max_grad_norm > 0:
@@ -111,11 +154,11 @@ class FusedTwoTowerOptimizer:
             coef = self.coef
         self.step_dev.add_(1)
         ops.adam_flat_(self.flat_p, self.flat_g, self.flat_m, self.flat_v, coef, self.lr, self.beta1, self.beta2,
-                       self.eps, self.step_dev)
-        for table, rows, row_grad, n_unique in self.sink.entries:
+                       self.eps, self.step_dev, self.lr_dev)
+        for table, rows, row_grad, n_unique in entries:
             m, v = self.table_state[id(table)]
             ops.rowwise_adam_(table.data, m, v, rows, row_grad, n_unique, coef, self.lr, self.beta1, self.beta2,
-                              self.eps, self.step_dev)
+                              self.eps, self.step_dev, self.lr_dev)
         self.sink.clear()
 
     # checkpoint surface: the SAME dict torch.optim.Adam(model.parameters()) produces (train_twotower.py:184-195 stores
@@ -155,6 +198,7 @@ class FusedTwoTowerOptimizer:
         self.beta1, self.beta2 = (float(b) for b in g.get("betas", (self.beta1, self.beta2)))
         self.eps = float(g.get("eps", self.eps))
         self.param_groups[0]["lr"] = self.lr
+        self.lr_dev.fill_(self.lr)
         step = 0.0
         with torch.no_grad():
             for i, (_, m, v) in enumerate(states):
@@ -219,6 +263,7 @@ class GraphedTrainStep:
     def __call__(self, batch: Optional[dict] = None):
         if batch is not None:
             self.load_batch(batch)
+        self.opt.sync_lr()
         self.graph.replay()
         return self.static_loss
 

@@ -210,7 +210,8 @@ def load_checkpoint(path, model, optimizer=None, map_location=None):
     """Resume (the reference only saves): restores model weights / BatchNorm statistics and, when given, the optimizer
     (torch.optim.Adam or FusedTwoTowerOptimizer; either kind of checkpoint loads into either kind of optimizer).
     Returns the checkpoint dict minus the two state dicts (epoch, losses, metrics, mappings, config)."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    # tensors + plain dicts / lists / scalars only: never unpickle arbitrary objects from a checkpoint file
+    ckpt = torch.load(path, map_location=map_location, weights_only=True)
     model.load_state_dict(ckpt["model_state_dict"])
     if optimizer is not None and ckpt.get("optimizer_state_dict") is not None:
         optimizer.load_state_dict(ckpt["optimizer_state_dict"])

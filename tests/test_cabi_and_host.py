@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/tt_b200.h but not exported"
     assert set(names) == set(_lib._SIGNATURES), "ctypes signature table out of sync with the header"
-    assert _lib.load().tt_abi_version() == 1
+    assert _lib.load().tt_abi_version() == 2
 
 
 def test_argument_errors_do_not_need_a_gpu():
