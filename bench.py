@@ -301,123 +301,133 @@ def _clock_wrap(rank, local_rank):
     return sampler
 
 
-def run_c3(args, rank, local_rank, world, dev, peaks):
-    """BASELINE configs[2], the part that sharding changes: three row-sharded tables (user id 12.5M rows per GPU,
-    history items and item ids 10M rows in total), pooled L=200 ragged history lookup, backward into the owners'
-    shards, global-norm clip, fused row-wise Adam.  Towers are data-parallel and measured by the default workload."""
+def build_c3(rank, world, dev, B_global, dropout=0.1, zipf=False, users_per_gpu=12_500_000, v_item=10_000_001, L=200,
+             tf32=True):
+    """BASELINE configs[2] as ONE model: 8 sparse features (D=128), row-sharded big tables, MLP [256,128]->128 towers,
+    in-batch softmax over the global batch.  The user table has `users_per_gpu` rows per rank (100M at 8 GPUs: the
+    whole table + fp32 Adam moments is 154 GB and does not fit one GPU); everything else is the config's size at any N."""
+    import recommendsystemproject_b200 as tt
+    from recommendsystemproject_b200 import synth
+    from recommendsystemproject_b200.dist import ShardedTrainStep
+    v_user = users_per_gpu * world + 1
+    cfg = synth.config_c3(v_user=v_user, v_item=v_item, dropout=dropout, shard=True, world=world, rank=rank)
+    torch.manual_seed(0)
+    with torch.device(dev):       # shards are born on the GPU (a 51 GB table never exists on the host)
+        model = tt.TwoTowerModel(tt.GenericTower(cfg, "user_tower"), tt.GenericTower(cfg, "item_tower"), *synth.MAPS_C3)
+    model = model.to(dev).train()
+    for m in model.modules():
+        if hasattr(m, "gather_on_save"):
+            m.gather_on_save = False
+    opt = tt.FusedTwoTowerOptimizer(model, lr=5e-4, max_grad_norm=1.0, table_mode="sparse")
+    B = B_global // world
+    host = [synth.make_batch_c3(B=B, L=L, v_user=v_user, v_item=v_item, seed=300 + 17 * rank + s, zipf=zipf) for s in range(2)]
+    host = [tree_to(h, None, pin=True) for h in host]
+    dev_batch = tree_to(host[0], dev)
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    step = ShardedTrainStep(model, opt, dev_batch, 0.05, restore_tables=False)
+    return model, opt, step, host, dev_batch, cfg, v_user
+
+
+def run_c3(args, rank, local_rank, world, dev, peaks, as_dict=False):
+    """BASELINE configs[2], integrated: gather (row-sharded) -> towers -> global in-batch softmax -> backward -> global-norm
+    clip -> dense Adam + row-wise Adam, global batch 65536 at every N (strong scaling in the batch)."""
     import torch.distributed as dist
-    from recommendsystemproject_b200 import dist as tdist
-    B, L, D = 8192, 200, 128
-    V_user, V_item = 12_500_000 * world, 10_000_001
-    bags = {"user": tdist.ShardedEmbeddingBag(V_user, D, rank, world, "sum", None, dev, seed=1),
-            "hist": tdist.ShardedEmbeddingBag(V_item, D, rank, world, "mean", 0, dev, seed=2),
-            "item": tdist.ShardedEmbeddingBag(V_item, D, rank, world, "sum", None, dev, seed=3)}
-    gen = torch.Generator().manual_seed(300 + rank)
-
-    def make_host():
-        hist = torch.randint(1, V_item, (B, L), generator=gen)
-        lens = torch.randint(1, L + 1, (B, 1), generator=gen)
-        hist[torch.arange(L)[None, :] >= lens] = 0
-        return {"user": torch.randint(0, V_user, (B, 1), generator=gen).pin_memory(), "hist": hist.pin_memory(),
-                "item": torch.randint(1, V_item, (B, 1), generator=gen).pin_memory()}
-    host = [make_host() for _ in range(2)]
-    up = {k: torch.randn(B, D, device=dev) * 1e-3 for k in bags}
-    step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-    n_valid = int((host[0]["hist"] != 0).sum())
-
-    def step(ids):
-        for b in bags.values():
-            b.zero_grad()
-        loss = sum((bags[k](ids[k]) * up[k]).sum() for k in bags)
-        loss.backward()
-        coef = tdist.global_clip_coef([b.sq_norm for b in bags.values()], 1.0)
-        step_dev.add_(1)
-        for b in bags.values():
-            b.step(coef, 5e-4, step_dev)
-        return loss.detach()
+    from recommendsystemproject_b200 import ops
+    B_global = args.c3_batch
+    model, opt, step, host, dev_batch, cfg, v_user = build_c3(rank, world, dev, B_global, zipf=args.zipf)
+    B = B_global // world
+    L, D = 200, 128
+    n_valid = int((host[0]["user_tower"]["sequence"]["hist_item_ids"] != 0).sum())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    dev_ids = {k: v.to(dev) for k, v in host[0].items()}
     for _ in range(args.warmup):
-        step(dev_ids)
-    # The exchange has no host-side sizes any more (equal-sized all-to-alls), so the whole step -- collectives
-    # included -- can be one CUDA graph: the eager step was host-bound (~80 launches + 10 NCCL calls from Python).
-    graphed = os.environ.get("TT_C3_GRAPH", "1") == "1"
-    if graphed:
-        torch.cuda.synchronize()
-        static_ids = {k: v.clone() for k, v in dev_ids.items()}
-        static_loss = torch.zeros((), device=dev)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            step(static_ids)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        for bag in bags.values():
-            bag.a2a_bytes = 0
-        with torch.cuda.graph(graph):
-            static_loss.copy_(step(static_ids))
-        a2a_per_step = sum(bag.a2a_bytes for bag in bags.values())   # counted while the step was captured
-
-        def step(ids):   # noqa: F811
-            for k in static_ids:
-                static_ids[k].copy_(ids[k], non_blocking=True)
-            graph.replay()
-            return static_loss
-        for _ in range(3):
-            step(dev_ids)
+        step()
+    step.check_flags()
     sampler = _clock_wrap(rank, local_rank)
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
-        step(dev_ids)
+        step()
     b.record()
     barrier()
     dev_ms = a.elapsed_time(b)
+    # e2e: pinned host batch -> H2D (copy stream, one step ahead) -> step -> D2H loss, all inside the timed region
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    for bag in bags.values():
-        bag.a2a_bytes = 0
+    copy_stream = torch.cuda.Stream()
+    staging = [tree_to(host[0], dev), tree_to(host[1], dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(s):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s % 2])
+            _copy_into(staging[s % 2], host[s % 2])
+            ready[s % 2].record(copy_stream)
+    for e in consumed:
+        e.record()
     barrier()
     a.record()
+    prefetch(0)
     for s in range(args.steps):
-        ids = {k: v.to(dev, non_blocking=True) for k, v in host[s % 2].items()}
-        loss_host.copy_(step(ids))
+        if s + 1 < args.steps:
+            prefetch(s + 1)
+        torch.cuda.current_stream().wait_event(ready[s % 2])
+        step.load_batch(staging[s % 2])          # device-to-device into the graph's static buffers
+        consumed[s % 2].record()
+        loss_host.copy_(step())
     b.record()
     barrier()
     e2e_ms = a.elapsed_time(b)
     clocks = sampler.stop() if rank == 0 else None
+    step.check_flags()
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        return
     dev_ms, e2e_ms = float(t[0]), float(t[1])
-    n_rows = n_valid + 2 * B
-    # algorithmic bytes of the owner-side-pooling step: every looked-up row read once (forward), one gradient row written
-    # per touched row (backward), row-wise Adam = 7 row-sized streams over the touched rows (<= n_rows), ids read twice
-    alg = n_rows * D * 4 * (1 + 1 + 7) + 2 * B * L * 8
-    a2a = a2a_per_step if graphed else sum(bag.a2a_bytes for bag in bags.values()) / args.steps
-    line = {"metric": "train samples/sec (row-sharded embedding fwd+bwd+clip+row-wise Adam)", "value": world * B * args.steps / (dev_ms / 1e3),
-            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2] embedding path: per GPU B=8192, hist L=200 ragged mean-pooled over a 10M-row "
-                                   "table + user id (12.5M rows per GPU) + item id (10M rows), D=128, tables row-sharded owner=row%W",
-                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"row-sharded tables x{world}",
-                       "l2": "working set (3 tables + Adam state, >40 GB per GPU) far exceeds L2", "peaks": peaks["source"]},
-            "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
-                    "h2d_bytes_per_step": sum(v.numel() * 8 for v in host[0].values()), "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(ops_count() - 0), "graphed": graphed, "roofline": {"bound": "hbm", "kernel": "gather_pool + segment_grad + rowwise_adam (whole step, owner-side pooling)",
-                                                                "achieved": alg / (dev_ms / args.steps) / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                                "frac": alg / (dev_ms / args.steps) / 1e6 / peaks["hbm_gbs"], "traffic": None,
-                                                                "alg_bytes": alg},
-            "nvlink_bytes_per_step_per_gpu": a2a, "cpu_baseline": None, "clocks": clocks}
+    # per-kernel device times of one step (CUDA events around eager phases would perturb the graph: use the profiler-free
+    # kernel section below instead); dominant kernel + roofline come from kernel_rooflines at this rank's shapes
+    if rank != 0:
+        return None
+    ms = dev_ms / args.steps
+    h2d = tree_bytes(host[0])
+    grp = model.shard_group
+    line = {"metric": "train samples/sec (fwd+bwd+clip+Adam), integrated C3 step", "value": B_global * args.steps / (dev_ms / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 tables + TF32 tower GEMMs + bf16 tcgen05 loss",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2]: 8 sparse features D=128 (user_id {v_user - 1} rows = 12.5M per GPU, u_cat1 1e5, u_cat2 1e3, "
+                                   f"u_cat3 32, hist_item_ids 10M x L=200 ragged mean-pooled; item_id 10M, i_cat 1e4, i_year 152), MLP [256,128]->128, "
+                                   f"in-batch softmax over the global batch {B_global}, dropout 0.1; tables >= 1 MB row-sharded owner=row%W "
+                                   f"({len(grp.tables)} tables), towers data-parallel with global BatchNorm statistics",
+                       "global_batch": B_global, "per_gpu_batch": B, "parallelism": f"row-sharded tables x{world} + dp{world}",
+                       "ids": "zipf(1.05)" if args.zipf else "uniform (every looked-up row distinct: HBM worst case)",
+                       "l2": "working set (tables + Adam state, > 40 GB per GPU) far exceeds L2", "peaks": peaks["source"],
+                       "step": "one CUDA graph per rank, NCCL collectives inside"},
+            "e2e": {"value": B_global * args.steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                    "note": "pinned host batch -> H2D on a copy stream one step ahead -> D2D into the graph's buffers -> step -> loss read-back"},
+            "gpu_launches": (step.launches_per_step or 0) * args.steps * 2, "gpu_launches_per_step": step.launches_per_step,
+            "nvlink_bytes_per_step_per_gpu": getattr(step, "a2a_bytes_per_step", 0), "hist_valid_positions_per_gpu": n_valid,
+            "clocks": clocks, "final_loss": float(loss_host)}
+    if as_dict:
+        return line
     print(json.dumps(line), flush=True)
+    return line
+
+
+def _copy_into(dst, src):
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_into(dst[k], src[k])
+    elif isinstance(dst, list):
+        for x, y in zip(dst, src):
+            _copy_into(x, y)
 
 
 def ops_count():
@@ -504,6 +514,8 @@ def main():
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
     ap.add_argument("--quick", action="store_true", help="smaller kernel-roofline shapes")
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--c3-batch", type=int, default=65536, help="global batch of the integrated C3 step")
+    ap.add_argument("--zipf", action="store_true", help="Zipf(1.05) item ids instead of uniform")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

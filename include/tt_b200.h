@@ -272,6 +272,40 @@ TT_API int tt_linear_wgrad(const float *grad_out, const float *input, int64_t ro
                     float *grad_bias, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
+ * 8. BatchNorm1d in training mode with the MLP block's ReLU + Dropout fused in (GenericTower.py:234, Tower.py:16-21:
+ * Linear -> BatchNorm1d -> ReLU -> Dropout), statistics optionally spanning several ranks (data-parallel towers: the
+ * reference normalises over the whole batch).
+ *   y = dropout(relu(gamma[c % P] * (x - mean_c) * rstd_c + beta[c % P])),  P = param_period (cols for a plain layer;
+ *   the [B, G*C] view of G item slabs that each keep their own batch statistics, TwoTowerModel.py:54-60, uses P = C)
+ *   tt_bn_stats      stats[2*cols + 1] = per-channel mean, M2 = sum (x - mean)^2, and the row count (this rank)
+ *   tt_bn_apply      merges n_ranks stats blocks (rank order, Chan's formula) -> save_mean / save_rstd [cols]
+ *                    (biased variance + eps), batch_var_unbiased [cols] (nullable), running stats (nullable; momentum
+ *                    update with the unbiased variance, *num_batches += 1), then normalises
+ *   tt_bn_bwd_stats  sums[2*cols] = per-channel sum g, sum g*xhat over this rank's rows (g = dy through dropout and
+ *                    ReLU); grad_gamma / grad_beta [P] from these LOCAL sums (stored, or added when accumulate != 0)
+ *   tt_bn_bwd_apply  dx = gamma rstd (g - sum_g / N - xhat sum_gx / N) with the GLOBAL sums and N = total_rows
+ * Dropout masks: counter-based hash of (*seed_dev, call_id, element); the backward rebuilds them and recomputes the
+ * ReLU mask from x.  cols, strides and P must be multiples of 4.  Deterministic (fixed reduction order).
+ * ---------------------------------------------------------------------- */
+TT_API int tt_bn_workspace(int64_t rows, int cols, size_t *bytes_host);
+TT_API int tt_bn_stats(const float *x, int64_t rows, int cols, int64_t x_stride, float *stats, void *workspace,
+                size_t workspace_bytes, void *stream);
+TT_API int tt_bn_apply(const float *x, int64_t rows, int cols, int64_t x_stride, const float *stats_all, int n_ranks,
+                const float *gamma, const float *beta, int param_period, float eps, int relu, float dropout_p,
+                const int64_t *seed_dev, int64_t call_id, float *y, int64_t y_stride, float *save_mean, float *save_rstd,
+                float *batch_var_unbiased, float *running_mean, float *running_var, float momentum, int64_t *num_batches,
+                void *stream);
+TT_API int tt_bn_bwd_stats(const float *dy, int64_t dy_stride, const float *x, int64_t rows, int cols, int64_t x_stride,
+                    const float *save_mean, const float *save_rstd, const float *gamma, const float *beta,
+                    int param_period, int relu, float dropout_p, const int64_t *seed_dev, int64_t call_id, float *sums,
+                    float *grad_gamma, float *grad_beta, int accumulate, void *workspace, size_t workspace_bytes,
+                    void *stream);
+TT_API int tt_bn_bwd_apply(const float *dy, int64_t dy_stride, const float *x, int64_t rows, int cols, int64_t x_stride,
+                    const float *save_mean, const float *save_rstd, const float *gamma, const float *beta,
+                    int param_period, int relu, float dropout_p, const int64_t *seed_dev, int64_t call_id,
+                    const float *sums_global, double total_rows, float *dx, int64_t dx_stride, void *stream);
+
+/* ------------------------------------------------------------------------
  * 7. Row-sharded embedding tables (owner = row % world, local row = row / world): device side of the exchange.
  * New (the reference is single-process); it is what GenericTower.py:141-183 becomes when a table of BASELINE
  * configs[2] (100M users / 10M items x 128) is spread over the GPUs of one NVSwitch box.

@@ -32,6 +32,14 @@ _SIGNATURES = {
                                  c_int64, P, P, c_int, P, c_int64, P]),
     "tt_shard_grad_pack": (c_int, [P, c_int64, c_int64, c_int, c_int, c_int, c_int, P, c_int64, c_int64, P, c_int64, c_int64,
                                    c_int64, P, c_int64, c_int64, P]),
+    "tt_bn_workspace": (c_int, [c_int64, c_int, P]),
+    "tt_bn_stats": (c_int, [P, c_int64, c_int, c_int64, P, P, c_size_t, P]),
+    "tt_bn_apply": (c_int, [P, c_int64, c_int, c_int64, P, c_int, P, P, c_int, c_float, c_int, c_float, P, c_int64, P, c_int64,
+                            P, P, P, P, P, c_float, P, P]),
+    "tt_bn_bwd_stats": (c_int, [P, c_int64, P, c_int64, c_int, c_int64, P, P, P, P, c_int, c_int, c_float, P, c_int64, P, P, P,
+                                c_int, P, c_size_t, P]),
+    "tt_bn_bwd_apply": (c_int, [P, c_int64, P, c_int64, c_int, c_int64, P, P, P, P, c_int, c_int, c_float, P, c_int64, P,
+                                c_double, P, c_int64, P]),
     "tt_emb_rowwise_adam": (c_int, [P, c_int, P, P, c_int, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, P, P, P]),
     "tt_emb_scatter_rows": (c_int, [P, c_int, P, P, P, c_int64, P]),
     "tt_sq_norm_accum": (c_int, [P, c_int64, P, P, c_size_t, P]),

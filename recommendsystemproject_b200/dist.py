@@ -91,6 +91,148 @@ class DataParallelStep:
         return self.static_loss
 
 
+class ShardedTrainStep:
+    """The integrated multi-GPU training step, one CUDA graph per rank, collectives included:
+
+        zero_grad
+        model(batch)        row-sharded tables: ONE batched exchange for every sharded feature of both towers
+                            (sharded.ShardedTableGroup: route -> all-to-all -> owner gather/pool -> all-to-all -> combine);
+                            towers data-parallel, BatchNorm statistics over the GLOBAL batch (ops.batch_norm_act: all-gather
+                            of per-channel (mean, M2, n) forward, all-reduce of the two gradient sums backward)
+        loss                in-batch softmax over the GLOBAL batch: item embeddings (+ item ids) all-gathered, every rank
+                            computes its B/W x B slab with the fused CE kernel (never in HBM), gradients of the gathered
+                            items flow back to their owners (sum)
+        backward            table gradients travel to the owning rank (all-to-all) and are segment-reduced there
+        all-reduce (SUM)    of the flat dense-gradient buffer; its trailing float carries the row-sharded tables' local
+                            sum of squares, so the global gradient norm costs no extra collective
+        clip + Adam         dense parameters (replicated, bit-identical on every rank) + row-wise Adam on the local shards
+
+    Scaling of the loss: rank r back-propagates mean_r / W, so every SUM above yields the gradient of the global-batch
+    mean -- what one process running the reference step on all W*B samples computes (TwoTowerModel.py:95-140,
+    GenericTower.py:234, training_utils.py:51-56).  Per-rank batches must have equal size.
+    Works at W = 1 (no collectives) and without sharded tables (then it is DataParallelStep with global-batch semantics)."""
+
+    def __init__(self, model, optimizer: FusedTwoTowerOptimizer, example_batch, temperature, item_id_col=0, warmup=3,
+                 graph=True, loss_precision="auto", global_loss=True, restore_tables=True):
+        self.model, self.opt, self.temperature, self.item_id_col = model, optimizer, temperature, item_id_col
+        self.restore_tables = restore_tables
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.loss_precision, self.global_loss = loss_precision, global_loss
+        if batch_has_hard_negatives(example_batch) and global_loss and self.world > 1:
+            raise ops.TTError("ShardedTrainStep: per-row hard negatives with a global in-batch loss are not supported")
+        self.static_batch = _clone_tree(example_batch)
+        if self.world > 1:
+            ops.bn_sync.world, ops.bn_sync.group = self.world, None
+            for m in model.modules():
+                if isinstance(m, torch.nn.BatchNorm1d):
+                    m._tt_sync = True
+            # replicas start identical: dense parameters, buffers (BatchNorm statistics, dropout seeds, pad rows)
+            dist.broadcast(optimizer.flat_p, src=0)
+            for b in model.buffers():
+                dist.broadcast(b, src=0)
+        optimizer._norm_staged_by_caller = True
+        snap = self._snapshot()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore(snap)
+        self.graph = None
+        self.launches_per_step = None
+        if graph:
+            grp = getattr(model, "shard_group", None)
+            if grp is not None:
+                grp.a2a_bytes = 0
+            self.graph = torch.cuda.CUDAGraph()
+            c0 = ops.launch_counter["calls"]
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._step_eager()
+            self.launches_per_step = ops.launch_counter["calls"] - c0
+            self.a2a_bytes_per_step = grp.a2a_bytes if grp is not None else 0
+            torch.cuda.synchronize()
+
+    def _snapshot(self):
+        """Warm-up steps are real optimizer steps: snapshot and restore so construction has no side effect.  The shards of
+        row-sharded tables are included only when `restore_tables` (default; switch off for tables of tens of GB)."""
+        o = self.opt
+        grp = getattr(self.model, "shard_group", None)
+        shard_w = {id(t.weight) for t in grp.tables.values()} if grp else set()
+        named = list(self.model.named_parameters()) + list(self.model.named_buffers())
+        state = [(v, v.detach().clone()) for _, v in named if id(v) not in shard_w]
+        shard = {}
+        if grp and self.restore_tables:
+            shard = {n: (t.weight.detach().clone(), t.exp_avg.clone(), t.exp_avg_sq.clone()) for n, t in grp.tables.items()}
+        return state, o.flat_m.clone(), o.flat_v.clone(), o.step_dev.clone(), shard
+
+    def _restore(self, snap):
+        state, m, v, step, shard = snap
+        o = self.opt
+        with torch.no_grad():
+            for dst, src in state:
+                dst.copy_(src)
+        o.flat_m.copy_(m); o.flat_v.copy_(v); o.step_dev.copy_(step)
+        grp = getattr(self.model, "shard_group", None)
+        for n, (w, ea, es) in shard.items():
+            t = grp.tables[n]
+            with torch.no_grad():
+                t.weight.copy_(w)
+            t.exp_avg.copy_(ea); t.exp_avg_sq.copy_(es)
+
+    def _loss(self, u, i, ids):
+        if self.world > 1 and self.global_loss:
+            return global_inbatch_ce(u, i, ids, None, self.temperature, precision=self._precision(u))
+        return ops.fused_inbatch_ce(u, i, ids, None, None, self.temperature, precision=self._precision(u))[0]
+
+    def _precision(self, u):
+        if self.loss_precision != "auto":
+            return self.loss_precision
+        return "bf16" if (u.shape[1] in (64, 128) and u.shape[0] * self.world >= 4096) else "fp32"
+
+    def _step_eager(self):
+        o = self.opt
+        o.zero_grad()
+        u, i, hn = self.model(self.static_batch)
+        ids = self.static_batch["item_tower"]["sparse"][:, self.item_id_col]
+        if hn is not None:
+            loss = self.model.compute_loss(u, i, item_ids=ids, hard_neg_emb=hn, temperature=self.temperature)
+        else:
+            loss = self._loss(u, i, ids)
+        (loss / self.world if self.world > 1 else loss).backward()
+        o.stage_sharded_norm()
+        if self.world > 1:
+            dist.all_reduce(o.flat_g_ext)
+        o.step()
+        out = loss.detach().clone()
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.AVG)      # the global-batch mean, for reporting
+        return out
+
+    def load_batch(self, batch, non_blocking=True):
+        _copy_tree(self.static_batch, batch, non_blocking)
+
+    def __call__(self, batch=None):
+        if batch is not None:
+            self.load_batch(batch)
+        self.opt.sync_lr()
+        if self.graph is None:
+            return self._step_eager()
+        self.graph.replay()
+        return self.static_loss
+
+    def check_flags(self):
+        grp = getattr(self.model, "shard_group", None)
+        if grp is not None:
+            grp.check_flags()
+
+
+def batch_has_hard_negatives(batch) -> bool:
+    return bool(batch.get("hard_negatives"))
+
+
 # ---------------------------------------------------------------------------
 # row-sharded embedding routing (owner = row % W), device-agnostic index logic
 # ---------------------------------------------------------------------------

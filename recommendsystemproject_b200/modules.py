@@ -35,36 +35,60 @@ def _need_cuda(t: torch.Tensor, what: str):
                       "move the model and the batch to the device (there is no CPU fallback)")
 
 
-def grouped_batch_norm(bn: nn.BatchNorm1d, x: torch.Tensor, groups: int) -> torch.Tensor:
-    """BatchNorm1d applied to `groups` independent slabs in ONE call.  Rows of x are ordered (sample, slab), so
-    x.view(B, groups*C) turns "statistics per slab" into plain per-channel statistics over B rows: numerically the
-    same as the reference's one-item-tower-pass-per-hard-negative-slab (TwoTowerModel.py:54-60: every pass
-    normalises with its own batch statistics and updates the running statistics once), in one kernel instead of
-    1+N.  Running statistics receive the 1+N updates in slab order:
-        r <- (1-m)^G r + m * sum_g (1-m)^(G-1-g) stat_g ."""
-    if groups == 1 or not bn.training:
-        return bn(x)
+def grouped_batch_norm(bn: nn.BatchNorm1d, x: torch.Tensor, groups: int, relu: bool = False, dropout_p: float = 0.0,
+                       seed: Optional[torch.Tensor] = None, call_id: int = 0) -> torch.Tensor:
+    """dropout(relu(BatchNorm1d(x))) applied to `groups` independent slabs in ONE call (relu / dropout optional: the
+    Linear -> BatchNorm1d -> ReLU -> Dropout block of Tower.py:16-21).  Rows of x are ordered (sample, slab), so
+    x.view(B, groups*C) turns "statistics per slab" into plain per-channel statistics over B rows: numerically the same
+    as the reference's one-item-tower-pass-per-hard-negative-slab (TwoTowerModel.py:54-60: every pass normalises with its
+    own batch statistics and updates the running statistics once).  Running statistics receive the 1+N updates in slab
+    order:  r <- (1-m)^G r + m * sum_g (1-m)^(G-1-g) stat_g .
+    Training mode on the GPU runs the library kernels (ops.batch_norm_act: statistics, normalise + ReLU + dropout, and
+    their backward; statistics span all ranks when the layer is marked `_tt_sync`); eval mode / odd shapes use torch."""
     rows, C = x.shape
-    B = rows // groups
-    w = bn.weight.repeat(groups)
-    b = bn.bias.repeat(groups)
-    mean = x.new_zeros(groups * C)
-    var = x.new_ones(groups * C)
-    y = F.batch_norm(x.view(B, groups * C), mean, var, w, b, True, 1.0, bn.eps)   # momentum 1: mean/var = batch stats
-    if bn.track_running_stats:
-        with torch.no_grad():
-            m = bn.momentum
-            cache = bn.__dict__.setdefault("_tt_group_coef", {})   # built once (eagerly), reused under graph capture
-            key = (groups, x.device, x.dtype)
-            if key not in cache:
-                cache[key] = torch.tensor([m * (1.0 - m) ** (groups - 1 - g) for g in range(groups)], dtype=x.dtype,
-                                          device=x.device)
-            coef = cache[key]
-            decay = (1.0 - m) ** groups
-            bn.running_mean.mul_(decay).add_(coef @ mean.view(groups, C))
-            bn.running_var.mul_(decay).add_(coef @ var.view(groups, C))
-            bn.num_batches_tracked.add_(groups)
-    return y.view(rows, C)
+    fused = (bn.training and x.is_cuda and x.dtype == torch.float32 and bn.affine and bn.track_running_stats
+             and bn.momentum is not None and C % 4 == 0 and getattr(bn, "_tt_fused", True))
+    if fused:
+        B = rows // groups
+        y, mean, var_u = ops.batch_norm_act(x.contiguous().view(B, groups * C), bn.weight, bn.bias, bn.running_mean,
+                                            bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps, C, relu,
+                                            dropout_p if bn.training else 0.0, seed, call_id,
+                                            sync=getattr(bn, "_tt_sync", False))
+        if groups > 1:
+            _grouped_running_update(bn, mean, var_u, groups, C, x)
+        return y.view(rows, C)
+    if groups == 1 or not bn.training:
+        y = bn(x)
+    else:
+        B = rows // groups
+        w = bn.weight.repeat(groups)
+        b = bn.bias.repeat(groups)
+        mean = x.new_zeros(groups * C)
+        var = x.new_ones(groups * C)
+        y = F.batch_norm(x.view(B, groups * C), mean, var, w, b, True, 1.0, bn.eps)   # momentum 1: mean/var = batch stats
+        if bn.track_running_stats:
+            _grouped_running_update(bn, mean, var, groups, C, x)
+        y = y.view(rows, C)
+    if relu:
+        y = F.relu(y)
+    if dropout_p > 0.0 and bn.training:
+        y = F.dropout(y, dropout_p, True)
+    return y
+
+
+def _grouped_running_update(bn, mean, var, groups, C, x):
+    with torch.no_grad():
+        m = bn.momentum
+        cache = bn.__dict__.setdefault("_tt_group_coef", {})   # built once (eagerly), reused under graph capture
+        key = (groups, x.device, x.dtype)
+        if key not in cache:
+            cache[key] = torch.tensor([m * (1.0 - m) ** (groups - 1 - g) for g in range(groups)], dtype=x.dtype,
+                                      device=x.device)
+        coef = cache[key]
+        decay = (1.0 - m) ** groups
+        bn.running_mean.mul_(decay).add_(coef @ mean.view(groups, C))
+        bn.running_var.mul_(decay).add_(coef @ var.view(groups, C))
+        bn.num_batches_tracked.add_(groups)
 
 
 class TTLinear(nn.Linear):
@@ -91,6 +115,10 @@ class MLP_Tower(nn.Module):
         layers.append(TTLinear(curr, output_dim))
         self.mlp = nn.Sequential(*layers)
         self.apply(self._init_weights)
+        # dropout seed of the fused BatchNorm + ReLU + Dropout kernels (device resident, bumped per training forward:
+        # a CUDA-graph replay draws new masks); own generator, the global stream the reference's init consumes is untouched
+        gen = torch.Generator().manual_seed((torch.initial_seed() + 7919 * input_dim) % (2 ** 63))
+        self.register_buffer("_drop_seed", torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, generator=gen, device="cpu"), persistent=False)
 
     def _init_weights(self, m):  # Tower.py:28-35
         if isinstance(m, nn.Linear):
@@ -102,10 +130,24 @@ class MLP_Tower(nn.Module):
             nn.init.constant_(m.bias, 0)
 
     def forward(self, x, groups: int = 1):
-        if groups == 1:
-            return F.normalize(self.mlp(x), p=2, dim=1)
-        for layer in self.mlp:
-            x = grouped_batch_norm(layer, x, groups) if isinstance(layer, nn.BatchNorm1d) else layer(x)
+        layers = list(self.mlp)
+        n = len(layers)
+        seed = None
+        if self.training and x.is_cuda and any(isinstance(l, nn.Dropout) and l.p > 0 for l in layers):
+            self._drop_seed.add_(1)
+            seed = self._drop_seed.clone()
+        i = 0
+        while i < n:
+            layer = layers[i]
+            if isinstance(layer, nn.BatchNorm1d):
+                relu = i + 1 < n and isinstance(layers[i + 1], nn.ReLU)
+                has_drop = relu and i + 2 < n and isinstance(layers[i + 2], nn.Dropout)
+                p = layers[i + 2].p if (has_drop and self.training) else 0.0
+                x = grouped_batch_norm(layer, x, groups, relu=relu, dropout_p=p, seed=seed, call_id=i)
+                i += 1 + (1 if relu else 0) + (1 if has_drop else 0)
+            else:
+                x = layer(x)
+                i += 1
         return F.normalize(x, p=2, dim=1)
 
 
@@ -182,7 +224,7 @@ class SequenceEncoder(nn.Module):
         # graph replay draws new masks every step; reproducible under torch.manual_seed
         # (own generator seeded from torch.initial_seed(): the global stream the reference's init consumes is untouched)
         gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 63))
-        self.register_buffer("_drop_seed", torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, generator=gen), persistent=False)
+        self.register_buffer("_drop_seed", torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, generator=gen, device="cpu"), persistent=False)
 
     def _fused_ok(self, x):
         d = x.shape[-1]
@@ -239,6 +281,66 @@ class SequenceEncoder(nn.Module):
         return seq_output[torch.arange(B, device=seq_output.device), idx]
 
 
+def _dist_rank_world(cfg_model):
+    """(rank, world) for row-sharded features: two_tower.sharding = {rank, world} when given, else torch.distributed."""
+    sh = cfg_model.get("sharding") or {}
+    if "world" in sh:
+        return int(sh.get("rank", 0)), int(sh["world"])
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class ShardedEmbedding(nn.Module):
+    """The local shard of a row-sharded table (owner = row % world, local row = row // world): what
+    ``nn.Embedding(vocab, dim, padding_idx)`` + ``xavier_uniform_`` of GenericTower.py:45-51 becomes for a sparse feature
+    whose YAML entry says ``row_sharded: true`` (BASELINE configs[2]: 100M users / 10M items x 128).
+
+    * ``weight`` is the [ceil((vocab - rank) / world), dim] shard, initialised uniform(+-sqrt(6 / (vocab + dim))) -- the
+      xavier bound of the WHOLE table, as the reference computes it; construct under ``with torch.device("cuda")`` for
+      tables that should never exist on the host.
+    * the pad row (the reference leaves it non-zero and frozen) is a replicated fp32 buffer; DataParallel-style setups
+      broadcast it from rank 0 (dist.ShardedTrainStep does).
+    * ``state_dict`` keeps the reference's key and, with ``gather_on_save`` (default), its [vocab, dim] shape: the
+      shards are all-gathered on save (collective!) and the full table is sliced on load -- a checkpoint written by the
+      reference loads here and vice versa.  ``gather_on_save = False`` stores / expects the shard."""
+
+    def __init__(self, vocab, dim, padding_idx, rank, world, dtype=torch.float32):
+        super().__init__()
+        self.num_embeddings, self.embedding_dim, self.padding_idx = int(vocab), int(dim), padding_idx
+        self.rank, self.world = int(rank), int(world)
+        local = (self.num_embeddings - self.rank + self.world - 1) // self.world
+        bound = (6.0 / (self.num_embeddings + self.embedding_dim)) ** 0.5
+        self.weight = nn.Parameter(torch.empty(local, dim, dtype=dtype))
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound)
+        pad = torch.empty(dim, dtype=torch.float32, device=self.weight.device).uniform_(-bound, bound)
+        self.register_buffer("pad_row", pad if padding_idx is not None else None, persistent=False)
+        self.gather_on_save = True
+        self.group = None            # sharded.ShardedTableGroup, attached by the tower / model
+        self.table_name = None
+        self._register_state_dict_hook(self._save_hook)
+        self._register_load_state_dict_pre_hook(self._load_hook)
+
+    @staticmethod
+    def _save_hook(module, state_dict, prefix, local_metadata):
+        if module.gather_on_save and module.group is not None:
+            state_dict[prefix + "weight"] = module.group.gather_full_weight(module.table_name)
+
+    def _load_hook(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        key = prefix + "weight"
+        w = state_dict.get(key)
+        if w is not None and w.shape[0] == self.num_embeddings and self.num_embeddings != self.weight.shape[0]:
+            if self.padding_idx is not None and self.pad_row is not None:
+                with torch.no_grad():
+                    self.pad_row.copy_(w[self.padding_idx].to(self.pad_row.device, torch.float32))
+            state_dict[key] = w[self.rank::self.world]
+        elif w is not None and self.world == 1 and self.padding_idx is not None and self.pad_row is not None:
+            with torch.no_grad():
+                self.pad_row.copy_(w[self.padding_idx].to(self.pad_row.device, torch.float32))
+
+
 class GenericTower(nn.Module):
     """YAML-driven tower (GenericTower.py:9-237): sparse / pooled / dense /
     sequence features -> concat -> BatchNorm1d -> MLP_Tower."""
@@ -260,6 +362,9 @@ class GenericTower(nn.Module):
         self.seq_features = tcfg.get("sequence_features", None)
         self.sparse_sink: Optional[ops.SparseGradSink] = None  # set by optim.FusedTwoTowerOptimizer
         self.sparse_grad_tables = set()
+        self.tower_name = tower_name
+        self.shard_group = None     # sharded.ShardedTableGroup serving this tower's `row_sharded: true` features
+        self.sharded_features = []
 
         sparse_total = 0
         if self.sparse_features is not None:
@@ -269,9 +374,16 @@ class GenericTower(nn.Module):
                     if missing:
                         raise ValueError(f"Sparse feature config missing keys {missing}: {feat}")
                 name = feat["name"]
-                self.embeddings[name] = nn.Embedding(feat["vocab_size"], feat["embedding_dim"],
-                                                     padding_idx=feat.get("padding_idx", 0))
-                nn.init.xavier_uniform_(self.embeddings[name].weight)  # overwrites the zeroed pad row (:51)
+                if feat.get("row_sharded", False):
+                    # extension: this table is row-sharded over the ranks; only the local shard exists here
+                    rank, world = _dist_rank_world(model_cfg)
+                    self.embeddings[name] = ShardedEmbedding(feat["vocab_size"], feat["embedding_dim"],
+                                                             feat.get("padding_idx", 0), rank, world)
+                    self.sharded_features.append(name)
+                else:
+                    self.embeddings[name] = nn.Embedding(feat["vocab_size"], feat["embedding_dim"],
+                                                         padding_idx=feat.get("padding_idx", 0))
+                    nn.init.xavier_uniform_(self.embeddings[name].weight)  # overwrites the zeroed pad row (:51)
                 if "pooling" in feat:
                     self.pooling_config[name] = feat["pooling"]
                 sparse_total += feat["embedding_dim"]
@@ -304,6 +416,54 @@ class GenericTower(nn.Module):
         self.total_embed_dim = sparse_total + dense_total + seq_total
         self.feature_bn = nn.BatchNorm1d(self.total_embed_dim)
         self.mlp = MLP_Tower(input_dim=self.total_embed_dim, hidden_dims=hidden, output_dim=out_dims, dropout=dropout)
+        if self.sharded_features:
+            from . import sharded
+            rank, world = _dist_rank_world(model_cfg)
+            self.attach_shard_group(sharded.ShardedTableGroup(rank, world,
+                                                              capacity_factor=float((model_cfg.get("sharding") or {}).get("capacity_factor", 1.25))))
+
+    def attach_shard_group(self, group):
+        """Register this tower's row-sharded tables with `group` (TwoTowerModel passes ONE group to both towers so that
+        a step has a single batched exchange)."""
+        self.shard_group = group
+        for feat in self.sparse_features or []:
+            name = feat["name"]
+            if name not in self.sharded_features:
+                continue
+            emb = self.embeddings[name]
+            if "pooling" in feat:
+                if feat["pooling"] not in ("mean", "sum"):
+                    raise ValueError(f"row-sharded feature {name}: pooling must be 'mean' or 'sum'")
+                mode = ops.POOL_MODES[feat["pooling"]]
+            else:
+                mode = ops.POOL_NONE
+            emb.group, emb.table_name = group, f"{self.tower_name}.{name}"
+            group.add_table(emb.table_name, emb.num_embeddings, emb.embedding_dim, mode, emb.padding_idx, None, None, holder=emb)
+
+    def sharded_ids(self, input_dict, mapping):
+        """{group table name: ids [B, L]} of this tower's row-sharded features."""
+        out = {}
+        sparse_matrix = input_dict.get("sparse")
+        seq_dict = input_dict.get("sequence", {}) or {}
+        for feat in self.sparse_features or []:
+            name = feat["name"]
+            if name not in self.sharded_features:
+                continue
+            if "pooling" in feat:
+                if name not in seq_dict:
+                    raise ValueError(f"Pooled feature {name} missing from sequence dict")
+                ids = seq_dict[name]
+            else:
+                if mapping and "sparse" in mapping:
+                    col = mapping["sparse"].get(name)
+                    if col is None:
+                        raise ValueError(f"Feature '{name}' not found in column mapping")
+                else:
+                    col = [f["name"] for f in self.sparse_features if "pooling" not in f].index(name)
+                ids = sparse_matrix[:, col]
+            _need_cuda(ids, "GenericTower")
+            out[f"{self.tower_name}.{name}"] = ids
+        return out
 
     # ------------------------------------------------------------------
     def _sparse_specs(self, input_dict, mapping):
@@ -312,6 +472,8 @@ class GenericTower(nn.Module):
         seq_dict = input_dict.get("sequence", {})
         for fi, feat in enumerate(self.sparse_features):
             name = feat["name"]
+            if name in self.sharded_features:
+                continue
             pad = feat.get("padding_idx", 0)
             if "pooling" in feat:
                 if name not in seq_dict:
@@ -359,12 +521,30 @@ class GenericTower(nn.Module):
         out = self.forward(merged, feature_column_mapping, groups=G)
         return out.view(out.shape[0] // G, G, out.shape[1])
 
-    def forward(self, input_dict, feature_column_mapping=None, groups: int = 1):
+    def forward(self, input_dict, feature_column_mapping=None, groups: int = 1, sharded_vecs=None):
         feats = []
         if self.sparse_features and "sparse" in input_dict:
             specs, tables = self._sparse_specs(input_dict, feature_column_mapping)
-            if specs:
-                feats.append(ops.MultiGatherPool.apply(specs, self.sparse_sink, *tables))
+            local = ops.MultiGatherPool.apply(specs, self.sparse_sink, *tables) if specs else None
+            if not self.sharded_features:
+                if local is not None:
+                    feats.append(local)
+            else:
+                # row-sharded features come from the group's batched exchange (done once for both towers by
+                # TwoTowerModel; a tower used on its own does its own); concat order = YAML order (GenericTower.py:131-233)
+                if sharded_vecs is None:
+                    sharded_vecs = self.shard_group.lookup(self.sharded_ids(input_dict, feature_column_mapping))
+                col = 0
+                k = 0
+                for feat in self.sparse_features:
+                    name = feat["name"]
+                    if name in self.sharded_features:
+                        feats.append(sharded_vecs[f"{self.tower_name}.{name}"])
+                    elif k < len(tables) and tables[k] is self.embeddings[name].weight:
+                        d = tables[k].shape[1]
+                        feats.append(local[:, col:col + d])
+                        col += d
+                        k += 1
         if self.dense_features and "dense" in input_dict:
             dense = input_dict["dense"]
             for feat in self.dense_features:
@@ -443,19 +623,44 @@ class TwoTowerModel(nn.Module):
         # its autograd backward too); inside a CUDA graph this becomes two concurrent branches
         self.parallel_towers = True
         self._side_streams = {}
+        # row-sharded tables of BOTH towers share one group => one batched exchange per step
+        self.shard_group = None
+        groups = [t.shard_group for t in (user_tower, item_tower) if getattr(t, "shard_group", None) is not None]
+        if groups:
+            from . import sharded
+            g0 = groups[0]
+            merged = sharded.ShardedTableGroup(g0.rank, g0.world, capacity_factor=g0.capacity_factor, dev_ops=g0.ops, group=g0.pg)
+            for t in (user_tower, item_tower):
+                if getattr(t, "shard_group", None) is not None:
+                    t.attach_shard_group(merged)
+            self.shard_group = merged
+        # loss kernel: "auto" = tcgen05 bf16 path when the shapes allow it and the batch is large, else exact fp32
+        self.loss_precision = "auto"
+        self.loss_tc_min_batch = 4096
 
     def set_feature_mappings(self, user_mapping, item_mapping):
         self.user_feature_mapping = user_mapping
         self.item_feature_mapping = item_mapping
 
+    def _sharded_prefetch(self, batch_data):
+        """The batched lookup of every row-sharded feature of both towers (None when there is nothing to prefetch:
+        no sharded tables, or hard-negative slabs -- those go through the towers' own lookups)."""
+        if self.shard_group is None or batch_data.get("hard_negatives"):
+            return None
+        ids = {}
+        ids.update(self.user_tower.sharded_ids(batch_data["user_tower"], self.user_feature_mapping))
+        ids.update(self.item_tower.sharded_ids(batch_data["item_tower"], self.item_feature_mapping))
+        return self.shard_group.lookup(ids) if ids else None
+
     def forward(self, batch_data):
+        vecs = self._sharded_prefetch(batch_data)
         if self.parallel_towers and torch.is_grad_enabled() and self.training and _on_cuda(batch_data):
-            return self._forward_two_streams(batch_data)
-        user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping)
-        item_emb, hard_neg_emb = self._item_side(batch_data)
+            return self._forward_two_streams(batch_data, vecs)
+        user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping, sharded_vecs=vecs)
+        item_emb, hard_neg_emb = self._item_side(batch_data, vecs)
         return user_emb, item_emb, hard_neg_emb
 
-    def _forward_two_streams(self, batch_data):
+    def _forward_two_streams(self, batch_data, vecs=None):
         cur = torch.cuda.current_stream()
         key = cur.device.index
         if key not in self._side_streams:
@@ -463,20 +668,20 @@ class TwoTowerModel(nn.Module):
         side = self._side_streams[key]
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            item_emb, hard_neg_emb = self._item_side(batch_data)
-        user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping)
+            item_emb, hard_neg_emb = self._item_side(batch_data, vecs)
+        user_emb = self.user_tower(batch_data["user_tower"], self.user_feature_mapping, sharded_vecs=vecs)
         cur.wait_stream(side)
         for t in (item_emb, hard_neg_emb):
             if t is not None:
                 t.record_stream(cur)
         return user_emb, item_emb, hard_neg_emb
 
-    def _item_side(self, batch_data):
+    def _item_side(self, batch_data, vecs=None):
         negs = batch_data.get("hard_negatives") or []
         if negs and self.group_hard_negatives and _same_layout(batch_data["item_tower"], negs):
             both = self.item_tower.forward_grouped([batch_data["item_tower"]] + list(negs), self.item_feature_mapping)
             return both[:, 0], both[:, 1:]
-        item_emb = self.item_tower(batch_data["item_tower"], self.item_feature_mapping)
+        item_emb = self.item_tower(batch_data["item_tower"], self.item_feature_mapping, sharded_vecs=vecs)
         hard_neg_emb = None
         if "hard_negatives" in batch_data and batch_data["hard_negatives"]:
             # one item-tower pass per slab: each slab keeps its own BatchNorm batch
@@ -514,6 +719,8 @@ class TwoTowerModel(nn.Module):
             raise RuntimeError("Found NaN in Item Embedding")
         if flags & 4:
             raise RuntimeError("Found NaN in Hard Negative Embedding")
+        if self.shard_group is not None and self.shard_group.tables:
+            self.shard_group.check_flags()
 
     def compute_loss(self, user_emb, item_emb, item_ids=None, hard_neg_emb=None, temperature=0.1,
                      hard_neg_pool=None):
@@ -523,8 +730,12 @@ class TwoTowerModel(nn.Module):
         if hard_neg_emb is not None:
             assert hard_neg_emb.dim() == 3, f"Expected shape [B, N, D], got {hard_neg_emb.shape}"
             assert hard_neg_emb.size(0) == user_emb.shape[0], "Batch size mismatch"
+        precision = self.loss_precision
+        if precision == "auto":
+            # the tensor-core kernel needs D in {64, 128}; below a few thousand rows the exact fp32 kernel is as fast
+            precision = "bf16" if (user_emb.shape[1] in (64, 128) and user_emb.shape[0] >= self.loss_tc_min_batch) else "fp32"
         loss, _, flags = ops.fused_inbatch_ce(user_emb, item_emb, item_ids=item_ids, hn_rows=hard_neg_emb,
-                                              pool=hard_neg_pool, temperature=temperature)
+                                              pool=hard_neg_pool, temperature=temperature, precision=precision)
         self.last_nan_flags = flags
         if self.strict_nan_check and not torch.cuda.is_current_stream_capturing():
             self.check_nan_flags()

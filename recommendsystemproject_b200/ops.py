@@ -115,7 +115,7 @@ class SparseGradSink:
 
     def __init__(self):
         self.entries: List[Tuple[torch.nn.Parameter, torch.Tensor, torch.Tensor, torch.Tensor, int]] = []
-        self.sq_terms: Optional[torch.Tensor] = None     # [1 + MAX_ENTRIES]: slot 0 = dense parameters
+        self.sq_terms: Optional[torch.Tensor] = None     # [2 + MAX_ENTRIES]: slot 0 = dense parameters, last = row-sharded tables
         self.sq_norm: Optional[torch.Tensor] = None      # legacy single slot (callers that own exactly one stream)
 
     def clear(self):
@@ -125,7 +125,7 @@ class SparseGradSink:
         if self.sq_terms is None:
             return self.sq_norm, -1
         k = 1 + len(self.entries)
-        if k >= self.sq_terms.numel():
+        if k > self.MAX_ENTRIES:
             raise TTError(f"more than {self.MAX_ENTRIES} sparse-gradient entries in one step")
         return self.sq_terms[k:k + 1], k
 
@@ -461,6 +461,101 @@ def attn_small(qkv, key_pad_u8, heads, dropout_p=0.0, seed_dev=None, call_id=0):
 
 def add_dropout_layer_norm(x, z, gamma, beta, eps=1e-5, dropout_p=0.0, seed_dev=None, call_id=0):
     return AddDropoutLayerNorm.apply(x, z, gamma, beta, eps, dropout_p, seed_dev, call_id)
+
+
+# --------------------------------------------------------------------------
+# 3c. BatchNorm1d (training) + ReLU + Dropout, statistics optionally over all ranks
+# --------------------------------------------------------------------------
+class _BnSync:
+    """How batch statistics cross ranks (data-parallel towers).  None = this rank only."""
+    group = None
+    world = 1
+
+
+bn_sync = _BnSync()
+
+
+def _bn_ws(rows, cols, dev):
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    check(lib.tt_bn_workspace(rows, cols, ctypes.byref(nbytes)), "tt_bn_workspace")
+    return _ws(nbytes.value, dev)
+
+
+class FusedBatchNormAct(torch.autograd.Function):
+    """y = dropout(relu(batch_norm(x))) in training mode (Tower.py:16-21, GenericTower.py:234); x [rows, cols] fp32 with
+    cols = groups * C (slab g of a row = columns [g*C, (g+1)*C): per-slab statistics).  Returns (y, batch mean [cols],
+    unbiased batch variance [cols]); running statistics are updated in the kernel for groups == 1."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, num_batches, momentum, eps, period, relu, dropout_p,
+                seed_dev, call_id, sync):
+        import torch.distributed as dist
+        lib = _lib.load()
+        _need_cuda(x, gamma)
+        x = x.contiguous()
+        rows, cols = x.shape
+        dev = x.device
+        world = bn_sync.world if sync else 1
+        stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
+        ws = _bn_ws(rows, cols, dev)
+        check(lib.tt_bn_stats(_p(x), rows, cols, x.stride(0), _p(stats), _p(ws), ws.numel(), _stream()), "tt_bn_stats")
+        if world > 1:
+            stats_all = torch.empty(world, 2 * cols + 1, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(stats_all, stats, group=bn_sync.group)
+        else:
+            stats_all = stats
+        y = torch.empty_like(x)
+        mean = torch.empty(cols, dtype=torch.float32, device=dev)
+        rstd = torch.empty(cols, dtype=torch.float32, device=dev)
+        var_u = torch.empty(cols, dtype=torch.float32, device=dev)
+        plain = period == cols and running_mean is not None
+        check(lib.tt_bn_apply(_p(x), rows, cols, x.stride(0), _p(stats_all), world, _p(gamma), _p(beta), period, float(eps),
+                              1 if relu else 0, float(dropout_p), _p(seed_dev), int(call_id), _p(y), y.stride(0), _p(mean),
+                              _p(rstd), _p(var_u), _p(running_mean if plain else None), _p(running_var if plain else None),
+                              float(momentum), _p(num_batches if plain else None), _stream()), "tt_bn_apply")
+        _count(3)
+        ctx.save_for_backward(x, mean, rstd, gamma, beta, seed_dev)
+        ctx.cfg = (period, bool(relu), float(dropout_p), int(call_id), world)
+        ctx.gamma_ref, ctx.beta_ref = gamma, beta
+        ctx.mark_non_differentiable(mean, var_u)
+        return y, mean, var_u
+
+    @staticmethod
+    def backward(ctx, dy, _gm, _gv):
+        import torch.distributed as dist
+        lib = _lib.load()
+        x, mean, rstd, gamma, beta, seed_dev = ctx.saved_tensors
+        period, relu, p, call_id, world = ctx.cfg
+        rows, cols = x.shape
+        dev = x.device
+        dy = dy.contiguous()
+        sums = torch.empty(2 * cols, dtype=torch.float32, device=dev)
+        ws = _bn_ws(rows, cols, dev)
+        g_ref, b_ref = ctx.gamma_ref, ctx.beta_ref
+        direct = _direct_grad(g_ref) and _direct_grad(b_ref)
+        if direct:
+            dgamma, dbeta = g_ref.grad, b_ref.grad
+        else:
+            dgamma = torch.empty(period, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(period, dtype=torch.float32, device=dev)
+        check(lib.tt_bn_bwd_stats(_p(dy), dy.stride(0), _p(x), rows, cols, x.stride(0), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                                  period, 1 if relu else 0, p, _p(seed_dev), call_id, _p(sums), _p(dgamma), _p(dbeta),
+                                  1 if direct else 0, _p(ws), ws.numel(), _stream()), "tt_bn_bwd_stats")
+        if world > 1:
+            dist.all_reduce(sums, group=bn_sync.group)
+        dx = torch.empty_like(x)
+        check(lib.tt_bn_bwd_apply(_p(dy), dy.stride(0), _p(x), rows, cols, x.stride(0), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                                  period, 1 if relu else 0, p, _p(seed_dev), call_id, _p(sums), float(rows * world), _p(dx),
+                                  dx.stride(0), _stream()), "tt_bn_bwd_apply")
+        _count(4)
+        return (dx, None if direct else dgamma, None if direct else dbeta) + (None,) * 11
+
+
+def batch_norm_act(x, gamma, beta, running_mean, running_var, num_batches, momentum, eps, period, relu=False,
+                   dropout_p=0.0, seed_dev=None, call_id=0, sync=False):
+    return FusedBatchNormAct.apply(x, gamma, beta, running_mean, running_var, num_batches, momentum, eps, period, relu,
+                                   dropout_p, seed_dev, call_id, sync)
 
 
 # --------------------------------------------------------------------------

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import GenericTower, SequenceFeatureProcessor, TwoTowerModel
+from .modules import GenericTower, SequenceFeatureProcessor, ShardedEmbedding, TwoTowerModel
 
 
 def _embedding_tables(model: nn.Module) -> Dict[int, nn.Parameter]:
@@ -58,12 +58,20 @@ class FusedTwoTowerOptimizer:
 
         tables = _embedding_tables(model) if table_mode == "sparse" else {}
         self.sparse_tables: List[nn.Parameter] = [p for p in params if id(p) in tables]
-        flat_params = [p for p in params if id(p) not in tables]
+        # row-sharded tables (modules.ShardedEmbedding): always touched-rows-only, updated on their owners by the group
+        self.shard_group = getattr(model, "shard_group", None)
+        sharded_ids = {id(m.weight) for m in model.modules() if isinstance(m, ShardedEmbedding)}
+        if sharded_ids and self.shard_group is None:
+            raise ops.TTError("model has row-sharded tables but no shard group (build it through TwoTowerModel)")
+        self.sharded_params = [p for p in params if id(p) in sharded_ids]
+        flat_params = [p for p in params if id(p) not in tables and id(p) not in sharded_ids]
 
         # one flat fp32 buffer each for params / grads / exp_avg / exp_avg_sq
         n = sum(p.numel() for p in flat_params)
         self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        # + one trailing float: the row-sharded tables' local sum of squares rides the dense-gradient all-reduce
+        self.flat_g_ext = torch.zeros(n + 1, dtype=torch.float32, device=dev)
+        self.flat_g = self.flat_g_ext[:n]
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
@@ -84,7 +92,7 @@ class FusedTwoTowerOptimizer:
                             for p in self.sparse_tables}
         # [0] dense parameters, [1..] one slot per sparse-gradient entry of the step (never shared: the two towers'
         # backward passes run on different streams)
-        self.sq_terms = torch.zeros(1 + ops.SparseGradSink.MAX_ENTRIES, dtype=torch.float32, device=dev)
+        self.sq_terms = torch.zeros(2 + ops.SparseGradSink.MAX_ENTRIES, dtype=torch.float32, device=dev)
         self.sink.sq_terms = self.sq_terms
         # learning rate on the device: the Adam kernels read it there, so a scheduler that edits
         # param_groups[0]["lr"] reaches a captured CUDA graph too (refreshed by step() / GraphedTrainStep.__call__)
@@ -101,12 +109,25 @@ class FusedTwoTowerOptimizer:
                     mod.sparse_grad_tables = {name for name, sub in mod.embeddings.items()
                                               if isinstance(sub, nn.Embedding) and id(sub.weight) in sparse_ids}
         self._sparse_param_ids = {id(p) for p in self.sparse_tables}
+        self._norm_staged_by_caller = False     # dist.ShardedTrainStep stages + all-reduces the sharded norm itself
+        if self.shard_group is not None:
+            self.shard_group.init_state()
 
     # torch.optim-like surface ------------------------------------------------
     def zero_grad(self, set_to_none: bool = False):
-        self.flat_g.zero_()
+        self.flat_g_ext.zero_()
         self.sq_terms.zero_()
         self.sink.clear()
+        if self.shard_group is not None:
+            self.shard_group.zero_grad()
+
+    SHARD_SLOT = 1 + ops.SparseGradSink.MAX_ENTRIES     # last slot of sq_terms: row-sharded tables, summed over ranks
+
+    def stage_sharded_norm(self):
+        """Put this rank's sum of squared row-sharded gradients behind the dense gradients (flat_g_ext[-1]); after the
+        caller's SUM all-reduce of flat_g_ext it holds the global value that step() feeds to the clip coefficient."""
+        if self.shard_group is not None and self.shard_group.tables:
+            self.flat_g_ext[-1:].copy_(self.shard_group.local_sq_norm())
 
     def sync_lr(self):
         """Copy param_groups[0]['lr'] (what torch LR schedulers edit) to the device scalar the kernels read.  Call
@@ -147,6 +168,10 @@ class FusedTwoTowerOptimizer:
         if not torch.cuda.is_current_stream_capturing():
             self.sync_lr()
         entries = self._merged_entries()
+        if self.shard_group is not None and self.shard_group.tables:
+            if not self._norm_staged_by_caller:
+                self.stage_sharded_norm()
+            self.sq_terms[self.SHARD_SLOT:self.SHARD_SLOT + 1].copy_(self.flat_g_ext[-1:])
         ops.sq_norm_accum_(self.flat_g, self.sq_terms[0:1], self._ws)
         coef = None
         if self.max_grad_norm > 0:
@@ -160,6 +185,8 @@ class FusedTwoTowerOptimizer:
             ops.rowwise_adam_(table.data, m, v, rows, row_grad, n_unique, coef, self.lr, self.beta1, self.beta2,
                               self.eps, self.step_dev, self.lr_dev)
         self.sink.clear()
+        if self.shard_group is not None and self.shard_group.tables:
+            self.shard_group.step(coef, self.lr, self.step_dev, (self.beta1, self.beta2), self.eps, self.lr_dev)
 
     # checkpoint surface: the SAME dict torch.optim.Adam(model.parameters()) produces (train_twotower.py:184-195 stores
     # optimizer.state_dict()), so checkpoints move freely between the reference's optimizer and this one
@@ -171,9 +198,12 @@ class FusedTwoTowerOptimizer:
             if id(p) in flat:
                 off, k = flat[id(p)]
                 out.append((p, self.flat_m[off:off + k].view_as(p), self.flat_v[off:off + k].view_as(p)))
-            else:
+            elif id(p) in self.table_state:
                 m, v = self.table_state[id(p)]
                 out.append((p, m, v))
+            else:   # row-sharded table: the moments of the LOCAL shard (checkpoints of sharded runs are per rank)
+                t = next(t for t in self.shard_group.tables.values() if t.weight is p)
+                out.append((p, t.exp_avg, t.exp_avg_sq))
         return out
 
     def state_dict(self):

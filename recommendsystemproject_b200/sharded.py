@@ -97,16 +97,30 @@ class _CudaShardOps:
         ops.rowwise_adam_(table, m, v, rows, row_grad, n_unique, coef, lr, b1, b2, eps, step_dev, lr_dev)
 
 
-class ShardedTable:
-    """One row-sharded table: local shard + Adam moments + wire-layout slots (filled by the group's plan)."""
+class _Holder:
+    def __init__(self, weight, pad_row):
+        self.weight, self.pad_row = weight, pad_row
 
-    def __init__(self, name, vocab, dim, mode, padding_idx, weight, pad_row):
+
+class ShardedTable:
+    """One row-sharded table: local shard + Adam moments.  `holder` owns `.weight` ([local_rows, dim] parameter / tensor,
+    fp32 or bf16) and `.pad_row` ([dim] fp32 replica of the frozen pad row, or None); they are read through the holder at
+    every use because nn.Module.to() replaces buffers."""
+
+    def __init__(self, name, vocab, dim, mode, padding_idx, holder):
         self.name, self.vocab, self.dim, self.mode, self.padding_idx = name, int(vocab), int(dim), mode, padding_idx
-        self.weight = weight                   # [local_rows, dim] parameter / tensor on the device (fp32 or bf16)
-        self.pad_row = pad_row                 # [dim] fp32 replica of the (frozen) pad row, or None
+        self.holder = holder
         self.exp_avg = None
         self.exp_avg_sq = None
         self.pending = None                    # (rows, row_grad, n_unique) of the last backward
+
+    @property
+    def weight(self):
+        return self.holder.weight
+
+    @property
+    def pad_row(self):
+        return self.holder.pad_row
 
     @property
     def local_rows(self):
@@ -119,37 +133,73 @@ class _Plan:
 
 
 class ShardedTableGroup:
-    def __init__(self, rank: int, world: int, device, capacity_factor: float = 1.25, dev_ops=None, group=None):
+    def __init__(self, rank: int, world: int, device=None, capacity_factor: float = 1.25, dev_ops=None, group=None):
         if not (1 <= world <= 32):
             raise TTError("ShardedTableGroup supports 1..32 ranks")
-        self.rank, self.world, self.device = int(rank), int(world), torch.device(device)
+        self.rank, self.world = int(rank), int(world)
+        self._device = None if device is None else torch.device(device)
         self.capacity_factor = float(capacity_factor)
         self.ops = dev_ops or _CudaShardOps
         self.pg = group
         self.tables: Dict[str, ShardedTable] = {}
         self._plans: Dict[tuple, _Plan] = {}
-        self.flags = torch.zeros(1, dtype=torch.int32, device=self.device)   # bit 0: id out of range, bit 1: capacity overflow
-        self.sq_terms = None
-        self.a2a_bytes = 0                                                    # bytes this rank SENT to other ranks (counted per call)
-        # autograd anchor: the lookup's inputs are integer ids, so something that requires grad must enter the node
-        self._anchor = torch.zeros(1, dtype=torch.float32, device=self.device, requires_grad=True)
+        self._flags = None                     # bit 0: id out of range, bit 1: capacity overflow
+        self._sq_terms = None
+        self._anchor_t = None
+        self.a2a_bytes = 0                     # bytes this rank SENT to other ranks (counted per call)
+
+    @property
+    def device(self):
+        """Where the shards live NOW (a model is built on the CPU and moved with .to(), like the reference's)."""
+        if self.tables:
+            return next(iter(self.tables.values())).weight.device
+        return self._device or torch.device("cpu")
+
+    def _dev_state(self):
+        dev = self.device
+        if self._flags is None or self._flags.device != dev:
+            self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._sq_terms = torch.zeros(max(1, len(self.tables)), dtype=torch.float32, device=dev)
+            # autograd anchor: the lookup's inputs are integer ids, so something that requires grad must enter the node
+            self._anchor_t = torch.zeros(1, dtype=torch.float32, device=dev, requires_grad=True)
+            self._plans.clear()
+            for t in self.tables.values():
+                t.exp_avg = t.exp_avg.to(dev) if t.exp_avg is not None else None
+                t.exp_avg_sq = t.exp_avg_sq.to(dev) if t.exp_avg_sq is not None else None
+
+    @property
+    def flags(self):
+        self._dev_state()
+        return self._flags
+
+    @property
+    def sq_terms(self):
+        self._dev_state()
+        return self._sq_terms
+
+    @property
+    def _anchor(self):
+        self._dev_state()
+        return self._anchor_t
 
     # ------------------------------------------------------------------ construction
     @staticmethod
     def local_row_count(vocab: int, rank: int, world: int) -> int:
         return (int(vocab) - rank + world - 1) // world
 
-    def add_table(self, name, vocab, dim, mode, padding_idx, weight, pad_row=None) -> ShardedTable:
+    def add_table(self, name, vocab, dim, mode, padding_idx, weight, pad_row=None, holder=None) -> ShardedTable:
+        """`holder` (an object with .weight / .pad_row, e.g. modules.ShardedEmbedding) or plain tensors."""
+        if holder is None:
+            holder = _Holder(weight, pad_row)
         if mode not in (ops.POOL_NONE, ops.POOL_SUM, ops.POOL_MEAN):
             raise TTError(f"row-sharded feature '{name}': pooling must be mean / sum (or a single id per sample)")
-        if weight.shape[0] != self.local_row_count(vocab, self.rank, self.world):
-            raise TTError(f"row-sharded feature '{name}': shard has {weight.shape[0]} rows, expected "
+        if holder.weight.shape[0] != self.local_row_count(vocab, self.rank, self.world):
+            raise TTError(f"row-sharded feature '{name}': shard has {holder.weight.shape[0]} rows, expected "
                           f"{self.local_row_count(vocab, self.rank, self.world)} (vocab {vocab}, rank {self.rank}/{self.world})")
-        t = ShardedTable(name, vocab, dim, mode, padding_idx, weight, pad_row)
+        t = ShardedTable(name, vocab, dim, mode, padding_idx, holder)
         self.tables[name] = t
         self._plans.clear()
-        n = len(self.tables)
-        self.sq_terms = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._flags = None          # device state is rebuilt (one norm slot per table)
         return t
 
     def init_state(self):
@@ -328,6 +378,8 @@ class ShardedTableGroup:
 
     def load_full_weight(self, name: str, full: torch.Tensor):
         t = self.tables[name]
+        if full.shape[0] != t.vocab:
+            raise TTError(f"row-sharded feature '{name}': full table has {full.shape[0]} rows, vocab is {t.vocab}")
         with torch.no_grad():
             t.weight.copy_(full[self.rank::self.world].to(t.weight.device, t.weight.dtype))
             if t.padding_idx is not None and t.pad_row is not None:

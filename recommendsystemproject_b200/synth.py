@@ -66,6 +66,68 @@ def config_c2(dropout_scale: float = 1.0):
     }
 
 
+def config_c3(v_user=100_000_001, v_item=10_000_001, dim=128, dropout=0.1, shard=True, world=None, rank=0,
+              capacity_factor=1.25):
+    """C3: 8 sparse features -- user {user_id 100M+1, u_cat1 1e5, u_cat2 1e3, u_cat3 32} + pooled
+    hist_item_ids (10M+1, L=200 ragged, mean); item {item_id 10M+1, i_cat 1e4, i_year 152}; all D_f = 128;
+    MLP [256, 128] -> 128.  Tables of 1 MB and more are row-sharded (`row_sharded: true`), the rest replicated."""
+    def feat(name, vocab, **kw):
+        f = {"name": name, "vocab_size": vocab, "embedding_dim": dim}
+        f.update(kw)
+        if shard and vocab * dim * 4 >= (1 << 20):
+            f["row_sharded"] = True
+        return f
+    cfg = {
+        "two_tower": {
+            "user_tower": {
+                "mlp_hidden_dim": [256, 128], "output_dims": 128, "dropout": dropout, "embedding_dim": dim,
+                "sparse_features": [feat("user_id", v_user), feat("u_cat1", 100_000), feat("u_cat2", 1000), feat("u_cat3", 32),
+                                    feat("hist_item_ids", v_item, padding_idx=0, pooling="mean")],
+            },
+            "item_tower": {
+                "mlp_hidden_dim": [256, 128], "output_dims": 128, "dropout": dropout, "embedding_dim": dim,
+                "sparse_features": [feat("item_id", v_item), feat("i_cat", 10_000), feat("i_year", 152)],
+            },
+        },
+        "train": {"batch_size": 65536, "learning_rate": 5e-4, "temperature": 0.05},
+    }
+    if world is not None:
+        cfg["two_tower"]["sharding"] = {"rank": rank, "world": world, "capacity_factor": capacity_factor}
+    return cfg
+
+
+MAPS_C3 = ({"sparse": {"user_id": 0, "u_cat1": 1, "u_cat2": 2, "u_cat3": 3}, "dense": {}, "sequence": {}},
+           {"sparse": {"item_id": 0, "i_cat": 1, "i_year": 2}, "dense": {}, "sequence": {}})
+
+
+def zipf_approx(gen, shape, vocab, s=1.05, device=None):
+    """ids in [1, vocab) with P(k) ~ k^-s for LARGE vocabularies (inverse CDF of the continuous law, then a
+    multiplicative hash so that popular ids are spread over the table instead of sitting in rows 1, 2, 3, ...)."""
+    u = torch.rand(shape, generator=gen, dtype=torch.float64, device=device)
+    n = float(vocab - 1)
+    x = ((n ** (1.0 - s) - 1.0) * u + 1.0) ** (1.0 / (1.0 - s))
+    k = x.floor().clamp_(1, vocab - 1).long() - 1
+    return (k * 2654435761 % (vocab - 1)) + 1
+
+
+def make_batch_c3(B=65536, L=200, v_user=100_000_001, v_item=10_000_001, seed=3, zipf=False, unique_items=False):
+    """One C3 batch (collate contract).  zipf=False: uniform ids (every looked-up row distinct: the HBM worst case);
+    zipf=True: Zipf(1.05) item ids as SURVEY 8d words it.  unique_items: distinct positive item ids (no in-batch
+    false negatives)."""
+    gen = torch.Generator().manual_seed(seed)
+    draw = (lambda shape: zipf_approx(gen, shape, v_item)) if zipf else (lambda shape: torch.randint(1, v_item, shape, generator=gen))
+    hist = draw((B, L))
+    lens = torch.randint(1, L + 1, (B,), generator=gen)
+    hist[torch.arange(L)[None, :] >= lens[:, None]] = 0
+    user = {"sparse": torch.stack([torch.randint(0, v_user, (B,), generator=gen), torch.randint(0, 100_000, (B,), generator=gen),
+                                   torch.randint(0, 1000, (B,), generator=gen), torch.randint(0, 32, (B,), generator=gen)], dim=1),
+            "sequence": {"hist_item_ids": hist}}
+    item_ids = (torch.randperm(v_item - 1, generator=gen)[:B] + 1) if unique_items else draw((B,))
+    item = {"sparse": torch.stack([item_ids, torch.randint(0, 10_000, (B,), generator=gen),
+                                   torch.randint(0, 152, (B,), generator=gen)], dim=1)}
+    return {"user_tower": user, "item_tower": item}
+
+
 MAPS_C1 = ({"sparse": {"user_id_enc": 0}, "dense": {}, "sequence": {}},
            {"sparse": {"movie_id_enc": 0}, "dense": {}, "sequence": {}})
 MAPS_C2 = ({"sparse": {"user_id_enc": 0}, "dense": {"user_activity_log": 0},

@@ -119,9 +119,58 @@ gp = pl.grad.clone()
 dist.all_reduce(gp)
 t5 &= bool(torch.allclose(gp / world, pr.grad, atol=1e-7, rtol=1e-4))
 ok &= t5
+# 6. the integrated step: row-sharded tables (one batched exchange) + data-parallel towers with global BatchNorm
+#    statistics + global in-batch softmax  ==  ONE process running the unsharded model on the global batch
+#    (TwoTowerModel.py:95-140, GenericTower.py:234, training_utils.py:51-56); dropout 0, distinct item ids
+Bl = 256
+cfg_s = synth.config_c3(v_user=40001, v_item=20001, dim=64, dropout=0.0, shard=True)
+cfg_u = synth.config_c3(v_user=40001, v_item=20001, dim=64, dropout=0.0, shard=False)
+torch.manual_seed(1234)
+ref_model = tt.TwoTowerModel(tt.GenericTower(cfg_u, "user_tower"), tt.GenericTower(cfg_u, "item_tower"), *synth.MAPS_C3).to(dev).train()
+full_state = {k: v.clone() for k, v in ref_model.state_dict().items()}
+sh_model = tt.TwoTowerModel(tt.GenericTower(cfg_s, "user_tower"), tt.GenericTower(cfg_s, "item_tower"), *synth.MAPS_C3).to(dev).train()
+sh_model.load_state_dict(full_state)          # full tables are sliced into the local shards
+gbatch = synth.make_batch_c3(B=Bl * world, L=30, v_user=40001, v_item=20001, seed=77, unique_items=True)
+def cut(o):
+    if isinstance(o, torch.Tensor): return o[rank * Bl:(rank + 1) * Bl].contiguous()
+    if isinstance(o, dict): return {k: cut(v) for k, v in o.items()}
+    return [cut(v) for v in o]
+lbatch = mv(cut(gbatch))
+opt_s = tt.FusedTwoTowerOptimizer(sh_model, lr=1e-2, max_grad_norm=1.0, table_mode="sparse")
+step_s = tdist.ShardedTrainStep(sh_model, opt_s, lbatch, 0.05, loss_precision="fp32")
+loss_s = step_s().clone()
+step_s.check_flags()
+opt_u = tt.FusedTwoTowerOptimizer(ref_model, lr=1e-2, max_grad_norm=1.0, table_mode="sparse")
+gb = mv(gbatch)
+opt_u.zero_grad()
+u_, i_, _ = ref_model(gb)
+loss_u = ref_model.compute_loss(u_, i_, item_ids=gb["item_tower"]["sparse"][:, 0], temperature=0.05)
+loss_u.backward()
+opt_u.step()
+torch.cuda.synchronize()
+t6 = abs(float(loss_s) - float(loss_u)) < 2e-5 * max(1.0, abs(float(loss_u)))
+t6 &= abs(float(opt_s.total_norm) - float(opt_u.total_norm)) < 1e-4 * float(opt_u.total_norm)
+new_state = sh_model.state_dict()             # gathers the shards (collective)
+worst, n_bad, n_all = 0.0, 0, 0
+for k, v in ref_model.state_dict().items():
+    if v.dtype.is_floating_point:
+        d = (new_state[k].float() - v.float()).abs()
+        worst = max(worst, float(d.max()))
+        n_bad += int((d > 1e-4).sum())
+        n_all += d.numel()
+# the first Adam step moves every touched element by ~lr * sign(g): elements whose gradient is rounding noise may differ
+t6 &= n_bad < 1e-3 * n_all
+# second step: the updated weights of both runs must give the same loss again
+loss_s2 = step_s().clone()
+opt_u.zero_grad()
+u_, i_, _ = ref_model(gb)
+loss_u2 = ref_model.compute_loss(u_, i_, item_ids=gb["item_tower"]["sparse"][:, 0], temperature=0.05)
+torch.cuda.synchronize()
+t6 &= abs(float(loss_s2) - float(loss_u2)) < 1e-4 * max(1.0, abs(float(loss_u2)))
+ok &= t6
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"dist_check world={world}: sharded_topk={t1} sharded_lookup={t2} dp_replicas_identical={t3} sharded_bag={t4} global_inbatch_ce={t5} all_ranks_ok={bool(flag.item())}")
+    print(f"dist_check world={world}: sharded_topk={t1} sharded_lookup={t2} dp_replicas_identical={t3} sharded_bag={t4} global_inbatch_ce={t5} integrated_sharded_step={t6} (loss {float(loss_s):.6f} vs {float(loss_u):.6f}, worst param diff {worst:.2e}) all_ranks_ok={bool(flag.item())}")
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)
