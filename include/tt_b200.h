@@ -316,6 +316,7 @@ TT_API int tt_bn_bwd_apply(const float *dy, int64_t dy_stride, const float *x, i
  * and the float block holds, at vec_base, [n_rows][dim] partial sums (len > 1) or [cap][dim] rows (len == 1).
  *   tt_shard_route        source: buckets ids [n_rows, len] by owner into send[world][block_ints] (count, scan, fill:
  *                         ballots only, order preserved); n_pad[n_rows] (nullable) = pads per sample;
+ *                         workspace: 4 * world * ceil(n_rows / 4096) bytes (tile totals of the scan);
  *                         *flags |= 1 (id outside [0, vocab)), |= 2 (an owner's entries exceed cap: dropped)
  *   tt_shard_owner_gather owner: pooled != 0: out[s][vec_base + b*dim] = sum of table rows of (source s, sample b) and
  *                         pos_src[s*cap + e] = s*n_rows + b (nullable; feeds tt_emb_segment_grad_lists);
@@ -327,7 +328,7 @@ TT_API int tt_bn_bwd_apply(const float *dy, int64_t dy_stride, const float *x, i
  * ---------------------------------------------------------------------- */
 TT_API int tt_shard_route(const int64_t *ids, int64_t n_rows, int len, int64_t padding_idx, int64_t vocab, int world,
                    int32_t *send, int64_t block_ints, int64_t off_base, int64_t rows_base, int64_t cap, int32_t *n_pad,
-                   int *flags, void *stream);
+                   int *flags, void *workspace, size_t workspace_bytes, void *stream);
 TT_API int tt_shard_owner_gather(const void *table, int table_dtype, int64_t local_rows, int dim, int world,
                           const int32_t *recv, int64_t block_ints, int64_t off_base, int64_t rows_base, int64_t cap,
                           int64_t n_rows, int pooled, float *out, int64_t block_floats, int64_t vec_base,

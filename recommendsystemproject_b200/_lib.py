@@ -25,7 +25,8 @@ _SIGNATURES = {
                                     c_size_t, P]),
     "tt_emb_segment_grad_lists": (c_int, [P, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, c_int, P, P, P, P, P,
                                           c_size_t, P]),
-    "tt_shard_route": (c_int, [P, c_int64, c_int, c_int64, c_int64, c_int, P, c_int64, c_int64, c_int64, c_int64, P, P, P]),
+    "tt_shard_route": (c_int, [P, c_int64, c_int, c_int64, c_int64, c_int, P, c_int64, c_int64, c_int64, c_int64, P, P, P,
+                               c_size_t, P]),
     "tt_shard_owner_gather": (c_int, [P, c_int, c_int64, c_int, c_int, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
                                       P, c_int64, c_int64, P, P]),
     "tt_shard_combine": (c_int, [P, c_int64, c_int64, c_int, P, c_int64, c_int, c_int64, c_int64, c_int, P, c_int64, c_int64,

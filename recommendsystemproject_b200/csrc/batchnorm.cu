@@ -78,20 +78,29 @@ __device__ __forceinline__ void chan_merge(float &n, float &mean, float &m2, flo
 }
 
 // stats[0..cols) = mean, [cols..2cols) = M2, stats[2*cols] = n  (this rank's rows)
-__global__ void bn_stats_final(const float *__restrict__ partial, int n_chunks, int64_t rows, int rows_per_chunk, int cols,
-                               float *__restrict__ stats) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// 32 columns x 8 chunk lanes per block: lane j merges chunks j, j+8, ... (Chan), the 8 results are merged in lane order
+__global__ void __launch_bounds__(256)
+bn_stats_final(const float *__restrict__ partial, int n_chunks, int64_t rows, int rows_per_chunk, int cols,
+               float *__restrict__ stats) {
+    __shared__ float sn[8][32], sm[8][32], s2[8][32];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     float n = 0.f, mean = 0.f, m2 = 0.f;
-    for (int k = 0; k < n_chunks; ++k) {
-        const float *p = partial + static_cast<int64_t>(k) * 3 * cols;
-        const float nk = static_cast<float>(min(static_cast<int64_t>(rows_per_chunk), rows - static_cast<int64_t>(k) * rows_per_chunk));
-        const float sd = p[cols + c], sq = p[2 * cols + c];
-        chan_merge(n, mean, m2, nk, p[c] + sd / nk, fmaxf(sq - sd * sd / nk, 0.f));
+    if (c < cols) {
+        for (int k = threadIdx.y; k < n_chunks; k += 8) {
+            const float *p = partial + static_cast<int64_t>(k) * 3 * cols;
+            const float nk = static_cast<float>(min(static_cast<int64_t>(rows_per_chunk), rows - static_cast<int64_t>(k) * rows_per_chunk));
+            const float sd = p[cols + c], sq = p[2 * cols + c];
+            chan_merge(n, mean, m2, nk, p[c] + sd / nk, fmaxf(sq - sd * sd / nk, 0.f));
+        }
     }
-    stats[c] = mean;
-    stats[cols + c] = m2;
-    if (c == 0) stats[2 * cols] = n;
+    sn[threadIdx.y][threadIdx.x] = n; sm[threadIdx.y][threadIdx.x] = mean; s2[threadIdx.y][threadIdx.x] = m2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        for (int j = 1; j < 8; ++j) chan_merge(n, mean, m2, sn[j][threadIdx.x], sm[j][threadIdx.x], s2[j][threadIdx.x]);
+        stats[c] = mean;
+        stats[cols + c] = m2;
+        if (c == 0) stats[2 * cols] = n;
+    }
 }
 
 // ---- forward apply -----------------------------------------------------------------------------------------------
@@ -240,23 +249,29 @@ bn_bwd_kernel(const float *__restrict__ dy, int64_t dy_stride, const float *__re
     }
 }
 
-// sums[0..cols) = sum g, sums[cols..2cols) = sum g xhat (chunks in fixed order); parameter gradients from the LOCAL sums
-// (a data-parallel caller all-reduces them with the other dense gradients): dgamma[c % P] (+)= sum g xhat, dbeta (+)= sum g
-__global__ void bn_bwd_final(const float *__restrict__ partial, int n_chunks, int cols, int period,
-                             float *__restrict__ sums, float *__restrict__ dgamma, float *__restrict__ dbeta,
-                             int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// sums[0..cols) = sum g, sums[cols..2cols) = sum g xhat: 32 columns x 8 chunk lanes per block, fixed order
+__global__ void __launch_bounds__(256)
+bn_bwd_final(const float *__restrict__ partial, int n_chunks, int cols, float *__restrict__ sums) {
+    __shared__ float sa[8][32], sb[8][32];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float a = 0.f, b = 0.f;
     if (c < cols) {
-        float a = 0.f, b = 0.f;
-        for (int k = 0; k < n_chunks; ++k) {
+        for (int k = threadIdx.y; k < n_chunks; k += 8) {
             a += partial[static_cast<int64_t>(k) * 2 * cols + c];
             b += partial[static_cast<int64_t>(k) * 2 * cols + cols + c];
         }
+    }
+    sa[threadIdx.y][threadIdx.x] = a; sb[threadIdx.y][threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        for (int j = 1; j < 8; ++j) { a += sa[j][threadIdx.x]; b += sb[j][threadIdx.x]; }
         sums[c] = a;
         sums[cols + c] = b;
     }
 }
 
+// parameter gradients from the LOCAL sums (a data-parallel caller all-reduces them with the other dense gradients):
+// dgamma[c % P] (+)= sum g xhat, dbeta (+)= sum g
 __global__ void bn_param_grads(const float *__restrict__ sums, int cols, int period, float *__restrict__ dgamma,
                                float *__restrict__ dbeta, int accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,7 +285,7 @@ __global__ void bn_param_grads(const float *__restrict__ sums, int cols, int per
 static inline int bn_rows_per_chunk(int64_t rows, int cols) {
     // enough blocks for ~2 waves, chunks of at least 8 rows; depends on the shape only (reproducible order)
     const int col_blocks = (cols + BN_TX * 4 - 1) / (BN_TX * 4);
-    int r = 256;
+    int r = 4096;
     while (r > 8 && ((rows + r - 1) / r) * col_blocks < 2 * 148) r >>= 1;
     return r;
 }
@@ -302,7 +317,7 @@ extern "C" int tt_bn_stats(const float *x, int64_t rows, int cols, int64_t x_str
     dim3 grid((cols + BN_TX * 4 - 1) / (BN_TX * 4), chunks), block(BN_TX, BN_TY);
     bn_stats_partial<<<grid, block, 0, st>>>(x, rows, cols, x_stride, rpc, partial);
     TT_LAUNCH_CHECK("bn_stats_partial");
-    bn_stats_final<<<(cols + 127) / 128, 128, 0, st>>>(partial, chunks, rows, rpc, cols, stats);
+    bn_stats_final<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, chunks, rows, rpc, cols, stats);
     TT_LAUNCH_CHECK("bn_stats_final");
     return 0;
 }
@@ -349,7 +364,7 @@ extern "C" int tt_bn_bwd_stats(const float *dy, int64_t dy_stride, const float *
                                                   param_period, relu, dropout_p, seed_dev, call_id, partial, nullptr, 0.f,
                                                   nullptr, 0);
     TT_LAUNCH_CHECK("bn_bwd_kernel<stats>");
-    bn_bwd_final<<<(cols + 127) / 128, 128, 0, st>>>(partial, chunks, cols, param_period, sums, dgamma, dbeta, accumulate);
+    bn_bwd_final<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, chunks, cols, sums);
     TT_LAUNCH_CHECK("bn_bwd_final");
     if (dgamma && dbeta) {
         bn_param_grads<<<(param_period + 127) / 128, 128, 0, st>>>(sums, cols, param_period, dgamma, dbeta, accumulate);

@@ -110,35 +110,66 @@ shard_single_kernel(const int64_t *__restrict__ ids, int64_t n_rows, int64_t pad
     }
 }
 
-// in-place exclusive scan of the n counts of one owner block (one CTA per owner); off[n] = total
+// in-place exclusive scan of the n counts of every owner block, two kernels, no single-CTA pass over the batch:
+//   shard_scan_tiles   grid (tiles, world): a tile of SCAN_TILE counts becomes its LOCAL exclusive scan, tile total aside
+//   shard_scan_bases   same grid: base = sum of the totals of the tiles before mine (at most a few dozen), added to the
+//                      tile; the last tile also writes off[n] = grand total and raises the overflow flag
+constexpr int SCAN_TILE = 4096;   // 1024 threads x 4
+
 __global__ void __launch_bounds__(1024)
-shard_scan_kernel(int32_t *__restrict__ send, int64_t block_ints, int64_t off_base, int64_t n, int64_t cap,
-                  int *__restrict__ flags) {
-    __shared__ int32_t sums[1024];
-    int32_t *off = send + static_cast<int64_t>(blockIdx.x) * block_ints + off_base;
-    const int t = threadIdx.x;
-    const int64_t per = (n + 1023) / 1024;
-    const int64_t a = min(n, per * t), b = min(n, a + per);
-    int32_t s = 0;
-    for (int64_t i = a; i < b; ++i) s += off[i];
-    sums[t] = s;
+shard_scan_tiles(int32_t *__restrict__ send, int64_t block_ints, int64_t off_base, int64_t n, int32_t *__restrict__ totals) {
+    __shared__ int32_t warp_sums[32];
+    int32_t *off = send + static_cast<int64_t>(blockIdx.y) * block_ints + off_base;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SCAN_TILE + t * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? off[i0 + k] : 0;
+    const int32_t mine = v[0] + v[1] + v[2] + v[3];
+    int32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 chunk sums
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int32_t v = (t >= o) ? sums[t - o] : 0;
-        __syncthreads();
-        sums[t] += v;
-        __syncthreads();
+    if (warp == 0) {
+        int32_t w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        warp_sums[lane] = w;   // inclusive over warps
     }
-    int32_t run = (t == 0) ? 0 : sums[t - 1];
-    for (int64_t i = a; i < b; ++i) {
-        const int32_t c = off[i];
-        off[i] = run;
-        run += c;
+    __syncthreads();
+    int32_t run = incl - mine + (warp > 0 ? warp_sums[warp - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k < n) off[i0 + k] = run;
+        run += v[k];
     }
-    if (t == 1023) {
-        off[n] = sums[1023];
-        if (sums[1023] > cap) atomicOr(flags, 2);   // capacity overflow: entries beyond cap were dropped
+    if (t == 1023) totals[blockIdx.y * gridDim.x + blockIdx.x] = warp_sums[31];
+}
+
+__global__ void __launch_bounds__(1024)
+shard_scan_bases(int32_t *__restrict__ send, int64_t block_ints, int64_t off_base, int64_t n, int64_t cap,
+                 const int32_t *__restrict__ totals, int *__restrict__ flags) {
+    int32_t *off = send + static_cast<int64_t>(blockIdx.y) * block_ints + off_base;
+    const int32_t *tot = totals + blockIdx.y * gridDim.x;
+    int32_t base = 0;
+    for (unsigned k = 0; k < blockIdx.x; ++k) base += tot[k];     // uniform across the block, L2 hits
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SCAN_TILE + threadIdx.x * 4;
+    if (base != 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < n) off[i0 + k] += base;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const int32_t total = base + tot[blockIdx.x];
+        off[n] = total;
+        if (total > cap) atomicOr(flags, 2);   // capacity overflow: entries beyond cap were dropped
     }
 }
 
@@ -333,9 +364,9 @@ static inline unsigned shard_grid(int64_t threads_needed, int threads) {
 
 extern "C" int tt_shard_route(const int64_t *ids, int64_t n_rows, int len, int64_t padding_idx, int64_t vocab, int world,
                               int32_t *send, int64_t block_ints, int64_t off_base, int64_t rows_base, int64_t cap,
-                              int32_t *n_pad, int *flags, void *stream) {
+                              int32_t *n_pad, int *flags, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace tt;
-    TT_CHECK_ARG(ids && send && flags, "null pointer");
+    TT_CHECK_ARG(ids && send && flags && workspace, "null pointer");
     TT_CHECK_ARG(n_rows > 0 && len > 0 && vocab > 0 && cap > 0, "non-positive size");
     TT_CHECK_ARG(world >= 1 && world <= SHARD_MAX_WORLD, "world must be in [1, 32]");
     TT_CHECK_ARG(off_base >= 0 && rows_base >= off_base + n_rows + 1 && block_ints >= rows_base + cap, "block layout");
@@ -343,6 +374,10 @@ extern "C" int tt_shard_route(const int64_t *ids, int64_t n_rows, int len, int64
     TT_CHECK_ARG(n_rows < (int64_t(1) << 31) && static_cast<int64_t>(n_rows) * len < (int64_t(1) << 31), "too many positions");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int narrow = vocab < (int64_t(1) << 32) ? 1 : 0;
+    const unsigned tiles = static_cast<unsigned>((n_rows + SCAN_TILE - 1) / SCAN_TILE);
+    if (workspace_bytes < sizeof(int32_t) * tiles * world) { set_error("shard_route workspace needs %zu bytes", sizeof(int32_t) * tiles * world); return TT_E_WORKSPACE; }
+    int32_t *totals = static_cast<int32_t *>(workspace);
+    const dim3 scan_grid(tiles, world);
     for (int w = 0; w < world; ++w) {   // unused row slots read as -1 on the owner
         cudaError_t e = cudaMemsetAsync(send + w * block_ints + rows_base, 0xff, sizeof(int32_t) * cap, st);
         if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(shard rows)");
@@ -352,8 +387,9 @@ extern "C" int tt_shard_route(const int64_t *ids, int64_t n_rows, int len, int64
         shard_rows_kernel<false><<<grid, 256, 0, st>>>(ids, n_rows, len, padding_idx, vocab, world, narrow, send, block_ints,
                                                         off_base, rows_base, cap, n_pad, flags);
         TT_LAUNCH_CHECK("shard_rows_kernel<count>");
-        shard_scan_kernel<<<world, 1024, 0, st>>>(send, block_ints, off_base, n_rows, cap, flags);
-        TT_LAUNCH_CHECK("shard_scan_kernel");
+        shard_scan_tiles<<<scan_grid, 1024, 0, st>>>(send, block_ints, off_base, n_rows, totals);
+        shard_scan_bases<<<scan_grid, 1024, 0, st>>>(send, block_ints, off_base, n_rows, cap, totals, flags);
+        TT_LAUNCH_CHECK("shard_scan");
         shard_rows_kernel<true><<<grid, 256, 0, st>>>(ids, n_rows, len, padding_idx, vocab, world, narrow, send, block_ints,
                                                        off_base, rows_base, cap, n_pad, flags);
         TT_LAUNCH_CHECK("shard_rows_kernel<fill>");
@@ -362,8 +398,9 @@ extern "C" int tt_shard_route(const int64_t *ids, int64_t n_rows, int len, int64
         shard_single_kernel<false><<<grid, 256, 0, st>>>(ids, n_rows, padding_idx, vocab, world, narrow, send, block_ints,
                                                           off_base, rows_base, cap, n_pad, flags);
         TT_LAUNCH_CHECK("shard_single_kernel<count>");
-        shard_scan_kernel<<<world, 1024, 0, st>>>(send, block_ints, off_base, n_rows, cap, flags);
-        TT_LAUNCH_CHECK("shard_scan_kernel");
+        shard_scan_tiles<<<scan_grid, 1024, 0, st>>>(send, block_ints, off_base, n_rows, totals);
+        shard_scan_bases<<<scan_grid, 1024, 0, st>>>(send, block_ints, off_base, n_rows, cap, totals, flags);
+        TT_LAUNCH_CHECK("shard_scan");
         shard_single_kernel<true><<<grid, 256, 0, st>>>(ids, n_rows, padding_idx, vocab, world, narrow, send, block_ints,
                                                          off_base, rows_base, cap, n_pad, flags);
         TT_LAUNCH_CHECK("shard_single_kernel<fill>");

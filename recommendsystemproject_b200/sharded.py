@@ -37,14 +37,19 @@ _p, _stream = ops._p, ops._stream
 
 class _CudaShardOps:
     """include/tt_b200.h section 7 + tt_emb_segment_grad_lists + tt_emb_rowwise_adam."""
+    _route_ws: Dict = {}      # tile totals of the route scan (per device; every route call on a stream runs in order)
 
     @staticmethod
     def route(ids, pad, vocab, world, send, block_ints, off_base, rows_base, cap, n_pad, flags):
         lib = _lib.load()
         n_rows, length = ids.shape
+        ws = _CudaShardOps._route_ws.get(ids.device)
+        need = 4 * world * ((n_rows + 4095) // 4096)
+        if ws is None or ws.numel() < need:
+            ws = _CudaShardOps._route_ws[ids.device] = torch.empty(max(need, 1024), dtype=torch.uint8, device=ids.device)
         check(lib.tt_shard_route(_p(ids), n_rows, length, -1 if pad is None else int(pad), vocab, world, _p(send), block_ints,
-                                 off_base, rows_base, cap, _p(n_pad), _p(flags), _stream()), "tt_shard_route")
-        ops._count(3)
+                                 off_base, rows_base, cap, _p(n_pad), _p(flags), _p(ws), ws.numel(), _stream()), "tt_shard_route")
+        ops._count(4)
 
     @staticmethod
     def owner_gather(table, local_rows, world, recv, block_ints, off_base, rows_base, cap, n_rows, pooled, out, block_floats,
