@@ -146,7 +146,9 @@ def test_owner_gather_combine_grad_pack_segment_grad_match_restatement(B, L, W, 
     U = int(r_nu.item())
     assert int(d_nu.item()) == U and U > 0
     assert torch.equal(d_rows.cpu()[:U], r_rows[:U])
-    assert torch.equal(d_grad.cpu()[:U], r_grad[:U])            # same summation order => same bits
+    # ascending positions inside a segment on both sides; segments longer than a chunk are summed chunk-wise by the
+    # kernel (fixed order, but not the restatement's left-to-right order): equal to rounding
+    assert torch.allclose(d_grad.cpu()[:U], r_grad[:U], atol=1e-5, rtol=1e-5)
     assert abs(float(d_sq) - float(r_sq)) <= 1e-5 * float(r_sq)
 
 
