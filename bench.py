@@ -1,25 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the two-tower DSSM hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|c3|c5|c2|c1]
 
-Prints ONE JSON line (rank 0).  A "step" is one full training step of the
-reference loop (training_utils.py:28-60: zero_grad -> model(batch) ->
-compute_loss -> backward -> clip_grad_norm_(1.0) -> Adam.step) on one batch of
-synthetic input shaped like BASELINE.json configs[1] (shipped config.yaml:
-Transformer 2L/4H/d64 user tower, B=512, 10 hard-negative slabs per step).
+Prints ONE JSON line (rank 0).  Default workload "all":
 
-  value : samples/s with the batch already resident in HBM (CUDA-graph replay,
-          CUDA events, L2 flushed between steps outside the timed region)
-  e2e   : same metric through the public API with HOST (pinned) batches: H2D
-          copy of the batch + step + D2H read of the loss inside the timed region
-  roofline / kernels : the dominant kernel of the step and the hot-path kernels
-          at their BASELINE-scale shapes, algorithmic bytes (flops) / CUDA-event
-          time against MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle port of the same step (oracle/twotower_oracle.py)
-          timed on this box's host cores, bounded sample
+  headline  BASELINE configs[2], INTEGRATED: one training step of the reference loop (training_utils.py:28-60:
+            zero_grad -> model(batch) -> compute_loss -> backward -> clip_grad_norm_(1.0) -> Adam.step) on the 8-feature
+            D=128 model with row-sharded tables (owner = row % W), data-parallel towers with global BatchNorm statistics
+            and the in-batch softmax over the GLOBAL batch of 65536 -- the same global batch at every N (strong scaling)
+  c5_topk   BASELINE configs[4]: top-100 over a 10M-item corpus sharded over the GPUs, Q=16384 queries per step
+  c2_step   BASELINE configs[1]: the shipped config.yaml step (Transformer encoder, B=512, 10 hard-negative slabs)
 
---impl reference runs ONLY the CPU port (no GPU work) on the same config.
+  value : samples/s with the batch already resident in HBM (CUDA-graph replay, CUDA events on the launching stream)
+  e2e   : same metric through the public API with HOST (pinned) batches: H2D + step + D2H read of the loss, timed
+  roofline : the step's dominant kernel timed live with CUDA events at the step's own shapes, algorithmic flops / bytes
+          against MEASURED_PEAKS.json; `kernels` lists the other hot kernels the same way
+  cpu_baseline : the reference's own CPU code (baseline/_ref, unmodified; the oracle port if it is absent) on a bounded
+          sample of the headline workload, N = 1 only
+
+--impl reference runs ONLY that CPU arm (rank 0; other ranks exit) and prints the same line shape.
 """
 import argparse
 import json
@@ -125,47 +125,112 @@ def workload(name):
     raise SystemExit(f"unknown workload {name}")
 
 
-# ----------------------------------------------------------------------------- CPU port (reference arm)
-def cpu_port_steps(wl, steps, warmup, seed=2):
-    """Time the CPU oracle port of the training step with all host threads."""
+# ----------------------------------------------------------------------------- CPU arm (reference / port)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_classes():
+    """(GenericTower, TwoTowerModel) of the UNMODIFIED reference from baseline/_ref (a verbatim copy of the reference's
+    Python package made by __graft_entry__.build() in the authoring container; git-ignored, shipped to the GPU box), or
+    None.  The reference's `project` is a namespace package and this repo's `project/` shim a regular one: the repo
+    root is kept off sys.path while importing, then restored."""
+    if not os.path.isdir(os.path.join(REF_DIR, "project", "models", "TwoTower")):
+        return None
+    saved_path = list(sys.path)
+    saved_mods = {k: v for k, v in sys.modules.items() if k == "project" or k.startswith("project.")}
+    for k in saved_mods:
+        del sys.modules[k]
+    sys.path[:] = [REF_DIR] + [q for q in sys.path if os.path.abspath(q or ".") != ROOT]
+    try:
+        from project.models.TwoTower.GenericTower import GenericTower
+        from project.models.TwoTower.TwoTowerModel import TwoTowerModel
+        return GenericTower, TwoTowerModel
+    except Exception:  # noqa: BLE001
+        return None
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k == "project" or k.startswith("project.")]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+
+
+CPU_C3 = dict(B=4096, L=200, v_user=1_000_001, v_item=1_000_001)
+
+
+def cpu_arm_c3(steps, warmup):
+    """The reference step on a BOUNDED sample of the headline workload: the C3 model with its three big tables cut to
+    1M rows and B=4096 (at full size the reference needs 154 GB of dense Adam state for the user table alone and an
+    18 GB logits matrix per step), shipped dropout, all host threads.  Returns (times, kind, sample)."""
+    from recommendsystemproject_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    c = CPU_C3
+    cfg = synth.config_c3(v_user=c["v_user"], v_item=c["v_item"], dropout=0.1, shard=False)
+    batch = synth.make_batch_c3(B=c["B"], L=c["L"], v_user=c["v_user"], v_item=c["v_item"], seed=303)
+    ref = reference_classes()
+    sample = (f"C3 model with the user / history / item tables cut to {c['v_user'] - 1} rows and B={c['B']} (L={c['L']}, D=128, "
+              f"dropout 0.1), {steps} full steps, fp32, {os.cpu_count()} threads")
+    times = []
+    if ref is not None:
+        GenericTower, TwoTowerModel = ref
+        torch.manual_seed(0)
+        model = TwoTowerModel(GenericTower(cfg, "user_tower"), GenericTower(cfg, "item_tower"), *synth.MAPS_C3).train()
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)        # train_twotower.py:111
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()                                          # training_utils.py:31-56
+            u, i, hn = model(batch)
+            loss = model.compute_loss(u, i, hard_neg_emb=hn, item_ids=batch["item_tower"]["sparse"][:, 0], temperature=0.05)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            float(loss.item())
+            if s >= warmup:
+                times.append(time.perf_counter() - t0)
+        return times, "reference", "unmodified reference (baseline/_ref): " + sample
     from oracle import twotower_oracle as O
     import recommendsystemproject_b200 as tt
-    torch.set_num_threads(os.cpu_count() or 1)
-    cfg = wl["cfg"]
-    # parity runs use dropout 0; the port has no dropout, which only makes the CPU arm faster
     torch.manual_seed(0)
-    model = tt.TwoTowerModel(tt.GenericTower(cfg, "user_tower"), tt.GenericTower(cfg, "item_tower"), *wl["maps"])
+    model = tt.TwoTowerModel(tt.GenericTower(cfg, "user_tower"), tt.GenericTower(cfg, "item_tower"), *synth.MAPS_C3)
     state = {k: v.clone() for k, v in model.state_dict().items()}
     opt = {"step": 0, "m": {}, "v": {}}
-    batch = wl["batch_fn"](seed)
-    times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        O.train_step(batch, state, opt, cfg, *wl["maps"], temperature=wl["T"], lr=wl["lr"])
-        dt = time.perf_counter() - t0
+        O.train_step(batch, state, opt, cfg, *synth.MAPS_C3, temperature=0.05, lr=5e-4)
         if s >= warmup:
-            times.append(dt)
-    return times
+            times.append(time.perf_counter() - t0)
+    return times, "port", "CPU port (oracle/twotower_oracle.py, no dropout; baseline/_ref absent): " + sample
+
+
+def c3_config_dict(world, B_global, zipf, peaks_source):
+    """The `config` of the headline line -- shared by both arms so that the driver sees the same workload."""
+    v_user = 12_500_000 * world
+    return {"workload": f"BASELINE configs[2], integrated step: 8 sparse features D=128 (user_id {v_user} rows = 12.5M per GPU, u_cat1 1e5, "
+                        f"u_cat2 1e3, u_cat3 32, hist_item_ids 10M x L=200 ragged mean-pooled; item_id 10M, i_cat 1e4, i_year 152), "
+                        f"MLP [256,128]->128, in-batch softmax over the global batch {B_global}, dropout 0.1, fwd+bwd+clip+Adam",
+            "global_batch": B_global, "per_gpu_batch": B_global // world,
+            "parallelism": f"row-sharded tables (>= 1 MB: 5 of 8, owner=row%W) x{world} + data-parallel towers dp{world}, global BatchNorm statistics",
+            "ids": "zipf(1.05)" if zipf else "uniform (every looked-up row distinct: HBM worst case)",
+            "l2": "working set (tables + Adam state, > 40 GB per GPU) far exceeds L2", "peaks": peaks_source,
+            "step": "one CUDA graph per rank, NCCL collectives inside"}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = workload(args.workload)
-    steps = max(1, min(args.steps, 20))
-    times = cpu_port_steps(wl, steps, max(1, min(args.warmup, 3)))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    times, kind, sample = cpu_arm_c3(steps, warm)
     total = sum(times)
-    value = wl["B"] * len(times) / total
+    value = CPU_C3["B"] * len(times) / total
     cores = os.cpu_count() or 1
     line = {
-        "impl": "reference", "metric": "train samples/sec (fwd+bwd+clip+Adam)", "value": value, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "arm": "CPU port of the reference step (oracle/twotower_oracle.py), torch fp32, "
-                                                  "dropout omitted"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} full steps of B={wl['B']}"},
+        "impl": "reference", "metric": "train samples/sec (fwd+bwd+clip+Adam), integrated C3 step", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": c3_config_dict(max(world, 1), args.c3_batch, args.zipf, load_peaks()["source"]),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,7 +275,7 @@ def kernel_rooflines(peaks, flush, quick=False):
     out.append({"kernel": "gather_pool_kernel", "workload": f"C3 slice: B={B} L={L} ragged mean-pool D={D} fp32, V={V}",
                 "bound": "hbm", "ms": ms, "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg,
-                "traffic": None if quick else 3.495e9, "traffic_source": "profiles/r1_hot_kernels_ncu.md (dram read+write, same shape)"})
+                "traffic": None, "traffic_note": "ncu dram read+write for this shape: profiles/r1_hot_kernels_ncu.md (3.49 GB)"})
     # --- sorted-segment gradient + row-wise Adam on the same ids
     g = torch.randn(B, D, device=dev)
     sq = torch.zeros(1, device=dev)
@@ -221,7 +286,9 @@ def kernel_rooflines(peaks, flush, quick=False):
     ms, best = time_op(seg, 5, flush)
     rows, row_grad, nu = res["r"]
     U = int(nu.item())
-    alg = B * L * 8 + n_valid * D * 4 + U * (D * 4 + 8)
+    # strict algorithmic bytes: ids once, the [B, D] upstream gradient once (its per-position re-reads are L2 hits),
+    # one gradient row + one row id written per unique row
+    alg = B * L * 8 + B * D * 4 + U * (D * 4 + 8)
     out.append({"kernel": "emb_segment_grad (keys + cub radix sort + scans + seg_reduce_rows_wide + norm)",
                 "workload": f"same ids, U={U} unique rows", "bound": "hbm", "ms": ms, "best_ms": best, "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg})
@@ -234,7 +301,7 @@ def kernel_rooflines(peaks, flush, quick=False):
     out.append({"kernel": "rowwise_adam_kernel", "workload": f"U={U} rows x D={D} fp32 state", "bound": "hbm", "ms": ms,
                 "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg,
-                "traffic": None if quick else 17.27e9, "traffic_source": "profiles/r1_hot_kernels_ncu.md (dram read+write, same shape)"})
+                "traffic": None, "traffic_note": "ncu dram read+write for this shape: profiles/r1_hot_kernels_ncu.md (17.27 GB)"})
     del table, m, v, ids, g, rows, row_grad, res
     torch.cuda.empty_cache()
     # --- C4 fused CE, tcgen05/TMA bf16 path, forward + backward: the B x (B+H) logits live only in TMEM
@@ -318,7 +385,8 @@ def build_c3(rank, world, dev, B_global, dropout=0.1, zipf=False, users_per_gpu=
     for m in model.modules():
         if hasattr(m, "gather_on_save"):
             m.gather_on_save = False
-    opt = tt.FusedTwoTowerOptimizer(model, lr=5e-4, max_grad_norm=1.0, table_mode="sparse")
+    # replicated (< 1 MB) tables: dense gradients, all-reduced with the tower parameters; row-sharded: owner-side row-wise Adam
+    opt = tt.FusedTwoTowerOptimizer(model, lr=5e-4, max_grad_norm=1.0, table_mode="dense")
     B = B_global // world
     host = [synth.make_batch_c3(B=B, L=L, v_user=v_user, v_item=v_item, seed=300 + 17 * rank + s, zipf=zipf) for s in range(2)]
     host = [tree_to(h, None, pin=True) for h in host]
@@ -328,7 +396,7 @@ def build_c3(rank, world, dev, B_global, dropout=0.1, zipf=False, users_per_gpu=
     return model, opt, step, host, dev_batch, cfg, v_user
 
 
-def run_c3(args, rank, local_rank, world, dev, peaks, as_dict=False):
+def run_c3(args, rank, local_rank, world, dev, peaks):
     """BASELINE configs[2], integrated: gather (row-sharded) -> towers -> global in-batch softmax -> backward -> global-norm
     clip -> dense Adam + row-wise Adam, global batch 65536 at every N (strong scaling in the batch)."""
     import torch.distributed as dist
@@ -388,35 +456,56 @@ def run_c3(args, rank, local_rank, world, dev, peaks, as_dict=False):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
-    # per-kernel device times of one step (CUDA events around eager phases would perturb the graph: use the profiler-free
-    # kernel section below instead); dominant kernel + roofline come from kernel_rooflines at this rank's shapes
+    final_loss = float(loss_host)
+    launches = step.launches_per_step or 0
+    a2a_bytes = getattr(step, "a2a_bytes_per_step", 0)
+    del staging
+    # ---- the step's dominant kernel (profiles/r2_c3_step_launches.md: ce_tc_kernel, three launches = ~1/3 of the step), timed
+    # live at the step's own shapes: this rank's B/W user rows against the global batch of items, forward + backward
+    roof = c3_dominant_kernel(B, B_global, 128, peaks, dev)
+    del step, opt, model
     if rank != 0:
         return None
     ms = dev_ms / args.steps
     h2d = tree_bytes(host[0])
-    grp = model.shard_group
     line = {"metric": "train samples/sec (fwd+bwd+clip+Adam), integrated C3 step", "value": B_global * args.steps / (dev_ms / 1e3),
             "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 tables + TF32 tower GEMMs + bf16 tcgen05 loss",
-            "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: 8 sparse features D=128 (user_id {v_user - 1} rows = 12.5M per GPU, u_cat1 1e5, u_cat2 1e3, "
-                                   f"u_cat3 32, hist_item_ids 10M x L=200 ragged mean-pooled; item_id 10M, i_cat 1e4, i_year 152), MLP [256,128]->128, "
-                                   f"in-batch softmax over the global batch {B_global}, dropout 0.1; tables >= 1 MB row-sharded owner=row%W "
-                                   f"({len(grp.tables)} tables), towers data-parallel with global BatchNorm statistics",
-                       "global_batch": B_global, "per_gpu_batch": B, "parallelism": f"row-sharded tables x{world} + dp{world}",
-                       "ids": "zipf(1.05)" if args.zipf else "uniform (every looked-up row distinct: HBM worst case)",
-                       "l2": "working set (tables + Adam state, > 40 GB per GPU) far exceeds L2", "peaks": peaks["source"],
-                       "step": "one CUDA graph per rank, NCCL collectives inside"},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (tables, activations, optimizer; tower GEMMs TF32; loss kernel bf16 operands, fp32 accumulate)",
+            "data": "synthetic", "config": c3_config_dict(world, B_global, args.zipf, peaks["source"]),
             "e2e": {"value": B_global * args.steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                     "note": "pinned host batch -> H2D on a copy stream one step ahead -> D2D into the graph's buffers -> step -> loss read-back"},
-            "gpu_launches": (step.launches_per_step or 0) * args.steps * 2, "gpu_launches_per_step": step.launches_per_step,
-            "nvlink_bytes_per_step_per_gpu": getattr(step, "a2a_bytes_per_step", 0), "hist_valid_positions_per_gpu": n_valid,
-            "clocks": clocks, "final_loss": float(loss_host)}
-    if as_dict:
-        return line
-    print(json.dumps(line), flush=True)
+            "gpu_launches": launches * args.steps * 2, "gpu_launches_per_step": launches,
+            "nvlink_bytes_per_step_per_gpu": a2a_bytes, "hist_valid_positions_per_gpu": n_valid,
+            "roofline": roof, "clocks": clocks, "final_loss": final_loss}
     return line
+
+
+def c3_dominant_kernel(B_loc, B_glob, D, peaks, dev):
+    """ce_tc_kernel (tcgen05): FWD + BWD_X + BWD_Y launches at [B_loc x B_glob], CUDA events on the launching stream."""
+    from recommendsystemproject_b200 import ops
+    gen = torch.Generator(device=dev).manual_seed(4)
+    u = torch.nn.functional.normalize(torch.randn(B_loc, D, device=dev, generator=gen), dim=1).requires_grad_(True)
+    it = torch.nn.functional.normalize(torch.randn(B_loc, D, device=dev, generator=gen), dim=1).requires_grad_(True)
+    others = B_glob - B_loc
+    pool = torch.nn.functional.normalize(torch.randn(others, D, device=dev, generator=gen), dim=1).requires_grad_(True) if others else None
+    ids = torch.randperm(B_glob, device=dev, generator=gen)[:B_loc] + 1
+    res = {}
+
+    def fwd_bwd():
+        res["l"] = ops.fused_inbatch_ce(u, it, ids, None, pool, 0.05, precision="bf16")[0]
+        res["l"].backward()
+    ms, best = time_op(fwd_bwd, 5, lambda: None)
+    flops = 6.0 * B_loc * B_glob * D
+    return {"bound": "tensor", "kernel": "ce_tc_kernel<fwd> + <bwd dU> + <bwd dI> (tcgen05 bf16, fp32 accumulate in TMEM): the fused global in-batch "
+                                         "softmax CE of the step, incl. its id sort / bf16 conversion / reductions",
+            "workload": f"{B_loc} local user rows x {B_glob} global item columns, D={D}, T=0.05", "ms": ms, "best_ms": best,
+            "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "peak_sustained": peaks["bf16_tflops_sustained"],
+            "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["bf16_tflops"],
+            "frac_of_sustained": flops / ms / 1e9 / peaks["bf16_tflops_sustained"], "alg_flops": flops, "traffic": None,
+            "l2": "operands (B x D bf16, <= 17 MB) are L2-resident by design; inputs are not flushed between repetitions",
+            "note": "algorithmic flops = 2 (fwd) + 4 (bwd) x B_loc x B_glob x D; the two backward passes recompute the logits (not counted)"}
 
 
 def _copy_into(dst, src):
@@ -482,7 +571,7 @@ def run_c5(args, rank, local_rank, world, dev, peaks):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank != 0:
-        return
+        return None
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     flops = 2.0 * Q * N_total * D / world      # per GPU per step
     ms = dev_ms / args.steps
@@ -498,49 +587,20 @@ def run_c5(args, rank, local_rank, world, dev, peaks):
             "roofline": {"bound": "tensor", "kernel": "topk_tc_kernel (sampling pass + full pass) + topk_tc_stage2 + topk_merge",
                          "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": flops / ms / 1e9 / peaks["bf16_tflops"], "traffic": None, "alg_flops": flops},
-            "cpu_baseline": None, "clocks": clocks, "resampled_queries": ops.topk_stats.get("resampled"),
+            "clocks": clocks, "resampled_queries": ops.topk_stats.get("resampled"),
             "fp32_fallback_queries": ops.topk_stats.get("unverified")}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ----------------------------------------------------------------------------- main GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="c2")
-    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
-    ap.add_argument("--quick", action="store_true", help="smaller kernel-roofline shapes")
-    ap.add_argument("--cpu-steps", type=int, default=8)
-    ap.add_argument("--c3-batch", type=int, default=65536, help="global batch of the integrated C3 step")
-    ap.add_argument("--zipf", action="store_true", help="Zipf(1.05) item ids instead of uniform")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
-    args.warmup = max(args.warmup, 3)
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+def run_c2(args, rank, local_rank, world, dev, peaks, wl_name="c2"):
+    """BASELINE configs[1] (or configs[0] with wl_name='c1'): the shipped-config training step, one CUDA graph; at N > 1
+    data-parallel replicas of the same step (per-rank batch, all-reduce of the flat gradient buffer)."""
     import torch.distributed as dist
     import recommendsystemproject_b200 as tt
-    from recommendsystemproject_b200 import _lib, ops
-    torch.cuda.set_device(local_rank)
-    _lib.require_device()
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    peaks = load_peaks()
-    if args.workload in ("c3", "c5"):
-        (run_c3 if args.workload == "c3" else run_c5)(args, rank, local_rank, world, dev, peaks)
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-    wl = workload(args.workload)
+    from recommendsystemproject_b200 import ops
+    wl = workload(wl_name)
+    steps = args.steps
 
     torch.manual_seed(0)
     model = tt.TwoTowerModel(tt.GenericTower(wl["cfg"], "user_tower"), tt.GenericTower(wl["cfg"], "item_tower"),
@@ -605,10 +665,7 @@ def main():
     final_loss = float(loss_host)
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        return None
 
     B = wl["B"]
     value = world * B * args.steps / (dev_ms / 1e3)
@@ -648,41 +705,101 @@ def main():
             torch.backends.cuda.matmul.allow_tf32 = False
             torch.backends.cudnn.allow_tf32 = False
 
-    kernels = []
-    if not args.no_kernels:
-        try:
-            kernels = kernel_rooflines(peaks, flush, quick=args.quick)
-        except torch.cuda.OutOfMemoryError as ex:  # report, never hide
-            kernels = [{"error": f"kernel roofline section skipped: {ex}"}]
     # dominant hand-written kernel of the C2 step (see profiles/r1_c2_step_launches_fused.md); its standalone roofline
     roof = step_roofline(model, wl, dev, peaks, flush, dev_batch)
 
-    cpu = None
-    try:
-        times = cpu_port_steps(wl, args.cpu_steps, 1)
-        cpu = {"value": B * len(times) / sum(times), "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"{len(times)} full steps of B={B} (oracle/twotower_oracle.py, torch fp32, all host threads)"}
-    except Exception as ex:  # noqa: BLE001
-        cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {ex}"}
-
-    line = {
+    return {
         "metric": "train samples/sec (fwd+bwd+clip+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "tf32_towers": tf32,
+        "scaling": "weak", "dtype": "f32", "data": "synthetic", "tf32_towers": tf32,
         "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "parallelism": f"dp{world} (per-rank in-batch negatives, gradients averaged)" if world > 1 else "single",
                    "l2": "flushed between steps by an untimed 256 MiB write; step = one CUDA-graph replay",
-                   "table_mode": "dense Adam on every table row (reference semantics)", "peaks": peaks["source"]},
+                   "table_mode": "dense Adam on every table row (reference semantics)"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": (launches_per_step or 0) * args.steps * 2,
-        "gpu_launches_per_step": launches_per_step,
-        "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "final_loss": final_loss,
+        "gpu_launches_per_step": launches_per_step, "roofline": roof, "final_loss": final_loss, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="all", help="all (headline C3 + C5 + C2 sub-objects) | c3 | c5 | c2 | c1")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
+    ap.add_argument("--quick", action="store_true", help="smaller kernel-roofline shapes")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--c3-batch", type=int, default=65536, help="global batch of the integrated C3 step")
+    ap.add_argument("--zipf", action="store_true", help="Zipf(1.05) item ids instead of uniform")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
+    from recommendsystemproject_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    _lib.require_device()
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    wl = args.workload
+    line = None
+    if wl in ("all", "c3"):
+        line = run_c3(args, rank, local_rank, world, dev, peaks)
+    elif wl == "c5":
+        line = run_c5(args, rank, local_rank, world, dev, peaks)
+    else:
+        line = run_c2(args, rank, local_rank, world, dev, peaks, wl)
+        if line is not None:
+            line["vs_baseline"] = None
+    if wl == "all":
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        sub = argparse.Namespace(**vars(args))
+        sub.steps = max(3, min(args.steps, 20))
+        c5 = run_c5(sub, rank, local_rank, world, dev, peaks)
+        gc.collect()
+        torch.cuda.empty_cache()
+        c2 = run_c2(sub, rank, local_rank, world, dev, peaks, "c2")
+        if line is not None:
+            line["c5_topk"], line["c2_step"] = c5, c2
+        gc.collect()
+        torch.cuda.empty_cache()
+    if rank == 0 and wl in ("all", "c3"):
+        flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        kernels = []
+        if not args.no_kernels and world == 1:      # hot-path kernels at BASELINE-scale shapes, one GPU's worth
+            try:
+                kernels = kernel_rooflines(peaks, lambda: flush_buf.fill_(1), quick=args.quick)
+            except torch.cuda.OutOfMemoryError as ex:  # report, never hide
+                kernels = [{"error": f"kernel roofline section skipped: {ex}"}]
+        line["kernels"] = kernels
+        cpu = None
+        if world == 1:      # bounded CPU sample of the headline workload (never at N > 1: the other ranks would idle)
+            try:
+                times, kind, sample = cpu_arm_c3(args.cpu_steps, 1)
+                cpu = {"value": CPU_C3["B"] * len(times) / sum(times), "unit": "samples/s", "cores": os.cpu_count() or 1,
+                       "kind": kind, "sample": sample}
+            except Exception as ex:  # noqa: BLE001
+                cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {ex}"}
+        line["cpu_baseline"] = cpu
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)     # captured graphs hold NCCL work: skip communicator teardown at interpreter exit
 
 
 def step_roofline(model, wl, dev, peaks, flush, batch):

@@ -122,6 +122,9 @@ class ShardedTrainStep:
         if batch_has_hard_negatives(example_batch) and global_loss and self.world > 1:
             raise ops.TTError("ShardedTrainStep: per-row hard negatives with a global in-batch loss are not supported")
         self.static_batch = _clone_tree(example_batch)
+        if self.world > 1 and optimizer.sparse_tables:
+            raise ops.TTError("ShardedTrainStep on several ranks: replicated tables need table_mode='dense' (their gradients "
+                              "ride the dense all-reduce); only row-sharded tables are updated touched-rows-only")
         if self.world > 1:
             ops.bn_sync.world, ops.bn_sync.group = self.world, None
             for m in model.modules():
