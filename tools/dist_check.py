@@ -138,11 +138,12 @@ def cut(o):
 lbatch = mv(cut(gbatch))
 # replicated (small) tables stay dense: their gradients ride the all-reduce of the flat buffer; row-sharded ones are
 # always touched-rows-only on their owner
-opt_s = tt.FusedTwoTowerOptimizer(sh_model, lr=1e-2, max_grad_norm=1.0, table_mode="dense")
+# eps = 1e-3 >> |g| keeps Adam's first step linear in g (rounding-level gradient differences stay rounding-level)
+opt_s = tt.FusedTwoTowerOptimizer(sh_model, lr=1e-2, eps=1e-3, max_grad_norm=1.0, table_mode="dense")
 step_s = tdist.ShardedTrainStep(sh_model, opt_s, lbatch, 0.05, loss_precision="fp32")
 loss_s = step_s().clone()
 step_s.check_flags()
-opt_u = tt.FusedTwoTowerOptimizer(ref_model, lr=1e-2, max_grad_norm=1.0, table_mode="sparse")
+opt_u = tt.FusedTwoTowerOptimizer(ref_model, lr=1e-2, eps=1e-3, max_grad_norm=1.0, table_mode="sparse")
 gb = mv(gbatch)
 opt_u.zero_grad()
 u_, i_, _ = ref_model(gb)
@@ -159,10 +160,9 @@ for k, v in ref_model.state_dict().items():
     if v.dtype.is_floating_point:
         d = (new_state[k].float() - v.float()).abs()
         worst = max(worst, float(d.max()))
-        n_bad += int((d > 1e-4).sum())
+        n_bad += int((d > 5e-6).sum())
         n_all += d.numel()
-# the first Adam step moves every touched element by ~lr * sign(g): elements whose gradient is rounding noise may differ
-t6c = n_bad < 1e-3 * n_all
+t6c = n_bad == 0
 t6 &= t6c
 # second step: the updated weights of both runs must give the same loss again
 loss_s2 = step_s().clone()
