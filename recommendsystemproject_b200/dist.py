@@ -169,11 +169,15 @@ class ShardedTrainStep:
         shard = {}
         if grp and self.restore_tables:
             shard = {n: (t.weight.detach().clone(), t.exp_avg.clone(), t.exp_avg_sq.clone()) for n, t in grp.tables.items()}
-        return state, o.flat_m.clone(), o.flat_v.clone(), o.step_dev.clone(), shard
+        tables = {k: (m.clone(), v.clone()) for k, (m, v) in o.table_state.items()}
+        return state, o.flat_m.clone(), o.flat_v.clone(), o.step_dev.clone(), shard, tables
 
     def _restore(self, snap):
-        state, m, v, step, shard = snap
+        state, m, v, step, shard, tables = snap
         o = self.opt
+        for k, (tm, tv) in tables.items():
+            o.table_state[k][0].copy_(tm)
+            o.table_state[k][1].copy_(tv)
         with torch.no_grad():
             for dst, src in state:
                 dst.copy_(src)
