@@ -271,6 +271,22 @@ TT_API int tt_linear_wgrad_workspace(int64_t rows, int n_out, int n_in, size_t *
 TT_API int tt_linear_wgrad(const float *grad_out, const float *input, int64_t rows, int n_out, int n_in, float *grad_weight,
                     float *grad_bias, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
 
+/* TF32 tensor-core versions of the three Linear GEMMs above (tcgen05.mma kind::tf32 straight from the fp32 operands,
+ * fp32 accumulation in TMEM, TMA staging; the weight is read through an MN-major descriptor for the input gradient and
+ * both operands are for the weight gradient, so nothing is transposed or converted in memory).  Same contracts; used
+ * when the caller allows TF32 matmuls (torch.backends.cuda.matmul.allow_tf32).  Needs n_out, n_in multiples of 4 and
+ * 16-byte aligned pointers (tt_linear_tc_supported).  Weight gradient: split over the rows across the chip, partials
+ * added in a fixed order. */
+TT_API int tt_linear_tc_supported(int64_t rows, int n_out, int n_in);
+TT_API int tt_linear_fwd_tc(const float *input, const float *weight, const float *bias, int64_t rows, int n_out, int n_in,
+                     int relu, float *out, void *stream);
+TT_API int tt_linear_dgrad_tc(const float *grad_out, const float *weight, int64_t rows, int n_out, int n_in,
+                       float *grad_input, void *stream);
+TT_API int tt_linear_wgrad_tc_workspace(int64_t rows, int n_out, int n_in, size_t *bytes_host);
+TT_API int tt_linear_wgrad_tc(const float *grad_out, const float *input, int64_t rows, int n_out, int n_in,
+                       float *grad_weight, float *grad_bias, int accumulate, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
 /* ------------------------------------------------------------------------
  * 8. BatchNorm1d in training mode with the MLP block's ReLU + Dropout fused in (GenericTower.py:234, Tower.py:16-21:
  * Linear -> BatchNorm1d -> ReLU -> Dropout), statistics optionally spanning several ranks (data-parallel towers: the

@@ -310,8 +310,10 @@ def _direct_grad(p) -> bool:
 
 
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b: forward, input gradient and the one-pass weight + bias gradient are library kernels
-    (linear_grad.cu), one launch each (two for the weight gradient)."""
+    """y = x W^T + b: forward, input gradient and the one-pass weight + bias gradient are library kernels, one launch
+    each (two-three for the weight gradient).  Exact fp32 FMA kernels (linear_grad.cu) by default -- the parity path;
+    with torch.backends.cuda.matmul.allow_tf32 the tcgen05 kind::tf32 kernels of linear_tc.cu (fp32 operands read as
+    TF32 by the tensor core, fp32 accumulation)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -319,14 +321,16 @@ class LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.bias_ref = bias
-        ctx.tf32 = bool(torch.backends.cuda.matmul.allow_tf32)
-        if ctx.tf32:     # the caller asked for TF32 tensor-core products: cuBLAS has them, the fp32 FMA kernels below do not
-            return F.linear(x, weight, bias)
         lib = _lib.load()
         n_out, n_in = weight.shape
         x2 = x.reshape(-1, n_in).contiguous()
+        ctx.tf32 = bool(torch.backends.cuda.matmul.allow_tf32) and bool(lib.tt_linear_tc_supported(x2.shape[0], n_out, n_in)) \
+            and weight.is_contiguous()
         out = torch.empty(x2.shape[0], n_out, dtype=torch.float32, device=x.device)
-        check(lib.tt_linear_fwd(_p(x2), _p(weight), _p(bias), x2.shape[0], n_out, n_in, 0, _p(out), _stream()), "tt_linear_fwd")
+        if ctx.tf32:
+            check(lib.tt_linear_fwd_tc(_p(x2), _p(weight), _p(bias), x2.shape[0], n_out, n_in, 0, _p(out), _stream()), "tt_linear_fwd_tc")
+        else:
+            check(lib.tt_linear_fwd(_p(x2), _p(weight), _p(bias), x2.shape[0], n_out, n_in, 0, _p(out), _stream()), "tt_linear_fwd")
         _count()
         return out.reshape(*x.shape[:-1], n_out)
 
@@ -339,11 +343,12 @@ class LinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, n_in).contiguous()
         rows = g2.shape[0]
         gx = None
-        if ctx.needs_input_grad[0] and ctx.tf32:
-            gx = (g2 @ weight).reshape(x.shape)
-        elif ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0]:
             gx = torch.empty(rows, n_in, dtype=torch.float32, device=g2.device)
-            check(lib.tt_linear_dgrad(_p(g2), _p(weight), rows, n_out, n_in, _p(gx), _stream()), "tt_linear_dgrad")
+            if ctx.tf32:
+                check(lib.tt_linear_dgrad_tc(_p(g2), _p(weight), rows, n_out, n_in, _p(gx), _stream()), "tt_linear_dgrad_tc")
+            else:
+                check(lib.tt_linear_dgrad(_p(g2), _p(weight), rows, n_out, n_in, _p(gx), _stream()), "tt_linear_dgrad")
             _count()
             gx = gx.reshape(x.shape)
         gw = gb = None
@@ -351,19 +356,20 @@ class LinearFn(torch.autograd.Function):
             if wgrad_shapes is not None:
                 wgrad_shapes.append((rows, n_out, n_in))
             nbytes = ctypes.c_size_t(0)
-            check(lib.tt_linear_wgrad_workspace(rows, n_out, n_in, ctypes.byref(nbytes)), "tt_linear_wgrad_workspace")
+            ws_fn, fn, name = ((lib.tt_linear_wgrad_tc_workspace, lib.tt_linear_wgrad_tc, "tt_linear_wgrad_tc") if ctx.tf32 else
+                               (lib.tt_linear_wgrad_workspace, lib.tt_linear_wgrad, "tt_linear_wgrad"))
+            check(ws_fn(rows, n_out, n_in, ctypes.byref(nbytes)), name + "_workspace")
             ws = _ws(nbytes.value, g2.device)
             bias = ctx.bias_ref
             if _direct_grad(weight) and (bias is None or _direct_grad(bias)):
                 # the optimizer owns preallocated .grad buffers: add into them here and hand autograd nothing
                 # (saves one accumulate kernel per parameter and step)
-                check(lib.tt_linear_wgrad(_p(g2), _p(x2), rows, n_out, n_in, _p(weight.grad), _p(None if bias is None else bias.grad),
-                                          1, _p(ws), ws.numel(), _stream()), "tt_linear_wgrad")
+                check(fn(_p(g2), _p(x2), rows, n_out, n_in, _p(weight.grad), _p(None if bias is None else bias.grad),
+                         1, _p(ws), ws.numel(), _stream()), name)
             else:
                 gw = torch.empty_like(weight)
                 gb = torch.empty(n_out, dtype=torch.float32, device=g2.device) if ctx.has_bias else None
-                check(lib.tt_linear_wgrad(_p(g2), _p(x2), rows, n_out, n_in, _p(gw), _p(gb), 0, _p(ws), ws.numel(), _stream()),
-                      "tt_linear_wgrad")
+                check(fn(_p(g2), _p(x2), rows, n_out, n_in, _p(gw), _p(gb), 0, _p(ws), ws.numel(), _stream()), name)
             _count(2)
         return gx, gw, gb
 
