@@ -9,8 +9,11 @@
 //   DGRAD  dX[R, I] = dY[R, O] . W[O, I]                  A = dY K-major,   B = W  MN-major (no transposed copy)
 //   WGRAD  dW[O, I] = dY[R, O]^T . X[R, I]                A = dY MN-major,  B = X  MN-major, split over R across the
 //                                                         chip; partials added in a fixed order (deterministic)
-// MN-major operands are what SWIZZLE_128B TMA boxes of [32 k-rows][32 fp32] already are (canonical layout
-// ((4,8,m),(8,k)) in 16-byte units: 8-row atoms 1024 B apart along K, 32-element blocks one box apart along M/N).
+// MN-major TF32 operands have ONE legal shared-memory layout (CUTLASS sm100_common.inl: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"): 128-byte rows of 32 fp32, one row per k, swizzled in 32-byte chunks
+// with a 4-row period (UMMA layout type SWIZZLE_128B_BASE32B, canonical ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte
+// units) -- exactly what a TMA box of [32 k-rows][32 fp32] with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes: 4-row atoms
+// 512 B apart along K (SBO), 32-element blocks one box = 4096 B apart along M/N (LBO).
 //
 // One persistent kernel, 6 warps per CTA: warp 0 TMA producer (ring of 4 stages of 32 k), warp 1 issues the MMAs
 // (M = 128, N = BN in {128, 256}, K = 8 per instruction) into one of two TMEM accumulators, warps 2..5 drain the other
@@ -38,6 +41,17 @@ __host__ __device__ constexpr uint32_t idesc_tf32_f32(int m, int n, int a_mn_maj
            | (static_cast<uint32_t>(b_mn_major) << 16)
            | (static_cast<uint32_t>(n >> 3) << 17)
            | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// MN-major TF32 operand: layout type 1 = SWIZZLE_128B_BASE32B (bit layout: UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(1) << 61;
+    return d;
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -151,11 +165,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (elect_one_sync()) {
                     const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t b_addr = a_addr + LT_A_BYTES;
-                    const uint64_t adesc = A_MN ? smem_desc_mn_sw128(a_addr, 4096, 1024) : smem_desc_k_sw128(a_addr);
-                    const uint64_t bdesc = B_MN ? smem_desc_mn_sw128(b_addr, 4096, 1024) : smem_desc_k_sw128(b_addr);
+                    const uint64_t adesc = A_MN ? smem_desc_mn_sw128_32b(a_addr, 4096, 512) : smem_desc_k_sw128(a_addr);
+                    const uint64_t bdesc = B_MN ? smem_desc_mn_sw128_32b(b_addr, 4096, 512) : smem_desc_k_sw128(b_addr);
 #pragma unroll
                     for (int j = 0; j < LT_BK / 8; ++j) {
-                        // K-major: 8 tf32 = 32 B inside the 128-byte swizzle row; MN-major: 8 k-rows = one 1024-byte atom
+                        // K-major: 8 tf32 = 32 B inside the 128-byte swizzle row; MN-major: 8 k-rows = two 512-byte atoms
                         const uint64_t ao = A_MN ? static_cast<uint64_t>((j * 1024) >> 4) : static_cast<uint64_t>((j * 32) >> 4);
                         const uint64_t bo = B_MN ? static_cast<uint64_t>((j * 1024) >> 4) : static_cast<uint64_t>((j * 32) >> 4);
                         umma_tf32(acc, adesc + ao, bdesc + bo, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
@@ -276,7 +290,7 @@ __global__ void colsum_final(const float *__restrict__ partial, int n_chunks, in
 }
 
 // row-major fp32 [rows, cols] -> boxes of {32 columns (128 B), box_rows rows}, 128B swizzle, zero fill out of range
-static int make_tmap_f32(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int box_rows) {
+static int make_tmap_f32(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int box_rows, bool atom32 = false) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return TT_E_DEVICE; }
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -284,8 +298,8 @@ static int make_tmap_f32(CUtensorMap *map, const void *base, int64_t rows, int64
     cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f32) failed (CUresult %d)", static_cast<int>(r)); return TT_E_BADARG; }
     return 0;
 }
@@ -344,7 +358,7 @@ extern "C" int tt_linear_dgrad_tc(const float *grad_out, const float *weight, in
     CUtensorMap ma, mb;
     int rc;
     if ((rc = make_tmap_f32(&ma, grad_out, rows, n_out, LT_BM))) return rc;
-    if ((rc = make_tmap_f32(&mb, weight, n_out, n_in, 32))) return rc;       // [32 k = out rows][32 n = in cols] boxes
+    if ((rc = make_tmap_f32(&mb, weight, n_out, n_in, 32, true))) return rc;       // [32 k = out rows][32 n = in cols] boxes
     LinTcParams p{};
     p.M = rows; p.N = n_in;
     p.m_tiles = static_cast<int>((rows + LT_BM - 1) / LT_BM);
@@ -383,8 +397,8 @@ extern "C" int tt_linear_wgrad_tc(const float *grad_out, const float *input, int
     const int bn = n_in > 128 ? 256 : 128;
     CUtensorMap ma, mb;
     int rc;
-    if ((rc = make_tmap_f32(&ma, grad_out, rows, n_out, 32))) return rc;    // [32 k = rows][32 m = out cols] boxes
-    if ((rc = make_tmap_f32(&mb, input, rows, n_in, 32))) return rc;       // [32 k = rows][32 n = in cols] boxes
+    if ((rc = make_tmap_f32(&ma, grad_out, rows, n_out, 32, true))) return rc;    // [32 k = rows][32 m = out cols] boxes
+    if ((rc = make_tmap_f32(&mb, input, rows, n_in, 32, true))) return rc;       // [32 k = rows][32 n = in cols] boxes
     LinTcParams p{};
     p.M = n_out; p.N = n_in;
     p.m_tiles = (n_out + LT_BM - 1) / LT_BM;
