@@ -97,8 +97,9 @@ TT_API int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, int 
                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* List form of tt_emb_segment_grad (owner side of the row-sharded exchange, section 7): position p = piece * piece_len + e
- * holds local row rows[piece * piece_stride + e] (negative or >= vocab: dropped) and reads gradient row
- * q = pos_src ? pos_src[p] : p, stored at grad[(q / grad_piece_rows) * grad_piece_stride + (q % grad_piece_rows) * dim].
+ * holds local row rows[piece * piece_stride + e] (negative or >= vocab: dropped) and reads the gradient row that
+ * starts at grad + 4 * pos_src[p] (pos_src: float4 offsets, written by tt_shard_owner_gather) or, when pos_src is NULL,
+ * row p of a buffer of pieces: grad[(p / grad_piece_rows) * grad_piece_stride + (p % grad_piece_rows) * dim].
  * Same outputs and the same determinism (stable sort => ascending positions inside a segment). */
 TT_API int tt_emb_segment_grad_lists(const int32_t *rows, int64_t n_pieces, int64_t piece_len, int64_t piece_stride,
                               const int32_t *pos_src, int64_t vocab, const float *grad, int64_t grad_piece_rows,
@@ -287,6 +288,12 @@ TT_API int tt_linear_wgrad_tc(const float *grad_out, const float *input, int64_t
                        float *grad_weight, float *grad_bias, int accumulate, void *workspace, size_t workspace_bytes,
                        void *stream);
 
+/* Row-wise L2 normalisation of the tower outputs (F.normalize(x, p=2, dim=1), Tower.py:41): y = x / max(||x||, eps),
+ * inv_norm[rows] saved for the backward dx = inv_norm (g - y <g, y>) (dx = g / eps for a clamped row).  dim % 4 == 0. */
+TT_API int tt_l2_normalize_fwd(const float *x, int64_t rows, int dim, float eps, float *y, float *inv_norm, void *stream);
+TT_API int tt_l2_normalize_bwd(const float *grad_y, const float *y, const float *inv_norm, int64_t rows, int dim, float eps,
+                        float *grad_x, void *stream);
+
 /* ------------------------------------------------------------------------
  * 8. BatchNorm1d in training mode with the MLP block's ReLU + Dropout fused in (GenericTower.py:234, Tower.py:16-21:
  * Linear -> BatchNorm1d -> ReLU -> Dropout), statistics optionally spanning several ranks (data-parallel towers: the
@@ -335,8 +342,9 @@ TT_API int tt_bn_bwd_apply(const float *dy, int64_t dy_stride, const float *x, i
  *                         workspace: 4 * world * ceil(n_rows / 4096) bytes (tile totals of the scan);
  *                         *flags |= 1 (id outside [0, vocab)), |= 2 (an owner's entries exceed cap: dropped)
  *   tt_shard_owner_gather owner: pooled != 0: out[s][vec_base + b*dim] = sum of table rows of (source s, sample b) and
- *                         pos_src[s*cap + e] = s*n_rows + b (nullable; feeds tt_emb_segment_grad_lists);
- *                         pooled == 0: out[s][vec_base + e*dim] = table[rows[s][e]]
+ *                         pos_src[s*cap + e] = (s*block_floats + vec_base + b*dim) / 4: where that entry's gradient row
+ *                         sits in the backward's float blocks (nullable; feeds tt_emb_segment_grad_lists);
+ *                         pooled == 0: out[s][vec_base + e*dim] = table[rows[s][e]], pos_src likewise with e for b
  *   tt_shard_combine      source: out[b] = sum_w recv_vec[w][b] in rank order + n_pad[b] * pad_row, / len for MEAN
  *                         (len > 1), or recv_vec[owner(b)][slot(b)] (len == 1; pad id -> pad_row)
  *   tt_shard_grad_pack    source, backward: grad_out[b] (x 1/len for MEAN) into every owner's block (len > 1) or into

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "tt_linear_dgrad_tc": (c_int, [P, P, c_int64, c_int, c_int, P, P]),
     "tt_linear_wgrad_tc_workspace": (c_int, [c_int64, c_int, c_int, P]),
     "tt_linear_wgrad_tc": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int, P, c_size_t, P]),
+    "tt_l2_normalize_fwd": (c_int, [P, c_int64, c_int, c_float, P, P, P]),
+    "tt_l2_normalize_bwd": (c_int, [P, P, P, c_int64, c_int, c_float, P, P]),
     "tt_attn_small_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_float, P, c_int64, P, P]),
     "tt_attn_small_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_float, P, c_int64, P, P]),
     "tt_add_dropout_ln_fwd": (c_int, [P, P, c_int64, c_int, P, P, c_float, c_float, P, c_int64, P, P, P, P]),

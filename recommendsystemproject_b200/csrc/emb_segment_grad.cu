@@ -206,9 +206,9 @@ struct GradSrc {
     int len;
     int mode;
     int dim;
-    // list form (tt_emb_segment_grad_lists): position p reads gradient row q = pos_src ? pos_src[p] : p, which lives in
-    // piece q / piece_rows of a buffer cut into pieces `piece_stride` floats apart (the per-source blocks of the
-    // row-sharded exchange); piece_rows == 0: the flat [n, grad_stride] form above
+    // list form (tt_emb_segment_grad_lists): position p reads the gradient row at float4 offset pos_src[p] from
+    // grad_out; without pos_src, row p of a buffer cut into pieces of piece_rows rows, `piece_stride` floats apart (the
+    // per-source blocks of the row-sharded exchange); piece_rows == 0: the flat [n, grad_stride] form above
     const int32_t *pos_src;
     int64_t piece_rows;
     int64_t piece_stride;
@@ -219,10 +219,11 @@ template <bool LISTS>
 __device__ __forceinline__ const float *seg_grad_row(const GradSrc &g, int32_t p, int &slot, int64_t &src) {
     slot = 0;
     if (LISTS) {
-        const int64_t q = g.pos_src ? static_cast<int64_t>(__ldg(g.pos_src + p)) : static_cast<int64_t>(p);
-        src = q;
-        const int64_t piece = q / g.piece_rows;
-        return g.grad_out + piece * g.piece_stride + (q - piece * g.piece_rows) * g.grad_stride;
+        src = p;
+        if (g.pos_src) return g.grad_out + 4 * static_cast<int64_t>(__ldg(g.pos_src + p));   // float4 offset, no division
+        const uint32_t q = static_cast<uint32_t>(p), pr = static_cast<uint32_t>(g.piece_rows);
+        const uint32_t piece = q / pr;
+        return g.grad_out + static_cast<int64_t>(piece) * g.piece_stride + static_cast<int64_t>(q - piece * pr) * g.grad_stride;
     }
     src = p;
     if (g.len > 1) { src = p / g.len; slot = p - static_cast<int32_t>(src) * g.len; }

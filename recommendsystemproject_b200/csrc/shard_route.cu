@@ -219,7 +219,9 @@ shard_owner_pool_kernel(const T *__restrict__ table, int64_t local_rows, int dim
                 int32_t my_row = -1;
                 if (j0 + sub < n_e) {
                     my_row = __ldg(blk + rows_base + e0 + j0 + sub);
-                    if (pos_src && c0 == 0) pos_src[s * cap + e0 + j0 + sub] = static_cast<int32_t>(item);
+                    // where this entry's gradient row will sit in the float block of the backward (float4 units)
+                    if (pos_src && c0 == 0)
+                        pos_src[s * cap + e0 + j0 + sub] = static_cast<int32_t>((s * block_floats + vec_base + b * dim) >> 2);
                 }
                 const int cnt = min(LPR, n_max - j0);
                 for (int j = 0; j < cnt; j += UNROLL) {
@@ -255,7 +257,7 @@ template <typename T, int LPR>
 __global__ void __launch_bounds__(256)
 shard_owner_rows_kernel(const T *__restrict__ table, int64_t local_rows, int dim, int world,
                         const int32_t *__restrict__ recv, int64_t block_ints, int64_t rows_base, int64_t cap,
-                        float *__restrict__ out, int64_t block_floats, int64_t vec_base) {
+                        float *__restrict__ out, int64_t block_floats, int64_t vec_base, int32_t *__restrict__ pos_src) {
     constexpr int VN = Vec16<T>::N;
     const int vpr = dim / VN;
     const int sub = threadIdx.x % LPR;
@@ -266,6 +268,7 @@ shard_owner_rows_kernel(const T *__restrict__ table, int64_t local_rows, int dim
         const int64_t s = item / cap;
         const int64_t e = item - s * cap;
         const int32_t r = __ldg(recv + s * block_ints + rows_base + e);
+        if (pos_src && sub == 0) pos_src[item] = static_cast<int32_t>((s * block_floats + vec_base + e * dim) >> 2);
         if (r < 0 || r >= local_rows) continue;
         for (int c = sub; c < vpr; c += LPR) {
             float v[VN];
@@ -426,7 +429,7 @@ static int owner_gather(const T *table, int64_t local_rows, int dim, int world, 
                                                                  rows_base, cap, n_rows, out, block_floats, vec_base, pos_src); \
         else                                                                                                              \
             shard_owner_rows_kernel<T, L><<<grid, 256, 0, st>>>(table, local_rows, dim, world, recv, block_ints, rows_base, \
-                                                                 cap, out, block_floats, vec_base);                       \
+                                                                 cap, out, block_floats, vec_base, pos_src);              \
     } while (0)
     switch (lpr) {
         case 1: TT_OG(1); break;
@@ -453,6 +456,7 @@ extern "C" int tt_shard_owner_gather(const void *table, int table_dtype, int64_t
     TT_CHECK_ARG(table_dtype == TT_F32 || table_dtype == TT_BF16, "unknown table dtype");
     TT_CHECK_ARG(dim % (table_dtype == TT_F32 ? 4 : 8) == 0, "sharded tables need 16-byte rows (dim % 4 == 0 fp32, % 8 bf16)");
     TT_CHECK_ARG(block_floats % 4 == 0 && vec_base % 4 == 0, "float block layout must be 16-byte aligned");
+    TT_CHECK_ARG(static_cast<int64_t>(world) * block_floats < (int64_t(1) << 33), "float blocks exceed the 31-bit float4 offsets of pos_src");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (table_dtype == TT_F32)
         return owner_gather<float>(static_cast<const float *>(table), local_rows, dim, world, recv, block_ints, off_base,

@@ -148,7 +148,7 @@ class MLP_Tower(nn.Module):
             else:
                 x = layer(x)
                 i += 1
-        return F.normalize(x, p=2, dim=1)
+        return ops.l2_normalize(x)
 
 
 class SequenceFeatureProcessor(nn.Module):

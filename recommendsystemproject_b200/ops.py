@@ -378,6 +378,40 @@ def linear(x, weight, bias=None):
     return LinearFn.apply(x, weight, bias)
 
 
+class L2Normalize(torch.autograd.Function):
+    """F.normalize(x, p=2, dim=1) (Tower.py:41), one kernel forward and one backward."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        _need_cuda(x)
+        lib = _lib.load()
+        x = x.contiguous()
+        rows, dim = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+        check(lib.tt_l2_normalize_fwd(_p(x), rows, dim, float(eps), _p(y), _p(inv), _stream()), "tt_l2_normalize_fwd")
+        _count()
+        ctx.save_for_backward(y, inv)
+        ctx.eps = float(eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        y, inv = ctx.saved_tensors
+        lib = _lib.load()
+        gy = gy.contiguous()
+        gx = torch.empty_like(y)
+        check(lib.tt_l2_normalize_bwd(_p(gy), _p(y), _p(inv), y.shape[0], y.shape[1], ctx.eps, _p(gx), _stream()), "tt_l2_normalize_bwd")
+        _count()
+        return gx, None
+
+
+def l2_normalize(x, eps: float = 1e-12):
+    if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] % 4 == 0:
+        return L2Normalize.apply(x, eps)
+    return F.normalize(x, p=2, dim=1, eps=eps)
+
+
 class AttnSmall(torch.autograd.Function):
     """softmax(q k^T / sqrt(dh) + key padding mask) -> dropout -> . v for L <= 32, straight from the packed in_proj
     output (what nn.MultiheadAttention computes between in_proj and out_proj, SequenceEncoder.py:13-21,60)."""

@@ -85,7 +85,9 @@ class _CudaShardOps:
         lib = _lib.load()
         check(lib.tt_emb_segment_grad_lists(ctypes.c_void_p(recv.data_ptr() + 4 * rows_base), world, cap, block_ints,
                                             _p(pos_src), max(local_rows, 1),
-                                            ctypes.c_void_p(grad.data_ptr() + 4 * vec_base), piece_rows, block_floats, dim,
+                                            # pos_src holds float4 offsets from the START of the gradient blocks
+                                            _p(grad) if pos_src is not None else ctypes.c_void_p(grad.data_ptr() + 4 * vec_base),
+                                            piece_rows, block_floats, dim,
                                             _p(rows_out), _p(row_grad), _p(n_unique), _p(sq_norm), _p(ws), ws.numel(),
                                             _stream()), "tt_emb_segment_grad_lists")
         ops._count(7)
@@ -252,7 +254,7 @@ class ShardedTableGroup:
             s, t = pl.slots[name], self.tables[name]
             pl.n_pad[name] = torch.zeros(B, dtype=torch.int32, device=dev)
             n_pos = W * s["cap"]
-            pl.pos_src[name] = torch.empty(n_pos, dtype=torch.int32, device=dev) if s["len"] > 1 else None
+            pl.pos_src[name] = torch.empty(n_pos, dtype=torch.int32, device=dev)
             ws_bytes = self.ops.segment_ws_bytes(n_pos, t.dim)
             pl.seg[name] = dict(rows=torch.empty(n_pos, dtype=torch.int64, device=dev),
                                 row_grad=torch.empty(n_pos, t.dim, dtype=torch.float32, device=dev),
@@ -312,7 +314,8 @@ class ShardedTableGroup:
             s, t = pl.slots[name], self.tables[name]
             if g is None:
                 g = torch.zeros(pl.B, t.dim, dtype=torch.float32, device=self.device)
-            g = g.contiguous()
+            if not (g.stride(1) == 1 and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0):
+                g = g.contiguous()      # a column slice of the tower's concat gradient is read in place (row stride)
             self.ops.grad_pack(g, t.mode, t.dim, W, x, t.padding_idx, t.vocab, pl.send_ids, pl.block_ints, s["off_base"],
                                s["cap"], pl.g_out, pl.block_floats, s["vec_base"])
         self._a2a(pl.g_in, pl.g_out)                                                           # all-to-all #3

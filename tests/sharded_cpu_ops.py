@@ -57,11 +57,13 @@ class CpuShardOps:
                         if 0 <= r < local_rows:
                             acc = acc + tab[r]
                         if pos_src is not None:
-                            pos_src[s * cap + e] = s * n_rows + b
+                            pos_src[s * cap + e] = (s * block_floats + vec_base + b * D) // 4
                     out[s, vec_base + b * D: vec_base + (b + 1) * D] = acc
             else:
                 for e in range(cap):
                     r = int(recv[s, rows_base + e])
+                    if pos_src is not None:
+                        pos_src[s * cap + e] = (s * block_floats + vec_base + e * D) // 4
                     if 0 <= r < local_rows:
                         out[s, vec_base + e * D: vec_base + (e + 1) * D] = tab[r]
 
@@ -119,9 +121,12 @@ class CpuShardOps:
                 r = int(recv[s, rows_base + e])
                 if r < 0 or r >= local_rows:
                     continue
-                q = int(pos_src[p]) if pos_src is not None else p
-                piece, i = divmod(q, piece_rows)
-                g = grad[piece, vec_base + i * dim: vec_base + (i + 1) * dim]
+                if pos_src is not None:
+                    o = 4 * int(pos_src[p])
+                    g = grad.reshape(-1)[o:o + dim]
+                else:
+                    piece, i = divmod(p, piece_rows)
+                    g = grad[piece, vec_base + i * dim: vec_base + (i + 1) * dim]
                 acc[r] = g.clone() if r not in acc else acc[r] + g      # ascending position order
         keys = sorted(acc)
         for k, r in enumerate(keys):

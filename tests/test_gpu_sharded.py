@@ -95,17 +95,16 @@ def test_owner_gather_combine_grad_pack_segment_grad_match_restatement(B, L, W, 
     recv = torch.stack([sends[s][0] for s in range(W)])
     # --- owner gather
     ref_out = torch.zeros(W, lay["block_floats"])
-    ref_pos = torch.full((W * lay["cap"],), -7, dtype=torch.int32) if L > 1 else None
+    ref_pos = torch.full((W * lay["cap"],), -7, dtype=torch.int32)
     CpuShardOps.owner_gather(table, local_rows, W, recv, lay["block_ints"], lay["off_base"], lay["rows_base"], lay["cap"], B,
                              L > 1, ref_out, lay["block_floats"], lay["vec_base"], ref_pos)
     out = torch.zeros(W, lay["block_floats"], device=DEV)
-    pos = torch.full((W * lay["cap"],), -7, dtype=torch.int32, device=DEV) if L > 1 else None
+    pos = torch.full((W * lay["cap"],), -7, dtype=torch.int32, device=DEV)
     recv_d = recv.to(DEV)
     C.owner_gather(table.to(DEV), local_rows, W, recv_d, lay["block_ints"], lay["off_base"], lay["rows_base"], lay["cap"], B,
                    L > 1, out, lay["block_floats"], lay["vec_base"], pos)
     assert torch.equal(out.cpu(), ref_out)
-    if L > 1:
-        assert torch.equal(pos.cpu(), ref_pos)
+    assert torch.equal(pos.cpu(), ref_pos)
     # --- combine on source 0 (vectors from W owners: reuse random data in the vec layout)
     vec_in = torch.randn(W, lay["block_floats"], generator=gen)
     n_pad = (src_ids[0] == pad).sum(1).to(torch.int32)
