@@ -392,7 +392,16 @@ def build_c3(rank, world, dev, B_global, dropout=0.1, zipf=False, users_per_gpu=
     host = [tree_to(h, None, pin=True) for h in host]
     dev_batch = tree_to(host[0], dev)
     torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
-    step = ShardedTrainStep(model, opt, dev_batch, 0.05, restore_tables=False)
+    if os.environ.get("TT_C3_LOCAL_BN", "0") == "1":
+        os.environ["TT_C3_LOCAL_BN"] = "done"
+        from recommendsystemproject_b200 import dist as _d
+        _d.SYNC_BN = False
+    # diagnosis knobs (never set by the driver's runs): TT_C3_LOCAL_LOSS=1 per-rank in-batch loss, TT_C3_LOCAL_BN=1 per-rank
+    # BatchNorm statistics -- what the global-batch semantics cost at N > 1
+    step = ShardedTrainStep(model, opt, dev_batch, 0.05, restore_tables=False,
+                            global_loss=os.environ.get("TT_C3_LOCAL_LOSS", "0") != "1")
+    if os.environ.get("TT_C3_LOCAL_BN", "0") == "1":
+        raise SystemExit("TT_C3_LOCAL_BN must be handled before the step is built")
     return model, opt, step, host, dev_batch, cfg, v_user
 
 
@@ -526,7 +535,7 @@ def ops_count():
 
 def run_c5(args, rank, local_rank, world, dev, peaks):
     """BASELINE configs[4]: top-100 over a 10M-item corpus sharded over the GPUs (each GPU: tcgen05 filter + exact
-    re-rank over its shard), all-gather of the [Q, K] lists, global merge.  Q = 16384 queries per step."""
+    re-rank over its shard), all-to-all of the [Q/W, K] candidate slices, per-rank merge.  Q = 16384 queries per step."""
     import torch.distributed as dist
     from recommendsystemproject_b200 import dist as tdist, ops
     N_total, Q, K, D = 10_000_000, 16384, 100, 128
@@ -539,7 +548,8 @@ def run_c5(args, rank, local_rank, world, dev, peaks):
     q_dev = host_q.to(dev)
 
     def step(q):
-        return tdist.sharded_topk(q, shard, K, rank, world, bounds[:-1],
+        # every rank keeps the merged top-K of its own Q/W queries (recall is then one all-reduce of hit counts)
+        return tdist.sharded_topk(q, shard, K, rank, world, bounds[:-1], gather_result=False,
                                   topk_fn=lambda a, e, k, off: ops.score_topk(a, e, k, off, precision="bf16", prepared=prep))
 
     def barrier():
@@ -557,7 +567,7 @@ def run_c5(args, rank, local_rank, world, dev, peaks):
     b.record()
     barrier()
     dev_ms = a.elapsed_time(b)
-    out_host = torch.empty(Q, K, dtype=torch.int64).pin_memory()
+    out_host = torch.empty((Q + world - 1) // world, K, dtype=torch.int64).pin_memory()
     barrier()
     a.record()
     for _ in range(args.steps):
@@ -582,9 +592,10 @@ def run_c5(args, rank, local_rank, world, dev, peaks):
                                    "bit-exact rows (score desc, row asc)", "parallelism": f"corpus-sharded x{world}",
                        "l2": "corpus shard (>= 320 MB bf16) exceeds L2", "peaks": peaks["source"]},
             "e2e": {"value": Q * args.steps / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4,
-                    "d2h_bytes_per_step": Q * K * 8, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": ((Q + world - 1) // world) * K * 8 * world, "ms_per_step": e2e_ms / args.steps,
+                    "note": "every rank uploads the Q queries and reads back the top-K rows of its own Q/W slice"},
             "gpu_launches": ops_count(),
-            "roofline": {"bound": "tensor", "kernel": "topk_tc_kernel (sampling pass + full pass) + topk_tc_stage2 + topk_merge",
+            "roofline": {"bound": "tensor", "kernel": "topk_tc_kernel (sampling pass + full pass) + topk_tc_stage2 + all-to-all + topk_merge",
                          "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": flops / ms / 1e9 / peaks["bf16_tflops"], "traffic": None, "alg_flops": flops},
             "clocks": clocks, "resampled_queries": ops.topk_stats.get("resampled"),

@@ -91,6 +91,9 @@ class DataParallelStep:
         return self.static_loss
 
 
+SYNC_BN = True      # diagnosis switch (bench.py TT_C3_LOCAL_BN): False = per-rank BatchNorm statistics
+
+
 class ShardedTrainStep:
     """The integrated multi-GPU training step, one CUDA graph per rank, collectives included:
 
@@ -129,7 +132,7 @@ class ShardedTrainStep:
             ops.bn_sync.world, ops.bn_sync.group = self.world, None
             for m in model.modules():
                 if isinstance(m, torch.nn.BatchNorm1d):
-                    m._tt_sync = True
+                    m._tt_sync = SYNC_BN
             # replicas start identical: dense parameters, buffers (BatchNorm statistics, dropout seeds, pad rows)
             dist.broadcast(optimizer.flat_p, src=0)
             for b in model.buffers():
@@ -281,19 +284,34 @@ def sharded_lookup(local_table_fn, ids: torch.Tensor, world: int) -> torch.Tenso
 
 
 def sharded_topk(query: torch.Tensor, local_corpus: torch.Tensor, k: int, rank: int, world: int,
-                 shard_offsets: List[int], topk_fn=None, merge_fn=None):
-    """Per-GPU top-K over the local corpus shard, all-gather of the [Bq, K] candidate lists, global merge with
-    the (score desc, global row asc) tie-break.  Every rank returns the full result."""
+                 shard_offsets: List[int], topk_fn=None, merge_fn=None, gather_result: bool = True):
+    """Corpus-sharded top-K (SURVEY 8e "Retrieval"): every GPU scores ALL queries against its corpus shard, then the
+    [Q, K] candidate lists are exchanged with ONE all-to-all so that rank r receives the W lists of ITS Q/W queries and
+    merges only those ((score desc, global row asc) tie-break, rows already carry the shard offset).
+    gather_result=True: the merged slices are all-gathered and every rank returns the full [Q, K] result;
+    False: returns (scores, rows) of this rank's query slice [ceil(Q/W), K] (its rows [r*ceil(Q/W), ...) of the batch;
+    slices past Q are padding)."""
     topk_fn = topk_fn or ops.score_topk
     merge_fn = merge_fn or ops.topk_merge
     s, i = topk_fn(query, local_corpus, k, shard_offsets[rank])
     if world == 1:
         return s, i
-    ss = [torch.empty_like(s) for _ in range(world)]
-    ii = [torch.empty_like(i) for _ in range(world)]
-    dist.all_gather(ss, s)
-    dist.all_gather(ii, i)
-    return merge_fn(torch.stack(ss), torch.stack(ii))
+    Q = s.shape[0]
+    per = (Q + world - 1) // world
+    if per * world != Q:                                    # pad the query dimension to a multiple of W
+        s = torch.cat([s, s.new_full((per * world - Q, k), float("-inf"))])
+        i = torch.cat([i, i.new_full((per * world - Q, k), -1)])
+    rs, ri = torch.empty_like(s), torch.empty_like(i)
+    dist.all_to_all_single(rs, s.contiguous())              # block w of rs = shard w's list for my query slice
+    dist.all_to_all_single(ri, i.contiguous())
+    ms, mi = merge_fn(rs.view(world, per, k), ri.view(world, per, k))
+    if not gather_result:
+        return ms, mi
+    fs = torch.empty(world * per, k, dtype=ms.dtype, device=ms.device)
+    fi = torch.empty(world * per, k, dtype=mi.dtype, device=mi.device)
+    dist.all_gather_into_tensor(fs, ms.contiguous())
+    dist.all_gather_into_tensor(fi, mi.contiguous())
+    return fs[:Q], fi[:Q]
 
 
 # ---------------------------------------------------------------------------
