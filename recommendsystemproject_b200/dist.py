@@ -203,19 +203,28 @@ class ShardedTrainStep:
         return "bf16" if (u.shape[1] in (64, 128) and u.shape[0] * self.world >= 4096) else "fp32"
 
     def _step_eager(self):
+        nvtx = torch.cuda.nvtx
         o = self.opt
         o.zero_grad()
+        nvtx.range_push("tt.forward (sharded exchange + towers)")
         u, i, hn = self.model(self.static_batch)
+        nvtx.range_pop()
         ids = self.static_batch["item_tower"]["sparse"][:, self.item_id_col]
+        nvtx.range_push("tt.loss (global in-batch softmax CE)")
         if hn is not None:
             loss = self.model.compute_loss(u, i, item_ids=ids, hard_neg_emb=hn, temperature=self.temperature)
         else:
             loss = self._loss(u, i, ids)
+        nvtx.range_pop()
+        nvtx.range_push("tt.backward (CE, towers, gradient exchange, segment reduce)")
         (loss / self.world if self.world > 1 else loss).backward()
+        nvtx.range_pop()
+        nvtx.range_push("tt.optimizer (all-reduce, clip, Adam, row-wise Adam)")
         o.stage_sharded_norm()
         if self.world > 1:
             dist.all_reduce(o.flat_g_ext)
         o.step()
+        nvtx.range_pop()
         out = loss.detach().clone()
         if self.world > 1:
             dist.all_reduce(out, op=dist.ReduceOp.AVG)      # the global-batch mean, for reporting
@@ -570,6 +579,10 @@ class _AllGatherWithGrad(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         g = g.contiguous()
+        if g.is_cuda:       # NCCL: reduce-scatter moves half the bytes of an all-reduce (gloo has none: CPU tests all-reduce)
+            out = torch.empty_like(g[0])
+            dist.reduce_scatter_tensor(out, g)
+            return out
         dist.all_reduce(g)
         return g[dist.get_rank()]
 

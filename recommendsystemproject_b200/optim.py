@@ -279,12 +279,21 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
 
     def _step_eager(self):
+        nvtx = torch.cuda.nvtx      # ranges show up in Nsight Systems / ncu --nvtx (tracing)
         self.opt.zero_grad()
+        nvtx.range_push("tt.forward")
         u, i, hn = self.model(self.static_batch)
+        nvtx.range_pop()
         ids = self.static_batch["item_tower"]["sparse"][:, self.item_id_col]
+        nvtx.range_push("tt.loss")
         loss = self.model.compute_loss(u, i, item_ids=ids, hard_neg_emb=hn, temperature=self.temperature)
+        nvtx.range_pop()
+        nvtx.range_push("tt.backward")
         loss.backward()
+        nvtx.range_pop()
+        nvtx.range_push("tt.optimizer")
         self.opt.step()
+        nvtx.range_pop()
         return loss.detach()
 
     def load_batch(self, batch: dict, non_blocking: bool = True):

@@ -135,3 +135,42 @@ def test_builder_feeds_the_model_and_checkpoint_resumes_across_optimizers(tmp_pa
         if sa[k].is_floating_point():
             assert torch.allclose(sa[k], sc[k], atol=1e-7, rtol=0), k          # same optimizer kind: same numbers
             assert torch.allclose(sa[k], sb[k], atol=2e-5, rtol=1e-4), k       # torch Adam after resume: fp32 noise only
+
+
+def test_gpu_batch_builder_matches_the_reference_collate_fixture():
+    """Pinned against the reference itself: tests/golden/collate_small.npz holds the batches the UNMODIFIED
+    CombinedTwoTowerDataLoader (CombineTwoTower.py:62-92 -> DataLoader.py:226-288) yields for a 43-row DataFrame with the
+    shipped config.yaml (batch 8, no shuffle: five full batches and a partial one), plus the DataFrame's columns."""
+    from golden_io import unflatten
+    from helpers import load_golden
+    npz, meta = load_golden("collate_small")
+    cols = unflatten(npz, "columns")
+    ref_batches = unflatten(npz, "batches")
+    builder = GpuBatchBuilder(cols["user"], cols["item"], device="cpu")
+    assert len(builder) == meta["n"]
+    bs = meta["batch_size"]
+    assert len(ref_batches) == (meta["n"] + bs - 1) // bs
+    for k, ref in enumerate(ref_batches):
+        idx = torch.arange(k * bs, min(meta["n"], (k + 1) * bs))
+        got = builder.batch(idx)
+        assert set(got.keys()) == set(ref.keys())
+        for tower in ("user_tower", "item_tower"):
+            assert _same(got[tower], ref[tower]), (k, tower)
+    # epoch(): same batches through the iterator interface
+    for got, ref in zip(builder.epoch(bs, shuffle=False), ref_batches):
+        assert _same(got["user_tower"], ref["user_tower"]) and _same(got["item_tower"], ref["item_tower"])
+    # the reference's feature -> column mappings are what synth.MAPS_C2 hard-codes for the shipped config
+    maps = unflatten(npz, "maps")
+    assert {k: int(v) for k, v in maps["user"]["sparse"].items()} == synth.MAPS_C2[0]["sparse"]
+    assert {k: int(v) for k, v in maps["item"]["sparse"].items()} == synth.MAPS_C2[1]["sparse"]
+    assert {k: int(v) for k, v in maps["user"]["dense"].items()} == synth.MAPS_C2[0]["dense"]
+
+
+def test_hard_negative_id_outside_the_catalog_range_maps_to_the_zero_row():
+    """ids above the catalog's largest id used to be clamped onto the LAST catalog item."""
+    user, item, catalog, catalog_ids, neg = _columns(50, 20, seed=9)
+    neg[0, 0] = int(catalog_ids.max()) + 1000
+    neg[1, 1] = -5
+    b = GpuBatchBuilder(user, item, catalog, catalog_ids, neg, device="cpu").batch(torch.tensor([0, 1]))
+    assert int(b["hard_negatives"][0]["sparse"][0].abs().sum()) == 0
+    assert int(b["hard_negatives"][1]["sparse"][1].abs().sum()) == 0
