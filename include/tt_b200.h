@@ -178,6 +178,23 @@ TT_API int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowneg, i
                  float *d_hn_rows, float *d_pool, void *fwd_workspace, size_t fwd_workspace_bytes, void *workspace,
                  size_t workspace_bytes, void *stream);
 
+/* Rectangular form of the two calls above for data-parallel towers (SURVEY 8e "towers + loss"): n_user LOCAL user
+ * rows against n_item >= n_user item rows -- the all-gathered GLOBAL batch -- where the positive of user b is item row
+ * item_offset + b.  item_ids_all [n_item] (nullable) masks every item row that carries the id of the user's positive
+ * (false negatives across ALL ranks, TwoTowerModel.py:98-114 applied to the global batch).  loss = mean over the
+ * n_user rows; d_item_all [n_item, dim] is this rank's contribution to EVERY item row (sum it over the ranks).
+ * n_item == n_user, item_offset == 0 is exactly tt_ce_fwd_tc / tt_ce_bwd_tc. */
+TT_API int tt_ce_tc_workspace_rect(int64_t n_user, int64_t n_item, int64_t pool, int n_rowneg, int dim, size_t *bytes_host);
+TT_API int tt_ce_fwd_tc_rect(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,
+                      const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
+                      int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
+                      int *nan_flags, void *workspace, size_t workspace_bytes, void *stream);
+TT_API int tt_ce_bwd_tc_workspace_rect(int64_t n_user, int64_t n_item, int64_t pool, int n_rowneg, int dim, size_t *bytes_host);
+TT_API int tt_ce_bwd_tc_rect(const float *user, const float *hn_rows, int n_rowneg, int64_t pool_rows, int64_t n_user,
+                      int64_t n_item, int dim, float inv_temp, const float *row_lse, const float *grad_loss,
+                      float *d_user, float *d_item_all, float *d_hn_rows, float *d_pool, void *fwd_workspace,
+                      size_t fwd_workspace_bytes, void *workspace, size_t workspace_bytes, void *stream);
+
 /* developer hook (tools/ce_trace.py): SM-clock stamps of CTA 0's pipeline events of the next tcgen05 CE
  * launches are written to dbg[11][256] (device memory); NULL disables.  Not used by the product path. */
 TT_API int tt_ce_tc_debug_trace(long long *dbg);

@@ -53,6 +53,12 @@ _SIGNATURES = {
     "tt_ce_fwd_tc": (c_int, [P, P, P, P, c_int, P, c_int64, c_int64, c_int, c_float, P, P, P, P, P, c_size_t, P]),
     "tt_ce_bwd_tc_workspace": (c_int, [c_int64, c_int64, c_int, c_int, P]),
     "tt_ce_bwd_tc": (c_int, [P, P, c_int, c_int64, c_int64, c_int, c_float, P, P, P, P, P, P, P, c_size_t, P, c_size_t, P]),
+    "tt_ce_tc_workspace_rect": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, P]),
+    "tt_ce_fwd_tc_rect": (c_int, [P, P, P, c_int64, P, c_int, P, c_int64, c_int64, c_int64, c_int, c_float, P, P, P, P, P,
+                                  c_size_t, P]),
+    "tt_ce_bwd_tc_workspace_rect": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, P]),
+    "tt_ce_bwd_tc_rect": (c_int, [P, P, c_int, c_int64, c_int64, c_int64, c_int, c_float, P, P, P, P, P, P, P, c_size_t, P,
+                                  c_size_t, P]),
     "tt_ce_tc_debug_trace": (c_int, [P]),
     "tt_score_topk_workspace": (c_int, [c_int64, c_int64, c_int, c_int, P]),
     "tt_score_topk_f32": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int64, P, P, P, P, P, c_size_t, P]),

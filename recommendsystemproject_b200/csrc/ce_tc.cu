@@ -22,11 +22,14 @@
 //               into registers, release the buffer, then exp2 on the MUFU while the tensor pipe already runs the
 //               next S; the backward packs bf16 (P - onehot) and tcgen05.st's it back to TMEM as the A operand.
 //
-// False-negative mask without per-element id compares: rows are processed in
-// item-id-sorted order (U and I permuted together while they are converted to
-// bf16; the loss is invariant to that permutation), so the columns that collide
-// with row p are the contiguous run [lo_p, hi_p) around the diagonal and only
-// tiles intersecting that run take the per-element path.
+// False-negative mask without per-element id compares: user rows and item rows are
+// processed in item-id-sorted order (permuted while they are converted to bf16; the
+// loss is invariant to that), so the item columns that collide with user row p are
+// the contiguous run [lo_p, hi_p) around its positive column diag_p, and only tiles
+// intersecting that run take the per-element path.
+// Rectangular form (data-parallel towers): n_user local user rows against
+// n_item >= n_user item rows (the all-gathered GLOBAL batch, user b's positive being
+// item row item_offset + b).  The square single-GPU case is n_item == n_user.
 //
 // Roofline: tensor pipe.  Algorithmic flops fwd = 2*B*(B+H)*D, bwd = 4*B*(B+H)*D
 // (the recomputation of S in the two backward passes is overhead, not counted).
@@ -85,29 +88,70 @@ __global__ void tc_iota_keys(const int64_t *__restrict__ ids, int64_t n, int64_t
     }
 }
 
-// [lo, hi) = run of equal ids around p in the sorted order; always contains p (identity perm when ids == NULL)
-__global__ void tc_runs(const int64_t *__restrict__ sorted_ids, int64_t n, int32_t *__restrict__ lo,
-                        int32_t *__restrict__ hi, int32_t *__restrict__ perm_identity) {
-    for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n;
-         p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        if (sorted_ids == nullptr) {  // no ids: the run is the diagonal element alone
-            lo[p] = static_cast<int32_t>(p); hi[p] = static_cast<int32_t>(p + 1);
-            perm_identity[p] = static_cast<int32_t>(p);
-            continue;
-        }
-        const int64_t key = sorted_ids[p];
-        int64_t a = 0, b = p;  // lower_bound in [0, p]
-        while (a < b) { const int64_t mid = (a + b) >> 1; if (sorted_ids[mid] < key) a = mid + 1; else b = mid; }
-        lo[p] = static_cast<int32_t>(a);
-        a = p; b = n;  // upper_bound in [p, n)
-        while (a < b) { const int64_t mid = (a + b) >> 1; if (sorted_ids[mid] <= key) a = mid + 1; else b = mid; }
-        hi[p] = static_cast<int32_t>(a);
+// keys of the user rows: the id of each user's own positive item
+__global__ void tc_user_keys(const int64_t *__restrict__ ids_all, int64_t item_offset, int64_t n_user,
+                             int64_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_user;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        keys[i] = ids_all[item_offset + i];
+        vals[i] = static_cast<int32_t>(i);
     }
+}
+
+__global__ void tc_invert_perm(const int32_t *__restrict__ perm, int64_t n, int32_t *__restrict__ inv) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        inv[perm[i]] = static_cast<int32_t>(i);
+}
+
+__device__ __forceinline__ int32_t tc_lower_bound(const int64_t *__restrict__ a, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return static_cast<int32_t>(lo);
+}
+__device__ __forceinline__ int32_t tc_upper_bound(const int64_t *__restrict__ a, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
+    return static_cast<int32_t>(lo);
+}
+
+// Per (sorted) row of the X side: [lo, hi) = the run of W-side rows carrying the same item id, diag = the W-side row
+// that is this row's positive partner (-1: none).
+//   user rows (FWD / BWD_X):  W side = sorted items;  diag = position of the user's own item
+//   item rows (BWD_Y):        W side = sorted users;  diag = position of the user whose positive this item is, -1 for
+//                             items of other ranks
+// ids == NULL (no false-negative masking): identity permutations, the run is the diagonal element alone.
+__global__ void tc_runs_rect(const int64_t *__restrict__ x_keys, int64_t n_x, const int64_t *__restrict__ w_keys, int64_t n_w,
+                             const int32_t *__restrict__ x_perm, const int32_t *__restrict__ w_inv, int64_t x_to_w_shift,
+                             int64_t w_valid, int32_t *__restrict__ lo, int32_t *__restrict__ hi, int32_t *__restrict__ diag) {
+    for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n_x;
+         p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        // partner in ORIGINAL W-side numbering: x_perm[p] + shift (users: + item_offset; items: - item_offset)
+        const int64_t partner = static_cast<int64_t>(x_perm ? x_perm[p] : p) + x_to_w_shift;
+        const bool has = partner >= 0 && partner < w_valid;
+        const int32_t d = has ? (w_inv ? w_inv[partner] : static_cast<int32_t>(partner)) : -1;
+        diag[p] = d;
+        if (x_keys == nullptr) {
+            lo[p] = has ? d : 0;
+            hi[p] = has ? d + 1 : 0;
+        } else {
+            const int64_t key = x_keys[p];
+            lo[p] = tc_lower_bound(w_keys, n_w, key);
+            hi[p] = tc_upper_bound(w_keys, n_w, key);
+        }
+    }
+}
+
+__global__ void tc_iota(int32_t *__restrict__ v, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        v[i] = static_cast<int32_t>(i);
 }
 
 // ---------------------------------------------------------------- main kernel
 struct CeTcParams {
-    int64_t batch;       // rows of U / I
+    int64_t x_rows;      // rows of the X-side "a" matrix (users in FWD / BWD_X, items in BWD_Y)
+    int64_t w_rows;      // rows of the W-side "a" matrix (items in FWD / BWD_X, users in BWD_Y)
     int64_t pool_rows;   // rows of the shared pool (0 if none)
     int xt_split;        // X row tiles (128) below this index come from map_xa, the rest from map_xb
     int wt_split;        // W tiles (256) below this index come from map_wa (item rows / U rows), the rest from map_wb (pool)
@@ -115,9 +159,9 @@ struct CeTcParams {
     int64_t per_cta, total;
     int max_seg;
     float scale2;        // inv_temp * log2(e)
-    const int32_t *lo, *hi;
-    const float *lse2p;      // BWD: [wt_item * 256] lse * log2(e) in sorted order, +inf past batch
-    float *part_m, *part_s;  // FWD: [2 * max_seg][batch]  (raw-logit max, sum of exp2)
+    const int32_t *lo, *hi, *diag;   // per X-side "a" row: run of masked W columns and the positive column
+    const float *lse2p;      // BWD: [wt_user * 256] lse * log2(e) of the (sorted) user rows, +inf past the end
+    float *part_m, *part_s;  // FWD: [2 * max_seg][x_rows]  (raw-logit max, sum of exp2)
     float *part;             // BWD: [max_seg][m_tiles * 128][D] raw fp32 accumulators
     long long *dbg;          // optional timeline of CTA 0 (tools/ce_trace.py): [event][tile] SM clock stamps
 };
@@ -338,7 +382,7 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
         Cursor c;
         c.init(g0, prm.n_tiles);
         // per-row state, reloaded at every row segment
-        int lo = 0, hi = 0, p = 0;
+        int lo = 0, hi = 0, p = 0, dg = -1;
         bool x_item = true;
         float row_stat = 0.f;             // BWD_X: lse2 of this row
         float m_run = -INFINITY, s_run = 0.f;   // FWD: running max of the raw logits / sum of exp2
@@ -348,15 +392,16 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                 x_item = !TRANS || c.m < prm.xt_split;
                 p = (c.m < prm.xt_split ? c.m : c.m - prm.xt_split) * TC_BM + r_in_tile;   // row index inside its matrix
                 lo = hi = 0;
-                if (x_item && p < prm.batch) { lo = prm.lo[p]; hi = prm.hi[p]; }
-                if (MODE == MODE_BWD_X) row_stat = (p < prm.batch) ? prm.lse2p[p] : INFINITY;
+                dg = -1;
+                if (x_item && p < prm.x_rows) { lo = prm.lo[p]; hi = prm.hi[p]; dg = prm.diag[p]; }
+                if (MODE == MODE_BWD_X) row_stat = (p < prm.x_rows) ? prm.lse2p[p] : INFINITY;
                 m_run = -INFINITY; s_run = 0.f;
             }
             {
                 const int b = BWD ? 0 : (i & 1);
                 const bool w_item = c.n < prm.wt_split;       // item columns (FWD / BWD_X) or U rows (BWD_Y)
                 const int col0 = (w_item ? c.n : c.n - prm.wt_split) * TC_BN + grp * TC_HALF;
-                const int ncol = static_cast<int>(w_item ? prm.batch : prm.pool_rows);
+                const int ncol = static_cast<int>(w_item ? prm.w_rows : prm.pool_rows);
                 // per-element path: columns past the end (zero-filled W rows would count as logit 0; BWD_Y handles
                 // them through lse = +inf) and the collision run / diagonal of this row
                 const bool special = (!TRANS && col0 + TC_HALF > ncol) || (x_item && w_item && hi > col0 && lo < col0 + TC_HALF);
@@ -378,7 +423,7 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 const int col = col0 + q * 32 + j;
-                                const bool dead = (col >= ncol) || (w_item && col >= lo && col < hi && col != p);
+                                const bool dead = (col >= ncol) || (w_item && col >= lo && col < hi && col != dg);
                                 if (dead) r[q][j] = 0xff800000u;   // -inf
                             }
                     }
@@ -482,7 +527,7 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                                     e[j] = ex2_approx(fmaf(__uint_as_float(r[qq][j]), prm.scale2, -st));
                                     const int col = col0 + q * 32 + j;
                                     if (col >= ncol) e[j] = 0.f;
-                                    else if (x_item && w_item && col >= lo && col < hi) e[j] = (col == p) ? e[j] - 1.0f : 0.f;
+                                    else if (x_item && w_item && col >= lo && col < hi) e[j] = (col == dg) ? e[j] - 1.0f : 0.f;
                                 }
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) g[qq * 16 + j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
@@ -505,8 +550,8 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
             if (c.n == prm.n_tiles - 1 || i == n_local - 1) {
                 const int seg = static_cast<int>(blockIdx.x) - sched_first_cta(c.m, prm.n_tiles, prm.per_cta);
                 if (MODE == MODE_FWD) {
-                    if (p < prm.batch) {
-                        const int64_t slot = static_cast<int64_t>(2 * seg + grp) * prm.batch + p;
+                    if (p < prm.x_rows) {
+                        const int64_t slot = static_cast<int64_t>(2 * seg + grp) * prm.x_rows + p;
                         prm.part_m[slot] = m_run;
                         prm.part_s[slot] = s_run;
                     }
@@ -543,7 +588,8 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
 __global__ void __launch_bounds__(256)
 ce_tc_finalize(const __nv_bfloat16 *__restrict__ ub, const __nv_bfloat16 *__restrict__ ib,
                const float *__restrict__ user32, const float *__restrict__ hn_rows, int n_rowneg,
-               const int32_t *__restrict__ perm, int64_t B, int dim, float inv_temp, int n_tiles, int64_t per_cta,
+               const int32_t *__restrict__ perm, const int32_t *__restrict__ diag, int64_t B, int dim, float inv_temp,
+               int n_tiles, int64_t per_cta,
                const float *__restrict__ part_m, const float *__restrict__ part_s, float *__restrict__ row_lse,
                float *__restrict__ row_pos, float *__restrict__ row_loss, int *__restrict__ nan_flags) {
     const int lane = threadIdx.x & 31;
@@ -579,8 +625,9 @@ ce_tc_finalize(const __nv_bfloat16 *__restrict__ ub, const __nv_bfloat16 *__rest
         }
         if (__any_sync(0xffffffffu, nan) && lane == 0) atomicOr(nan_flags, 4);
         float pos = 0.f;
+        const int64_t pi = diag[p];     // sorted position of this user's own item
         for (int k = lane; k < dim; k += 32)
-            pos = fmaf(__bfloat162float(ub[p * dim + k]), __bfloat162float(ib[p * dim + k]), pos);
+            pos = fmaf(__bfloat162float(ub[p * dim + k]), __bfloat162float(ib[pi * dim + k]), pos);
         pos = warp_sum(pos) * inv_temp;
         if (lane == 0) {
             const float lse = (m + log2f(s)) * (1.0f / LOG2E);
@@ -671,53 +718,66 @@ ce_tc_reduce_rows(const float *__restrict__ part, int64_t part_rows, int n_tiles
 
 // ---------------------------------------------------------------- host side
 struct CeTcPlan {
-    int xt_item, xt_pool;      // 128-row X tiles of the item (= user) rows / the pool
-    int wt_item, wt_pool;      // 256-row W tiles
+    int xt_user, xt_item, xt_pool;      // 128-row X tiles of the user rows / the item rows / the pool
+    int wt_user, wt_item, wt_pool;      // 256-row W tiles
     Sched fwd, bwd_x, bwd_y;
     size_t sort_bytes;
 };
 
-static CeTcPlan ce_tc_plan(int64_t batch, int64_t pool_rows) {
+static CeTcPlan ce_tc_plan(int64_t n_user, int64_t n_item, int64_t pool_rows) {
     CeTcPlan p;
-    p.xt_item = static_cast<int>((batch + TC_BM - 1) / TC_BM);
+    p.xt_user = static_cast<int>((n_user + TC_BM - 1) / TC_BM);
+    p.xt_item = static_cast<int>((n_item + TC_BM - 1) / TC_BM);
     p.xt_pool = static_cast<int>((pool_rows + TC_BM - 1) / TC_BM);
-    p.wt_item = static_cast<int>((batch + TC_BN - 1) / TC_BN);
+    p.wt_user = static_cast<int>((n_user + TC_BN - 1) / TC_BN);
+    p.wt_item = static_cast<int>((n_item + TC_BN - 1) / TC_BN);
     p.wt_pool = static_cast<int>((pool_rows + TC_BN - 1) / TC_BN);
-    p.fwd = make_sched(p.xt_item, p.wt_item + p.wt_pool);
+    p.fwd = make_sched(p.xt_user, p.wt_item + p.wt_pool);
     p.bwd_x = p.fwd;
-    p.bwd_y = make_sched(p.xt_item + p.xt_pool, p.wt_item);
+    p.bwd_y = make_sched(p.xt_item + p.xt_pool, p.wt_user);
     p.sort_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, p.sort_bytes, static_cast<int64_t *>(nullptr),
                                     static_cast<int64_t *>(nullptr), static_cast<int32_t *>(nullptr),
-                                    static_cast<int32_t *>(nullptr), static_cast<int>(batch));
+                                    static_cast<int32_t *>(nullptr), static_cast<int>(n_item));
     return p;
 }
 
 struct CeTcWs {
     __nv_bfloat16 *ub, *ib, *pb;
-    int64_t *keys_in, *keys_out;
-    int32_t *vals_in, *perm, *lo, *hi;
+    int64_t *ikeys_in, *ikeys, *ukeys_in, *ukeys;     // item / user sort keys (unsorted, sorted)
+    int32_t *vals_in, *perm_i, *inv_i, *perm_u, *inv_u;
+    int32_t *lo_u, *hi_u, *diag_u, *lo_i, *hi_i, *diag_i;
     float *part_m, *part_s, *row_loss;
     void *cub_tmp;
     bool ok;
     size_t used;
 };
 
-static CeTcWs ce_tc_carve(void *workspace, size_t bytes, int64_t batch, int64_t pool_rows, int dim, const CeTcPlan &pl) {
+static CeTcWs ce_tc_carve(void *workspace, size_t bytes, int64_t n_user, int64_t n_item, int64_t pool_rows, int dim,
+                          const CeTcPlan &pl) {
     Workspace ws(workspace, bytes);
     CeTcWs w;
-    w.ub = ws.take<__nv_bfloat16>(batch * dim);
-    w.ib = ws.take<__nv_bfloat16>(batch * dim);
+    w.ub = ws.take<__nv_bfloat16>(n_user * dim);
+    w.ib = ws.take<__nv_bfloat16>(n_item * dim);
     w.pb = ws.take<__nv_bfloat16>((pool_rows > 0 ? pool_rows : 1) * dim);
-    w.keys_in = ws.take<int64_t>(batch);
-    w.keys_out = ws.take<int64_t>(batch);
-    w.vals_in = ws.take<int32_t>(batch);
-    w.perm = ws.take<int32_t>(batch);
-    w.lo = ws.take<int32_t>(batch);
-    w.hi = ws.take<int32_t>(batch);
-    w.part_m = ws.take<float>(static_cast<size_t>(2 * pl.fwd.max_seg) * batch);
-    w.part_s = ws.take<float>(static_cast<size_t>(2 * pl.fwd.max_seg) * batch);
-    w.row_loss = ws.take<float>(batch);
+    w.ikeys_in = ws.take<int64_t>(n_item);
+    w.ikeys = ws.take<int64_t>(n_item);
+    w.ukeys_in = ws.take<int64_t>(n_user);
+    w.ukeys = ws.take<int64_t>(n_user);
+    w.vals_in = ws.take<int32_t>(n_item);
+    w.perm_i = ws.take<int32_t>(n_item);
+    w.inv_i = ws.take<int32_t>(n_item);
+    w.perm_u = ws.take<int32_t>(n_user);
+    w.inv_u = ws.take<int32_t>(n_user);
+    w.lo_u = ws.take<int32_t>(n_user);
+    w.hi_u = ws.take<int32_t>(n_user);
+    w.diag_u = ws.take<int32_t>(n_user);
+    w.lo_i = ws.take<int32_t>(n_item);
+    w.hi_i = ws.take<int32_t>(n_item);
+    w.diag_i = ws.take<int32_t>(n_item);
+    w.part_m = ws.take<float>(static_cast<size_t>(2 * pl.fwd.max_seg) * n_user);
+    w.part_s = ws.take<float>(static_cast<size_t>(2 * pl.fwd.max_seg) * n_user);
+    w.row_loss = ws.take<float>(n_user);
     w.cub_tmp = ws.take<char>(pl.sort_bytes);
     w.ok = ws.ok();
     w.used = ws.off;
@@ -731,14 +791,14 @@ struct CeBwdWs {
     size_t used;
 };
 
-static CeBwdWs ce_bwd_carve(void *workspace, size_t bytes, int64_t batch, int n_rowneg, int dim, const CeTcPlan &pl) {
+static CeBwdWs ce_bwd_carve(void *workspace, size_t bytes, int64_t n_user, int n_rowneg, int dim, const CeTcPlan &pl) {
     Workspace ws(workspace, bytes);
     CeBwdWs w;
-    w.rows_x = static_cast<int64_t>(pl.xt_item) * TC_BM;
+    w.rows_x = static_cast<int64_t>(pl.xt_user) * TC_BM;
     w.rows_y = static_cast<int64_t>(pl.xt_item + pl.xt_pool) * TC_BM;
-    w.lse_rows = static_cast<int64_t>(pl.wt_item) * TC_BN;
+    w.lse_rows = static_cast<int64_t>(pl.wt_user) * TC_BN;
     w.lse2p = ws.take<float>(w.lse_rows);
-    w.extra = ws.take<float>(n_rowneg > 0 ? batch * dim : 1);
+    w.extra = ws.take<float>(n_rowneg > 0 ? n_user * dim : 1);
     w.part_x = ws.take<float>(static_cast<size_t>(pl.bwd_x.max_seg) * w.rows_x * dim);
     w.part_y = ws.take<float>(static_cast<size_t>(pl.bwd_y.max_seg) * w.rows_y * dim);
     w.ok = ws.ok();
@@ -774,15 +834,15 @@ static int launch_ce_tc_dim(int dim, const CUtensorMap &xa, const CUtensorMap &x
 struct CeMaps {
     CUtensorMap u128, i128, p128, u256, i256, p256;
 };
-static int make_ce_maps(CeMaps &m, const CeTcWs &f, int64_t batch, int64_t pool_rows, int dim) {
+static int make_ce_maps(CeMaps &m, const CeTcWs &f, int64_t n_user, int64_t n_item, int64_t pool_rows, int dim) {
     int rc;
     const void *pb = pool_rows ? static_cast<const void *>(f.pb) : static_cast<const void *>(f.ib);
-    const int64_t pr = pool_rows ? pool_rows : batch;
-    if ((rc = make_tmap_bf16_rows(&m.u128, f.ub, batch, dim, TC_BM))) return rc;
-    if ((rc = make_tmap_bf16_rows(&m.i128, f.ib, batch, dim, TC_BM))) return rc;
+    const int64_t pr = pool_rows ? pool_rows : n_item;
+    if ((rc = make_tmap_bf16_rows(&m.u128, f.ub, n_user, dim, TC_BM))) return rc;
+    if ((rc = make_tmap_bf16_rows(&m.i128, f.ib, n_item, dim, TC_BM))) return rc;
     if ((rc = make_tmap_bf16_rows(&m.p128, pb, pr, dim, TC_BM))) return rc;
-    if ((rc = make_tmap_bf16_rows(&m.u256, f.ub, batch, dim, TC_BN))) return rc;
-    if ((rc = make_tmap_bf16_rows(&m.i256, f.ib, batch, dim, TC_BN))) return rc;
+    if ((rc = make_tmap_bf16_rows(&m.u256, f.ub, n_user, dim, TC_BN))) return rc;
+    if ((rc = make_tmap_bf16_rows(&m.i256, f.ib, n_item, dim, TC_BN))) return rc;
     if ((rc = make_tmap_bf16_rows(&m.p256, pb, pr, dim, TC_BN))) return rc;
     return 0;
 }
@@ -803,131 +863,116 @@ static inline unsigned tc_grid(int64_t n, int threads) {
     return static_cast<unsigned>(b);
 }
 
-}  // namespace tt
-
-extern "C" int tt_ce_tc_workspace(int64_t batch, int64_t pool, int n_rowneg, int dim, size_t *bytes_host) {
-    using namespace tt;
-    TT_CHECK_ARG(bytes_host && batch > 0 && pool >= 0 && n_rowneg >= 0 && dim > 0, "bad size");
-    const CeTcPlan pl = ce_tc_plan(batch, pool);
-    const CeTcWs w = ce_tc_carve(nullptr, ~size_t(0), batch, pool, dim, pl);
-    *bytes_host = w.used + 1024;
-    return 0;
-}
-
-extern "C" int tt_ce_fwd_tc(const float *user, const float *item, const int64_t *item_ids, const float *hn_rows,
-                            int n_rowneg, const float *pool, int64_t pool_rows, int64_t batch, int dim, float inv_temp,
-                            float *loss, float *row_lse, float *row_pos, int *nan_flags, void *workspace,
-                            size_t workspace_bytes, void *stream) {
-    using namespace tt;
-    TT_CHECK_ARG(user && item && loss && row_lse && row_pos && nan_flags && workspace, "null pointer");
-    TT_CHECK_ARG((hn_rows != nullptr) == (n_rowneg > 0), "hn_rows / n_rowneg mismatch");
-    TT_CHECK_ARG((pool != nullptr) == (pool_rows > 0), "pool / pool_rows mismatch");
-    TT_CHECK_ARG(batch > 0 && batch < (int64_t(1) << 30) && pool_rows < (int64_t(1) << 30), "bad batch");
-    TT_CHECK_ARG(inv_temp > 0.f, "temperature must be positive");
-    if (dim != 64 && dim != 128) { set_error("tensor-core CE path supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const CeTcPlan pl = ce_tc_plan(batch, pool_rows);
-    CeTcWs w = ce_tc_carve(workspace, workspace_bytes, batch, pool_rows, dim, pl);
+static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *item_ids, int64_t item_offset,
+                          const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
+                          int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
+                          int *nan_flags, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    const CeTcPlan pl = ce_tc_plan(n_user, n_item, pool_rows);
+    CeTcWs w = ce_tc_carve(workspace, workspace_bytes, n_user, n_item, pool_rows, dim, pl);
     if (!w.ok) { set_error("ce_tc workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) { set_error("ce_tc workspace must be 256-byte aligned"); return TT_E_BADARG; }
 
-    // 1. item-id sorted order -> perm, collision runs
+    // 1. item-id sorted orders of the item rows and of the user rows -> permutations, collision runs, positive columns
+    const int64_t *ikeys = nullptr, *ukeys = nullptr;
     if (item_ids != nullptr) {
-        tc_iota_keys<<<tc_grid(batch, 256), 256, 0, st>>>(item_ids, batch, w.keys_in, w.vals_in);
+        tc_iota_keys<<<tc_grid(n_item, 256), 256, 0, st>>>(item_ids, n_item, w.ikeys_in, w.vals_in);
         TT_LAUNCH_CHECK("tc_iota_keys");
         size_t tmp = pl.sort_bytes;
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.perm,
-                                                        static_cast<int>(batch), 0, 64, st);
-        if (e != cudaSuccess) return cuda_status(e, "cub SortPairs(ce_tc)");
-        tc_runs<<<tc_grid(batch, 256), 256, 0, st>>>(w.keys_out, batch, w.lo, w.hi, nullptr);
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikeys_in, w.ikeys, w.vals_in, w.perm_i,
+                                                        static_cast<int>(n_item), 0, 64, st);
+        if (e != cudaSuccess) return cuda_status(e, "cub SortPairs(ce_tc items)");
+        tc_user_keys<<<tc_grid(n_user, 256), 256, 0, st>>>(item_ids, item_offset, n_user, w.ukeys_in, w.vals_in);
+        TT_LAUNCH_CHECK("tc_user_keys");
+        tmp = pl.sort_bytes;
+        e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukeys_in, w.ukeys, w.vals_in, w.perm_u,
+                                            static_cast<int>(n_user), 0, 64, st);
+        if (e != cudaSuccess) return cuda_status(e, "cub SortPairs(ce_tc users)");
+        ikeys = w.ikeys; ukeys = w.ukeys;
     } else {
-        tc_runs<<<tc_grid(batch, 256), 256, 0, st>>>(nullptr, batch, w.lo, w.hi, w.perm);
+        tc_iota<<<tc_grid(n_item, 256), 256, 0, st>>>(w.perm_i, n_item);
+        tc_iota<<<tc_grid(n_user, 256), 256, 0, st>>>(w.perm_u, n_user);
     }
-    TT_LAUNCH_CHECK("tc_runs");
+    tc_invert_perm<<<tc_grid(n_item, 256), 256, 0, st>>>(w.perm_i, n_item, w.inv_i);
+    tc_invert_perm<<<tc_grid(n_user, 256), 256, 0, st>>>(w.perm_u, n_user, w.inv_u);
+    // user rows: W side = items, partner = own item (original index perm_u[p] + item_offset)
+    tc_runs_rect<<<tc_grid(n_user, 256), 256, 0, st>>>(ukeys, n_user, ikeys, n_item, w.perm_u, w.inv_i, item_offset, n_item,
+                                                       w.lo_u, w.hi_u, w.diag_u);
+    // item rows (backward over the items): W side = users, partner = the local user this item belongs to, if any
+    tc_runs_rect<<<tc_grid(n_item, 256), 256, 0, st>>>(ikeys, n_item, ukeys, n_user, w.perm_i, w.inv_u, -item_offset, n_user,
+                                                       w.lo_i, w.hi_i, w.diag_i);
+    TT_LAUNCH_CHECK("tc_runs_rect");
     // 2. bf16 operands in sorted order
-    tc_convert_rows<<<tc_grid(batch * 32, 256), 256, 0, st>>>(user, w.perm, batch, dim, w.ub, nan_flags, 1);
-    tc_convert_rows<<<tc_grid(batch * 32, 256), 256, 0, st>>>(item, w.perm, batch, dim, w.ib, nan_flags, 2);
+    tc_convert_rows<<<tc_grid(n_user * 32, 256), 256, 0, st>>>(user, w.perm_u, n_user, dim, w.ub, nan_flags, 1);
+    tc_convert_rows<<<tc_grid(n_item * 32, 256), 256, 0, st>>>(item, w.perm_i, n_item, dim, w.ib, nan_flags, 2);
     if (pool) tc_convert_rows<<<tc_grid(pool_rows * 32, 256), 256, 0, st>>>(pool, nullptr, pool_rows, dim, w.pb, nan_flags, 4);
     TT_LAUNCH_CHECK("tc_convert_rows");
     // 3. tensor maps + main kernel
     CeMaps mp;
     int rc;
-    if ((rc = make_ce_maps(mp, w, batch, pool_rows, dim))) return rc;
+    if ((rc = make_ce_maps(mp, w, n_user, n_item, pool_rows, dim))) return rc;
     CeTcParams prm{};
-    prm.batch = batch; prm.pool_rows = pool_rows;
-    prm.xt_split = pl.xt_item; prm.wt_split = pl.wt_item;
+    prm.x_rows = n_user; prm.w_rows = n_item; prm.pool_rows = pool_rows;
+    prm.xt_split = pl.xt_user; prm.wt_split = pl.wt_item;
     fill_sched(prm, pl.fwd);
     prm.scale2 = inv_temp * LOG2E;
-    prm.lo = w.lo; prm.hi = w.hi; prm.part_m = w.part_m; prm.part_s = w.part_s;
+    prm.lo = w.lo_u; prm.hi = w.hi_u; prm.diag = w.diag_u; prm.part_m = w.part_m; prm.part_s = w.part_s;
     if ((rc = launch_ce_tc_dim<MODE_FWD>(dim, mp.u128, mp.u128, mp.i256, mp.p256, prm, pl.fwd.grid, st))) return rc;
     // 4. finalize
-    ce_tc_finalize<<<tc_grid(batch * 32, 256), 256, 0, st>>>(w.ub, w.ib, user, hn_rows, n_rowneg, w.perm, batch, dim,
-                                                            inv_temp, pl.fwd.n_tiles, pl.fwd.per_cta, w.part_m, w.part_s,
-                                                            row_lse, row_pos, w.row_loss, nan_flags);
+    ce_tc_finalize<<<tc_grid(n_user * 32, 256), 256, 0, st>>>(w.ub, w.ib, user, hn_rows, n_rowneg, w.perm_u, w.diag_u, n_user, dim,
+                                                             inv_temp, pl.fwd.n_tiles, pl.fwd.per_cta, w.part_m, w.part_s,
+                                                             row_lse, row_pos, w.row_loss, nan_flags);
     TT_LAUNCH_CHECK("ce_tc_finalize");
-    ce_tc_mean<<<1, 1024, 0, st>>>(w.row_loss, batch, loss);
+    ce_tc_mean<<<1, 1024, 0, st>>>(w.row_loss, n_user, loss);
     TT_LAUNCH_CHECK("ce_tc_mean");
     return 0;
 }
 
-extern "C" int tt_ce_bwd_tc_workspace(int64_t batch, int64_t pool, int n_rowneg, int dim, size_t *bytes_host) {
-    using namespace tt;
-    TT_CHECK_ARG(bytes_host && batch > 0 && pool >= 0 && n_rowneg >= 0 && dim > 0, "bad size");
-    const CeTcPlan pl = ce_tc_plan(batch, pool);
-    const CeBwdWs w = ce_bwd_carve(nullptr, ~size_t(0), batch, n_rowneg, dim, pl);
-    *bytes_host = w.used + 1024;
-    return 0;
-}
-
-extern "C" int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowneg, int64_t pool_rows, int64_t batch,
-                            int dim, float inv_temp, const float *row_lse, const float *grad_loss, float *d_user,
-                            float *d_item, float *d_hn_rows, float *d_pool, void *fwd_workspace,
-                            size_t fwd_workspace_bytes, void *workspace, size_t workspace_bytes, void *stream) {
-    using namespace tt;
-    TT_CHECK_ARG(user && row_lse && grad_loss && d_user && d_item && fwd_workspace && workspace, "null pointer");
-    TT_CHECK_ARG((hn_rows != nullptr) == (n_rowneg > 0), "hn_rows / n_rowneg mismatch");
-    TT_CHECK_ARG(pool_rows == 0 || d_pool != nullptr, "d_pool required with a pool");
-    TT_CHECK_ARG(batch > 0 && batch < (int64_t(1) << 30) && pool_rows < (int64_t(1) << 30), "bad batch");
-    if (dim != 64 && dim != 128) { set_error("tensor-core CE path supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const CeTcPlan pl = ce_tc_plan(batch, pool_rows);
-    const CeTcWs f = ce_tc_carve(fwd_workspace, fwd_workspace_bytes, batch, pool_rows, dim, pl);
+static int ce_bwd_tc_impl(const float *user, const float *hn_rows, int n_rowneg, int64_t pool_rows, int64_t n_user,
+                          int64_t n_item, int dim, float inv_temp, const float *row_lse, const float *grad_loss,
+                          float *d_user, float *d_item, float *d_hn_rows, float *d_pool, void *fwd_workspace,
+                          size_t fwd_workspace_bytes, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    const CeTcPlan pl = ce_tc_plan(n_user, n_item, pool_rows);
+    const CeTcWs f = ce_tc_carve(fwd_workspace, fwd_workspace_bytes, n_user, n_item, pool_rows, dim, pl);
     if (!f.ok) { set_error("ce_tc forward workspace too small: need %zu have %zu", f.used, fwd_workspace_bytes); return TT_E_WORKSPACE; }
-    const CeBwdWs w = ce_bwd_carve(workspace, workspace_bytes, batch, n_rowneg, dim, pl);
+    const CeBwdWs w = ce_bwd_carve(workspace, workspace_bytes, n_user, n_rowneg, dim, pl);
     if (!w.ok) { set_error("ce_tc backward workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) { set_error("ce_tc workspace must be 256-byte aligned"); return TT_E_BADARG; }
 
-    ce_tc_bwd_prep<<<tc_grid(w.lse_rows, 256), 256, 0, st>>>(row_lse, f.perm, batch, w.lse_rows, w.lse2p);
+    ce_tc_bwd_prep<<<tc_grid(w.lse_rows, 256), 256, 0, st>>>(row_lse, f.perm_u, n_user, w.lse_rows, w.lse2p);
     TT_LAUNCH_CHECK("ce_tc_bwd_prep");
     CeMaps mp;
     int rc;
-    if ((rc = make_ce_maps(mp, f, batch, pool_rows, dim))) return rc;
+    if ((rc = make_ce_maps(mp, f, n_user, n_item, pool_rows, dim))) return rc;
     CeTcParams prm{};
-    prm.batch = batch; prm.pool_rows = pool_rows;
+    prm.pool_rows = pool_rows;
     prm.scale2 = inv_temp * LOG2E;
-    prm.lo = f.lo; prm.hi = f.hi; prm.lse2p = w.lse2p;
+    prm.lse2p = w.lse2p;
     // pass 1: dU   (X = U row tiles, W = [item ; pool] 256-row tiles)
     fill_sched(prm, pl.bwd_x);
-    prm.xt_split = pl.xt_item; prm.wt_split = pl.wt_item;
+    prm.x_rows = n_user; prm.w_rows = n_item;
+    prm.lo = f.lo_u; prm.hi = f.hi_u; prm.diag = f.diag_u;
+    prm.xt_split = pl.xt_user; prm.wt_split = pl.wt_item;
     prm.part = w.part_x;
     if ((rc = launch_ce_tc_dim<MODE_BWD_X>(dim, mp.u128, mp.u128, mp.i256, mp.p256, prm, pl.bwd_x.grid, st))) return rc;
     // pass 2: dI, dPool   (X = [item ; pool] row tiles, W = U 256-row tiles)
     fill_sched(prm, pl.bwd_y);
-    prm.xt_split = pl.xt_item; prm.wt_split = pl.wt_item;
+    prm.x_rows = n_item; prm.w_rows = n_user;
+    prm.lo = f.lo_i; prm.hi = f.hi_i; prm.diag = f.diag_i;
+    prm.xt_split = pl.xt_item; prm.wt_split = pl.wt_user;
     prm.part = w.part_y;
     if ((rc = launch_ce_tc_dim<MODE_BWD_Y>(dim, mp.i128, mp.p128, mp.u256, mp.u256, prm, pl.bwd_y.grid, st))) return rc;
     if (hn_rows) {
-        ce_tc_bwd_hn_rows<<<tc_grid(batch * 32, 256), 256, 0, st>>>(user, hn_rows, n_rowneg, batch, dim, inv_temp, row_lse,
-                                                                   grad_loss, d_hn_rows, w.extra);
+        ce_tc_bwd_hn_rows<<<tc_grid(n_user * 32, 256), 256, 0, st>>>(user, hn_rows, n_rowneg, n_user, dim, inv_temp, row_lse,
+                                                                    grad_loss, d_hn_rows, w.extra);
         TT_LAUNCH_CHECK("ce_tc_bwd_hn_rows");
     }
-    const float scale = inv_temp / static_cast<float>(batch);
+    const float scale = inv_temp / static_cast<float>(n_user);      // mean over THIS call's user rows
     const int64_t vec = dim / 4;
-    ce_tc_reduce_rows<<<tc_grid(batch * vec, 256), 256, 0, st>>>(w.part_x, w.rows_x, pl.bwd_x.n_tiles, pl.bwd_x.per_cta, 0,
-                                                                batch, dim, f.perm, grad_loss, scale,
-                                                                hn_rows ? w.extra : nullptr, inv_temp, d_user);
-    ce_tc_reduce_rows<<<tc_grid(batch * vec, 256), 256, 0, st>>>(w.part_y, w.rows_y, pl.bwd_y.n_tiles, pl.bwd_y.per_cta, 0,
-                                                                batch, dim, f.perm, grad_loss, scale, nullptr, 0.f, d_item);
+    ce_tc_reduce_rows<<<tc_grid(n_user * vec, 256), 256, 0, st>>>(w.part_x, w.rows_x, pl.bwd_x.n_tiles, pl.bwd_x.per_cta, 0,
+                                                                 n_user, dim, f.perm_u, grad_loss, scale,
+                                                                 hn_rows ? w.extra : nullptr, inv_temp, d_user);
+    ce_tc_reduce_rows<<<tc_grid(n_item * vec, 256), 256, 0, st>>>(w.part_y, w.rows_y, pl.bwd_y.n_tiles, pl.bwd_y.per_cta, 0,
+                                                                 n_item, dim, f.perm_i, grad_loss, scale, nullptr, 0.f, d_item);
     if (pool_rows > 0)
         ce_tc_reduce_rows<<<tc_grid(pool_rows * vec, 256), 256, 0, st>>>(w.part_y, w.rows_y, pl.bwd_y.n_tiles,
                                                                         pl.bwd_y.per_cta,
@@ -936,6 +981,82 @@ extern "C" int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowne
                                                                         0.f, d_pool);
     TT_LAUNCH_CHECK("ce_tc_reduce_rows");
     return 0;
+}
+
+}  // namespace tt
+
+#define TT_CE_TC_COMMON_CHECKS()                                                                                        \
+    TT_CHECK_ARG((hn_rows != nullptr) == (n_rowneg > 0), "hn_rows / n_rowneg mismatch");                                \
+    TT_CHECK_ARG(n_user > 0 && n_item >= n_user && n_item < (int64_t(1) << 30) && pool_rows < (int64_t(1) << 30), "bad batch"); \
+    if (dim != 64 && dim != 128) { tt::set_error("tensor-core CE path supports dim 64 or 128 (got %d)", dim); return TT_E_UNSUPPORTED; }
+
+extern "C" int tt_ce_tc_workspace_rect(int64_t n_user, int64_t n_item, int64_t pool, int n_rowneg, int dim, size_t *bytes_host) {
+    using namespace tt;
+    TT_CHECK_ARG(bytes_host && n_user > 0 && n_item >= n_user && pool >= 0 && n_rowneg >= 0 && dim > 0, "bad size");
+    const CeTcPlan pl = ce_tc_plan(n_user, n_item, pool);
+    const CeTcWs w = ce_tc_carve(nullptr, ~size_t(0), n_user, n_item, pool, dim, pl);
+    *bytes_host = w.used + 1024;
+    return 0;
+}
+
+extern "C" int tt_ce_tc_workspace(int64_t batch, int64_t pool, int n_rowneg, int dim, size_t *bytes_host) {
+    return tt_ce_tc_workspace_rect(batch, batch, pool, n_rowneg, dim, bytes_host);
+}
+
+extern "C" int tt_ce_fwd_tc_rect(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,
+                                 const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
+                                 int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
+                                 int *nan_flags, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(user && item_all && loss && row_lse && row_pos && nan_flags && workspace, "null pointer");
+    TT_CHECK_ARG((pool != nullptr) == (pool_rows > 0), "pool / pool_rows mismatch");
+    TT_CE_TC_COMMON_CHECKS();
+    TT_CHECK_ARG(item_offset >= 0 && item_offset + n_user <= n_item, "item_offset + n_user must lie inside the item rows");
+    TT_CHECK_ARG(inv_temp > 0.f, "temperature must be positive");
+    return ce_fwd_tc_impl(user, item_all, item_ids_all, item_offset, hn_rows, n_rowneg, pool, pool_rows, n_user, n_item, dim,
+                          inv_temp, loss, row_lse, row_pos, nan_flags, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tt_ce_fwd_tc(const float *user, const float *item, const int64_t *item_ids, const float *hn_rows,
+                            int n_rowneg, const float *pool, int64_t pool_rows, int64_t batch, int dim, float inv_temp,
+                            float *loss, float *row_lse, float *row_pos, int *nan_flags, void *workspace,
+                            size_t workspace_bytes, void *stream) {
+    return tt_ce_fwd_tc_rect(user, item, item_ids, 0, hn_rows, n_rowneg, pool, pool_rows, batch, batch, dim, inv_temp, loss,
+                             row_lse, row_pos, nan_flags, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tt_ce_bwd_tc_workspace_rect(int64_t n_user, int64_t n_item, int64_t pool, int n_rowneg, int dim, size_t *bytes_host) {
+    using namespace tt;
+    TT_CHECK_ARG(bytes_host && n_user > 0 && n_item >= n_user && pool >= 0 && n_rowneg >= 0 && dim > 0, "bad size");
+    const CeTcPlan pl = ce_tc_plan(n_user, n_item, pool);
+    const CeBwdWs w = ce_bwd_carve(nullptr, ~size_t(0), n_user, n_rowneg, dim, pl);
+    *bytes_host = w.used + 1024;
+    return 0;
+}
+
+extern "C" int tt_ce_bwd_tc_workspace(int64_t batch, int64_t pool, int n_rowneg, int dim, size_t *bytes_host) {
+    return tt_ce_bwd_tc_workspace_rect(batch, batch, pool, n_rowneg, dim, bytes_host);
+}
+
+extern "C" int tt_ce_bwd_tc_rect(const float *user, const float *hn_rows, int n_rowneg, int64_t pool_rows, int64_t n_user,
+                                 int64_t n_item, int dim, float inv_temp, const float *row_lse, const float *grad_loss,
+                                 float *d_user, float *d_item_all, float *d_hn_rows, float *d_pool, void *fwd_workspace,
+                                 size_t fwd_workspace_bytes, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(user && row_lse && grad_loss && d_user && d_item_all && fwd_workspace && workspace, "null pointer");
+    TT_CHECK_ARG(pool_rows == 0 || d_pool != nullptr, "d_pool required with a pool");
+    TT_CE_TC_COMMON_CHECKS();
+    return ce_bwd_tc_impl(user, hn_rows, n_rowneg, pool_rows, n_user, n_item, dim, inv_temp, row_lse, grad_loss, d_user,
+                          d_item_all, d_hn_rows, d_pool, fwd_workspace, fwd_workspace_bytes, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tt_ce_bwd_tc(const float *user, const float *hn_rows, int n_rowneg, int64_t pool_rows, int64_t batch,
+                            int dim, float inv_temp, const float *row_lse, const float *grad_loss, float *d_user,
+                            float *d_item, float *d_hn_rows, float *d_pool, void *fwd_workspace,
+                            size_t fwd_workspace_bytes, void *workspace, size_t workspace_bytes, void *stream) {
+    return tt_ce_bwd_tc_rect(user, hn_rows, n_rowneg, pool_rows, batch, batch, dim, inv_temp, row_lse, grad_loss, d_user, d_item,
+                             d_hn_rows, d_pool, fwd_workspace, fwd_workspace_bytes, workspace, workspace_bytes, stream);
 }
 
 /* developer hook: record SM-clock stamps of CTA 0's pipeline events into dbg[11][256] (NULL disables) */

@@ -589,18 +589,31 @@ class _AllGatherWithGrad(torch.autograd.Function):
 
 def global_inbatch_ce(user, item, item_ids, pool, temperature, precision: str = "fp32", ce_fn=None):
     """SURVEY 8e, "towers + loss": the in-batch softmax over the GLOBAL batch of W*B items while every rank keeps only
-    its own B rows.  item embeddings are all-gathered; on rank r the other ranks' items enter the fused CE kernel as
-    extra shared negatives (its pool argument), so the [B, W*B + H] logit slab never exists in HBM either; their
-    gradients flow back to the owners through the all-gather's backward (sum), the dense-gradient all-reduce (AVG) of
-    DataParallelStep then yields exactly d(mean of the W rank losses) = d(global-batch loss).
-    Returns this rank's mean loss over its B rows (global loss = mean over ranks).  False-negative masking
-    (TwoTowerModel.py:101-104) covers the rank's own B x B block, like the single-process code at batch B; an item id
-    repeated on ANOTHER rank counts as a negative.  `ce_fn(user, item, item_ids, pool, temperature)` overrides the CUDA
-    kernel (CPU gloo tests inject the oracle)."""
+    its own B user rows.  Item embeddings (and item ids) are all-gathered; their gradients flow back to the owners
+    through the all-gather's backward (reduce-scatter / sum); with the loss of rank r scaled by 1/W and the dense
+    gradients SUM-reduced (ShardedTrainStep) the result is d(global-batch mean loss).
+    Returns this rank's mean loss over its B rows (global loss = mean over ranks).
+
+    precision='bf16' (tensor-core kernel): the RECTANGULAR form of the fused kernel -- B user rows against the W*B
+    gathered item rows, the positive of user b being row rank*B + b -- with the false-negative mask
+    (TwoTowerModel.py:101-104) applied against the item ids of ALL ranks, exactly what one process computes on the
+    global batch.  The [B, W*B + H] logit slab never exists in HBM.
+    precision='fp32' (exact SIMT kernel, small batches): the other ranks' items enter as extra shared negatives (the
+    kernel's pool argument); the mask then covers the rank's own B x B block only -- an item id repeated on ANOTHER
+    rank counts as a negative there.
+    `ce_fn(user, item, item_ids, pool, temperature)` overrides the CUDA kernel (CPU gloo tests inject the oracle)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world > 1:
         rank = dist.get_rank()
-        blocks = _AllGatherWithGrad.apply(item)
+        blocks = _AllGatherWithGrad.apply(item)                      # [W, B, D]
+        if precision == "bf16" and ce_fn is None:
+            B = item.shape[0]
+            ids_all = None
+            if item_ids is not None:
+                ids_all = torch.empty(world * B, dtype=torch.int64, device=item.device)
+                dist.all_gather_into_tensor(ids_all, item_ids.reshape(-1).contiguous().long())
+            return ops.fused_inbatch_ce(user, blocks.reshape(world * B, -1), ids_all, None, pool, temperature,
+                                        precision="bf16", item_offset=rank * B)[0]
         others = torch.cat([blocks[r] for r in range(world) if r != rank], dim=0)
         pool = others if pool is None else torch.cat([others, pool], dim=0)
     if ce_fn is not None:

@@ -208,12 +208,14 @@ def gather_rows(table: torch.Tensor, ids: torch.Tensor, mode: Optional[str], pad
 # 3. fused in-batch softmax cross-entropy
 # --------------------------------------------------------------------------
 class FusedInBatchCE(torch.autograd.Function):
-    """loss = mean_b(logsumexp(Z_b) - Z_bb), Z as in TwoTowerModel.py:95-134; the
-    logits never reach HBM.  Inputs fp32 [B, D]; hn_rows [B, N, D] and/or pool
-    [H, D] optional; item_ids int64 [B] optional."""
+    """loss = mean_b(logsumexp(Z_b) - Z_b,pos(b)), Z as in TwoTowerModel.py:95-134; the logits never reach HBM.
+    Inputs fp32: user [B, D]; item [Bi, D] with Bi == B (the reference's square in-batch form) or, precision 'bf16'
+    only, Bi > B: the all-gathered GLOBAL batch of a data-parallel run, the positive of user b being item row
+    item_offset + b; hn_rows [B, N, D] and/or pool [H, D] optional; item_ids int64 [Bi] optional."""
 
     @staticmethod
-    def forward(ctx, user, item, hn_rows, pool, item_ids, inv_temp: float, nan_flags, precision: str = "fp32"):
+    def forward(ctx, user, item, hn_rows, pool, item_ids, inv_temp: float, nan_flags, precision: str = "fp32",
+                item_offset: int = 0):
         _need_cuda(user, item)
         lib = _lib.load()
         user = user.contiguous().float()
@@ -222,24 +224,31 @@ class FusedInBatchCE(torch.autograd.Function):
         pool = None if pool is None else pool.contiguous().float()
         item_ids = None if item_ids is None else item_ids.reshape(-1).contiguous().long()
         B, D = user.shape
+        Bi = item.shape[0]
+        rect = Bi != B or item_offset != 0
+        if rect and precision != "bf16":
+            raise TTError("the rectangular (global-batch) in-batch CE runs on the tensor-core path only (precision='bf16')")
+        if item_ids is not None and item_ids.numel() != Bi:
+            raise TTError(f"item_ids has {item_ids.numel()} entries, expected one per item row ({Bi})")
         N = 0 if hn_rows is None else hn_rows.shape[1]
         H = 0 if pool is None else pool.shape[0]
         dev = user.device
         nbytes = ctypes.c_size_t(0)
-        check(lib.tt_ce_workspace(B, H, N, D, ctypes.byref(nbytes)), "tt_ce_workspace")
         loss = torch.empty((), dtype=torch.float32, device=dev)
         row_lse = torch.empty(B, dtype=torch.float32, device=dev)
         row_pos = torch.empty(B, dtype=torch.float32, device=dev)
+        tcws = None
         if precision == "bf16":
             # tcgen05 / TMA tensor-core path (D in {64, 128})
             tcbytes = ctypes.c_size_t(0)
-            check(lib.tt_ce_tc_workspace(B, H, N, D, ctypes.byref(tcbytes)), "tt_ce_tc_workspace")
+            check(lib.tt_ce_tc_workspace_rect(B, Bi, H, N, D, ctypes.byref(tcbytes)), "tt_ce_tc_workspace_rect")
             tcws = _ws(tcbytes.value, dev)
-            check(lib.tt_ce_fwd_tc(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D,
-                                   float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(tcws),
-                                   tcws.numel(), _stream()), "tt_ce_fwd_tc")
-            _count(7 + (1 if pool is not None else 0) + (1 if item_ids is not None else 0))
+            check(lib.tt_ce_fwd_tc_rect(_p(user), _p(item), _p(item_ids), int(item_offset), _p(hn_rows), N, _p(pool), H, B, Bi, D,
+                                        float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(tcws),
+                                        tcws.numel(), _stream()), "tt_ce_fwd_tc_rect")
+            _count(10 + (1 if pool is not None else 0) + (2 if item_ids is not None else 0))
         elif precision == "fp32":
+            check(lib.tt_ce_workspace(B, H, N, D, ctypes.byref(nbytes)), "tt_ce_workspace")
             ws = _ws(nbytes.value, dev)
             check(lib.tt_ce_fwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D,
                                     float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(ws),
@@ -251,7 +260,7 @@ class FusedInBatchCE(torch.autograd.Function):
         ctx.inv_temp = float(inv_temp)
         ctx.ws_bytes = nbytes.value
         ctx.precision = precision
-        ctx.tcws = tcws if precision == "bf16" else None  # bf16 operands / permutation / runs for the backward
+        ctx.tcws = tcws   # bf16 operands / permutations / runs for the backward
         ctx.mark_non_differentiable(row_lse)
         return loss, row_lse
 
@@ -260,6 +269,7 @@ class FusedInBatchCE(torch.autograd.Function):
         lib = _lib.load()
         user, item, hn_rows, pool, item_ids, row_lse = ctx.saved_tensors
         B, D = user.shape
+        Bi = item.shape[0]
         N = 0 if hn_rows is None else hn_rows.shape[1]
         H = 0 if pool is None else pool.shape[0]
         dev = user.device
@@ -270,28 +280,29 @@ class FusedInBatchCE(torch.autograd.Function):
         d_pool = None if pool is None else torch.empty_like(pool)
         if ctx.precision == "bf16":
             nbytes = ctypes.c_size_t(0)
-            check(lib.tt_ce_bwd_tc_workspace(B, H, N, D, ctypes.byref(nbytes)), "tt_ce_bwd_tc_workspace")
+            check(lib.tt_ce_bwd_tc_workspace_rect(B, Bi, H, N, D, ctypes.byref(nbytes)), "tt_ce_bwd_tc_workspace_rect")
             ws = _ws(nbytes.value, dev)
-            check(lib.tt_ce_bwd_tc(_p(user), _p(hn_rows), N, H, B, D, ctx.inv_temp, _p(row_lse), _p(g), _p(d_user),
-                                   _p(d_item), _p(d_hn), _p(d_pool), _p(ctx.tcws), ctx.tcws.numel(), _p(ws), ws.numel(),
-                                   _stream()), "tt_ce_bwd_tc")
+            check(lib.tt_ce_bwd_tc_rect(_p(user), _p(hn_rows), N, H, B, Bi, D, ctx.inv_temp, _p(row_lse), _p(g), _p(d_user),
+                                        _p(d_item), _p(d_hn), _p(d_pool), _p(ctx.tcws), ctx.tcws.numel(), _p(ws), ws.numel(),
+                                        _stream()), "tt_ce_bwd_tc_rect")
             _count(5 + (1 if hn_rows is not None else 0) + (1 if pool is not None else 0))
-            return d_user, d_item, d_hn, d_pool, None, None, None, None
+            return d_user, d_item, d_hn, d_pool, None, None, None, None, None
         ws = _ws(ctx.ws_bytes, dev)
         check(lib.tt_ce_bwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D, ctx.inv_temp,
                                 _p(row_lse), _p(g), _p(d_user), _p(d_item), _p(d_hn), _p(d_pool), _p(ws), ws.numel(),
                                 _stream()), "tt_ce_bwd_f32")
         _count(6)
-        return d_user, d_item, d_hn, d_pool, None, None, None, None
+        return d_user, d_item, d_hn, d_pool, None, None, None, None, None
 
 
 def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, temperature: float = 0.1,
-                     nan_flags: Optional[torch.Tensor] = None, precision: str = "fp32"):
-    """precision='fp32': exact SIMT path; 'bf16': tcgen05/TMA tensor-core path (dim 64 or 128)."""
+                     nan_flags: Optional[torch.Tensor] = None, precision: str = "fp32", item_offset: int = 0):
+    """precision='fp32': exact SIMT path; 'bf16': tcgen05/TMA tensor-core path (dim 64 or 128), which also takes the
+    rectangular global-batch form (item [Bi >= B, D], item_ids [Bi], user b's positive = item row item_offset + b)."""
     if nan_flags is None:
         nan_flags = torch.zeros(1, dtype=torch.int32, device=user.device)
     loss, row_lse = FusedInBatchCE.apply(user, item, hn_rows, pool, item_ids, 1.0 / float(temperature), nan_flags,
-                                         precision)
+                                         precision, item_offset)
     return loss, row_lse, nan_flags
 
 
