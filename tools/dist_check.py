@@ -119,6 +119,21 @@ gp = pl.grad.clone()
 dist.all_reduce(gp)
 t5 &= bool(torch.allclose(gp / world, pr.grad, atol=1e-7, rtol=1e-4))
 ok &= t5
+# 5b. the same over the tensor-core kernel's RECTANGULAR form with item ids that collide ACROSS ranks: the false-negative
+#     mask must cover the gathered global batch (one process on the whole batch is the reference)
+idc = torch.randint(1, 300, (world * Bg,), device=dev, generator=torch.Generator(device=dev).manual_seed(31))
+ul, il = (t.clone().requires_grad_(True) for t in (Ug[slg], Ig[slg]))
+lossc = tdist.global_inbatch_ce(ul, il, idc[slg], None, Tg, precision="bf16")
+lossc.backward()
+ur, ir = (t.clone().requires_grad_(True) for t in (Ug, Ig))
+refc = ops.fused_inbatch_ce(ur, ir, idc, None, None, Tg, precision="bf16")[0]
+refc.backward()
+totc = lossc.detach().clone()
+dist.all_reduce(totc)
+t5b = abs(float(totc) / world - float(refc)) < 2e-5
+t5b &= float((ul.grad / world - ur.grad[slg]).norm() / ur.grad[slg].norm()) < 1e-4
+t5b &= float((il.grad / world - ir.grad[slg]).norm() / ir.grad[slg].norm()) < 1e-4
+ok &= t5b
 # 6. the integrated step: row-sharded tables (one batched exchange) + data-parallel towers with global BatchNorm
 #    statistics + global in-batch softmax  ==  ONE process running the unsharded model on the global batch
 #    (TwoTowerModel.py:95-140, GenericTower.py:234, training_utils.py:51-56); dropout 0, distinct item ids
@@ -178,7 +193,7 @@ ok &= t6
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"dist_check world={world}: sharded_topk={t1} sharded_lookup={t2} dp_replicas_identical={t3} sharded_bag={t4} global_inbatch_ce={t5} integrated_sharded_step={t6} (loss {float(loss_s):.6f} vs {float(loss_u):.6f}, worst param diff {worst:.2e}) all_ranks_ok={bool(flag.item())}")
+    print(f"dist_check world={world}: sharded_topk={t1} sharded_lookup={t2} dp_replicas_identical={t3} sharded_bag={t4} global_inbatch_ce={t5} global_ce_cross_rank_mask_tc={t5b} integrated_sharded_step={t6} (loss {float(loss_s):.6f} vs {float(loss_u):.6f}, worst param diff {worst:.2e}) all_ranks_ok={bool(flag.item())}")
 rc = 0 if flag.item() else 1
 dist.barrier()
 torch.cuda.synchronize()
