@@ -23,7 +23,7 @@ ids[torch.arange(L, device=dev)[None, :] >= lens[:, None]] = 0
 up = torch.randn(B, D, device=dev)
 step = torch.ones(1, dtype=torch.int64, device=dev)
 coef = torch.ones(1, device=dev)
-for _ in range(2):
+for _ in range(int(os.environ.get("TT_PROF_REPS", "2"))):
     grp.zero_grad()
     out = grp.lookup({"hist": ids})["hist"]
     (out * up).sum().backward()
@@ -39,7 +39,7 @@ bs = torch.zeros(256, device=dev, requires_grad=True)
 gamma, beta = torch.ones(256, device=dev, requires_grad=True), torch.zeros(256, device=dev, requires_grad=True)
 rm, rv, nb = torch.zeros(256, device=dev), torch.ones(256, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
 seed = torch.tensor([7], dtype=torch.int64, device=dev)
-for _ in range(2):
+for _ in range(int(os.environ.get("TT_PROF_REPS", "2"))):
     y = ops.linear(x, wt, bs)
     z, _, _ = ops.batch_norm_act(y, gamma, beta, rm, rv, nb, 0.1, 1e-5, 256, relu=True, dropout_p=0.1, seed_dev=seed, call_id=1)
     z.sum().backward()
@@ -50,16 +50,16 @@ torch.cuda.empty_cache()
 u = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1).requires_grad_(True)
 it = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=1).requires_grad_(True)
 iid = torch.randint(1, 10_000_001, (B,), device=dev)
-for _ in range(2):
+for _ in range(int(os.environ.get("TT_PROF_REPS", "2"))):
     ops.fused_inbatch_ce(u, it, iid, None, None, 0.05, precision="bf16")[0].backward()
 us = u[:8192].detach().requires_grad_(True)
-for _ in range(2):
+for _ in range(int(os.environ.get("TT_PROF_REPS", "2"))):
     ops.fused_inbatch_ce(us, it, iid, None, None, 0.05, precision="bf16", item_offset=8192)[0].backward()
 torch.cuda.synchronize()
 q = torch.nn.functional.normalize(torch.randn(16384, D, device=dev), dim=1)
 e = torch.nn.functional.normalize(torch.randn(1_250_000, D, device=dev), dim=1)
 prep = ops.PreparedCorpus(e)
-for _ in range(2):
+for _ in range(int(os.environ.get("TT_PROF_REPS", "2"))):
     ops.score_topk(q, e, 100, precision="bf16", prepared=prep)
 torch.cuda.synchronize()
 print("prof_hot_r2 done")
