@@ -24,6 +24,8 @@
 //   rare append path, warp-cooperative prune by value bisection.
 //
 // Roofline: tensor pipe, 2*Q*N*D flops; one pass over the bf16 corpus per 128 queries per CTA (L2-resident ring).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "topk_common.cuh"
 
@@ -59,7 +61,16 @@ __host__ __device__ __forceinline__ int ks_first_cta(const KSched &s, int sb, in
     return static_cast<int>((static_cast<int64_t>(m) * ks_cnt(s, sb)) / s.per_cta);
 }
 
-constexpr int KT_SB_TILES = 768;   // 768 tiles x 256 rows x 256 B = 50 MB of a D=128 bf16 corpus per super-block
+constexpr int KT_SB_TILES_DEFAULT = 768;   // 768 tiles x 256 rows x 256 B = 50 MB of a D=128 bf16 corpus per super-block
+// developer knob (tools/kbench.py): TT_TOPK_SB_TILES overrides the super-block size
+static int kt_sb_tiles() {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("TT_TOPK_SB_TILES");
+        v = (e && atoi(e) >= 64) ? atoi(e) : KT_SB_TILES_DEFAULT;
+    }
+    return v;
+}
 
 static KSched make_ksched(int q_tiles, int n_tiles, bool super_blocks, int cl) {
     KSched s;
@@ -67,6 +78,7 @@ static KSched make_ksched(int q_tiles, int n_tiles, bool super_blocks, int cl) {
     const int n_sm = sm_count() / cl;
     s.cl = cl;
     s.m_tiles = m_tiles; s.n_tiles = n_tiles;
+    const int KT_SB_TILES = kt_sb_tiles();
     s.sbt = (super_blocks && m_tiles >= 8 && n_tiles >= 2 * KT_SB_TILES) ? KT_SB_TILES : n_tiles;
     s.n_sb = (n_tiles + s.sbt - 1) / s.sbt;
     const int64_t sb_total = static_cast<int64_t>(m_tiles) * s.sbt;
