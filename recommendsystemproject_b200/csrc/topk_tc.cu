@@ -61,7 +61,12 @@ __host__ __device__ __forceinline__ int ks_first_cta(const KSched &s, int sb, in
     return static_cast<int>((static_cast<int64_t>(m) * ks_cnt(s, sb)) / s.per_cta);
 }
 
-constexpr int KT_SB_TILES_DEFAULT = 768;   // 768 tiles x 256 rows x 256 B = 50 MB of a D=128 bf16 corpus per super-block
+// 512 tiles x 256 rows x 256 B = 33.5 MB of a D=128 bf16 corpus per super-block.  Round 1 used 768 (50 MB): ncu showed
+// 1.83 GB of DRAM reads per launch for a 320 MB shard -- the clusters sit at DIFFERENT corpus tiles of the super-block,
+// so the whole super-block has to stay resident, and 50 MB does not survive in B200's two-partition L2 next to the
+// candidate-list traffic.  Measured (Q=16384, K=100): 1.25M-row shard 6.22 -> 5.20 ms (50 % -> 60 % of the bf16 peak),
+// 10M rows 36.5 -> 36.2 ms; 384 tiles: 5.11 / 38.1 ms, 256: 5.23 / 38.7 ms (more runs => more lists for stage 2).
+constexpr int KT_SB_TILES_DEFAULT = 512;
 // developer knob (tools/kbench.py): TT_TOPK_SB_TILES overrides the super-block size
 static int kt_sb_tiles() {
     static int v = 0;
