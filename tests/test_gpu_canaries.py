@@ -1,0 +1,108 @@
+"""Out-of-bounds canaries for the kernels added in round 2.  compute-sanitizer is closed on this pool
+(profiles/r2_sanitizer_closed.log: "compute-sanitizer is closed on this pool and stays closed"), so writes past the end
+of an output are looked for directly: every output lives in the middle of a larger buffer whose margins hold a
+sentinel that must survive the launch, at shapes that are NOT multiples of the kernels' tile sizes."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SENT = -12345.0
+
+
+class Guarded:
+    """A tensor view with `margin` sentinel elements on both sides."""
+
+    def __init__(self, shape, dtype=torch.float32, margin=4096):
+        n = 1
+        for s in shape:
+            n *= s
+        self.buf = torch.full((n + 2 * margin,), SENT if dtype.is_floating_point else -12345, dtype=dtype, device=DEV)
+        self.t = self.buf[margin:margin + n].view(*shape)
+        self.margin, self.n = margin, n
+
+    def intact(self):
+        s = SENT if self.buf.dtype.is_floating_point else -12345
+        return bool((self.buf[:self.margin] == s).all()) and bool((self.buf[self.margin + self.n:] == s).all())
+
+
+def test_linear_tc_outputs_stay_in_bounds():
+    from recommendsystemproject_b200 import _lib, ops
+    lib = _lib.load()
+    for rows, n_out, n_in in ((129, 64, 48), (333, 136, 200), (1000, 260, 132)):
+        x = torch.randn(rows, n_in, device=DEV)
+        w = torch.randn(n_out, n_in, device=DEV) * 0.1
+        g = torch.randn(rows, n_out, device=DEV)
+        y, gx, gw, gb = Guarded((rows, n_out)), Guarded((rows, n_in)), Guarded((n_out, n_in)), Guarded((n_out,))
+        st = ops._stream()
+        ops.check(lib.tt_linear_fwd_tc(ops._p(x), ops._p(w), None, rows, n_out, n_in, 0, ops._p(y.t), st), "fwd")
+        ops.check(lib.tt_linear_dgrad_tc(ops._p(g), ops._p(w), rows, n_out, n_in, ops._p(gx.t), st), "dgrad")
+        nb = ctypes.c_size_t(0)
+        ops.check(lib.tt_linear_wgrad_tc_workspace(rows, n_out, n_in, ctypes.byref(nb)), "ws")
+        ws = Guarded((nb.value,), dtype=torch.uint8)
+        ops.check(lib.tt_linear_wgrad_tc(ops._p(g), ops._p(x), rows, n_out, n_in, ops._p(gw.t), ops._p(gb.t), 0, ops._p(ws.t),
+                                         nb.value, st), "wgrad")
+        torch.cuda.synchronize()
+        assert y.intact() and gx.intact() and gw.intact() and gb.intact() and ws.intact(), (rows, n_out, n_in)
+        assert float((y.t.double() - x.double() @ w.double().t()).norm() / (x.double() @ w.double().t()).norm()) < 2e-3
+
+
+def test_batchnorm_outputs_stay_in_bounds():
+    from recommendsystemproject_b200 import _lib, ops
+    lib = _lib.load()
+    for rows, cols in ((77, 132), (1001, 48), (513, 260)):
+        x = torch.randn(rows, cols, device=DEV)
+        gamma, beta = torch.ones(cols, device=DEV), torch.zeros(cols, device=DEV)
+        nb = ctypes.c_size_t(0)
+        ops.check(lib.tt_bn_workspace(rows, cols, ctypes.byref(nb)), "ws")
+        ws = Guarded((nb.value,), dtype=torch.uint8)
+        stats, y, mean, rstd = Guarded((2 * cols + 1,)), Guarded((rows, cols)), Guarded((cols,)), Guarded((cols,))
+        st = ops._stream()
+        ops.check(lib.tt_bn_stats(ops._p(x), rows, cols, cols, ops._p(stats.t), ops._p(ws.t), nb.value, st), "stats")
+        ops.check(lib.tt_bn_apply(ops._p(x), rows, cols, cols, ops._p(stats.t), 1, ops._p(gamma), ops._p(beta), cols, 1e-5, 1, 0.0,
+                                  None, 0, ops._p(y.t), cols, ops._p(mean.t), ops._p(rstd.t), None, None, None, 0.1, None, st), "apply")
+        dy = torch.randn(rows, cols, device=DEV)
+        sums, dx, dg, db = Guarded((2 * cols,)), Guarded((rows, cols)), Guarded((cols,)), Guarded((cols,))
+        ops.check(lib.tt_bn_bwd_stats(ops._p(dy), cols, ops._p(x), rows, cols, cols, ops._p(mean.t), ops._p(rstd.t), ops._p(gamma),
+                                      ops._p(beta), cols, 1, 0.0, None, 0, ops._p(sums.t), ops._p(dg.t), ops._p(db.t), 0, ops._p(ws.t),
+                                      nb.value, st), "bwd stats")
+        ops.check(lib.tt_bn_bwd_apply(ops._p(dy), cols, ops._p(x), rows, cols, cols, ops._p(mean.t), ops._p(rstd.t), ops._p(gamma),
+                                      ops._p(beta), cols, 1, 0.0, None, 0, ops._p(sums.t), float(rows), ops._p(dx.t), cols, st), "bwd apply")
+        torch.cuda.synchronize()
+        for gbuf in (ws, stats, y, mean, rstd, sums, dx, dg, db):
+            assert gbuf.intact(), (rows, cols)
+
+
+def test_shard_kernels_stay_inside_their_blocks():
+    """The exchange writes into per-table slots of shared blocks: neighbours of a slot must not change."""
+    from recommendsystemproject_b200 import ops, sharded
+    C = sharded._CudaShardOps
+    gen = torch.Generator().manual_seed(2)
+    B, L, W, V, D = 37, 50, 4, 1003, 128
+    cap = 600
+    off_base, rows_base = 64, 64 + 40
+    block_ints = rows_base + cap + 64
+    ids = torch.randint(1, V, (B, L), generator=gen).to(DEV)
+    send = torch.full((W, block_ints), -777, dtype=torch.int32, device=DEV)
+    npad, flags = Guarded((B,), dtype=torch.int32), torch.zeros(1, dtype=torch.int32, device=DEV)
+    C.route(ids, 0, V, W, send, block_ints, off_base, rows_base, cap, npad.t, flags)
+    torch.cuda.synchronize()
+    assert bool((send[:, :off_base] == -777).all()) and bool((send[:, off_base + B + 1:rows_base] == -777).all())
+    assert bool((send[:, rows_base + cap:] == -777).all()) and npad.intact()
+    local_rows = (V + W - 1) // W
+    table = torch.randn(local_rows, D, generator=gen).to(DEV)
+    vec_base, block_floats = 256, 256 + B * D + 256
+    out = torch.full((W, block_floats), SENT, device=DEV)
+    pos = Guarded((W * cap,), dtype=torch.int32)
+    C.owner_gather(table, local_rows, W, send, block_ints, off_base, rows_base, cap, B, True, out, block_floats, vec_base, pos.t)
+    torch.cuda.synchronize()
+    assert bool((out[:, :vec_base] == SENT).all()) and bool((out[:, vec_base + B * D:] == SENT).all()) and pos.intact()
+    res = Guarded((B, D))
+    C.combine(out, block_floats, vec_base, W, ids, 0, V, ops.POOL_MEAN, send, block_ints, off_base, cap, npad.t, table[0].contiguous(), D, res.t)
+    gout = torch.full((W, block_floats), SENT, device=DEV)
+    C.grad_pack(torch.randn(B, D, device=DEV), ops.POOL_MEAN, D, W, ids, 0, V, send, block_ints, off_base, cap, gout, block_floats, vec_base)
+    torch.cuda.synchronize()
+    assert res.intact()
+    assert bool((gout[:, :vec_base] == SENT).all()) and bool((gout[:, vec_base + B * D:] == SENT).all())
