@@ -19,12 +19,13 @@ class Guarded:
         n = 1
         for s in shape:
             n *= s
-        self.buf = torch.full((n + 2 * margin,), SENT if dtype.is_floating_point else -12345, dtype=dtype, device=DEV)
+        self.sent = SENT if dtype.is_floating_point else (173 if dtype == torch.uint8 else -12345)
+        self.buf = torch.full((n + 2 * margin,), self.sent, dtype=dtype, device=DEV)
         self.t = self.buf[margin:margin + n].view(*shape)
         self.margin, self.n = margin, n
 
     def intact(self):
-        s = SENT if self.buf.dtype.is_floating_point else -12345
+        s = self.sent
         return bool((self.buf[:self.margin] == s).all()) and bool((self.buf[self.margin + self.n:] == s).all())
 
 
