@@ -323,7 +323,8 @@ TT_API int tt_l2_normalize_bwd(const float *grad_y, const float *y, const float 
  *                    update with the unbiased variance, *num_batches += 1), then normalises
  *   tt_bn_bwd_stats  sums[2*cols] = per-channel sum g, sum g*xhat over this rank's rows (g = dy through dropout and
  *                    ReLU); grad_gamma / grad_beta [P] from these LOCAL sums (stored, or added when accumulate != 0)
- *   tt_bn_bwd_apply  dx = gamma rstd (g - sum_g / N - xhat sum_gx / N) with the GLOBAL sums and N = total_rows
+ *   tt_bn_bwd_apply  dx = gamma rstd (g - sum_g / N - xhat sum_gx / N); the global sums are the n_ranks blocks
+ *                    sums_all[n_ranks][2*cols] added in rank order (deterministic), N = total_rows
  * Dropout masks: counter-based hash of (*seed_dev, call_id, element); the backward rebuilds them and recomputes the
  * ReLU mask from x.  cols, strides and P must be multiples of 4.  Deterministic (fixed reduction order).
  * ---------------------------------------------------------------------- */
@@ -343,7 +344,17 @@ TT_API int tt_bn_bwd_stats(const float *dy, int64_t dy_stride, const float *x, i
 TT_API int tt_bn_bwd_apply(const float *dy, int64_t dy_stride, const float *x, int64_t rows, int cols, int64_t x_stride,
                     const float *save_mean, const float *save_rstd, const float *gamma, const float *beta,
                     int param_period, int relu, float dropout_p, const int64_t *seed_dev, int64_t call_id,
-                    const float *sums_global, double total_rows, float *dx, int64_t dx_stride, void *stream);
+                    const float *sums_all, int n_ranks, double total_rows, float *dx, int64_t dx_stride, void *stream);
+
+/* One-shot all-gather of a small fp32 vector over NVLink peer memory (the cross-rank BatchNorm statistics above):
+ * every rank stores src[n] into slot [rank] of EVERY peer's symmetric buffer (peer_bufs_host[w] = rank w's buffer as
+ * mapped in this process; region at region_off_floats, slots slot_floats apart), publishes a system-scope release flag
+ * to each peer (uint32 flags at flag_off_floats, one per source rank) and waits for all W flags of its own buffer.
+ * *epoch_dev (device, starts at 0) is bumped by the kernel, so CUDA-graph replays need no host update.  A (region, flag)
+ * pair must be used by ONE call site, once per step.  world <= 16. */
+TT_API int tt_p2p_allgather_small(const float *src, int n, int rank, int world, const void *const *peer_bufs_host,
+                           int64_t region_off_floats, int64_t slot_floats, int64_t flag_off_floats,
+                           unsigned int *epoch_dev, void *stream);
 
 /* ------------------------------------------------------------------------
  * 7. Row-sharded embedding tables (owner = row % world, local row = row / world): device side of the exchange.

@@ -182,7 +182,8 @@ bn_bwd_kernel(const float *__restrict__ dy, int64_t dy_stride, const float *__re
               int64_t stride, int rows_per_chunk, const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
               const float *__restrict__ gamma, const float *__restrict__ beta, int period, int relu, float dropout_p,
               const int64_t *__restrict__ seed_dev, int64_t call_id, float *__restrict__ partial,
-              const float *__restrict__ sums_global, float inv_total_rows, float *__restrict__ dx, int64_t dx_stride) {
+              const float *__restrict__ sums_global, int n_ranks, float inv_total_rows, float *__restrict__ dx,
+              int64_t dx_stride) {
     __shared__ float4 sh[2][BN_TY][BN_TX];
     const int c4 = blockIdx.x * BN_TX + threadIdx.x;
     const bool ok = c4 * 4 < cols;
@@ -199,8 +200,15 @@ bn_bwd_kernel(const float *__restrict__ dy, int64_t dy_stride, const float *__re
         const float m[4] = {mu.x, mu.y, mu.z, mu.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
         float k1[4] = {0.f, 0.f, 0.f, 0.f}, k2[4] = {0.f, 0.f, 0.f, 0.f};
         if (APPLY) {
-            const float4 t1 = __ldg(reinterpret_cast<const float4 *>(sums_global) + c4);
-            const float4 t2 = __ldg(reinterpret_cast<const float4 *>(sums_global + cols) + c4);
+            // the per-rank sums blocks [n_ranks][2 * cols] added in rank order (one block: the caller's global sums)
+            float4 t1 = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t1;
+            for (int rk = 0; rk < n_ranks; ++rk) {
+                const float *sg = sums_global + static_cast<int64_t>(rk) * 2 * cols;
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(sg) + c4);
+                const float4 b2 = __ldg(reinterpret_cast<const float4 *>(sg + cols) + c4);
+                t1.x += a.x; t1.y += a.y; t1.z += a.z; t1.w += a.w;
+                t2.x += b2.x; t2.y += b2.y; t2.z += b2.z; t2.w += b2.w;
+            }
             k1[0] = t1.x * inv_total_rows; k1[1] = t1.y * inv_total_rows; k1[2] = t1.z * inv_total_rows; k1[3] = t1.w * inv_total_rows;
             k2[0] = t2.x * inv_total_rows; k2[1] = t2.y * inv_total_rows; k2[2] = t2.z * inv_total_rows; k2[3] = t2.w * inv_total_rows;
         }
@@ -361,7 +369,7 @@ extern "C" int tt_bn_bwd_stats(const float *dy, int64_t dy_stride, const float *
     float *partial = static_cast<float *>(workspace);
     dim3 grid((cols + BN_TX * 4 - 1) / (BN_TX * 4), chunks), block(BN_TX, BN_TY);
     bn_bwd_kernel<false><<<grid, block, 0, st>>>(dy, dy_stride, x, rows, cols, x_stride, rpc, save_mean, save_rstd, gamma, beta,
-                                                  param_period, relu, dropout_p, seed_dev, call_id, partial, nullptr, 0.f,
+                                                  param_period, relu, dropout_p, seed_dev, call_id, partial, nullptr, 1, 0.f,
                                                   nullptr, 0);
     TT_LAUNCH_CHECK("bn_bwd_kernel<stats>");
     bn_bwd_final<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, chunks, cols, sums);
@@ -376,9 +384,10 @@ extern "C" int tt_bn_bwd_stats(const float *dy, int64_t dy_stride, const float *
 extern "C" int tt_bn_bwd_apply(const float *dy, int64_t dy_stride, const float *x, int64_t rows, int cols, int64_t x_stride,
                                const float *save_mean, const float *save_rstd, const float *gamma, const float *beta,
                                int param_period, int relu, float dropout_p, const int64_t *seed_dev, int64_t call_id,
-                               const float *sums_global, double total_rows, float *dx, int64_t dx_stride, void *stream) {
+                               const float *sums_all, int n_ranks, double total_rows, float *dx, int64_t dx_stride,
+                               void *stream) {
     using namespace tt;
-    TT_CHECK_ARG(dy && x && save_mean && save_rstd && gamma && beta && sums_global && dx, "null pointer");
+    TT_CHECK_ARG(dy && x && save_mean && save_rstd && gamma && beta && sums_all && dx && n_ranks >= 1, "null pointer");
     TT_BN_CHECKS();
     TT_CHECK_ARG(dy_stride % 4 == 0 && dx_stride % 4 == 0 && reinterpret_cast<uintptr_t>(dy) % 16 == 0 &&
                  reinterpret_cast<uintptr_t>(dx) % 16 == 0, "bn: dy / dx alignment");
@@ -388,7 +397,7 @@ extern "C" int tt_bn_bwd_apply(const float *dy, int64_t dy_stride, const float *
     dim3 grid((cols + BN_TX * 4 - 1) / (BN_TX * 4), chunks), block(BN_TX, BN_TY);
     bn_bwd_kernel<true><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
         dy, dy_stride, x, rows, cols, x_stride, rpc, save_mean, save_rstd, gamma, beta, param_period, relu, dropout_p, seed_dev,
-        call_id, nullptr, sums_global, static_cast<float>(1.0 / total_rows), dx, dx_stride);
+        call_id, nullptr, sums_all, n_ranks, static_cast<float>(1.0 / total_rows), dx, dx_stride);
     TT_LAUNCH_CHECK("bn_bwd_kernel<apply>");
     return 0;
 }

@@ -92,6 +92,7 @@ class DataParallelStep:
 
 
 SYNC_BN = True      # diagnosis switch (bench.py TT_C3_LOCAL_BN): False = per-rank BatchNorm statistics
+P2P_BN = True       # BatchNorm exchanges over NVLink peer memory (ops.P2PSmallGather); False = NCCL all-gathers
 
 
 class ShardedTrainStep:
@@ -129,10 +130,23 @@ class ShardedTrainStep:
             raise ops.TTError("ShardedTrainStep on several ranks: replicated tables need table_mode='dense' (their gradients "
                               "ride the dense all-reduce); only row-sharded tables are updated touched-rows-only")
         if self.world > 1:
-            ops.bn_sync.world, ops.bn_sync.group = self.world, None
+            ops.bn_sync.world, ops.bn_sync.rank, ops.bn_sync.group = self.world, self.rank, None
+            if SYNC_BN and P2P_BN and ops.bn_sync.p2p is None and optimizer.flat_p.is_cuda:
+                # BatchNorm vectors cross ranks through NVLink peer memory (one kernel, one round trip); NCCL if the
+                # ranks cannot map each other's memory (every rank must take the same branch: agree on it)
+                ok = torch.ones(1, device=optimizer.flat_p.device)
+                try:
+                    p2p = ops.P2PSmallGather(self.rank, self.world, optimizer.flat_p.device)
+                except Exception as ex:  # noqa: BLE001
+                    p2p, ok = None, torch.zeros(1, device=optimizer.flat_p.device)
+                    self.p2p_error = repr(ex)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                ops.bn_sync.p2p = p2p if float(ok) > 0 else None
+            k = 0
             for m in model.modules():
                 if isinstance(m, torch.nn.BatchNorm1d):
-                    m._tt_sync = SYNC_BN
+                    m._tt_sync = k if SYNC_BN else False      # call-site key of this layer's exchanges
+                    k += 1
             # replicas start identical: dense parameters, buffers (BatchNorm statistics, dropout seeds, pad rows)
             dist.broadcast(optimizer.flat_p, src=0)
             for b in model.buffers():

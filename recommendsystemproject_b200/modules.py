@@ -53,7 +53,7 @@ def grouped_batch_norm(bn: nn.BatchNorm1d, x: torch.Tensor, groups: int, relu: b
         y, mean, var_u = ops.batch_norm_act(x.contiguous().view(B, groups * C), bn.weight, bn.bias, bn.running_mean,
                                             bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps, C, relu,
                                             dropout_p if bn.training else 0.0, seed, call_id,
-                                            sync=getattr(bn, "_tt_sync", False))
+                                            sync=getattr(bn, "_tt_sync", None))
         if groups > 1:
             _grouped_running_update(bn, mean, var_u, groups, C, x)
         return y.view(rows, C)

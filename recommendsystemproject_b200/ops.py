@@ -517,10 +517,66 @@ def add_dropout_layer_norm(x, z, gamma, beta, eps=1e-5, dropout_p=0.0, seed_dev=
 # --------------------------------------------------------------------------
 # 3c. BatchNorm1d (training) + ReLU + Dropout, statistics optionally over all ranks
 # --------------------------------------------------------------------------
+class P2PSmallGather:
+    """All-gather of small fp32 vectors through NVLink peer memory (tt_p2p_allgather_small): a symmetric buffer
+    (torch.distributed._symmetric_memory: every rank maps every peer's allocation), carved into one (region, flags)
+    pair per call site.  Call sites must be hit in the same order on every rank (they are: the ranks run the same
+    graph)."""
+
+    def __init__(self, rank, world, device, group=None, capacity_floats=1 << 20):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = int(rank), int(world)
+        self.buf = symm_mem.empty(capacity_floats, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(x) for x in self.handle.buffer_ptrs]
+        self.ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.sites = {}
+        self.next = 0
+        self.capacity = capacity_floats
+        torch.cuda.synchronize()
+        dist.barrier(group=group)       # every buffer is zeroed before anybody's first flag arrives
+
+    def gather(self, vec: torch.Tensor, site) -> torch.Tensor:
+        lib = _lib.load()
+        vec = vec.contiguous()
+        n = vec.numel()
+        st = self.sites.get(site)
+        if st is None:
+            region = self.next
+            flags = region + (self.world * n + 3) // 4 * 4
+            self.next = flags + (self.world + 3) // 4 * 4
+            if self.next > self.capacity:
+                raise TTError("P2PSmallGather: symmetric buffer exhausted")
+            st = self.sites[site] = (region, n, flags, torch.zeros(1, dtype=torch.int32, device=vec.device))
+        region, n0, flags, epoch = st
+        if n0 != n:
+            raise TTError(f"P2PSmallGather: call site {site} changed its vector length ({n0} -> {n})")
+        check(lib.tt_p2p_allgather_small(_p(vec), n, self.rank, self.world, self.ptrs, region, n, flags, _p(epoch), _stream()),
+              "tt_p2p_allgather_small")
+        _count()
+        return self.buf[region:region + self.world * n].view(self.world, n)
+
+
 class _BnSync:
-    """How batch statistics cross ranks (data-parallel towers).  None = this rank only."""
+    """How per-rank BatchNorm vectors (statistics forward, gradient sums backward) cross ranks in data-parallel towers:
+    an all-gather whose W rows the kernels merge in rank order.  p2p (P2PSmallGather) when the ranks could map each
+    other's memory, else NCCL all_gather_into_tensor.  world == 1: this rank only."""
     group = None
     world = 1
+    rank = 0
+    p2p = None
+
+    def gather(self, vec: torch.Tensor, site) -> torch.Tensor:
+        if self.world == 1 or site is None:
+            return vec.view(1, -1)
+        if self.p2p is not None:
+            return self.p2p.gather(vec, site)
+        import torch.distributed as dist
+        out = torch.empty(self.world, vec.numel(), dtype=vec.dtype, device=vec.device)
+        dist.all_gather_into_tensor(out, vec.contiguous(), group=self.group)
+        return out
 
 
 bn_sync = _BnSync()
@@ -541,21 +597,18 @@ class FusedBatchNormAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, num_batches, momentum, eps, period, relu, dropout_p,
                 seed_dev, call_id, sync):
-        import torch.distributed as dist
         lib = _lib.load()
         _need_cuda(x, gamma)
         x = x.contiguous()
         rows, cols = x.shape
         dev = x.device
-        world = bn_sync.world if sync else 1
+        # sync: None / False = this rank's statistics; otherwise the call-site key of the cross-rank exchange
+        site = None if (sync is None or sync is False or bn_sync.world == 1) else sync
+        world = bn_sync.world if site is not None else 1
         stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
         ws = _bn_ws(rows, cols, dev)
         check(lib.tt_bn_stats(_p(x), rows, cols, x.stride(0), _p(stats), _p(ws), ws.numel(), _stream()), "tt_bn_stats")
-        if world > 1:
-            stats_all = torch.empty(world, 2 * cols + 1, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(stats_all, stats, group=bn_sync.group)
-        else:
-            stats_all = stats
+        stats_all = bn_sync.gather(stats, None if site is None else (site, "fwd"))
         y = torch.empty_like(x)
         mean = torch.empty(cols, dtype=torch.float32, device=dev)
         rstd = torch.empty(cols, dtype=torch.float32, device=dev)
@@ -567,17 +620,16 @@ class FusedBatchNormAct(torch.autograd.Function):
                               float(momentum), _p(num_batches if plain else None), _stream()), "tt_bn_apply")
         _count(3)
         ctx.save_for_backward(x, mean, rstd, gamma, beta, seed_dev)
-        ctx.cfg = (period, bool(relu), float(dropout_p), int(call_id), world)
+        ctx.cfg = (period, bool(relu), float(dropout_p), int(call_id), world, site)
         ctx.gamma_ref, ctx.beta_ref = gamma, beta
         ctx.mark_non_differentiable(mean, var_u)
         return y, mean, var_u
 
     @staticmethod
     def backward(ctx, dy, _gm, _gv):
-        import torch.distributed as dist
         lib = _lib.load()
         x, mean, rstd, gamma, beta, seed_dev = ctx.saved_tensors
-        period, relu, p, call_id, world = ctx.cfg
+        period, relu, p, call_id, world, site = ctx.cfg
         rows, cols = x.shape
         dev = x.device
         dy = dy.contiguous()
@@ -593,12 +645,11 @@ class FusedBatchNormAct(torch.autograd.Function):
         check(lib.tt_bn_bwd_stats(_p(dy), dy.stride(0), _p(x), rows, cols, x.stride(0), _p(mean), _p(rstd), _p(gamma), _p(beta),
                                   period, 1 if relu else 0, p, _p(seed_dev), call_id, _p(sums), _p(dgamma), _p(dbeta),
                                   1 if direct else 0, _p(ws), ws.numel(), _stream()), "tt_bn_bwd_stats")
-        if world > 1:
-            dist.all_reduce(sums, group=bn_sync.group)
+        sums_all = bn_sync.gather(sums, None if site is None else (site, "bwd"))     # [world, 2 * cols], merged in rank order
         dx = torch.empty_like(x)
         check(lib.tt_bn_bwd_apply(_p(dy), dy.stride(0), _p(x), rows, cols, x.stride(0), _p(mean), _p(rstd), _p(gamma), _p(beta),
-                                  period, 1 if relu else 0, p, _p(seed_dev), call_id, _p(sums), float(rows * world), _p(dx),
-                                  dx.stride(0), _stream()), "tt_bn_bwd_apply")
+                                  period, 1 if relu else 0, p, _p(seed_dev), call_id, _p(sums_all), world, float(rows * world),
+                                  _p(dx), dx.stride(0), _stream()), "tt_bn_bwd_apply")
         _count(4)
         return (dx, None if direct else dgamma, None if direct else dbeta) + (None,) * 11
 

@@ -70,7 +70,7 @@ def test_batchnorm_outputs_stay_in_bounds():
                                       ops._p(beta), cols, 1, 0.0, None, 0, ops._p(sums.t), ops._p(dg.t), ops._p(db.t), 0, ops._p(ws.t),
                                       nb.value, st), "bwd stats")
         ops.check(lib.tt_bn_bwd_apply(ops._p(dy), cols, ops._p(x), rows, cols, cols, ops._p(mean.t), ops._p(rstd.t), ops._p(gamma),
-                                      ops._p(beta), cols, 1, 0.0, None, 0, ops._p(sums.t), float(rows), ops._p(dx.t), cols, st), "bwd apply")
+                                      ops._p(beta), cols, 1, 0.0, None, 0, ops._p(sums.t), 1, float(rows), ops._p(dx.t), cols, st), "bwd apply")
         torch.cuda.synchronize()
         for gbuf in (ws, stats, y, mean, rstd, sums, dx, dg, db):
             assert gbuf.intact(), (rows, cols)
