@@ -468,6 +468,7 @@ def run_c3(args, rank, local_rank, world, dev, peaks):
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     final_loss = float(loss_host)
     launches = step.launches_per_step or 0
+    bn_exchange = step.bn_exchange
     a2a_bytes = getattr(step, "a2a_bytes_per_step", 0)
     del staging
     # ---- the step's dominant kernel (profiles/r2_c3_step_launches.md: ce_tc_kernel, three launches = ~1/3 of the step), timed
@@ -488,6 +489,7 @@ def run_c3(args, rank, local_rank, world, dev, peaks):
                     "note": "pinned host batch -> H2D on a copy stream one step ahead -> D2D into the graph's buffers -> step -> loss read-back"},
             "gpu_launches": launches * args.steps * 2, "gpu_launches_per_step": launches,
             "nvlink_bytes_per_step_per_gpu": a2a_bytes, "hist_valid_positions_per_gpu": n_valid,
+            "batchnorm_exchange": bn_exchange,
             "roofline": roof, "clocks": clocks, "final_loss": final_loss}
     return line
 

@@ -151,6 +151,9 @@ class ShardedTrainStep:
             dist.broadcast(optimizer.flat_p, src=0)
             for b in model.buffers():
                 dist.broadcast(b, src=0)
+        self.bn_exchange = ("none" if self.world == 1 or not SYNC_BN else
+                            ("nvlink-p2p kernel (symmetric memory)" if ops.bn_sync.p2p is not None else
+                             "nccl all-gather" + (f" (p2p unavailable: {getattr(self, 'p2p_error', 'disabled')})")))
         optimizer._norm_staged_by_caller = True
         snap = self._snapshot()
         side = torch.cuda.Stream()
