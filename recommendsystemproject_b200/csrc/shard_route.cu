@@ -381,9 +381,9 @@ extern "C" int tt_shard_route(const int64_t *ids, int64_t n_rows, int len, int64
     if (workspace_bytes < sizeof(int32_t) * tiles * world) { set_error("shard_route workspace needs %zu bytes", sizeof(int32_t) * tiles * world); return TT_E_WORKSPACE; }
     int32_t *totals = static_cast<int32_t *>(workspace);
     const dim3 scan_grid(tiles, world);
-    for (int w = 0; w < world; ++w) {   // unused row slots read as -1 on the owner
-        cudaError_t e = cudaMemsetAsync(send + w * block_ints + rows_base, 0xff, sizeof(int32_t) * cap, st);
-        if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(shard rows)");
+    {   // unused row slots read as -1 on the owner: one strided memset over the W owner blocks
+        cudaError_t e = cudaMemset2DAsync(send + rows_base, sizeof(int32_t) * block_ints, 0xff, sizeof(int32_t) * cap, world, st);
+        if (e != cudaSuccess) return cuda_status(e, "cudaMemset2DAsync(shard rows)");
     }
     if (len > 1) {
         const unsigned grid = shard_grid(n_rows * 32, 256);
