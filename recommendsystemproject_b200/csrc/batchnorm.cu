@@ -19,6 +19,7 @@ namespace tt {
 
 constexpr int BN_TX = 32;    // float4 column groups per block (128 columns)
 constexpr int BN_TY = 8;     // row lanes per block
+constexpr int BN_SMALL_ROWS = 2048;   // at or below: statistics in one launch (one block per 128 columns)
 
 __device__ __forceinline__ uint32_t bn_hash(uint64_t seed, uint64_t call_id, uint64_t idx) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * (call_id + 1) + idx * 0xD1B54A32D192ED03ull;
@@ -100,6 +101,42 @@ bn_stats_final(const float *__restrict__ partial, int n_chunks, int64_t rows, in
         stats[c] = mean;
         stats[cols + c] = m2;
         if (c == 0) stats[2 * cols] = n;
+    }
+}
+
+// few rows (the B = 512 step of the shipped config): partial + final in ONE launch, one block per 128 columns
+__global__ void __launch_bounds__(BN_TX *BN_TY)
+bn_stats_small(const float *__restrict__ x, int64_t rows, int cols, int64_t stride, float *__restrict__ stats) {
+    __shared__ float4 sh[2][BN_TY][BN_TX];
+    const int c4 = blockIdx.x * BN_TX + threadIdx.x;
+    const bool ok = c4 * 4 < cols;
+    float4 K = make_float4(0.f, 0.f, 0.f, 0.f), s = K, q = K;
+    if (ok) {
+        K = __ldg(reinterpret_cast<const float4 *>(x) + c4);
+        for (int64_t r = threadIdx.y; r < rows; r += BN_TY) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * stride) + c4);
+            const float dx = v.x - K.x, dy = v.y - K.y, dz = v.z - K.z, dw = v.w - K.w;
+            s.x += dx; s.y += dy; s.z += dz; s.w += dw;
+            q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+        }
+    }
+    sh[0][threadIdx.y][threadIdx.x] = s;
+    sh[1][threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0 && ok) {
+        for (int k = 1; k < BN_TY; ++k) {
+            const float4 a = sh[0][k][threadIdx.x], b = sh[1][k][threadIdx.x];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+        }
+        const float n = static_cast<float>(rows);
+        const float sv[4] = {s.x, s.y, s.z, s.w}, qv[4] = {q.x, q.y, q.z, q.w}, kv[4] = {K.x, K.y, K.z, K.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            stats[c4 * 4 + e] = kv[e] + sv[e] / n;
+            stats[cols + c4 * 4 + e] = fmaxf(qv[e] - sv[e] * sv[e] / n, 0.f);
+        }
+        if (c4 == 0) stats[2 * cols] = n;
     }
 }
 
@@ -323,6 +360,11 @@ extern "C" int tt_bn_stats(const float *x, int64_t rows, int cols, int64_t x_str
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *partial = static_cast<float *>(workspace);
     dim3 grid((cols + BN_TX * 4 - 1) / (BN_TX * 4), chunks), block(BN_TX, BN_TY);
+    if (rows <= BN_SMALL_ROWS) {
+        bn_stats_small<<<grid.x, block, 0, st>>>(x, rows, cols, x_stride, stats);
+        TT_LAUNCH_CHECK("bn_stats_small");
+        return 0;
+    }
     bn_stats_partial<<<grid, block, 0, st>>>(x, rows, cols, x_stride, rpc, partial);
     TT_LAUNCH_CHECK("bn_stats_partial");
     bn_stats_final<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, chunks, rows, rpc, cols, stats);
@@ -368,12 +410,21 @@ extern "C" int tt_bn_bwd_stats(const float *dy, int64_t dy_stride, const float *
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *partial = static_cast<float *>(workspace);
     dim3 grid((cols + BN_TX * 4 - 1) / (BN_TX * 4), chunks), block(BN_TX, BN_TY);
-    bn_bwd_kernel<false><<<grid, block, 0, st>>>(dy, dy_stride, x, rows, cols, x_stride, rpc, save_mean, save_rstd, gamma, beta,
-                                                  param_period, relu, dropout_p, seed_dev, call_id, partial, nullptr, 1, 0.f,
-                                                  nullptr, 0);
-    TT_LAUNCH_CHECK("bn_bwd_kernel<stats>");
-    bn_bwd_final<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, chunks, cols, sums);
-    TT_LAUNCH_CHECK("bn_bwd_final");
+    if (rows <= BN_SMALL_ROWS) {
+        // one chunk = all rows: the "partial" of chunk 0 IS the result, written straight into sums
+        dim3 g1(grid.x, 1);
+        bn_bwd_kernel<false><<<g1, block, 0, st>>>(dy, dy_stride, x, rows, cols, x_stride, static_cast<int>(rows), save_mean,
+                                                    save_rstd, gamma, beta, param_period, relu, dropout_p, seed_dev, call_id,
+                                                    sums, nullptr, 1, 0.f, nullptr, 0);
+        TT_LAUNCH_CHECK("bn_bwd_kernel<stats, small>");
+    } else {
+        bn_bwd_kernel<false><<<grid, block, 0, st>>>(dy, dy_stride, x, rows, cols, x_stride, rpc, save_mean, save_rstd, gamma, beta,
+                                                      param_period, relu, dropout_p, seed_dev, call_id, partial, nullptr, 1, 0.f,
+                                                      nullptr, 0);
+        TT_LAUNCH_CHECK("bn_bwd_kernel<stats>");
+        bn_bwd_final<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, chunks, cols, sums);
+        TT_LAUNCH_CHECK("bn_bwd_final");
+    }
     if (dgamma && dbeta) {
         bn_param_grads<<<(param_period + 127) / 128, 128, 0, st>>>(sums, cols, param_period, dgamma, dbeta, accumulate);
         TT_LAUNCH_CHECK("bn_param_grads");

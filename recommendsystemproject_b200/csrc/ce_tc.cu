@@ -781,6 +781,13 @@ static CeTcWs ce_tc_carve(void *workspace, size_t bytes, int64_t n_user, int64_t
     w.cub_tmp = ws.take<char>(pl.sort_bytes);
     w.ok = ws.ok();
     w.used = ws.off;
+    if (n_user == n_item) {
+        // square form (item_offset is necessarily 0): user rows and item rows carry the same keys, so one sort, one
+        // permutation and one set of (run, positive column) arrays serve both sides
+        w.ukeys_in = w.ikeys_in; w.ukeys = w.ikeys;
+        w.perm_u = w.perm_i; w.inv_u = w.inv_i;
+        w.lo_u = w.lo_i; w.hi_u = w.hi_i; w.diag_u = w.diag_i;
+    }
     return w;
 }
 
@@ -874,6 +881,7 @@ static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *i
 
     // 1. item-id sorted orders of the item rows and of the user rows -> permutations, collision runs, positive columns
     const int64_t *ikeys = nullptr, *ukeys = nullptr;
+    const bool square = n_user == n_item;
     if (item_ids != nullptr) {
         tc_iota_keys<<<tc_grid(n_item, 256), 256, 0, st>>>(item_ids, n_item, w.ikeys_in, w.vals_in);
         TT_LAUNCH_CHECK("tc_iota_keys");
@@ -881,22 +889,25 @@ static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *i
         cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikeys_in, w.ikeys, w.vals_in, w.perm_i,
                                                         static_cast<int>(n_item), 0, 64, st);
         if (e != cudaSuccess) return cuda_status(e, "cub SortPairs(ce_tc items)");
-        tc_user_keys<<<tc_grid(n_user, 256), 256, 0, st>>>(item_ids, item_offset, n_user, w.ukeys_in, w.vals_in);
-        TT_LAUNCH_CHECK("tc_user_keys");
-        tmp = pl.sort_bytes;
-        e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukeys_in, w.ukeys, w.vals_in, w.perm_u,
-                                            static_cast<int>(n_user), 0, 64, st);
-        if (e != cudaSuccess) return cuda_status(e, "cub SortPairs(ce_tc users)");
+        if (!square) {
+            tc_user_keys<<<tc_grid(n_user, 256), 256, 0, st>>>(item_ids, item_offset, n_user, w.ukeys_in, w.vals_in);
+            TT_LAUNCH_CHECK("tc_user_keys");
+            tmp = pl.sort_bytes;
+            e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukeys_in, w.ukeys, w.vals_in, w.perm_u,
+                                                static_cast<int>(n_user), 0, 64, st);
+            if (e != cudaSuccess) return cuda_status(e, "cub SortPairs(ce_tc users)");
+        }
         ikeys = w.ikeys; ukeys = w.ukeys;
     } else {
         tc_iota<<<tc_grid(n_item, 256), 256, 0, st>>>(w.perm_i, n_item);
-        tc_iota<<<tc_grid(n_user, 256), 256, 0, st>>>(w.perm_u, n_user);
+        if (!square) tc_iota<<<tc_grid(n_user, 256), 256, 0, st>>>(w.perm_u, n_user);
     }
     tc_invert_perm<<<tc_grid(n_item, 256), 256, 0, st>>>(w.perm_i, n_item, w.inv_i);
-    tc_invert_perm<<<tc_grid(n_user, 256), 256, 0, st>>>(w.perm_u, n_user, w.inv_u);
+    if (!square) tc_invert_perm<<<tc_grid(n_user, 256), 256, 0, st>>>(w.perm_u, n_user, w.inv_u);
     // user rows: W side = items, partner = own item (original index perm_u[p] + item_offset)
-    tc_runs_rect<<<tc_grid(n_user, 256), 256, 0, st>>>(ukeys, n_user, ikeys, n_item, w.perm_u, w.inv_i, item_offset, n_item,
-                                                       w.lo_u, w.hi_u, w.diag_u);
+    if (!square)
+        tc_runs_rect<<<tc_grid(n_user, 256), 256, 0, st>>>(ukeys, n_user, ikeys, n_item, w.perm_u, w.inv_i, item_offset, n_item,
+                                                           w.lo_u, w.hi_u, w.diag_u);
     // item rows (backward over the items): W side = users, partner = the local user this item belongs to, if any
     tc_runs_rect<<<tc_grid(n_item, 256), 256, 0, st>>>(ikeys, n_item, ukeys, n_user, w.perm_i, w.inv_u, -item_offset, n_user,
                                                        w.lo_i, w.hi_i, w.diag_i);
