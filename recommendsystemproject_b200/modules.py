@@ -29,6 +29,12 @@ from . import ops
 from ._lib import TTError
 
 
+import os as _os
+# developer knobs: TT_BN_FUSED=0 sends every BatchNorm through torch; TT_BN_FUSED_MIN_ROWS = smallest batch for the library path
+_BN_FUSED_DEFAULT = _os.environ.get("TT_BN_FUSED", "1") == "1"
+_BN_FUSED_MIN_ROWS = int(_os.environ.get("TT_BN_FUSED_MIN_ROWS", "1"))
+
+
 def _need_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise TTError(f"{what}: recommendsystemproject_b200 modules run on CUDA (B200) only; "
@@ -47,7 +53,8 @@ def grouped_batch_norm(bn: nn.BatchNorm1d, x: torch.Tensor, groups: int, relu: b
     their backward; statistics span all ranks when the layer is marked `_tt_sync`); eval mode / odd shapes use torch."""
     rows, C = x.shape
     fused = (bn.training and x.is_cuda and x.dtype == torch.float32 and bn.affine and bn.track_running_stats
-             and bn.momentum is not None and C % 4 == 0 and getattr(bn, "_tt_fused", True))
+             and bn.momentum is not None and C % 4 == 0 and getattr(bn, "_tt_fused", _BN_FUSED_DEFAULT)
+             and (rows // groups) >= _BN_FUSED_MIN_ROWS)
     if fused:
         B = rows // groups
         y, mean, var_u = ops.batch_norm_act(x.contiguous().view(B, groups * C), bn.weight, bn.bias, bn.running_mean,
