@@ -19,7 +19,10 @@ namespace tt {
 
 constexpr int BN_TX = 32;    // float4 column groups per block (128 columns)
 constexpr int BN_TY = 8;     // row lanes per block
-constexpr int BN_SMALL_ROWS = 2048;   // at or below: statistics in one launch (one block per 128 columns)
+// at or below: statistics in one launch (one block per 128 columns).  Measured on the B = 512 step (torch profiler,
+// graph replay): 9 us (forward) / 38 us (backward) per launch against ~3 + 3 us for the chunked pair -- a [512, 2816]
+// slab view gives the single launch only 22 blocks -- so the one-launch path is kept for tiny inputs only.
+constexpr int BN_SMALL_ROWS = 64;
 
 __device__ __forceinline__ uint32_t bn_hash(uint64_t seed, uint64_t call_id, uint64_t idx) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * (call_id + 1) + idx * 0xD1B54A32D192ED03ull;
