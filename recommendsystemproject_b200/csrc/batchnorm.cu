@@ -82,25 +82,41 @@ __device__ __forceinline__ void chan_merge(float &n, float &mean, float &m2, flo
 }
 
 // stats[0..cols) = mean, [cols..2cols) = M2, stats[2*cols] = n  (this rank's rows)
-// 32 columns x 8 chunk lanes per block: lane j merges chunks j, j+8, ... (Chan), the 8 results are merged in lane order
-__global__ void __launch_bounds__(256)
+// 32 columns x 32 chunk lanes per block: lane j merges chunks j, j+32, ... (Chan), the 32 results are merged in lane
+// order.  The loads of four chunks are issued before their (dependent, division-heavy) merges: with 8 lanes and one
+// chunk in flight this kernel was a 28 us chain of L2 latencies (ncu launch list, 512 chunks).
+constexpr int BN_FL = 32;   // chunk lanes of the final kernels
+__global__ void __launch_bounds__(32 * BN_FL)
 bn_stats_final(const float *__restrict__ partial, int n_chunks, int64_t rows, int rows_per_chunk, int cols,
                float *__restrict__ stats) {
-    __shared__ float sn[8][32], sm[8][32], s2[8][32];
+    __shared__ float sn[BN_FL][32], sm[BN_FL][32], s2[BN_FL][32];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float n = 0.f, mean = 0.f, m2 = 0.f;
     if (c < cols) {
-        for (int k = threadIdx.y; k < n_chunks; k += 8) {
-            const float *p = partial + static_cast<int64_t>(k) * 3 * cols;
-            const float nk = static_cast<float>(min(static_cast<int64_t>(rows_per_chunk), rows - static_cast<int64_t>(k) * rows_per_chunk));
-            const float sd = p[cols + c], sq = p[2 * cols + c];
-            chan_merge(n, mean, m2, nk, p[c] + sd / nk, fmaxf(sq - sd * sd / nk, 0.f));
+        for (int k0 = threadIdx.y; k0 < n_chunks; k0 += 4 * BN_FL) {
+            float kk[4], sd[4], sq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * BN_FL;
+                if (k < n_chunks) {
+                    const float *p = partial + static_cast<int64_t>(k) * 3 * cols;
+                    kk[u] = p[c]; sd[u] = p[cols + c]; sq[u] = p[2 * cols + c];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * BN_FL;
+                if (k < n_chunks) {
+                    const float nk = static_cast<float>(min(static_cast<int64_t>(rows_per_chunk), rows - static_cast<int64_t>(k) * rows_per_chunk));
+                    chan_merge(n, mean, m2, nk, kk[u] + sd[u] / nk, fmaxf(sq[u] - sd[u] * sd[u] / nk, 0.f));
+                }
+            }
         }
     }
     sn[threadIdx.y][threadIdx.x] = n; sm[threadIdx.y][threadIdx.x] = mean; s2[threadIdx.y][threadIdx.x] = m2;
     __syncthreads();
     if (threadIdx.y == 0 && c < cols) {
-        for (int j = 1; j < 8; ++j) chan_merge(n, mean, m2, sn[j][threadIdx.x], sm[j][threadIdx.x], s2[j][threadIdx.x]);
+        for (int j = 1; j < BN_FL; ++j) chan_merge(n, mean, m2, sn[j][threadIdx.x], sm[j][threadIdx.x], s2[j][threadIdx.x]);
         stats[c] = mean;
         stats[cols + c] = m2;
         if (c == 0) stats[2 * cols] = n;
@@ -297,22 +313,31 @@ bn_bwd_kernel(const float *__restrict__ dy, int64_t dy_stride, const float *__re
     }
 }
 
-// sums[0..cols) = sum g, sums[cols..2cols) = sum g xhat: 32 columns x 8 chunk lanes per block, fixed order
-__global__ void __launch_bounds__(256)
+// sums[0..cols) = sum g, sums[cols..2cols) = sum g xhat: 32 columns x 32 chunk lanes per block, fixed order
+__global__ void __launch_bounds__(32 * BN_FL)
 bn_bwd_final(const float *__restrict__ partial, int n_chunks, int cols, float *__restrict__ sums) {
-    __shared__ float sa[8][32], sb[8][32];
+    __shared__ float sa[BN_FL][32], sb[BN_FL][32];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float a = 0.f, b = 0.f;
     if (c < cols) {
-        for (int k = threadIdx.y; k < n_chunks; k += 8) {
-            a += partial[static_cast<int64_t>(k) * 2 * cols + c];
-            b += partial[static_cast<int64_t>(k) * 2 * cols + cols + c];
+        for (int k0 = threadIdx.y; k0 < n_chunks; k0 += 4 * BN_FL) {
+            float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * BN_FL;
+                if (k < n_chunks) {
+                    va[u] = partial[static_cast<int64_t>(k) * 2 * cols + c];
+                    vb[u] = partial[static_cast<int64_t>(k) * 2 * cols + cols + c];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a += va[u]; b += vb[u]; }
         }
     }
     sa[threadIdx.y][threadIdx.x] = a; sb[threadIdx.y][threadIdx.x] = b;
     __syncthreads();
     if (threadIdx.y == 0 && c < cols) {
-        for (int j = 1; j < 8; ++j) { a += sa[j][threadIdx.x]; b += sb[j][threadIdx.x]; }
+        for (int j = 1; j < BN_FL; ++j) { a += sa[j][threadIdx.x]; b += sb[j][threadIdx.x]; }
         sums[c] = a;
         sums[cols + c] = b;
     }
@@ -370,7 +395,7 @@ extern "C" int tt_bn_stats(const float *x, int64_t rows, int cols, int64_t x_str
     }
     bn_stats_partial<<<grid, block, 0, st>>>(x, rows, cols, x_stride, rpc, partial);
     TT_LAUNCH_CHECK("bn_stats_partial");
-    bn_stats_final<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, chunks, rows, rpc, cols, stats);
+    bn_stats_final<<<(cols + 31) / 32, dim3(32, BN_FL), 0, st>>>(partial, chunks, rows, rpc, cols, stats);
     TT_LAUNCH_CHECK("bn_stats_final");
     return 0;
 }
@@ -425,7 +450,7 @@ extern "C" int tt_bn_bwd_stats(const float *dy, int64_t dy_stride, const float *
                                                       param_period, relu, dropout_p, seed_dev, call_id, partial, nullptr, 1, 0.f,
                                                       nullptr, 0);
         TT_LAUNCH_CHECK("bn_bwd_kernel<stats>");
-        bn_bwd_final<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(partial, chunks, cols, sums);
+        bn_bwd_final<<<(cols + 31) / 32, dim3(32, BN_FL), 0, st>>>(partial, chunks, cols, sums);
         TT_LAUNCH_CHECK("bn_bwd_final");
     }
     if (dgamma && dbeta) {

@@ -281,12 +281,35 @@ colsum_partial(const float *__restrict__ x, int64_t rows, int cols, int rows_per
         *(reinterpret_cast<float4 *>(partial + static_cast<int64_t>(blockIdx.y) * cols) + c4) = s;
     }
 }
-__global__ void colsum_final(const float *__restrict__ partial, int n_chunks, int cols, float *__restrict__ out, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// 32 columns x 32 chunk lanes per block; lane j adds chunks j, j+32, ... (four loads in flight), lanes added in order
+__global__ void __launch_bounds__(1024)
+colsum_final(const float *__restrict__ partial, int n_chunks, int cols, float *__restrict__ out, int accumulate) {
+    __shared__ float sh[32][32];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     float a = 0.f;
-    for (int k = 0; k < n_chunks; ++k) a += partial[static_cast<int64_t>(k) * cols + c];
-    out[c] = accumulate ? out[c] + a : a;
+    if (c < cols) {
+        for (int k0 = threadIdx.y; k0 < n_chunks; k0 += 128) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k0 + u * 32 < n_chunks) v[u] = partial[static_cast<int64_t>(k0 + u * 32) * cols + c];
+            a += (v[0] + v[1]) + (v[2] + v[3]);
+        }
+    }
+    sh[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        for (int j = 1; j < 32; ++j) a += sh[j][threadIdx.x];
+        out[c] = accumulate ? out[c] + a : a;
+    }
+}
+
+static inline int colsum_rows_per_chunk(int64_t rows, int cols) {
+    // ~2 waves of 128-column blocks, at least 32 rows per chunk; a function of the shape only (reproducible order)
+    const int col_blocks = (cols / 4 + 31) / 32;
+    int r = 1024;
+    while (r > 32 && ((rows + r - 1) / r) * col_blocks < 2 * 148) r >>= 1;
+    return r;
 }
 
 // row-major fp32 [rows, cols] -> boxes of {32 columns (128 B), box_rows rows}, 128B swizzle, zero fill out of range
@@ -379,7 +402,7 @@ extern "C" int tt_linear_wgrad_tc_workspace(int64_t rows, int n_out, int n_in, s
     int64_t splits = sm_count() / (m_tiles * n_tiles);
     if (splits < 1) splits = 1;
     if (splits > k_blocks) splits = k_blocks;
-    const int64_t chunks = (rows + 1023) / 1024;
+    const int64_t chunks = (rows + 31) / 32;     // upper bound of colsum_rows_per_chunk's chunk count
     *bytes_host = static_cast<size_t>(splits * m_tiles * LT_BM * n_tiles * bn + chunks * n_out) * sizeof(float) + 512;
     return 0;
 }
@@ -424,10 +447,11 @@ extern "C" int tt_linear_wgrad_tc(const float *grad_out, const float *input, int
     TT_LAUNCH_CHECK("linear_tc_reduce");
     if (grad_bias) {
         float *cs = partial + static_cast<int64_t>(real_splits) * m_pad * n_pad;
-        const int chunks = static_cast<int>((rows + 1023) / 1024);
+        const int rpc = colsum_rows_per_chunk(rows, n_out);
+        const int chunks = static_cast<int>((rows + rpc - 1) / rpc);
         dim3 grid((n_out / 4 + 31) / 32, chunks), block(32, 8);
-        colsum_partial<<<grid, block, 0, st>>>(grad_out, rows, n_out, 1024, cs);
-        colsum_final<<<(n_out + 127) / 128, 128, 0, st>>>(cs, chunks, n_out, grad_bias, accumulate);
+        colsum_partial<<<grid, block, 0, st>>>(grad_out, rows, n_out, rpc, cs);
+        colsum_final<<<(n_out + 31) / 32, dim3(32, 32), 0, st>>>(cs, chunks, n_out, grad_bias, accumulate);
         TT_LAUNCH_CHECK("colsum");
     }
     return 0;
