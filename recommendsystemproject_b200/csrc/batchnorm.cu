@@ -72,6 +72,13 @@ bn_stats_partial(const float *__restrict__ x, int64_t rows, int cols, int64_t st
     }
 }
 
+// The affine form of the normalisation, spelled with explicit roundings: the backward RECOMPUTES the ReLU mask from x, so
+// forward and backward must evaluate bit-identical expressions (left to the compiler, one side contracted
+// beta - a * mean into an FMA and the other did not: one element in ~10^6 sat within an ulp of zero and flipped).
+__device__ __forceinline__ float bn_scale(float gamma, float rstd) { return __fmul_rn(gamma, rstd); }
+__device__ __forceinline__ float bn_shift(float a, float mean, float beta) { return __fsub_rn(beta, __fmul_rn(a, mean)); }
+__device__ __forceinline__ float bn_affine(float a, float b, float x) { return __fmaf_rn(a, x, b); }
+
 __device__ __forceinline__ void chan_merge(float &n, float &mean, float &m2, float nk, float mk, float m2k) {
     if (nk <= 0.f) return;
     const float tot = n + nk;
@@ -206,8 +213,10 @@ bn_apply_kernel(const float *__restrict__ x, int64_t rows, int cols, int64_t str
     const int pc = (c4 * 4) % period;   // period % 4 == 0 (checked on the host): a float4 never straddles slabs
     const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + pc));
     const float4 b = __ldg(reinterpret_cast<const float4 *>(beta + pc));
-    const float a0 = g.x * s_rstd[cl], a1 = g.y * s_rstd[cl + 1], a2 = g.z * s_rstd[cl + 2], a3 = g.w * s_rstd[cl + 3];
-    const float b0 = b.x - a0 * s_mean[cl], b1 = b.y - a1 * s_mean[cl + 1], b2 = b.z - a2 * s_mean[cl + 2], b3 = b.w - a3 * s_mean[cl + 3];
+    const float a0 = bn_scale(g.x, s_rstd[cl]), a1 = bn_scale(g.y, s_rstd[cl + 1]), a2 = bn_scale(g.z, s_rstd[cl + 2]),
+                a3 = bn_scale(g.w, s_rstd[cl + 3]);
+    const float b0 = bn_shift(a0, s_mean[cl], b.x), b1 = bn_shift(a1, s_mean[cl + 1], b.y), b2 = bn_shift(a2, s_mean[cl + 2], b.z),
+                b3 = bn_shift(a3, s_mean[cl + 3], b.w);
     const bool drop = dropout_p > 0.f && seed_dev != nullptr;
     const uint64_t seed = drop ? static_cast<uint64_t>(*seed_dev) : 0;
     const uint32_t thresh = drop ? static_cast<uint32_t>(fminf(dropout_p, 0.999999f) * 4294967296.0f) : 0u;
@@ -216,7 +225,7 @@ bn_apply_kernel(const float *__restrict__ x, int64_t rows, int cols, int64_t str
     const int64_t r1 = min(rows, r0 + rows_per_chunk);
     for (int64_t r = r0 + threadIdx.y; r < r1; r += BN_TY) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * stride) + c4);
-        float o[4] = {fmaf(a0, v.x, b0), fmaf(a1, v.y, b1), fmaf(a2, v.z, b2), fmaf(a3, v.w, b3)};
+        float o[4] = {bn_affine(a0, b0, v.x), bn_affine(a1, b1, v.y), bn_affine(a2, b2, v.z), bn_affine(a3, b3, v.w)};
         if (relu) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
@@ -285,9 +294,9 @@ bn_bwd_kernel(const float *__restrict__ dy, int64_t dy_stride, const float *__re
                 const float xh = (xe[e] - m[e]) * rr[e];
                 if (drop) ge[e] = bn_keep(seed, call_id, base + e, thresh) ? ge[e] * keep_scale : 0.f;
                 if (relu) {
-                    // same expression as the forward (fmaf(a, x, b) with a = gamma rstd, b = beta - a mean)
-                    const float a = gm[e] * rr[e];
-                    if (!(fmaf(a, xe[e], bt[e] - a * m[e]) > 0.f)) ge[e] = 0.f;
+                    // bit-identical to the forward's value (bn_scale / bn_shift / bn_affine)
+                    const float a = bn_scale(gm[e], rr[e]);
+                    if (!(bn_affine(a, bn_shift(a, m[e], bt[e]), xe[e]) > 0.f)) ge[e] = 0.f;
                 }
                 if (APPLY) o[e] = gm[e] * rr[e] * (ge[e] - k1[e] - xh * k2[e]);
                 else { a1[e] += ge[e]; a2[e] = fmaf(ge[e], xh, a2[e]); }
