@@ -117,8 +117,11 @@ def test_two_training_steps_match_reference(name, opt_kind):
         if opt_kind != "torch":
             assert abs(float(opt.total_norm.item()) - float(gold["total_norm"])) < 1e-4 * float(gold["total_norm"])
         if opt_kind != "graphed":
+            # step 1 starts from weights that carry Adam's amplification of step 0's rounding-noise gradients (+-lr on
+            # elements with |g| ~ 1e-8, see _check_state): its gradients are compared a little more loosely
+            g_atol = 2e-5 if step == 0 else 6e-5
             for k, g in gold["grads"].items():
-                assert torch.allclose(grads[k].cpu(), g, atol=2e-5, rtol=2e-4), (step, k, float((grads[k].cpu() - g).abs().max()))
+                assert torch.allclose(grads[k].cpu(), g, atol=g_atol, rtol=2e-4), (step, k, float((grads[k].cpu() - g).abs().max()))
         carried = _check_state(model, gold, cfg, step, grad_noise, carried)
 
 
