@@ -220,7 +220,9 @@ __device__ __forceinline__ const float *seg_grad_row(const GradSrc &g, int32_t p
     slot = 0;
     if (LISTS) {
         src = p;
-        if (g.pos_src) return g.grad_out + 4 * static_cast<int64_t>(__ldg(g.pos_src + p));   // float4 offset, no division
+        // pos_src given: the sort carried each position's float4 gradient offset as its VALUE (seg_build_keys_lists), so
+        // the "sorted position" p already is that offset -- no second dependent load, no division
+        if (g.pos_src) return g.grad_out + 4 * static_cast<int64_t>(p);
         const uint32_t q = static_cast<uint32_t>(p), pr = static_cast<uint32_t>(g.piece_rows);
         const uint32_t piece = q / pr;
         return g.grad_out + static_cast<int64_t>(piece) * g.piece_stride + static_cast<int64_t>(q - piece * pr) * g.grad_stride;
@@ -603,14 +605,18 @@ extern "C" int tt_emb_segment_grad_workspace(int64_t n_pos, int dim, size_t *byt
 namespace tt {
 
 // keys of the list form: key[p] = rows[(p / piece_len) * piece_stride + p % piece_len] (negative / >= vocab: dropped)
+// value carried through the (stable) sort: the position p, or -- when pos_src is given -- the float4 offset of p's
+// gradient row (what the reduce kernels would otherwise fetch through a second dependent load per position)
 __global__ void seg_build_keys_lists(const int32_t *__restrict__ rows, int64_t n, int64_t piece_len, int64_t piece_stride,
-                                     int64_t vocab, uint32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+                                     int64_t vocab, const int32_t *__restrict__ pos_src, uint32_t *__restrict__ keys,
+                                     int32_t *__restrict__ vals) {
     for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n;
          p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t piece = p / piece_len;
         const int32_t r = __ldg(rows + piece * piece_stride + (p - piece * piece_len));
-        keys[p] = (r < 0 || r >= vocab) ? static_cast<uint32_t>(vocab) : static_cast<uint32_t>(r);
-        vals[p] = static_cast<int32_t>(p);
+        const bool drop = r < 0 || r >= vocab;
+        keys[p] = drop ? static_cast<uint32_t>(vocab) : static_cast<uint32_t>(r);
+        vals[p] = (pos_src && !drop) ? __ldg(pos_src + p) : static_cast<int32_t>(p);
     }
 }
 
@@ -619,6 +625,7 @@ struct KeySrc {
     int64_t pad;
     const int32_t *rows;      // list form (ids == nullptr)
     int64_t piece_len, piece_stride;
+    const int32_t *pos_src;   // list form: per-position float4 gradient offsets (become the sort values)
 };
 
 template <bool LISTS>
@@ -660,7 +667,7 @@ static int segment_grad_run(const KeySrc &ks, const GradSrc &g, int64_t n, int64
         else rc2 = launch_seg_small<8>(ks.ids, nn, ks.pad, vocab, pos_bits, pos_bits + id_bits, plan.chunk, vals_out, seg_start, unique_rows, chunk_base, counters, st);
         if (rc2) return rc2;
     } else {
-        if (LISTS) seg_build_keys_lists<<<g1, threads, 0, st>>>(ks.rows, n, ks.piece_len, ks.piece_stride, vocab, keys_in, vals_in);
+        if (LISTS) seg_build_keys_lists<<<g1, threads, 0, st>>>(ks.rows, n, ks.piece_len, ks.piece_stride, vocab, ks.pos_src, keys_in, vals_in);
         else seg_build_keys<<<g1, threads, 0, st>>>(ks.ids, n, ks.pad, vocab, keys_in, vals_in);
         TT_LAUNCH_CHECK("seg_build_keys");
         int end_bit = 1;
@@ -750,7 +757,7 @@ extern "C" int tt_emb_segment_grad(const int64_t *ids, int64_t n_rows, int len, 
     TT_CHECK_ARG(vocab < (int64_t(1) << 31) - 1, "vocab must fit 31 bits");
     const int64_t n = n_rows * len;
     TT_CHECK_ARG(n < (int64_t(1) << 31) - 2, "more than 2^31 positions per call");
-    const KeySrc ks{ids, padding_idx, nullptr, 0, 0};
+    const KeySrc ks{ids, padding_idx, nullptr, 0, 0, nullptr};
     const GradSrc g{grad_out, grad_stride, argmax, len, mode, dim, nullptr, 0, 0};
     const float scale = (mode == TT_POOL_MEAN) ? 1.0f / static_cast<float>(len) : 1.0f;
     return segment_grad_run<false>(ks, g, n, vocab, scale, unique_rows, row_grad, n_unique, sq_norm, workspace,
@@ -769,7 +776,7 @@ extern "C" int tt_emb_segment_grad_lists(const int32_t *rows, int64_t n_pieces, 
     TT_CHECK_ARG(vocab < (int64_t(1) << 31) - 1, "vocab must fit 31 bits");
     const int64_t n = n_pieces * piece_len;
     TT_CHECK_ARG(n < (int64_t(1) << 31) - 2, "more than 2^31 positions per call");
-    const KeySrc ks{nullptr, -1, rows, piece_len, piece_stride};
+    const KeySrc ks{nullptr, -1, rows, piece_len, piece_stride, pos_src};
     const GradSrc g{grad, dim, nullptr, 1, TT_POOL_SUM, dim, pos_src, grad_piece_rows, grad_piece_stride};
     return segment_grad_run<true>(ks, g, n, vocab, 1.0f, unique_rows, row_grad, n_unique, sq_norm, workspace,
                                   workspace_bytes, static_cast<cudaStream_t>(stream));
