@@ -1,19 +1,21 @@
-"""Multi-GPU pieces (one process per GPU, torch.distributed / NCCL over NVLink).
+"""Multi-GPU pieces (one process per GPU, torch.distributed / NCCL over NVLink + own peer-memory kernels).
 
 The reference is single-process (no collective of any
-kind), so everything here is new:
-  * DataParallelStep   -- towers data-parallel: per-rank batch, NCCL all-reduce
-                          (mean) of the flat dense-gradient buffer between the
-                          backward graph and the optimizer graph; the clip
-                          norm is therefore the norm of the AVERAGED gradient,
-                          identical on every rank.
-  * shard helpers       -- row-sharded embedding routing (owner = row % W) and
-                          corpus-sharded top-K + global merge.
-  * global_inbatch_ce   -- in-batch softmax over the global batch: all-gather of
-                          item embeddings with a gradient-carrying backward.
-Host-side routing logic is plain index arithmetic on tensors of either device
-so that it can be exercised with gloo on CPU (tests/test_dist_cpu.py); the
-kernels it feeds are CUDA-only.
+kind), so everything here is new (SURVEY.md section 8e):
+  * ShardedTrainStep    -- THE integrated step: row-sharded tables (one batched exchange per step, sharded.py),
+                          data-parallel towers with BatchNorm statistics over the global batch, in-batch softmax over
+                          the global batch (rectangular tcgen05 CE, false-negative mask across ranks), SUM all-reduce of
+                          the flat gradient buffer, dense Adam + owner-side row-wise Adam; one CUDA graph per rank.
+  * global_inbatch_ce   -- the loss of that step: all-gather of item embeddings (+ ids) with a gradient-carrying
+                          backward (reduce-scatter).
+  * sharded_topk        -- corpus-sharded top-K: per-GPU top-K, ONE all-to-all of the [Q/W, K] candidate slices,
+                          per-rank merge.
+  * DataParallelStep    -- round 1's data parallelism (per-rank in-batch negatives, gradients averaged); still used for
+                          batches with per-row hard-negative slabs.
+  * ShardedEmbeddingBag -- round 1's single-table bag (kept for its bitwise exchange="rows" mode); ShardedTableGroup
+                          in sharded.py supersedes it (compacted per-owner lists, all tables in one exchange).
+Host-side logic is plain index arithmetic on tensors of either device so that it can be exercised with gloo on CPU
+(tests/test_dist_cpu.py, tests/test_sharded_cpu.py); the kernels it feeds are CUDA-only.
 """
 from __future__ import annotations
 
