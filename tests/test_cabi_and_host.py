@@ -114,3 +114,21 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == ("reference" if ref_installed else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["steps"] == 1 and d["warmup"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_torch_custom_ops_are_registered_and_cuda_only():
+    """torch.ops.tt_b200.* (torch.library custom ops over the C ABI): schemas exist, fake (meta) implementations infer
+    shapes, and a CPU tensor is refused by the dispatcher -- there is no CPU kernel to fall back to."""
+    ns = torch.ops.tt_b200
+    for name in ("gather_pool", "segment_grad", "inbatch_ce", "inbatch_ce_backward", "score_topk"):
+        assert hasattr(ns, name), name
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        out = ns.gather_pool(torch.empty(100, 16), torch.empty(7, 5, dtype=torch.int64), ops.POOL_MEAN, 0)
+        assert out.shape == (7, 16) and out.dtype == torch.float32
+        loss, lse = ns.inbatch_ce(torch.empty(8, 64), torch.empty(8, 64), torch.empty(8, dtype=torch.int64), 0.1, 0)
+        assert loss.shape == () and lse.shape == (8,)
+        s, i = ns.score_topk(torch.empty(4, 64), torch.empty(50, 64), 10, 0)
+        assert s.shape == (4, 10) and s.dtype == torch.float64 and i.dtype == torch.int64
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ns.gather_pool(torch.zeros(10, 8), torch.zeros(3, 2, dtype=torch.int64), ops.POOL_SUM, -1)
