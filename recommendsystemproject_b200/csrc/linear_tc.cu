@@ -249,8 +249,18 @@ linear_tc_reduce(const float *__restrict__ partial, int splits, int64_t m_pad, i
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t m = i / n4, c = (i - m * n4) * 4;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < splits; ++s) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(partial + (static_cast<int64_t>(s) * m_pad + m) * n_pad + c));
+        const float4 *src = reinterpret_cast<const float4 *>(partial + m * n_pad + c);
+        const int64_t step = m_pad * n_pad / 4;   // float4s between two splits (n_pad % 4 == 0)
+        int s = 0;
+        for (; s + 8 <= splits; s += 8) {         // eight loads in flight, added in split order
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (s + j) * step);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+        }
+        for (; s < splits; ++s) {
+            const float4 v = __ldg(src + s * step);
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
         float *o = out + m * ldo + c;

@@ -24,6 +24,7 @@ tests inject a restatement (tests/sharded_cpu_ops.py) -- the product itself has 
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -37,16 +38,17 @@ _p, _stream = ops._p, ops._stream
 
 class _CudaShardOps:
     """include/tt_b200.h section 7 + tt_emb_segment_grad_lists + tt_emb_rowwise_adam."""
-    _route_ws: Dict = {}      # tile totals of the route scan (per device; every route call on a stream runs in order)
+    _route_ws: Dict = {}      # tile totals of the route scan, one per (device, stream): calls on ONE stream run in order
 
     @staticmethod
     def route(ids, pad, vocab, world, send, block_ints, off_base, rows_base, cap, n_pad, flags):
         lib = _lib.load()
         n_rows, length = ids.shape
-        ws = _CudaShardOps._route_ws.get(ids.device)
+        key = (ids.device, _stream().value)
+        ws = _CudaShardOps._route_ws.get(key)
         need = 4 * world * ((n_rows + 4095) // 4096)
         if ws is None or ws.numel() < need:
-            ws = _CudaShardOps._route_ws[ids.device] = torch.empty(max(need, 1024), dtype=torch.uint8, device=ids.device)
+            ws = _CudaShardOps._route_ws[key] = torch.empty(max(need, 1024), dtype=torch.uint8, device=ids.device)
         check(lib.tt_shard_route(_p(ids), n_rows, length, -1 if pad is None else int(pad), vocab, world, _p(send), block_ints,
                                  off_base, rows_base, cap, _p(n_pad), _p(flags), _p(ws), ws.numel(), _stream()), "tt_shard_route")
         ops._count(4)
@@ -154,6 +156,12 @@ class ShardedTableGroup:
         self._sq_terms = None
         self._anchor_t = None
         self.a2a_bytes = 0                     # bytes this rank SENT to other ranks (counted per call)
+        # per-table chains (route / owner gather / combine / segment reduction / Adam) touch disjoint buffers: on a GPU
+        # each table gets its own stream between the collectives ("lanes"), forked from and joined back into the
+        # current stream -- inside a CUDA-graph capture they become parallel branches, which is what hides the
+        # ~15 short launches per small table behind the big table's HBM-bound kernels.  TT_SHARD_LANES=0 disables.
+        self.parallel_lanes = os.environ.get("TT_SHARD_LANES", "1") != "0"
+        self._lanes: Dict = {}
 
     @property
     def device(self):
@@ -263,6 +271,27 @@ class ShardedTableGroup:
         self._plans[key] = pl
         return pl
 
+    def _fan(self, jobs):
+        """Run the zero-argument callables of `jobs` (one per table, disjoint outputs, NO allocations inside) each on
+        its own lane stream, forked from the current stream and joined back into it before returning."""
+        jobs = list(jobs)
+        dev = self.device
+        if not (self.parallel_lanes and dev.type == "cuda" and len(jobs) > 1):
+            for job in jobs:
+                job()
+            return
+        cur = torch.cuda.current_stream(dev)
+        lanes = self._lanes.setdefault(dev.index, [])
+        while len(lanes) < len(jobs) - 1:
+            lanes.append(torch.cuda.Stream(device=dev))
+        jobs[0]()                                   # the first table stays on the current stream
+        for lane, job in zip(lanes, jobs[1:]):
+            lane.wait_stream(cur)
+            with torch.cuda.stream(lane):
+                job()
+        for lane in lanes[:len(jobs) - 1]:
+            cur.wait_stream(lane)
+
     def _a2a(self, out, inp):
         if self.world == 1:
             return
@@ -289,46 +318,77 @@ class ShardedTableGroup:
     def _forward(self, names, ids):
         W = self.world
         pl = self._plan(names, [tuple(x.shape) for x in ids])
-        for name, x in zip(names, ids):
+        flags = self.flags
+
+        def route(name, x):
             s, t = pl.slots[name], self.tables[name]
-            self.ops.route(x, t.padding_idx, t.vocab, W, pl.send_ids, pl.block_ints, s["off_base"], s["rows_base"], s["cap"],
-                           pl.n_pad[name], self.flags)
+            return lambda: self.ops.route(x, t.padding_idx, t.vocab, W, pl.send_ids, pl.block_ints, s["off_base"], s["rows_base"],
+                                          s["cap"], pl.n_pad[name], flags)
+
+        def owner(name):
+            s, t = pl.slots[name], self.tables[name]
+            weight = t.weight.detach()
+            return lambda: self.ops.owner_gather(weight, t.local_rows, W, pl.recv_ids, pl.block_ints, s["off_base"],
+                                                 s["rows_base"], s["cap"], pl.B, s["len"] > 1, pl.vec_out, pl.block_floats,
+                                                 s["vec_base"], pl.pos_src[name])
+
+        def combine(name, x, out):
+            s, t = pl.slots[name], self.tables[name]
+            pad_row = t.pad_row
+            return lambda: self.ops.combine(pl.vec_in, pl.block_floats, s["vec_base"], W, x, t.padding_idx, t.vocab, t.mode,
+                                            pl.send_ids, pl.block_ints, s["off_base"], s["cap"], pl.n_pad[name], pad_row,
+                                            t.dim, out)
+
+        order = self._big_first(pl, names)
+        by_name = dict(zip(names, ids))
+        self._fan(route(n, by_name[n]) for n in order)
         self._a2a(pl.recv_ids, pl.send_ids)                                                    # all-to-all #1
-        for name in names:
-            s, t = pl.slots[name], self.tables[name]
-            self.ops.owner_gather(t.weight.detach(), t.local_rows, W, pl.recv_ids, pl.block_ints, s["off_base"], s["rows_base"],
-                                  s["cap"], pl.B, s["len"] > 1, pl.vec_out, pl.block_floats, s["vec_base"], pl.pos_src[name])
+        self._fan(owner(n) for n in order)
         self._a2a(pl.vec_in, pl.vec_out)                                                       # all-to-all #2
-        outs = []
-        for name, x in zip(names, ids):
-            s, t = pl.slots[name], self.tables[name]
-            out = torch.empty(pl.B, t.dim, dtype=torch.float32, device=self.device)
-            self.ops.combine(pl.vec_in, pl.block_floats, s["vec_base"], W, x, t.padding_idx, t.vocab, t.mode, pl.send_ids,
-                             pl.block_ints, s["off_base"], s["cap"], pl.n_pad[name], t.pad_row, t.dim, out)
-            outs.append(out)
-        return pl, outs
+        outs = {n: torch.empty(pl.B, self.tables[n].dim, dtype=torch.float32, device=self.device) for n in names}
+        self._fan(combine(n, by_name[n], outs[n]) for n in order)
+        return pl, [outs[n] for n in names]
+
+    @staticmethod
+    def _big_first(pl, names):
+        """Lane order: the table with the most positions first (it stays on the current stream)."""
+        return sorted(names, key=lambda n: -pl.slots[n]["len"] * pl.B)
 
     def _backward(self, pl, names, ids, grads):
         W = self.world
+        packed = []
         for name, x, g in zip(names, ids, grads):
-            s, t = pl.slots[name], self.tables[name]
+            t = self.tables[name]
             if g is None:
                 g = torch.zeros(pl.B, t.dim, dtype=torch.float32, device=self.device)
             if not (g.stride(1) == 1 and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0):
                 g = g.contiguous()      # a column slice of the tower's concat gradient is read in place (row stride)
-            self.ops.grad_pack(g, t.mode, t.dim, W, x, t.padding_idx, t.vocab, pl.send_ids, pl.block_ints, s["off_base"],
-                               s["cap"], pl.g_out, pl.block_floats, s["vec_base"])
-        self._a2a(pl.g_in, pl.g_out)                                                           # all-to-all #3
-        for k, name in enumerate(self.tables):
-            if name not in pl.slots:
-                continue
+            packed.append((name, x, g))
+
+        def pack(name, x, g):
+            s, t = pl.slots[name], self.tables[name]
+            return lambda: self.ops.grad_pack(g, t.mode, t.dim, W, x, t.padding_idx, t.vocab, pl.send_ids, pl.block_ints,
+                                              s["off_base"], s["cap"], pl.g_out, pl.block_floats, s["vec_base"])
+
+        def reduce(k, name):
             s, t, sg = pl.slots[name], self.tables[name], pl.seg[name]
-            self.ops.segment_grad_lists(pl.recv_ids, W, pl.block_ints, s["rows_base"], s["cap"], pl.pos_src[name], t.local_rows,
-                                        pl.g_in, s["vec_rows"], pl.block_floats, s["vec_base"], t.dim, sg["rows"],
-                                        sg["row_grad"], sg["n_unique"], self.sq_terms[k:k + 1], sg["ws"])
-            if t.pending is not None:
+            sq = self.sq_terms[k:k + 1]
+            return lambda: self.ops.segment_grad_lists(pl.recv_ids, W, pl.block_ints, s["rows_base"], s["cap"], pl.pos_src[name],
+                                                       t.local_rows, pl.g_in, s["vec_rows"], pl.block_floats, s["vec_base"],
+                                                       t.dim, sg["rows"], sg["row_grad"], sg["n_unique"], sq, sg["ws"])
+
+        self._fan(pack(*job) for job in packed)
+        self._a2a(pl.g_in, pl.g_out)                                                           # all-to-all #3
+        slot_of = {name: k for k, name in enumerate(self.tables)}
+        todo = self._big_first(pl, [n for n in self.tables if n in pl.slots])
+        for name in todo:
+            if self.tables[name].pending is not None:
                 raise TTError(f"row-sharded feature '{name}' met two backward passes in one step; call zero_grad() between steps")
-            t.pending = (sg["rows"], sg["row_grad"], sg["n_unique"])
+        self._fan(reduce(slot_of[n], n) for n in todo)
+        for name in todo:
+            sg = pl.seg[name]
+            self.tables[name].pending = (sg["rows"], sg["row_grad"], sg["n_unique"])
+            self.tables[name].pending_positions = pl.slots[name]["len"] * pl.B
 
     # ------------------------------------------------------------------ optimizer side
     def zero_grad(self):
@@ -343,12 +403,16 @@ class ShardedTableGroup:
 
     def step(self, clip_coef, lr, step_dev, betas=(0.9, 0.999), eps=1e-8, lr_dev=None):
         self.init_state()
-        for t in self.tables.values():
-            if t.pending is None:
-                continue
+        live = sorted((t for t in self.tables.values() if t.pending is not None), key=lambda t: -getattr(t, "pending_positions", 0))
+
+        def adam(t):
             rows, row_grad, n_unique = t.pending
-            self.ops.adam(t.weight.data if isinstance(t.weight, torch.nn.Parameter) else t.weight, t.exp_avg, t.exp_avg_sq,
-                          rows, row_grad, n_unique, clip_coef, lr, betas[0], betas[1], eps, step_dev, lr_dev)
+            weight = t.weight.data if isinstance(t.weight, torch.nn.Parameter) else t.weight
+            return lambda: self.ops.adam(weight, t.exp_avg, t.exp_avg_sq, rows, row_grad, n_unique, clip_coef, lr, betas[0],
+                                         betas[1], eps, step_dev, lr_dev)
+
+        self._fan(adam(t) for t in live)
+        for t in live:
             t.pending = None
 
     def check_flags(self):
