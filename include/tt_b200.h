@@ -189,6 +189,13 @@ TT_API int tt_ce_fwd_tc_rect(const float *user, const float *item_all, const int
                       const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
                       int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
                       int *nan_flags, void *workspace, size_t workspace_bytes, void *stream);
+/* tt_ce_fwd_tc_rect with a declared id range: every item id lies in [0, 2^id_bits) (id_bits = bits of vocab_size - 1
+ * when the ids index an embedding table, 64 = anything), so the sort that groups equal ids runs ceil(id_bits / 8) radix
+ * passes instead of 8.  An id outside the range raises bit 3 (value 8) of *nan_flags. */
+TT_API int tt_ce_fwd_tc_rect_bits(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,
+                           const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
+                           int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
+                           int *nan_flags, void *workspace, size_t workspace_bytes, int id_bits, void *stream);
 TT_API int tt_ce_bwd_tc_workspace_rect(int64_t n_user, int64_t n_item, int64_t pool, int n_rowneg, int dim, size_t *bytes_host);
 TT_API int tt_ce_bwd_tc_rect(const float *user, const float *hn_rows, int n_rowneg, int64_t pool_rows, int64_t n_user,
                       int64_t n_item, int dim, float inv_temp, const float *row_lse, const float *grad_loss,

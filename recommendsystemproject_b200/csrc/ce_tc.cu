@@ -79,12 +79,20 @@ tc_convert_rows(const float *__restrict__ in, const int32_t *__restrict__ perm, 
     }
 }
 
+// id_bits < 64: the caller declared 0 <= id < 2^id_bits and only those bits are sorted; an id outside raises bit 3
+// of nan_flags (the mask would silently group different ids otherwise)
+constexpr int CE_TC_FLAG_ID_RANGE = 8;
+__device__ __forceinline__ void tc_check_id(int64_t id, int id_bits, int *nan_flags) {
+    if (id_bits < 64 && (static_cast<uint64_t>(id) >> id_bits) != 0) atomicOr(nan_flags, CE_TC_FLAG_ID_RANGE);
+}
+
 __global__ void tc_iota_keys(const int64_t *__restrict__ ids, int64_t n, int64_t *__restrict__ keys,
-                             int32_t *__restrict__ vals) {
+                             int32_t *__restrict__ vals, int id_bits, int *__restrict__ nan_flags) {
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         keys[i] = ids[i];
         vals[i] = static_cast<int32_t>(i);
+        tc_check_id(ids[i], id_bits, nan_flags);
     }
 }
 
@@ -873,7 +881,7 @@ static inline unsigned tc_grid(int64_t n, int threads) {
 static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *item_ids, int64_t item_offset,
                           const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
                           int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
-                          int *nan_flags, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                          int *nan_flags, void *workspace, size_t workspace_bytes, int id_bits, cudaStream_t st) {
     const CeTcPlan pl = ce_tc_plan(n_user, n_item, pool_rows);
     CeTcWs w = ce_tc_carve(workspace, workspace_bytes, n_user, n_item, pool_rows, dim, pl);
     if (!w.ok) { set_error("ce_tc workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
@@ -883,18 +891,18 @@ static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *i
     const int64_t *ikeys = nullptr, *ukeys = nullptr;
     const bool square = n_user == n_item;
     if (item_ids != nullptr) {
-        tc_iota_keys<<<tc_grid(n_item, 256), 256, 0, st>>>(item_ids, n_item, w.ikeys_in, w.vals_in);
+        tc_iota_keys<<<tc_grid(n_item, 256), 256, 0, st>>>(item_ids, n_item, w.ikeys_in, w.vals_in, id_bits, nan_flags);
         TT_LAUNCH_CHECK("tc_iota_keys");
         size_t tmp = pl.sort_bytes;
         cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikeys_in, w.ikeys, w.vals_in, w.perm_i,
-                                                        static_cast<int>(n_item), 0, 64, st);
+                                                        static_cast<int>(n_item), 0, id_bits, st);
         if (e != cudaSuccess) return cuda_status(e, "cub SortPairs(ce_tc items)");
         if (!square) {
             tc_user_keys<<<tc_grid(n_user, 256), 256, 0, st>>>(item_ids, item_offset, n_user, w.ukeys_in, w.vals_in);
             TT_LAUNCH_CHECK("tc_user_keys");
             tmp = pl.sort_bytes;
             e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukeys_in, w.ukeys, w.vals_in, w.perm_u,
-                                                static_cast<int>(n_user), 0, 64, st);
+                                                static_cast<int>(n_user), 0, id_bits, st);
             if (e != cudaSuccess) return cuda_status(e, "cub SortPairs(ce_tc users)");
         }
         ikeys = w.ikeys; ukeys = w.ukeys;
@@ -1014,18 +1022,28 @@ extern "C" int tt_ce_tc_workspace(int64_t batch, int64_t pool, int n_rowneg, int
     return tt_ce_tc_workspace_rect(batch, batch, pool, n_rowneg, dim, bytes_host);
 }
 
-extern "C" int tt_ce_fwd_tc_rect(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,
+extern "C" int tt_ce_fwd_tc_rect_bits(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,
                                  const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
                                  int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
-                                 int *nan_flags, void *workspace, size_t workspace_bytes, void *stream) {
+                                 int *nan_flags, void *workspace, size_t workspace_bytes, int id_bits, void *stream) {
     using namespace tt;
     TT_CHECK_ARG(user && item_all && loss && row_lse && row_pos && nan_flags && workspace, "null pointer");
+    TT_CHECK_ARG(id_bits >= 1 && id_bits <= 64, "id_bits must be in 1..64");
     TT_CHECK_ARG((pool != nullptr) == (pool_rows > 0), "pool / pool_rows mismatch");
     TT_CE_TC_COMMON_CHECKS();
     TT_CHECK_ARG(item_offset >= 0 && item_offset + n_user <= n_item, "item_offset + n_user must lie inside the item rows");
     TT_CHECK_ARG(inv_temp > 0.f, "temperature must be positive");
     return ce_fwd_tc_impl(user, item_all, item_ids_all, item_offset, hn_rows, n_rowneg, pool, pool_rows, n_user, n_item, dim,
-                          inv_temp, loss, row_lse, row_pos, nan_flags, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                          inv_temp, loss, row_lse, row_pos, nan_flags, workspace, workspace_bytes, id_bits,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tt_ce_fwd_tc_rect(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,
+                                 const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
+                                 int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
+                                 int *nan_flags, void *workspace, size_t workspace_bytes, void *stream) {
+    return tt_ce_fwd_tc_rect_bits(user, item_all, item_ids_all, item_offset, hn_rows, n_rowneg, pool, pool_rows, n_user, n_item,
+                                  dim, inv_temp, loss, row_lse, row_pos, nan_flags, workspace, workspace_bytes, 64, stream);
 }
 
 extern "C" int tt_ce_fwd_tc(const float *user, const float *item, const int64_t *item_ids, const float *hn_rows,

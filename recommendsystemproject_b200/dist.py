@@ -128,6 +128,12 @@ class ShardedTrainStep:
         if batch_has_hard_negatives(example_batch) and global_loss and self.world > 1:
             raise ops.TTError("ShardedTrainStep: per-row hard negatives with a global in-batch loss are not supported")
         self.static_batch = _clone_tree(example_batch)
+        # the in-batch ids are column `item_id_col` of the item tower's sparse block, i.e. indices into that feature's
+        # table: the loss kernel sorts only the bits such an index can have (an id outside the table raises the
+        # feature's out-of-range flag in the gather AND bit 3 of the loss flags)
+        feats = getattr(model.item_tower, "sparse_features", None) or []
+        self.id_bits = ops.id_bits_for(feats[item_id_col]["vocab_size"]) if item_id_col < len(feats) else 64
+        self.loss_flags = torch.zeros(1, dtype=torch.int32, device=optimizer.flat_p.device)
         if self.world > 1 and optimizer.sparse_tables:
             raise ops.TTError("ShardedTrainStep on several ranks: replicated tables need table_mode='dense' (their gradients "
                               "ride the dense all-reduce); only row-sharded tables are updated touched-rows-only")
@@ -213,8 +219,10 @@ class ShardedTrainStep:
 
     def _loss(self, u, i, ids):
         if self.world > 1 and self.global_loss:
-            return global_inbatch_ce(u, i, ids, None, self.temperature, precision=self._precision(u))
-        return ops.fused_inbatch_ce(u, i, ids, None, None, self.temperature, precision=self._precision(u))[0]
+            return global_inbatch_ce(u, i, ids, None, self.temperature, precision=self._precision(u),
+                                     nan_flags=self.loss_flags, id_bits=self.id_bits)
+        return ops.fused_inbatch_ce(u, i, ids, None, None, self.temperature, nan_flags=self.loss_flags,
+                                    precision=self._precision(u), id_bits=self.id_bits)[0]
 
     def _precision(self, u):
         if self.loss_precision != "auto":
@@ -262,6 +270,17 @@ class ShardedTrainStep:
         return self.static_loss
 
     def check_flags(self):
+        """One host read of the step's device flags (call it between steps, never inside the capture): NaN embeddings
+        raise the reference's RuntimeError texts (TwoTowerModel.py:84-92), an item id outside its table IndexError."""
+        flags = int(self.loss_flags.item()) if self.loss_flags.is_cuda else 0
+        if flags:
+            self.loss_flags.zero_()
+        if flags & 8:
+            raise IndexError(f"item id outside [0, 2**{self.id_bits}) in the in-batch loss (ids must index the item table)")
+        if flags & 1:
+            raise RuntimeError("Found NaN in User Embedding")
+        if flags & 2:
+            raise RuntimeError("Found NaN in Item Embedding")
         grp = getattr(self.model, "shard_group", None)
         if grp is not None:
             grp.check_flags()
@@ -606,7 +625,8 @@ class _AllGatherWithGrad(torch.autograd.Function):
         return g[dist.get_rank()]
 
 
-def global_inbatch_ce(user, item, item_ids, pool, temperature, precision: str = "fp32", ce_fn=None):
+def global_inbatch_ce(user, item, item_ids, pool, temperature, precision: str = "fp32", ce_fn=None, nan_flags=None,
+                      id_bits: int = 64):
     """SURVEY 8e, "towers + loss": the in-batch softmax over the GLOBAL batch of W*B items while every rank keeps only
     its own B user rows.  Item embeddings (and item ids) are all-gathered; their gradients flow back to the owners
     through the all-gather's backward (reduce-scatter / sum); with the loss of rank r scaled by 1/W and the dense
@@ -632,12 +652,13 @@ def global_inbatch_ce(user, item, item_ids, pool, temperature, precision: str = 
                 ids_all = torch.empty(world * B, dtype=torch.int64, device=item.device)
                 dist.all_gather_into_tensor(ids_all, item_ids.reshape(-1).contiguous().long())
             return ops.fused_inbatch_ce(user, blocks.reshape(world * B, -1), ids_all, None, pool, temperature,
-                                        precision="bf16", item_offset=rank * B)[0]
+                                        nan_flags=nan_flags, precision="bf16", item_offset=rank * B, id_bits=id_bits)[0]
         others = torch.cat([blocks[r] for r in range(world) if r != rank], dim=0)
         pool = others if pool is None else torch.cat([others, pool], dim=0)
     if ce_fn is not None:
         return ce_fn(user, item, item_ids, pool, temperature)
-    return ops.fused_inbatch_ce(user, item, item_ids, None, pool, temperature, precision=precision)[0]
+    return ops.fused_inbatch_ce(user, item, item_ids, None, pool, temperature, nan_flags=nan_flags, precision=precision,
+                                id_bits=id_bits)[0]
 
 
 def global_clip_coef(sq_terms: List[torch.Tensor], max_norm: float = 1.0) -> torch.Tensor:

@@ -215,7 +215,7 @@ class FusedInBatchCE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, user, item, hn_rows, pool, item_ids, inv_temp: float, nan_flags, precision: str = "fp32",
-                item_offset: int = 0):
+                item_offset: int = 0, id_bits: int = 64):
         _need_cuda(user, item)
         lib = _lib.load()
         user = user.contiguous().float()
@@ -243,9 +243,9 @@ class FusedInBatchCE(torch.autograd.Function):
             tcbytes = ctypes.c_size_t(0)
             check(lib.tt_ce_tc_workspace_rect(B, Bi, H, N, D, ctypes.byref(tcbytes)), "tt_ce_tc_workspace_rect")
             tcws = _ws(tcbytes.value, dev)
-            check(lib.tt_ce_fwd_tc_rect(_p(user), _p(item), _p(item_ids), int(item_offset), _p(hn_rows), N, _p(pool), H, B, Bi, D,
-                                        float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(tcws),
-                                        tcws.numel(), _stream()), "tt_ce_fwd_tc_rect")
+            check(lib.tt_ce_fwd_tc_rect_bits(_p(user), _p(item), _p(item_ids), int(item_offset), _p(hn_rows), N, _p(pool), H, B,
+                                             Bi, D, float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags),
+                                             _p(tcws), tcws.numel(), int(id_bits), _stream()), "tt_ce_fwd_tc_rect_bits")
             _count(10 + (1 if pool is not None else 0) + (2 if item_ids is not None else 0))
         elif precision == "fp32":
             check(lib.tt_ce_workspace(B, H, N, D, ctypes.byref(nbytes)), "tt_ce_workspace")
@@ -286,23 +286,32 @@ class FusedInBatchCE(torch.autograd.Function):
                                         _p(d_item), _p(d_hn), _p(d_pool), _p(ctx.tcws), ctx.tcws.numel(), _p(ws), ws.numel(),
                                         _stream()), "tt_ce_bwd_tc_rect")
             _count(5 + (1 if hn_rows is not None else 0) + (1 if pool is not None else 0))
-            return d_user, d_item, d_hn, d_pool, None, None, None, None, None
+            return d_user, d_item, d_hn, d_pool, None, None, None, None, None, None
         ws = _ws(ctx.ws_bytes, dev)
         check(lib.tt_ce_bwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D, ctx.inv_temp,
                                 _p(row_lse), _p(g), _p(d_user), _p(d_item), _p(d_hn), _p(d_pool), _p(ws), ws.numel(),
                                 _stream()), "tt_ce_bwd_f32")
         _count(6)
-        return d_user, d_item, d_hn, d_pool, None, None, None, None, None
+        return d_user, d_item, d_hn, d_pool, None, None, None, None, None, None
+
+
+def id_bits_for(vocab_size: int) -> int:
+    """Bits needed by the ids of a table with vocab_size rows (what fused_inbatch_ce's id_bits takes)."""
+    return max(1, (max(int(vocab_size), 2) - 1).bit_length())
 
 
 def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, temperature: float = 0.1,
-                     nan_flags: Optional[torch.Tensor] = None, precision: str = "fp32", item_offset: int = 0):
+                     nan_flags: Optional[torch.Tensor] = None, precision: str = "fp32", item_offset: int = 0,
+                     id_bits: int = 64):
     """precision='fp32': exact SIMT path; 'bf16': tcgen05/TMA tensor-core path (dim 64 or 128), which also takes the
-    rectangular global-batch form (item [Bi >= B, D], item_ids [Bi], user b's positive = item row item_offset + b)."""
+    rectangular global-batch form (item [Bi >= B, D], item_ids [Bi], user b's positive = item row item_offset + b).
+    id_bits < 64 ('bf16' only) declares 0 <= item id < 2**id_bits (ids that index a table of vocab_size rows:
+    ``id_bits_for(vocab_size)``): the sorts that group equal ids run over those bits only; an id outside the range
+    raises bit 3 (value 8) of nan_flags."""
     if nan_flags is None:
         nan_flags = torch.zeros(1, dtype=torch.int32, device=user.device)
     loss, row_lse = FusedInBatchCE.apply(user, item, hn_rows, pool, item_ids, 1.0 / float(temperature), nan_flags,
-                                         precision, item_offset)
+                                         precision, item_offset, id_bits)
     return loss, row_lse, nan_flags
 
 

@@ -97,3 +97,23 @@ def test_cross_rank_false_negatives_are_masked():
     # without ids nothing is masked
     loss, _, _ = ops.fused_inbatch_ce(u[:128].to(DEV), it.to(DEV), None, None, None, 0.05, precision="bf16", item_offset=0)
     assert float(loss) > 1.0
+
+
+def test_declared_id_range_gives_the_same_loss_and_flags_ids_outside():
+    """id_bits (tt_ce_fwd_tc_rect_bits): the id sorts run over the declared bits only.  Same stable permutation => the
+    forward is bitwise the undeclared call's; an id outside the declared range raises bit 3 of the flag word."""
+    from recommendsystemproject_b200 import ops
+    u, it, _, ids = _data(1024, 128, 0, 300, 11)
+    assert ops.id_bits_for(300) == 9 and ops.id_bits_for(2) == 1 and ops.id_bits_for(10_000_001) == 24
+    for off, rows in ((0, 1024), (256, 256)):                       # square form, and one rank's rectangular slab
+        ud = u[off:off + rows].to(DEV)
+        kw = {} if rows == 1024 else {"item_offset": off}
+        ref, lse_ref, f0 = ops.fused_inbatch_ce(ud, it.to(DEV), ids.to(DEV), None, None, 0.05, precision="bf16", **kw)
+        got, lse, f1 = ops.fused_inbatch_ce(ud, it.to(DEV), ids.to(DEV), None, None, 0.05, precision="bf16",
+                                            id_bits=ops.id_bits_for(300), **kw)
+        assert torch.equal(ref, got) and torch.equal(lse_ref, lse)
+        assert int(f0) == 0 and int(f1) == 0
+    bad = ids.clone()
+    bad[17] = 1 << 20
+    _, _, f2 = ops.fused_inbatch_ce(u.to(DEV), it.to(DEV), bad.to(DEV), None, None, 0.05, precision="bf16", id_bits=9)
+    assert int(f2) & 8
