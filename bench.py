@@ -313,14 +313,24 @@ def kernel_rooflines(peaks, flush, quick=False):
     item_ids = torch.randint(1, Bc * 50, (Bc,), device=dev)
     res = {}
 
+    sp = {"on": ops.single_pass_ok(0.05)}
+
     def ce_f():
-        res["l"] = ops.fused_inbatch_ce(u, it, item_ids, None, pool, 0.05, precision="bf16")[0]
-    ms_f, best_f = time_op(ce_f, 5, flush)
+        res["l"] = ops.fused_inbatch_ce(u, it, item_ids, None, pool, 0.05, precision="bf16", single_pass=sp["on"])[0]
+    with torch.no_grad():
+        ms_f, best_f = time_op(ce_f, 5, flush)            # evaluation form: ce_tc_kernel<fwd> alone
     ms_b, best_b = time_op(lambda: (ce_f(), res["l"].backward()), 5, flush)
+    ms_3 = None
+    if sp["on"]:                                          # the general three-pass kernels, for comparison
+        sp["on"] = False
+        ms_3, _ = time_op(lambda: (ce_f(), res["l"].backward()), 5, flush)
+        sp["on"] = True
     flops = 6.0 * Bc * (Bc + Hc) * Dc
-    out.append({"kernel": "ce_tc_kernel<fwd> + ce_tc_kernel<bwd dU> + ce_tc_kernel<bwd dI,dPool> (tcgen05, bf16 in / fp32 acc)",
+    out.append({"kernel": ("ce_tc_kernel<fwd + dU, single pass> + ce_tc_kernel<bwd dI,dPool>" if sp["on"] else
+                           "ce_tc_kernel<fwd> + ce_tc_kernel<bwd dU> + ce_tc_kernel<bwd dI,dPool>") + " (tcgen05, bf16 in / fp32 acc)",
                 "workload": f"C4: B={Bc} H={Hc} D={Dc} T=0.05, fwd+bwd incl. id sort + bf16 conversion", "bound": "tensor",
-                "ms": ms_b, "best_ms": best_b, "ms_fwd": ms_f, "achieved": flops / ms_b / 1e9, "peak": peaks["bf16_tflops"],
+                "ms": ms_b, "best_ms": best_b, "ms_fwd_only_no_grad": ms_f, "ms_three_pass": ms_3,
+                "achieved": flops / ms_b / 1e9, "peak": peaks["bf16_tflops"],
                 "peak_sustained": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": flops / ms_b / 1e9 / peaks["bf16_tflops"], "frac_of_sustained": flops / ms_b / 1e9 / peaks["bf16_tflops_sustained"],
                 "alg_flops": flops, "loss": float(res["l"])})
@@ -469,6 +479,7 @@ def run_c3(args, rank, local_rank, world, dev, peaks):
     final_loss = float(loss_host)
     launches = step.launches_per_step or 0
     bn_exchange = step.bn_exchange
+    ce_single = bool(step.single_pass)
     a2a_bytes = getattr(step, "a2a_bytes_per_step", 0)
     del staging
     # ---- the step's dominant kernel (profiles/r2_c3_step_launches.md: ce_tc_kernel, three launches = ~1/3 of the step), timed
@@ -487,6 +498,8 @@ def run_c3(args, rank, local_rank, world, dev, peaks):
             "e2e": {"value": B_global * args.steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                     "note": "pinned host batch -> H2D on a copy stream one step ahead -> D2D into the graph's buffers -> step -> loss read-back"},
+            "loss_kernel": ("tcgen05 single pass: forward + dU in one walk over the logit tiles, then the dI pass" if ce_single
+                            else "tcgen05 three passes: forward, dU, dI"),
             "gpu_launches": launches * args.steps * 2, "gpu_launches_per_step": launches,
             "nvlink_bytes_per_step_per_gpu": a2a_bytes, "hist_valid_positions_per_gpu": n_valid,
             "batchnorm_exchange": bn_exchange,
@@ -494,30 +507,36 @@ def run_c3(args, rank, local_rank, world, dev, peaks):
     return line
 
 
-def c3_dominant_kernel(B_loc, B_glob, D, peaks, dev):
-    """ce_tc_kernel (tcgen05): FWD + BWD_X + BWD_Y launches at [B_loc x B_glob], CUDA events on the launching stream."""
+def c3_dominant_kernel(B_loc, B_glob, D, peaks, dev, temperature=0.05, v_item=10_000_001):
+    """ce_tc_kernel (tcgen05) exactly as the step calls it: the rectangular [B_loc x B_glob] form (rank 0's slab of the
+    global batch), declared id range, single-pass training form when the temperature allows it; CUDA events on the
+    launching stream."""
     from recommendsystemproject_b200 import ops
     gen = torch.Generator(device=dev).manual_seed(4)
     u = torch.nn.functional.normalize(torch.randn(B_loc, D, device=dev, generator=gen), dim=1).requires_grad_(True)
-    it = torch.nn.functional.normalize(torch.randn(B_loc, D, device=dev, generator=gen), dim=1).requires_grad_(True)
-    others = B_glob - B_loc
-    pool = torch.nn.functional.normalize(torch.randn(others, D, device=dev, generator=gen), dim=1).requires_grad_(True) if others else None
-    ids = torch.randperm(B_glob, device=dev, generator=gen)[:B_loc] + 1
+    it = torch.nn.functional.normalize(torch.randn(B_glob, D, device=dev, generator=gen), dim=1).requires_grad_(True)
+    ids = torch.randperm(v_item - 1, device=dev, generator=gen)[:B_glob] + 1
+    single = ops.single_pass_ok(temperature)
     res = {}
 
-    def fwd_bwd():
-        res["l"] = ops.fused_inbatch_ce(u, it, ids, None, pool, 0.05, precision="bf16")[0]
+    def fwd_bwd(sp=single):
+        res["l"] = ops.fused_inbatch_ce(u, it, ids, None, None, temperature, precision="bf16", item_offset=0,
+                                        id_bits=ops.id_bits_for(v_item), single_pass=sp)[0]
         res["l"].backward()
     ms, best = time_op(fwd_bwd, 5, lambda: None)
+    ms3 = time_op(lambda: fwd_bwd(False), 5, lambda: None)[0] if single else None
     flops = 6.0 * B_loc * B_glob * D
-    return {"bound": "tensor", "kernel": "ce_tc_kernel<fwd> + <bwd dU> + <bwd dI> (tcgen05 bf16, fp32 accumulate in TMEM): the fused global in-batch "
+    return {"bound": "tensor", "kernel": ("ce_tc_kernel<fwd + dU, single pass> + <bwd dI>" if single else "ce_tc_kernel<fwd> + <bwd dU> + <bwd dI>") +
+                                         " (tcgen05 bf16, fp32 accumulate in TMEM): the fused global in-batch "
                                          "softmax CE of the step, incl. its id sort / bf16 conversion / reductions",
-            "workload": f"{B_loc} local user rows x {B_glob} global item columns, D={D}, T=0.05", "ms": ms, "best_ms": best,
+            "workload": f"{B_loc} local user rows x {B_glob} global item columns, D={D}, T={temperature}", "ms": ms, "best_ms": best,
+            "ms_three_pass": ms3,
             "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "peak_sustained": peaks["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["bf16_tflops"],
             "frac_of_sustained": flops / ms / 1e9 / peaks["bf16_tflops_sustained"], "alg_flops": flops, "traffic": None,
             "l2": "operands (B x D bf16, <= 17 MB) are L2-resident by design; inputs are not flushed between repetitions",
-            "note": "algorithmic flops = 2 (fwd) + 4 (bwd) x B_loc x B_glob x D; the two backward passes recompute the logits (not counted)"}
+            "note": "algorithmic flops = 2 (fwd) + 4 (bwd) x B_loc x B_glob x D; the logits recomputed by the dI pass (and, in the "
+                    "three-pass form, by the dU pass) are not counted"}
 
 
 def _copy_into(dst, src):

@@ -202,6 +202,23 @@ TT_API int tt_ce_bwd_tc_rect(const float *user, const float *hn_rows, int n_rown
                       float *d_user, float *d_item_all, float *d_hn_rows, float *d_pool, void *fwd_workspace,
                       size_t fwd_workspace_bytes, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Single-pass TRAINING form of the tensor-core CE (TwoTowerModel.py:95-140 forward + the dU half of its autograd in ONE
+ * walk over the logit tiles; the logits are evaluated twice per step instead of three times).
+ * tt_ce_fwd_tc_fused = tt_ce_fwd_tc_rect_bits without per-row hard negatives, and it ALSO leaves dU's raw partial sums in
+ * `bwd_workspace` (tt_ce_bwd_tc_workspace_rect(n_user, n_item, pool, 0, dim) bytes, 256-byte aligned), which must reach
+ * tt_ce_bwd_tc_fused untouched together with `workspace`.  tt_ce_bwd_tc_fused then runs only the dI / dPool pass.
+ * Precondition: bounded logits, max|u| * max|item or pool row| / T * log2(e) <= 96 (L2-normalised embeddings at any
+ * T >= 0.015): the exponentials are taken without a row shift.  The forward checks the bound on the device and raises
+ * bit 4 (value 16) of *nan_flags when it is violated -- results are then unusable, call the three-pass entry points. */
+TT_API int tt_ce_fwd_tc_fused(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,
+                       const float *pool, int64_t pool_rows, int64_t n_user, int64_t n_item, int dim, float inv_temp,
+                       float *loss, float *row_lse, float *row_pos, int *nan_flags, void *workspace, size_t workspace_bytes,
+                       void *bwd_workspace, size_t bwd_workspace_bytes, int id_bits, void *stream);
+TT_API int tt_ce_bwd_tc_fused(const float *user, int64_t pool_rows, int64_t n_user, int64_t n_item, int dim, float inv_temp,
+                       const float *row_lse, const float *grad_loss, float *d_user, float *d_item_all, float *d_pool,
+                       void *fwd_workspace, size_t fwd_workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes,
+                       void *stream);
+
 /* developer hook (tools/ce_trace.py): SM-clock stamps of CTA 0's pipeline events of the next tcgen05 CE
  * launches are written to dbg[11][256] (device memory); NULL disables.  Not used by the product path. */
 TT_API int tt_ce_tc_debug_trace(long long *dbg);

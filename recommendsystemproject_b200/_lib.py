@@ -59,6 +59,9 @@ _SIGNATURES = {
                                   c_size_t, P]),
     "tt_ce_fwd_tc_rect_bits": (c_int, [P, P, P, c_int64, P, c_int, P, c_int64, c_int64, c_int64, c_int, c_float, P, P, P, P, P,
                                        c_size_t, c_int, P]),
+    "tt_ce_fwd_tc_fused": (c_int, [P, P, P, c_int64, P, c_int64, c_int64, c_int64, c_int, c_float, P, P, P, P, P, c_size_t, P,
+                                   c_size_t, c_int, P]),
+    "tt_ce_bwd_tc_fused": (c_int, [P, c_int64, c_int64, c_int64, c_int, c_float, P, P, P, P, P, P, c_size_t, P, c_size_t, P]),
     "tt_ce_bwd_tc_workspace_rect": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, P]),
     "tt_ce_bwd_tc_rect": (c_int, [P, P, c_int, c_int64, c_int64, c_int64, c_int, c_float, P, P, P, P, P, P, P, c_size_t, P,
                                   c_size_t, P]),

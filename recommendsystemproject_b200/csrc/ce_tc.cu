@@ -7,10 +7,18 @@
 // TwoTowerModel.py:95-140 of the reference and their autograd.  The B x (B+H)
 // logits and probabilities live only in TMEM.
 //
-// ONE persistent kernel template, three modes:
+// ONE persistent kernel template, four modes:
 //   FWD    X = U rows,            W = [item ; pool] tiles   -> per-row online (max, sum)
 //   BWD_X  X = U rows,            W = [item ; pool] tiles   -> dU  = c (P - 1) W
 //   BWD_Y  X = item / pool rows,  W = U tiles               -> dI, dPool = c (P - 1)^T U
+//   FWD_X  X = U rows,            W = [item ; pool] tiles   -> per-row sum of exp AND sum_j exp(z_j) W_j in ONE pass:
+//          the training form (tt_ce_fwd_tc_fused).  FWD and BWD_X walk the same tiles with the same operands and
+//          differ only in the row statistic they subtract, so when the logits are known to be bounded
+//          (|z| log2(e) <= 96: L2-normalised towers at any temperature >= 0.015) the exponentials are taken unshifted,
+//          E = exp2(z log2 e), and one pass yields  s_b = sum_j E_bj  (-> lse_b = ln s_b)  and  O_b = sum_j E_bj W_j
+//          (-> dU_b = c (O_b / s_b - W_pos(b))).  The positive column is left out of the tile work and re-enters in
+//          fp32 in the epilogue kernels (its weight P_pos - 1 = -s_excl / s would cancel in bf16).  The exponential is
+//          evaluated twice per logit (this pass + BWD_Y) instead of three times.
 // The 128x128 tiles (X row tile m, W tile n) are numbered m * n_tiles + n and
 // cut into one contiguous range per CTA (stream-K: every SM gets the same
 // number of tiles +-1, a row tile that straddles CTAs leaves one partial per
@@ -53,19 +61,25 @@ constexpr float LOG2E = 1.4426950408889634f;
 // right away), G 128 (bf16 pairs of the 256 probabilities), Out D.
 constexpr uint32_t TM_S = 0, TM_G = 256, TM_OUT = 384;
 
-enum { MODE_FWD = 0, MODE_BWD_X = 1, MODE_BWD_Y = 2 };
+enum { MODE_FWD = 0, MODE_BWD_X = 1, MODE_BWD_Y = 2, MODE_FWD_X = 3 };
+// FWD_X takes exp2 of the unshifted logits: |z| * log2(e) must stay below this (sums of 2^24 terms then stay finite in
+// fp32, no term underflows); beyond it the forward raises CE_TC_FLAG_RANGE and the caller must use the three-pass form
+constexpr float CE_TC_FUSED_MAX_LOG2 = 96.0f;
+constexpr int CE_TC_FLAG_RANGE = 16;
 
 // ---------------------------------------------------------------- prep kernels
 // out[p, :] = bf16(in[perm ? perm[p] : p, :]); one warp per row; NaN detection for the flag word
 __global__ void __launch_bounds__(256)
 tc_convert_rows(const float *__restrict__ in, const int32_t *__restrict__ perm, int64_t n, int dim,
-                __nv_bfloat16 *__restrict__ out, int *__restrict__ nan_flags, int nan_bit) {
+                __nv_bfloat16 *__restrict__ out, int *__restrict__ nan_flags, int nan_bit,
+                int *__restrict__ max_norm2 = nullptr) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     for (int64_t p = warp; p < n; p += n_warps) {
         const int64_t src = perm ? perm[p] : p;
         bool nan = false;
+        float n2 = 0.f;
         for (int c = lane * 4; c < dim; c += 128) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(in + src * dim + c));
             nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
@@ -74,8 +88,18 @@ tc_convert_rows(const float *__restrict__ in, const int32_t *__restrict__ perm, 
             raw.x = *reinterpret_cast<uint32_t *>(&a);
             raw.y = *reinterpret_cast<uint32_t *>(&b);
             *reinterpret_cast<uint2 *>(out + p * dim + c) = raw;
+            if (max_norm2) {   // squared norm of the ROUNDED row (what the tensor core multiplies)
+                const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+                n2 += fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+            }
         }
         if (__any_sync(0xffffffffu, nan) && lane == 0) atomicOr(nan_flags, nan_bit);
+        if (max_norm2) {
+            n2 = warp_sum(n2);
+            // non-negative floats order like their bit patterns (inf above every finite value); NaN rows are reported
+            // through nan_flags
+            if (lane == 0 && n2 == n2) atomicMax(max_norm2, __float_as_int(n2));
+        }
     }
 }
 
@@ -197,8 +221,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__ CUtensorMap map_xb,
              const __grid_constant__ CUtensorMap map_wa, const __grid_constant__ CUtensorMap map_wb,
              const CeTcParams prm) {
-    constexpr bool BWD = MODE != MODE_FWD;
+    constexpr bool BWD = MODE != MODE_FWD;           // FWD_X has the backward's structure (G back to TMEM, Out chain)
     constexpr bool TRANS = MODE == MODE_BWD_Y;
+    constexpr bool FUSED = MODE == MODE_FWD_X;
     constexpr int KB = D / 64;                       // 64-column (128-byte) K blocks
     constexpr int X_BYTES = TC_BM * D * 2;
     constexpr int W_BYTES = TC_BN * D * 2;
@@ -403,6 +428,7 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                 dg = -1;
                 if (x_item && p < prm.x_rows) { lo = prm.lo[p]; hi = prm.hi[p]; dg = prm.diag[p]; }
                 if (MODE == MODE_BWD_X) row_stat = (p < prm.x_rows) ? prm.lse2p[p] : INFINITY;
+                if (FUSED) row_stat = (p < prm.x_rows) ? 0.f : INFINITY;     // unshifted exponentials (CE_TC_FUSED_MAX_LOG2)
                 m_run = -INFINITY; s_run = 0.f;
             }
             {
@@ -484,6 +510,7 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                         tc_fence_before();
                         mbar_arrive(&sfree[b]);          // the tensor pipe may overwrite the S buffer now
                         if (lane == 0 && quarter == 0) TT_DBG(7, i);
+                        float t_sum = 0.f;               // FWD_X: this tile's share of the row sum
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             uint32_t g[32];
@@ -500,6 +527,7 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                                     const float e3 = ex2_mixed<j + 3>(fmaf(__uint_as_float(r[q][j + 3]), prm.scale2, -st.w));
                                     g[qq * 16 + j / 2] = pack_bf16x2(e0, e1);
                                     g[qq * 16 + j / 2 + 1] = pack_bf16x2(e2, e3);
+                                    if (FUSED) t_sum += (e0 + e1) + (e2 + e3);
                                 };
                                 static_for<8>(quad);
                             }
@@ -510,9 +538,11 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                             }
                             tmem_st_32x32(lane_addr + TM_G + grp * (TC_HALF / 2) + h * 32, g);
                         }
+                        if (FUSED) s_run += t_sum;
                     } else {
                         // tile with the diagonal / a collision run / columns past the end (one or two per row of
                         // tiles): 64 columns at a time with the per-element fix-ups
+                        float t_sum = 0.f;
 #pragma unroll 1
                         for (int h = 0; h < 2; ++h) {
                             uint32_t r[2][32];
@@ -535,7 +565,9 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                                     e[j] = ex2_approx(fmaf(__uint_as_float(r[qq][j]), prm.scale2, -st));
                                     const int col = col0 + q * 32 + j;
                                     if (col >= ncol) e[j] = 0.f;
-                                    else if (x_item && w_item && col >= lo && col < hi) e[j] = (col == dg) ? e[j] - 1.0f : 0.f;
+                                    // FWD_X leaves the whole run out, positive included: it re-enters in fp32 in the epilogue
+                                    else if (x_item && w_item && col >= lo && col < hi) e[j] = (!FUSED && col == dg) ? e[j] - 1.0f : 0.f;
+                                    if (FUSED) t_sum += e[j];
                                 }
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) g[qq * 16 + j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
@@ -547,6 +579,7 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                             }
                             tmem_st_32x32(lane_addr + TM_G + grp * (TC_HALF / 2) + h * 32, g);
                         }
+                        if (FUSED) s_run += t_sum;
                     }
                     tmem_st_wait();
                     tc_fence_before();
@@ -564,6 +597,8 @@ ce_tc_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__
                         prm.part_s[slot] = s_run;
                     }
                 } else {
+                    if (FUSED && p < prm.x_rows)     // this (CTA segment, column half)'s share of the row sum, positive excluded
+                        prm.part_s[static_cast<int64_t>(2 * seg + grp) * prm.x_rows + p] = s_run;
                     // both groups drain Out (group = column half) once its last MMA has retired
                     mbar_wait(ofull, c.r & 1);
                     tc_fence_after();
@@ -657,6 +692,78 @@ __global__ void __launch_bounds__(1024) ce_tc_mean(const float *__restrict__ x, 
         __syncthreads();
     }
     if (threadIdx.x == 0) *out = sh[0] / static_cast<float>(n);
+}
+
+// FWD_X epilogue, one warp per (sorted) user row: s_excl = the row's sum of exp2 over every live column except the
+// positive (CTA-segment partials in fixed order), the positive logit in fp32 from the same bf16 rows,
+//   s = s_excl + exp2(pos2),  lse = ln s,  loss_row = lse - pos;
+// kept for the dU reduction: 1 / s and s_excl / s (= 1 - P_pos, free of cancellation).
+// Thread 0 of block 0 checks the Cauchy-Schwarz bound of every logit of the call against the range FWD_X can hold.
+__global__ void __launch_bounds__(256)
+ce_tc_finalize_fused(const __nv_bfloat16 *__restrict__ ub, const __nv_bfloat16 *__restrict__ ib,
+                     const int32_t *__restrict__ perm, const int32_t *__restrict__ diag, int64_t B, int dim, float inv_temp,
+                     int n_tiles, int64_t per_cta, const float *__restrict__ part_s, const int *__restrict__ max_norm2,
+                     float *__restrict__ row_lse, float *__restrict__ row_pos, float *__restrict__ row_loss,
+                     float *__restrict__ fs_inv, float *__restrict__ fs_ratio, int *__restrict__ nan_flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const float scale2 = inv_temp * LOG2E;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const float un = sqrtf(__int_as_float(max_norm2[0])), wn = sqrtf(__int_as_float(max_norm2[1]));
+        if (!(un * wn * scale2 <= CE_TC_FUSED_MAX_LOG2)) atomicOr(nan_flags, CE_TC_FLAG_RANGE);
+    }
+    for (int64_t p = warp; p < B; p += n_warps) {
+        const int mt = static_cast<int>(p / TC_BM);
+        const int n_slots = 2 * (sched_last_cta(mt, n_tiles, per_cta) - sched_first_cta(mt, n_tiles, per_cta) + 1);
+        float s_excl = 0.f;
+        for (int k = 0; k < n_slots; ++k) s_excl += part_s[static_cast<int64_t>(k) * B + p];
+        float pos = 0.f;
+        const int64_t pi = diag[p];     // sorted position of this user's own item
+        for (int k = lane; k < dim; k += 32)
+            pos = fmaf(__bfloat162float(ub[p * dim + k]), __bfloat162float(ib[pi * dim + k]), pos);
+        pos = warp_sum(pos);
+        if (lane == 0) {
+            const float s = s_excl + exp2f(pos * scale2);
+            const float lse = log2f(s) * (1.0f / LOG2E);
+            const int64_t orig = perm[p];
+            row_lse[orig] = lse;
+            row_pos[orig] = pos * inv_temp;
+            row_loss[p] = lse - pos * inv_temp;
+            fs_inv[p] = 1.0f / s;
+            fs_ratio[p] = s_excl / s;
+        }
+    }
+}
+
+// dU of the fused form: out[perm[p], :] = (*grad_loss * scale) * (sum_seg part[seg][p, :] / s_p - (s_excl_p / s_p) * W_pos(p))
+__global__ void __launch_bounds__(256)
+ce_tc_reduce_rows_fused(const float *__restrict__ part, int64_t part_rows, int n_tiles, int64_t per_cta, int64_t n_rows,
+                        int dim, const int32_t *__restrict__ perm, const float *__restrict__ grad_loss, float scale,
+                        const float *__restrict__ fs_inv, const float *__restrict__ fs_ratio,
+                        const __nv_bfloat16 *__restrict__ ib, const int32_t *__restrict__ diag, float *__restrict__ out) {
+    const int vpr = dim / 4;
+    const float c = (*grad_loss) * scale;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_rows * vpr;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t p = i / vpr;
+        const int c4 = static_cast<int>(i - p * vpr) * 4;
+        const int mt = static_cast<int>(p / TC_BM);
+        const int n_seg = sched_last_cta(mt, n_tiles, per_cta) - sched_first_cta(mt, n_tiles, per_cta) + 1;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sg = 0; sg < n_seg; ++sg) {
+            const float4 v = *reinterpret_cast<const float4 *>(part + (static_cast<int64_t>(sg) * part_rows + p) * dim + c4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        const float inv = fs_inv[p], ratio = fs_ratio[p];
+        const uint2 raw = *reinterpret_cast<const uint2 *>(ib + static_cast<int64_t>(diag[p]) * dim + c4);
+        const float w0 = __uint_as_float(raw.x << 16), w1 = __uint_as_float(raw.x & 0xffff0000u);
+        const float w2 = __uint_as_float(raw.y << 16), w3 = __uint_as_float(raw.y & 0xffff0000u);
+        const int64_t dst = perm[p];
+        *reinterpret_cast<float4 *>(out + dst * dim + c4) =
+            make_float4(c * (a.x * inv - ratio * w0), c * (a.y * inv - ratio * w1), c * (a.z * inv - ratio * w2),
+                        c * (a.w * inv - ratio * w3));
+    }
 }
 
 // ---------------------------------------------------------------- backward helper kernels
@@ -756,6 +863,8 @@ struct CeTcWs {
     int32_t *vals_in, *perm_i, *inv_i, *perm_u, *inv_u;
     int32_t *lo_u, *hi_u, *diag_u, *lo_i, *hi_i, *diag_i;
     float *part_m, *part_s, *row_loss;
+    float *fs_inv, *fs_ratio;      // fused form: per sorted user row 1 / s and s_excl / s
+    int *max_norm2;                // fused form: [2] bit patterns of max |u~|^2, max |w~|^2 (bf16-rounded rows)
     void *cub_tmp;
     bool ok;
     size_t used;
@@ -787,6 +896,9 @@ static CeTcWs ce_tc_carve(void *workspace, size_t bytes, int64_t n_user, int64_t
     w.part_s = ws.take<float>(static_cast<size_t>(2 * pl.fwd.max_seg) * n_user);
     w.row_loss = ws.take<float>(n_user);
     w.cub_tmp = ws.take<char>(pl.sort_bytes);
+    w.fs_inv = ws.take<float>(n_user);
+    w.fs_ratio = ws.take<float>(n_user);
+    w.max_norm2 = ws.take<int>(2);
     w.ok = ws.ok();
     w.used = ws.off;
     if (n_user == n_item) {
@@ -881,11 +993,21 @@ static inline unsigned tc_grid(int64_t n, int threads) {
 static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *item_ids, int64_t item_offset,
                           const float *hn_rows, int n_rowneg, const float *pool, int64_t pool_rows, int64_t n_user,
                           int64_t n_item, int dim, float inv_temp, float *loss, float *row_lse, float *row_pos,
-                          int *nan_flags, void *workspace, size_t workspace_bytes, int id_bits, cudaStream_t st) {
+                          int *nan_flags, void *workspace, size_t workspace_bytes, int id_bits, cudaStream_t st,
+                          void *bwd_workspace = nullptr, size_t bwd_workspace_bytes = 0) {
+    const bool fused = bwd_workspace != nullptr;      // FWD_X: the pass also accumulates dU's partials there
     const CeTcPlan pl = ce_tc_plan(n_user, n_item, pool_rows);
     CeTcWs w = ce_tc_carve(workspace, workspace_bytes, n_user, n_item, pool_rows, dim, pl);
     if (!w.ok) { set_error("ce_tc workspace too small: need %zu have %zu", w.used, workspace_bytes); return TT_E_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) { set_error("ce_tc workspace must be 256-byte aligned"); return TT_E_BADARG; }
+    CeBwdWs bw{};
+    if (fused) {
+        bw = ce_bwd_carve(bwd_workspace, bwd_workspace_bytes, n_user, 0, dim, pl);
+        if (!bw.ok) { set_error("ce_tc backward workspace too small: need %zu have %zu", bw.used, bwd_workspace_bytes); return TT_E_WORKSPACE; }
+        if (reinterpret_cast<uintptr_t>(bwd_workspace) % 256 != 0) { set_error("ce_tc workspace must be 256-byte aligned"); return TT_E_BADARG; }
+        const cudaError_t e = cudaMemsetAsync(w.max_norm2, 0, 2 * sizeof(int), st);
+        if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(ce_tc norms)");
+    }
 
     // 1. item-id sorted orders of the item rows and of the user rows -> permutations, collision runs, positive columns
     const int64_t *ikeys = nullptr, *ukeys = nullptr;
@@ -921,9 +1043,10 @@ static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *i
                                                        w.lo_i, w.hi_i, w.diag_i);
     TT_LAUNCH_CHECK("tc_runs_rect");
     // 2. bf16 operands in sorted order
-    tc_convert_rows<<<tc_grid(n_user * 32, 256), 256, 0, st>>>(user, w.perm_u, n_user, dim, w.ub, nan_flags, 1);
-    tc_convert_rows<<<tc_grid(n_item * 32, 256), 256, 0, st>>>(item, w.perm_i, n_item, dim, w.ib, nan_flags, 2);
-    if (pool) tc_convert_rows<<<tc_grid(pool_rows * 32, 256), 256, 0, st>>>(pool, nullptr, pool_rows, dim, w.pb, nan_flags, 4);
+    int *const un2 = fused ? w.max_norm2 : nullptr, *const wn2 = fused ? w.max_norm2 + 1 : nullptr;
+    tc_convert_rows<<<tc_grid(n_user * 32, 256), 256, 0, st>>>(user, w.perm_u, n_user, dim, w.ub, nan_flags, 1, un2);
+    tc_convert_rows<<<tc_grid(n_item * 32, 256), 256, 0, st>>>(item, w.perm_i, n_item, dim, w.ib, nan_flags, 2, wn2);
+    if (pool) tc_convert_rows<<<tc_grid(pool_rows * 32, 256), 256, 0, st>>>(pool, nullptr, pool_rows, dim, w.pb, nan_flags, 4, wn2);
     TT_LAUNCH_CHECK("tc_convert_rows");
     // 3. tensor maps + main kernel
     CeMaps mp;
@@ -935,6 +1058,18 @@ static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *i
     fill_sched(prm, pl.fwd);
     prm.scale2 = inv_temp * LOG2E;
     prm.lo = w.lo_u; prm.hi = w.hi_u; prm.diag = w.diag_u; prm.part_m = w.part_m; prm.part_s = w.part_s;
+    if (fused) {
+        // one pass: row sums AND the dU partials (pl.bwd_x is the forward's schedule)
+        prm.part = bw.part_x;
+        if ((rc = launch_ce_tc_dim<MODE_FWD_X>(dim, mp.u128, mp.u128, mp.i256, mp.p256, prm, pl.bwd_x.grid, st))) return rc;
+        ce_tc_finalize_fused<<<tc_grid(n_user * 32, 256), 256, 0, st>>>(w.ub, w.ib, w.perm_u, w.diag_u, n_user, dim, inv_temp,
+                                                                       pl.bwd_x.n_tiles, pl.bwd_x.per_cta, w.part_s, w.max_norm2,
+                                                                       row_lse, row_pos, w.row_loss, w.fs_inv, w.fs_ratio, nan_flags);
+        TT_LAUNCH_CHECK("ce_tc_finalize_fused");
+        ce_tc_mean<<<1, 1024, 0, st>>>(w.row_loss, n_user, loss);
+        TT_LAUNCH_CHECK("ce_tc_mean");
+        return 0;
+    }
     if ((rc = launch_ce_tc_dim<MODE_FWD>(dim, mp.u128, mp.u128, mp.i256, mp.p256, prm, pl.fwd.grid, st))) return rc;
     // 4. finalize
     ce_tc_finalize<<<tc_grid(n_user * 32, 256), 256, 0, st>>>(w.ub, w.ib, user, hn_rows, n_rowneg, w.perm_u, w.diag_u, n_user, dim,
@@ -949,7 +1084,9 @@ static int ce_fwd_tc_impl(const float *user, const float *item, const int64_t *i
 static int ce_bwd_tc_impl(const float *user, const float *hn_rows, int n_rowneg, int64_t pool_rows, int64_t n_user,
                           int64_t n_item, int dim, float inv_temp, const float *row_lse, const float *grad_loss,
                           float *d_user, float *d_item, float *d_hn_rows, float *d_pool, void *fwd_workspace,
-                          size_t fwd_workspace_bytes, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                          size_t fwd_workspace_bytes, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                          bool fused = false) {
+    // fused: `workspace` is the one the FWD_X forward filled (part_x holds dU's partials); only the dI pass runs here
     const CeTcPlan pl = ce_tc_plan(n_user, n_item, pool_rows);
     const CeTcWs f = ce_tc_carve(fwd_workspace, fwd_workspace_bytes, n_user, n_item, pool_rows, dim, pl);
     if (!f.ok) { set_error("ce_tc forward workspace too small: need %zu have %zu", f.used, fwd_workspace_bytes); return TT_E_WORKSPACE; }
@@ -972,7 +1109,7 @@ static int ce_bwd_tc_impl(const float *user, const float *hn_rows, int n_rowneg,
     prm.lo = f.lo_u; prm.hi = f.hi_u; prm.diag = f.diag_u;
     prm.xt_split = pl.xt_user; prm.wt_split = pl.wt_item;
     prm.part = w.part_x;
-    if ((rc = launch_ce_tc_dim<MODE_BWD_X>(dim, mp.u128, mp.u128, mp.i256, mp.p256, prm, pl.bwd_x.grid, st))) return rc;
+    if (!fused && (rc = launch_ce_tc_dim<MODE_BWD_X>(dim, mp.u128, mp.u128, mp.i256, mp.p256, prm, pl.bwd_x.grid, st))) return rc;
     // pass 2: dI, dPool   (X = [item ; pool] row tiles, W = U 256-row tiles)
     fill_sched(prm, pl.bwd_y);
     prm.x_rows = n_item; prm.w_rows = n_user;
@@ -987,9 +1124,14 @@ static int ce_bwd_tc_impl(const float *user, const float *hn_rows, int n_rowneg,
     }
     const float scale = inv_temp / static_cast<float>(n_user);      // mean over THIS call's user rows
     const int64_t vec = dim / 4;
-    ce_tc_reduce_rows<<<tc_grid(n_user * vec, 256), 256, 0, st>>>(w.part_x, w.rows_x, pl.bwd_x.n_tiles, pl.bwd_x.per_cta, 0,
-                                                                 n_user, dim, f.perm_u, grad_loss, scale,
-                                                                 hn_rows ? w.extra : nullptr, inv_temp, d_user);
+    if (fused)
+        ce_tc_reduce_rows_fused<<<tc_grid(n_user * vec, 256), 256, 0, st>>>(w.part_x, w.rows_x, pl.bwd_x.n_tiles, pl.bwd_x.per_cta,
+                                                                           n_user, dim, f.perm_u, grad_loss, scale, f.fs_inv,
+                                                                           f.fs_ratio, f.ib, f.diag_u, d_user);
+    else
+        ce_tc_reduce_rows<<<tc_grid(n_user * vec, 256), 256, 0, st>>>(w.part_x, w.rows_x, pl.bwd_x.n_tiles, pl.bwd_x.per_cta, 0,
+                                                                     n_user, dim, f.perm_u, grad_loss, scale,
+                                                                     hn_rows ? w.extra : nullptr, inv_temp, d_user);
     ce_tc_reduce_rows<<<tc_grid(n_item * vec, 256), 256, 0, st>>>(w.part_y, w.rows_y, pl.bwd_y.n_tiles, pl.bwd_y.per_cta, 0,
                                                                  n_item, dim, f.perm_i, grad_loss, scale, nullptr, 0.f, d_item);
     if (pool_rows > 0)
@@ -1036,6 +1178,40 @@ extern "C" int tt_ce_fwd_tc_rect_bits(const float *user, const float *item_all, 
     return ce_fwd_tc_impl(user, item_all, item_ids_all, item_offset, hn_rows, n_rowneg, pool, pool_rows, n_user, n_item, dim,
                           inv_temp, loss, row_lse, row_pos, nan_flags, workspace, workspace_bytes, id_bits,
                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tt_ce_fwd_tc_fused(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,
+                                  const float *pool, int64_t pool_rows, int64_t n_user, int64_t n_item, int dim, float inv_temp,
+                                  float *loss, float *row_lse, float *row_pos, int *nan_flags, void *workspace,
+                                  size_t workspace_bytes, void *bwd_workspace, size_t bwd_workspace_bytes, int id_bits,
+                                  void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(user && item_all && loss && row_lse && row_pos && nan_flags && workspace && bwd_workspace, "null pointer");
+    TT_CHECK_ARG(id_bits >= 1 && id_bits <= 64, "id_bits must be in 1..64");
+    TT_CHECK_ARG((pool != nullptr) == (pool_rows > 0), "pool / pool_rows mismatch");
+    const float *hn_rows = nullptr;
+    const int n_rowneg = 0;
+    TT_CE_TC_COMMON_CHECKS();
+    TT_CHECK_ARG(item_offset >= 0 && item_offset + n_user <= n_item, "item_offset + n_user must lie inside the item rows");
+    TT_CHECK_ARG(inv_temp > 0.f, "temperature must be positive");
+    return ce_fwd_tc_impl(user, item_all, item_ids_all, item_offset, nullptr, 0, pool, pool_rows, n_user, n_item, dim, inv_temp,
+                          loss, row_lse, row_pos, nan_flags, workspace, workspace_bytes, id_bits,
+                          static_cast<cudaStream_t>(stream), bwd_workspace, bwd_workspace_bytes);
+}
+
+extern "C" int tt_ce_bwd_tc_fused(const float *user, int64_t pool_rows, int64_t n_user, int64_t n_item, int dim, float inv_temp,
+                                  const float *row_lse, const float *grad_loss, float *d_user, float *d_item_all, float *d_pool,
+                                  void *fwd_workspace, size_t fwd_workspace_bytes, void *bwd_workspace,
+                                  size_t bwd_workspace_bytes, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(user && row_lse && grad_loss && d_user && d_item_all && fwd_workspace && bwd_workspace, "null pointer");
+    TT_CHECK_ARG(pool_rows == 0 || d_pool != nullptr, "d_pool required with a pool");
+    const float *hn_rows = nullptr;
+    const int n_rowneg = 0;
+    TT_CE_TC_COMMON_CHECKS();
+    return ce_bwd_tc_impl(user, nullptr, 0, pool_rows, n_user, n_item, dim, inv_temp, row_lse, grad_loss, d_user, d_item_all,
+                          nullptr, d_pool, fwd_workspace, fwd_workspace_bytes, bwd_workspace, bwd_workspace_bytes,
+                          static_cast<cudaStream_t>(stream), true);
 }
 
 extern "C" int tt_ce_fwd_tc_rect(const float *user, const float *item_all, const int64_t *item_ids_all, int64_t item_offset,

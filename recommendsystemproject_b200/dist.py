@@ -134,6 +134,9 @@ class ShardedTrainStep:
         feats = getattr(model.item_tower, "sparse_features", None) or []
         self.id_bits = ops.id_bits_for(feats[item_id_col]["vocab_size"]) if item_id_col < len(feats) else 64
         self.loss_flags = torch.zeros(1, dtype=torch.int32, device=optimizer.flat_p.device)
+        # tensor-core loss: forward + dU in one walk over the logit tiles (ops.FusedInBatchCE single_pass) when the
+        # temperature keeps L2-normalised embeddings inside that kernel's range; checked on the device, see below
+        self.single_pass = ops.single_pass_ok(temperature) and not batch_has_hard_negatives(example_batch)
         if self.world > 1 and optimizer.sparse_tables:
             raise ops.TTError("ShardedTrainStep on several ranks: replicated tables need table_mode='dense' (their gradients "
                               "ride the dense all-reduce); only row-sharded tables are updated touched-rows-only")
@@ -165,13 +168,23 @@ class ShardedTrainStep:
         optimizer._norm_staged_by_caller = True
         snap = self._snapshot()
         side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._step_eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self._restore(snap)
+        for attempt in range(2):
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._step_eager()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._restore(snap)
+            # embeddings outside the single-pass loss kernel's range (towers that do not normalise): every rank falls
+            # back to the three-pass kernels together and warms up again
+            bad = (self.loss_flags & ops.CE_FLAG_LOGIT_RANGE).clamp(max=1).float()
+            if self.world > 1:
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if not (self.single_pass and float(bad) > 0):
+                break
+            self.single_pass = False
+            self.loss_flags.zero_()
         self.graph = None
         self.launches_per_step = None
         if graph:
@@ -220,9 +233,9 @@ class ShardedTrainStep:
     def _loss(self, u, i, ids):
         if self.world > 1 and self.global_loss:
             return global_inbatch_ce(u, i, ids, None, self.temperature, precision=self._precision(u),
-                                     nan_flags=self.loss_flags, id_bits=self.id_bits)
+                                     nan_flags=self.loss_flags, id_bits=self.id_bits, single_pass=self.single_pass)
         return ops.fused_inbatch_ce(u, i, ids, None, None, self.temperature, nan_flags=self.loss_flags,
-                                    precision=self._precision(u), id_bits=self.id_bits)[0]
+                                    precision=self._precision(u), id_bits=self.id_bits, single_pass=self.single_pass)[0]
 
     def _precision(self, u):
         if self.loss_precision != "auto":
@@ -275,6 +288,9 @@ class ShardedTrainStep:
         flags = int(self.loss_flags.item()) if self.loss_flags.is_cuda else 0
         if flags:
             self.loss_flags.zero_()
+        if flags & ops.CE_FLAG_LOGIT_RANGE:
+            raise RuntimeError("in-batch loss: |logit| exceeds the single-pass tensor-core kernel's range; "
+                               "build ShardedTrainStep and set .single_pass = False before capture")
         if flags & 8:
             raise IndexError(f"item id outside [0, 2**{self.id_bits}) in the in-batch loss (ids must index the item table)")
         if flags & 1:
@@ -626,7 +642,7 @@ class _AllGatherWithGrad(torch.autograd.Function):
 
 
 def global_inbatch_ce(user, item, item_ids, pool, temperature, precision: str = "fp32", ce_fn=None, nan_flags=None,
-                      id_bits: int = 64):
+                      id_bits: int = 64, single_pass: bool = False):
     """SURVEY 8e, "towers + loss": the in-batch softmax over the GLOBAL batch of W*B items while every rank keeps only
     its own B user rows.  Item embeddings (and item ids) are all-gathered; their gradients flow back to the owners
     through the all-gather's backward (reduce-scatter / sum); with the loss of rank r scaled by 1/W and the dense
@@ -652,13 +668,14 @@ def global_inbatch_ce(user, item, item_ids, pool, temperature, precision: str = 
                 ids_all = torch.empty(world * B, dtype=torch.int64, device=item.device)
                 dist.all_gather_into_tensor(ids_all, item_ids.reshape(-1).contiguous().long())
             return ops.fused_inbatch_ce(user, blocks.reshape(world * B, -1), ids_all, None, pool, temperature,
-                                        nan_flags=nan_flags, precision="bf16", item_offset=rank * B, id_bits=id_bits)[0]
+                                        nan_flags=nan_flags, precision="bf16", item_offset=rank * B, id_bits=id_bits,
+                                        single_pass=single_pass)[0]
         others = torch.cat([blocks[r] for r in range(world) if r != rank], dim=0)
         pool = others if pool is None else torch.cat([others, pool], dim=0)
     if ce_fn is not None:
         return ce_fn(user, item, item_ids, pool, temperature)
     return ops.fused_inbatch_ce(user, item, item_ids, None, pool, temperature, nan_flags=nan_flags, precision=precision,
-                                id_bits=id_bits)[0]
+                                id_bits=id_bits, single_pass=single_pass)[0]
 
 
 def global_clip_coef(sq_terms: List[torch.Tensor], max_norm: float = 1.0) -> torch.Tensor:

@@ -644,6 +644,11 @@ class TwoTowerModel(nn.Module):
         # loss kernel: "auto" = tcgen05 bf16 path when the shapes allow it and the batch is large, else exact fp32
         self.loss_precision = "auto"
         self.loss_tc_min_batch = 4096
+        # tensor-core loss in training: forward + dU in ONE walk over the logit tiles (ops.FusedInBatchCE single_pass).
+        # "auto" = whenever it applies (no per-row hard negatives, gradients on, temperature >= 0.0155: the towers
+        # L2-normalise, so |logit| <= 1/T); embeddings that break the kernel's range raise its device flag and the loss
+        # is recomputed by the three-pass kernels (and single-pass switched off) at the next flag check
+        self.loss_single_pass = "auto"
 
     def set_feature_mappings(self, user_mapping, item_mapping):
         self.user_feature_mapping = user_mapping
@@ -726,6 +731,9 @@ class TwoTowerModel(nn.Module):
             raise RuntimeError("Found NaN in Item Embedding")
         if flags & 4:
             raise RuntimeError("Found NaN in Hard Negative Embedding")
+        if flags & ops.CE_FLAG_LOGIT_RANGE:
+            raise RuntimeError("in-batch loss: |logit| exceeds the single-pass tensor-core kernel's range "
+                               "(|u||i|/T * log2(e) > 96); set model.loss_single_pass = False")
         if self.shard_group is not None and self.shard_group.tables:
             self.shard_group.check_flags()
 
@@ -741,9 +749,20 @@ class TwoTowerModel(nn.Module):
         if precision == "auto":
             # the tensor-core kernel needs D in {64, 128}; below a few thousand rows the exact fp32 kernel is as fast
             precision = "bf16" if (user_emb.shape[1] in (64, 128) and user_emb.shape[0] >= self.loss_tc_min_batch) else "fp32"
+        single = self.loss_single_pass
+        if single == "auto":
+            single = (precision == "bf16" and hard_neg_emb is None and torch.is_grad_enabled()
+                      and ops.single_pass_ok(temperature))
         loss, _, flags = ops.fused_inbatch_ce(user_emb, item_emb, item_ids=item_ids, hn_rows=hard_neg_emb,
-                                              pool=hard_neg_pool, temperature=temperature, precision=precision)
+                                              pool=hard_neg_pool, temperature=temperature, precision=precision,
+                                              single_pass=bool(single))
         self.last_nan_flags = flags
         if self.strict_nan_check and not torch.cuda.is_current_stream_capturing():
+            if single and int(flags) & ops.CE_FLAG_LOGIT_RANGE:
+                # un-normalised embeddings: outside the single-pass kernel's range -> the general three-pass kernels
+                self.loss_single_pass = False
+                loss, _, flags = ops.fused_inbatch_ce(user_emb, item_emb, item_ids=item_ids, hn_rows=hard_neg_emb,
+                                                      pool=hard_neg_pool, temperature=temperature, precision=precision)
+                self.last_nan_flags = flags
             self.check_nan_flags()
         return loss

@@ -7,6 +7,7 @@ is no CPU path: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -211,11 +212,15 @@ class FusedInBatchCE(torch.autograd.Function):
     """loss = mean_b(logsumexp(Z_b) - Z_b,pos(b)), Z as in TwoTowerModel.py:95-134; the logits never reach HBM.
     Inputs fp32: user [B, D]; item [Bi, D] with Bi == B (the reference's square in-batch form) or, precision 'bf16'
     only, Bi > B: the all-gathered GLOBAL batch of a data-parallel run, the positive of user b being item row
-    item_offset + b; hn_rows [B, N, D] and/or pool [H, D] optional; item_ids int64 [Bi] optional."""
+    item_offset + b; hn_rows [B, N, D] and/or pool [H, D] optional; item_ids int64 [Bi] optional.
+    single_pass ('bf16', no per-row hard negatives, some input requires grad): the forward walk over the logit tiles also
+    accumulates dU (tt_ce_fwd_tc_fused), the backward runs the dI / dPool pass only -- the logits are evaluated twice per
+    step instead of three times.  Needs bounded logits (L2-normalised embeddings, T >= 0.015); a violation raises bit 4
+    (value 16) of nan_flags (see include/tt_b200.h)."""
 
     @staticmethod
     def forward(ctx, user, item, hn_rows, pool, item_ids, inv_temp: float, nan_flags, precision: str = "fp32",
-                item_offset: int = 0, id_bits: int = 64):
+                item_offset: int = 0, id_bits: int = 64, single_pass: bool = False):
         _need_cuda(user, item)
         lib = _lib.load()
         user = user.contiguous().float()
@@ -238,11 +243,23 @@ class FusedInBatchCE(torch.autograd.Function):
         row_lse = torch.empty(B, dtype=torch.float32, device=dev)
         row_pos = torch.empty(B, dtype=torch.float32, device=dev)
         tcws = None
+        fused_ws = None
+        fuse = bool(single_pass) and precision == "bf16" and hn_rows is None and any(ctx.needs_input_grad[:4])
         if precision == "bf16":
             # tcgen05 / TMA tensor-core path (D in {64, 128})
             tcbytes = ctypes.c_size_t(0)
             check(lib.tt_ce_tc_workspace_rect(B, Bi, H, N, D, ctypes.byref(tcbytes)), "tt_ce_tc_workspace_rect")
             tcws = _ws(tcbytes.value, dev)
+        if fuse:
+            bbytes = ctypes.c_size_t(0)
+            check(lib.tt_ce_bwd_tc_workspace_rect(B, Bi, H, 0, D, ctypes.byref(bbytes)), "tt_ce_bwd_tc_workspace_rect")
+            fused_ws = _ws(bbytes.value, dev)
+            check(lib.tt_ce_fwd_tc_fused(_p(user), _p(item), _p(item_ids), int(item_offset), _p(pool), H, B, Bi, D,
+                                         float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags), _p(tcws),
+                                         tcws.numel(), _p(fused_ws), fused_ws.numel(), int(id_bits), _stream()),
+                  "tt_ce_fwd_tc_fused")
+            _count(10 + (1 if pool is not None else 0) + (2 if item_ids is not None else 0))
+        elif precision == "bf16":
             check(lib.tt_ce_fwd_tc_rect_bits(_p(user), _p(item), _p(item_ids), int(item_offset), _p(hn_rows), N, _p(pool), H, B,
                                              Bi, D, float(inv_temp), _p(loss), _p(row_lse), _p(row_pos), _p(nan_flags),
                                              _p(tcws), tcws.numel(), int(id_bits), _stream()), "tt_ce_fwd_tc_rect_bits")
@@ -261,6 +278,7 @@ class FusedInBatchCE(torch.autograd.Function):
         ctx.ws_bytes = nbytes.value
         ctx.precision = precision
         ctx.tcws = tcws   # bf16 operands / permutations / runs for the backward
+        ctx.fused_ws = fused_ws   # single-pass form: dU's partial sums, written by the forward
         ctx.mark_non_differentiable(row_lse)
         return loss, row_lse
 
@@ -278,6 +296,12 @@ class FusedInBatchCE(torch.autograd.Function):
         d_item = torch.empty_like(item)
         d_hn = None if hn_rows is None else torch.empty_like(hn_rows)
         d_pool = None if pool is None else torch.empty_like(pool)
+        if ctx.fused_ws is not None:
+            check(lib.tt_ce_bwd_tc_fused(_p(user), H, B, Bi, D, ctx.inv_temp, _p(row_lse), _p(g), _p(d_user), _p(d_item),
+                                         _p(d_pool), _p(ctx.tcws), ctx.tcws.numel(), _p(ctx.fused_ws), ctx.fused_ws.numel(),
+                                         _stream()), "tt_ce_bwd_tc_fused")
+            _count(4 + (1 if pool is not None else 0))
+            return d_user, d_item, d_hn, d_pool, None, None, None, None, None, None, None
         if ctx.precision == "bf16":
             nbytes = ctypes.c_size_t(0)
             check(lib.tt_ce_bwd_tc_workspace_rect(B, Bi, H, N, D, ctypes.byref(nbytes)), "tt_ce_bwd_tc_workspace_rect")
@@ -286,13 +310,13 @@ class FusedInBatchCE(torch.autograd.Function):
                                         _p(d_item), _p(d_hn), _p(d_pool), _p(ctx.tcws), ctx.tcws.numel(), _p(ws), ws.numel(),
                                         _stream()), "tt_ce_bwd_tc_rect")
             _count(5 + (1 if hn_rows is not None else 0) + (1 if pool is not None else 0))
-            return d_user, d_item, d_hn, d_pool, None, None, None, None, None, None
+            return d_user, d_item, d_hn, d_pool, None, None, None, None, None, None, None
         ws = _ws(ctx.ws_bytes, dev)
         check(lib.tt_ce_bwd_f32(_p(user), _p(item), _p(item_ids), _p(hn_rows), N, _p(pool), H, B, D, ctx.inv_temp,
                                 _p(row_lse), _p(g), _p(d_user), _p(d_item), _p(d_hn), _p(d_pool), _p(ws), ws.numel(),
                                 _stream()), "tt_ce_bwd_f32")
         _count(6)
-        return d_user, d_item, d_hn, d_pool, None, None, None, None, None, None
+        return d_user, d_item, d_hn, d_pool, None, None, None, None, None, None, None
 
 
 def id_bits_for(vocab_size: int) -> int:
@@ -300,18 +324,34 @@ def id_bits_for(vocab_size: int) -> int:
     return max(1, (max(int(vocab_size), 2) - 1).bit_length())
 
 
+CE_FLAG_ID_RANGE, CE_FLAG_LOGIT_RANGE = 8, 16      # nan_flags bits beyond the three NaN bits (include/tt_b200.h section 3)
+
+
+# developer switch: TT_CE_SINGLE_PASS=0 keeps the three-pass kernels everywhere (A/B timing)
+SINGLE_PASS_DEFAULT = os.environ.get("TT_CE_SINGLE_PASS", "1") != "0"
+
+
+def single_pass_ok(temperature: float) -> bool:
+    """Whether unit-norm embeddings keep |logit| * log2(e) inside the single-pass CE kernel's range (96), with a margin
+    for rounding: T >= 0.0155."""
+    return SINGLE_PASS_DEFAULT and 1.4426950408889634 / float(temperature) * 1.03 <= 96.0
+
+
 def fused_inbatch_ce(user, item, item_ids=None, hn_rows=None, pool=None, temperature: float = 0.1,
                      nan_flags: Optional[torch.Tensor] = None, precision: str = "fp32", item_offset: int = 0,
-                     id_bits: int = 64):
+                     id_bits: int = 64, single_pass: bool = False):
     """precision='fp32': exact SIMT path; 'bf16': tcgen05/TMA tensor-core path (dim 64 or 128), which also takes the
     rectangular global-batch form (item [Bi >= B, D], item_ids [Bi], user b's positive = item row item_offset + b).
     id_bits < 64 ('bf16' only) declares 0 <= item id < 2**id_bits (ids that index a table of vocab_size rows:
     ``id_bits_for(vocab_size)``): the sorts that group equal ids run over those bits only; an id outside the range
-    raises bit 3 (value 8) of nan_flags."""
+    raises bit 3 (value 8) of nan_flags.
+    single_pass ('bf16' without hn_rows, when a gradient is needed): forward + dU in one walk over the logit tiles
+    (FusedInBatchCE); callers must read nan_flags bit 4 (value 16) = "logits outside the range this form can hold"
+    (``single_pass_ok(temperature)`` says whether L2-normalised embeddings satisfy it)."""
     if nan_flags is None:
         nan_flags = torch.zeros(1, dtype=torch.int32, device=user.device)
     loss, row_lse = FusedInBatchCE.apply(user, item, hn_rows, pool, item_ids, 1.0 / float(temperature), nan_flags,
-                                         precision, item_offset, id_bits)
+                                         precision, item_offset, id_bits, single_pass)
     return loss, row_lse, nan_flags
 
 

@@ -172,9 +172,10 @@ def test_compute_loss_selects_the_tensor_core_kernel_for_large_batches():
     i = synth.normalized(gen, 4096, 128).to(DEV).requires_grad_(True)
     ids = torch.randint(1, 2000, (4096,), generator=gen).to(DEV)
     auto = model.compute_loss(u, i, item_ids=ids, temperature=0.1)
-    tc = ops.fused_inbatch_ce(u, i, ids, None, None, 0.1, precision="bf16")[0]
+    tc = ops.fused_inbatch_ce(u, i, ids, None, None, 0.1, precision="bf16", single_pass=True)[0]   # the training form
+    tc3 = ops.fused_inbatch_ce(u, i, ids, None, None, 0.1, precision="bf16")[0]
     exact = ops.fused_inbatch_ce(u, i, ids, None, None, 0.1, precision="fp32")[0]
-    assert torch.equal(auto.detach(), tc.detach())
+    assert torch.equal(auto.detach(), tc.detach()) and abs(float(tc) - float(tc3)) < 2e-5
     assert abs(float(auto) - float(exact)) < 3e-3
     auto.backward()
     g_auto = u.grad.clone()

@@ -134,6 +134,19 @@ t5b = abs(float(totc) / world - float(refc)) < 2e-5
 t5b &= float((ul.grad / world - ur.grad[slg]).norm() / ur.grad[slg].norm()) < 1e-4
 t5b &= float((il.grad / world - ir.grad[slg]).norm() / ir.grad[slg].norm()) < 1e-4
 ok &= t5b
+# 5c. the single-pass training form (forward + dU in one walk over the logit tiles) through the same all-gather, declared
+#     id range: against the three-pass reference above (bf16 tolerances: the two forms round different quantities to bf16)
+ul, il = (t.clone().requires_grad_(True) for t in (Ug[slg], Ig[slg]))
+fl = torch.zeros(1, dtype=torch.int32, device=dev)
+loss1 = tdist.global_inbatch_ce(ul, il, idc[slg], None, Tg, precision="bf16", nan_flags=fl, id_bits=ops.id_bits_for(300),
+                                single_pass=True)
+loss1.backward()
+tot1 = loss1.detach().clone()
+dist.all_reduce(tot1)
+t5c = int(fl) == 0 and abs(float(tot1) / world - float(refc)) < 2e-5
+t5c &= float((ul.grad / world - ur.grad[slg]).norm() / ur.grad[slg].norm()) < 6e-3
+t5c &= float((il.grad / world - ir.grad[slg]).norm() / ir.grad[slg].norm()) < 2e-3
+ok &= t5c
 # 6. the integrated step: row-sharded tables (one batched exchange) + data-parallel towers with global BatchNorm
 #    statistics + global in-batch softmax  ==  ONE process running the unsharded model on the global batch
 #    (TwoTowerModel.py:95-140, GenericTower.py:234, training_utils.py:51-56); dropout 0, distinct item ids
@@ -193,7 +206,7 @@ ok &= t6
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"dist_check world={world}: sharded_topk={t1} sharded_lookup={t2} dp_replicas_identical={t3} sharded_bag={t4} global_inbatch_ce={t5} global_ce_cross_rank_mask_tc={t5b} integrated_sharded_step={t6} (loss {float(loss_s):.6f} vs {float(loss_u):.6f}, worst param diff {worst:.2e}) all_ranks_ok={bool(flag.item())}")
+    print(f"dist_check world={world}: sharded_topk={t1} sharded_lookup={t2} dp_replicas_identical={t3} sharded_bag={t4} global_inbatch_ce={t5} global_ce_cross_rank_mask_tc={t5b} global_ce_single_pass={t5c} integrated_sharded_step={t6} (loss {float(loss_s):.6f} vs {float(loss_u):.6f}, worst param diff {worst:.2e}) all_ranks_ok={bool(flag.item())}")
 rc = 0 if flag.item() else 1
 dist.barrier()
 torch.cuda.synchronize()
