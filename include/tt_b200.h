@@ -106,6 +106,22 @@ TT_API int tt_emb_segment_grad_lists(const int32_t *rows, int64_t n_pieces, int6
                               int64_t grad_piece_stride, int dim, int64_t *unique_rows, float *row_grad,
                               int32_t *n_unique, float *sq_norm, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Deferred form of the pair (tt_emb_segment_grad_lists, tt_emb_rowwise_adam): "a deterministic sorted-segment scatter-add
+ * with a fused row-wise optimizer update".  The global-norm clip (training_utils.py:53-54) needs every gradient before
+ * any update, so the work is split differently instead:
+ *   phase 1  tt_emb_segment_grad_lists(..., row_grad = NULL, ...): sort, segments, per-row sums -> only their squares
+ *            (*sq_norm), unique_rows and *n_unique leave the kernel; `workspace` keeps the sorted lists;
+ *   phase 2  tt_emb_segment_adam_lists: forms each row's sum AGAIN (same order, same bits) from the same gradient buffer
+ *            and applies Adam to the row in the same kernel.
+ * A [U, D] row_grad buffer is never written or read: 7 instead of 9 HBM streams of U x D x 4 bytes per step (the
+ * upstream [B, D] gradients are L2-resident).  Between the phases `workspace`, `grad`, `pos_src` and `unique_rows` must
+ * stay untouched; n_positions = n_pieces * piece_len of phase 1; dim in {64, 96, 128, 192, 256}, fp32 table. */
+TT_API int tt_emb_segment_adam_lists(int64_t n_positions, const int32_t *pos_src, const float *grad, int64_t grad_piece_rows,
+                              int64_t grad_piece_stride, int dim, const int64_t *unique_rows, int64_t max_rows,
+                              void *workspace, size_t workspace_bytes, float *table, float *exp_avg, float *exp_avg_sq,
+                              const float *clip_coef, double lr, double beta1, double beta2, double eps,
+                              const int64_t *step_dev, const double *lr_dev, void *stream);
+
 /* Adam on the touched rows only ("lazy" Adam; equals dense Adam the first
  * time a row is touched).  g = row_grad * (*clip_coef) (NULL -> 1).  The step
  * count t is read from *step_dev (so CUDA graphs can replay); lr_dev (nullable,

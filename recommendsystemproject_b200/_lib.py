@@ -42,6 +42,8 @@ _SIGNATURES = {
     "tt_bn_bwd_apply": (c_int, [P, c_int64, P, c_int64, c_int, c_int64, P, P, P, P, c_int, c_int, c_float, P, c_int64, P,
                                 c_int, c_double, P, c_int64, P]),
     "tt_p2p_allgather_small": (c_int, [P, c_int, c_int, c_int, P, c_int64, c_int64, c_int64, P, P]),
+    "tt_emb_segment_adam_lists": (c_int, [c_int64, P, P, c_int64, c_int64, c_int, P, c_int64, P, c_size_t, P, P, P, P, c_double,
+                                          c_double, c_double, c_double, P, P, P]),
     "tt_emb_rowwise_adam": (c_int, [P, c_int, P, P, c_int, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, P, P, P]),
     "tt_emb_scatter_rows": (c_int, [P, c_int, P, P, P, c_int64, P]),
     "tt_sq_norm_accum": (c_int, [P, c_int64, P, P, c_size_t, P]),

@@ -60,13 +60,17 @@ __global__ void seg_heads(const uint32_t *__restrict__ keys, int64_t n, uint32_t
 __global__ void seg_starts(const uint32_t *__restrict__ keys, const int32_t *__restrict__ head,
                            const int32_t *__restrict__ seg_id, int64_t n, uint32_t sentinel,
                            int32_t *__restrict__ seg_start, int64_t *__restrict__ unique_rows,
-                           int32_t *__restrict__ counters) {
+                           int32_t *__restrict__ counters, const int32_t *__restrict__ vals = nullptr,
+                           int32_t *__restrict__ seg_first = nullptr) {
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t k = keys[i];
         if (head[i]) {
             seg_start[seg_id[i]] = static_cast<int32_t>(i);
             unique_rows[seg_id[i]] = static_cast<int64_t>(k);
+            // the segment's first sorted value, next to its start: seg_adam_rows_wide reaches the first gradient row
+            // (most segments have one or two) without the dependent load through sorted_pos
+            if (seg_first) seg_first[seg_id[i]] = vals[i];
         }
         if (k == sentinel && (i == 0 || keys[i - 1] != sentinel)) counters[1] = static_cast<int32_t>(i);
         if (i == n - 1) {
@@ -360,12 +364,76 @@ seg_reduce_rows(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t
     }
 }
 
+// sum of one segment's gradient rows for the "wide" layout (8 lanes per segment, lane l owns float4 columns l, l+8, ...),
+// positions in sorted (= ascending position) order; a long segment adds its chunk partials in chunk order.  ONE function
+// for seg_reduce_rows_wide and seg_adam_rows_wide: the deferred (fused-Adam) form must add the same numbers in the same
+// order as the form that stores row_grad.
+template <int CPL, bool LISTS, bool FIRST = false>
+__device__ __forceinline__ void seg_wide_accumulate(const GradSrc &g, const int32_t *__restrict__ sorted_pos, int p0, int p1,
+                                                    int SEG_CHUNK, const int32_t *__restrict__ chunk_base,
+                                                    const float *__restrict__ partial, int64_t s, int sub,
+                                                    float (&acc)[CPL][4], int32_t first = 0) {   // FIRST: sorted_pos[p0], preloaded
+    constexpr int LPR = 8;
+    const int len = p1 - p0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+    if (len <= SEG_CHUNK) {
+        constexpr int UN = (CPL <= 2) ? 2 : 1;   // positions in flight per lane (register budget: 64)
+        for (int i = p0; i < p1; i += UN) {
+            float4 v[UN][CPL];
+            bool use[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                use[u] = (i + u) < p1;
+                if (use[u]) {
+                    const int32_t p = (FIRST && i + u == p0) ? first : __ldg(sorted_pos + i + u);
+                    int64_t src;
+                    int slot;
+                    const float *grow = seg_grad_row<LISTS>(g, p, slot, src);
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        const int c = sub + LPR * k;
+                        v[u][k] = __ldg(reinterpret_cast<const float4 *>(grow + c * 4));
+                        if (!LISTS && g.mode == TT_POOL_MAX) {
+                            const int4 am = __ldg(reinterpret_cast<const int4 *>(g.argmax + src * g.dim + c * 4));
+                            if (am.x != slot) v[u][k].x = 0.f;
+                            if (am.y != slot) v[u][k].y = 0.f;
+                            if (am.z != slot) v[u][k].z = 0.f;
+                            if (am.w != slot) v[u][k].w = 0.f;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+                if (use[u]) {
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        acc[k][0] += v[u][k].x; acc[k][1] += v[u][k].y; acc[k][2] += v[u][k].z; acc[k][3] += v[u][k].w;
+                    }
+                }
+        }
+    } else {
+        const int nck = (len + SEG_CHUNK - 1) / SEG_CHUNK;
+        const int64_t cb = chunk_base[s];
+        for (int c2 = 0; c2 < nck; ++c2) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const float4 v = *reinterpret_cast<const float4 *>(partial + (cb + c2) * g.dim + (sub + LPR * k) * 4);
+                acc[k][0] += v.x; acc[k][1] += v.y; acc[k][2] += v.z; acc[k][3] += v.w;
+            }
+        }
+    }
+}
+
 // D >= 64: 8 lanes per segment, CPL float4 columns per lane (lane l owns columns l, l+8, ...: every load instruction
 // of a segment is one contiguous 128-byte line), 4 segments per warp and CPL * 2 independent 16-byte loads in flight
 // per lane.  Most segments of a 10M-row table hold one or two positions, so the kernel lives on memory-level
 // parallelism, not on the length of the inner loop.
 // <= 64 registers at D <= 128: 4 blocks = 32 warps per SM (ncu: long_scoreboard-bound at the 2 blocks per SM that 86
 // registers allowed)
+// row_grad == NULL: the deferred form's first phase -- per-segment squares (the gradient norm) only; the update
+// phase (seg_adam_rows_wide) forms the sums again instead of reading them back from HBM.
 template <int CPL, bool LISTS = false>
 __global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2)
 seg_reduce_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
@@ -386,68 +454,100 @@ seg_reduce_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const in
         if (ok) {
             const int p0 = seg_start[s];
             const int p1 = (s + 1 < U) ? seg_start[s + 1] : n_valid;
-            const int len = p1 - p0;
             float acc[CPL][4];
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
-            if (len <= SEG_CHUNK) {
-                constexpr int UN = (CPL <= 2) ? 2 : 1;   // positions in flight per lane (register budget: 64)
-                for (int i = p0; i < p1; i += UN) {
-                    float4 v[UN][CPL];
-                    bool use[UN];
-#pragma unroll
-                    for (int u = 0; u < UN; ++u) {
-                        use[u] = (i + u) < p1;
-                        if (use[u]) {
-                            const int32_t p = __ldg(sorted_pos + i + u);
-                            int64_t src;
-                            int slot;
-                            const float *grow = seg_grad_row<LISTS>(g, p, slot, src);
-#pragma unroll
-                            for (int k = 0; k < CPL; ++k) {
-                                const int c = sub + LPR * k;
-                                v[u][k] = __ldg(reinterpret_cast<const float4 *>(grow + c * 4));
-                                if (!LISTS && g.mode == TT_POOL_MAX) {
-                                    const int4 am = __ldg(reinterpret_cast<const int4 *>(g.argmax + src * g.dim + c * 4));
-                                    if (am.x != slot) v[u][k].x = 0.f;
-                                    if (am.y != slot) v[u][k].y = 0.f;
-                                    if (am.z != slot) v[u][k].z = 0.f;
-                                    if (am.w != slot) v[u][k].w = 0.f;
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < UN; ++u)
-                        if (use[u]) {
-#pragma unroll
-                            for (int k = 0; k < CPL; ++k) {
-                                acc[k][0] += v[u][k].x; acc[k][1] += v[u][k].y; acc[k][2] += v[u][k].z; acc[k][3] += v[u][k].w;
-                            }
-                        }
-                }
-            } else {
-                const int nck = (len + SEG_CHUNK - 1) / SEG_CHUNK;
-                const int64_t cb = chunk_base[s];
-                for (int c2 = 0; c2 < nck; ++c2) {
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        const float4 v = *reinterpret_cast<const float4 *>(partial + (cb + c2) * g.dim + (sub + LPR * k) * 4);
-                        acc[k][0] += v.x; acc[k][1] += v.y; acc[k][2] += v.z; acc[k][3] += v.w;
-                    }
-                }
-            }
+            seg_wide_accumulate<CPL, LISTS>(g, sorted_pos, p0, p1, SEG_CHUNK, chunk_base, partial, s, sub, acc);
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
                 acc[k][0] *= scale; acc[k][1] *= scale; acc[k][2] *= scale; acc[k][3] *= scale;
-                *reinterpret_cast<float4 *>(row_grad + s * g.dim + (sub + LPR * k) * 4) =
-                    make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                if (row_grad)
+                    *reinterpret_cast<float4 *>(row_grad + s * g.dim + (sub + LPR * k) * 4) =
+                        make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
                 sq += acc[k][0] * acc[k][0] + acc[k][1] * acc[k][1] + acc[k][2] * acc[k][2] + acc[k][3] * acc[k][3];
             }
         }
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         if (ok && sub == 0) seg_sq[s] = sq;
+    }
+}
+
+// Deferred form, second phase: segment sum (same order as above) -> Adam on the row, in one kernel.  The sum is formed
+// from the upstream gradient rows again ([B, D] pooled gradients: L2 hits) instead of a [U, D] row_grad buffer that
+// would be written once and read once through HBM (2 x U x D x 4 bytes of the 9 x U x D x 4 the two-kernel form moves).
+// The row's parameter / moment loads are issued BEFORE the gather chain (they depend on the row number only).
+template <int CPL, bool LISTS>
+__global__ void __launch_bounds__(256, 2)
+seg_adam_rows_wide(GradSrc g, const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ seg_start,
+                   const int32_t *__restrict__ chunk_base, const int32_t *__restrict__ counters,
+                   const float *__restrict__ partial, float scale, int SEG_CHUNK, const int64_t *__restrict__ rows,
+                   const int32_t *__restrict__ seg_first, float *__restrict__ table, float *__restrict__ m,
+                   float *__restrict__ v, const float *__restrict__ clip_coef, AdamHyper h,
+                   const int64_t *__restrict__ step_dev) {
+    constexpr int LPR = 8;
+    const int U = counters[0];
+    const int n_valid = counters[1];
+    const float coef = clip_coef ? *clip_coef : 1.0f;
+    float step_size, bc2_sqrt;
+    adam_step_consts(h, step_dev, step_size, bc2_sqrt);
+    const int sub = threadIdx.x % LPR;
+    const int64_t group0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+    const int64_t n_groups = static_cast<int64_t>(gridDim.x) * blockDim.x / LPR;
+    // (row, start, end, first sorted value) of a segment are four independent loads; the NEXT segment's are issued at
+    // the top of an iteration, so that inside an iteration both dependent chains are one load deep: first gradient row
+    // (<- first) and the row's state (<- row).  Measured without this: 3.19 ms against 2.87 ms for the plain Adam kernel
+    // (every 8-lane group sat through seg_start -> sorted_pos -> gradient row before its stores).
+    int64_t r_n = 0;
+    int p0_n = 0, p1_n = 0;
+    int32_t f_n = 0;
+    if (group0 < U) {
+        r_n = rows[group0]; p0_n = seg_start[group0]; f_n = seg_first[group0];
+        p1_n = (group0 + 1 < U) ? seg_start[group0 + 1] : n_valid;
+    }
+    for (int64_t s = group0; s < U; s += n_groups) {
+        const int64_t r = r_n;
+        const int p0 = p0_n, p1 = p1_n;
+        const int32_t first = f_n;
+        const int64_t sn = s + n_groups;
+        if (sn < U) {
+            r_n = rows[sn]; p0_n = seg_start[sn]; f_n = seg_first[sn];
+            p1_n = (sn + 1 < U) ? seg_start[sn + 1] : n_valid;
+        }
+        constexpr bool PREFETCH = CPL <= 4;      // D <= 128: 12 float4 of row state fit next to the accumulators (128 registers)
+        float4 p4[PREFETCH ? CPL : 1], m4[PREFETCH ? CPL : 1], v4[PREFETCH ? CPL : 1];
+        if (PREFETCH) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int64_t o = r * g.dim + (sub + LPR * k) * 4;
+                p4[k] = *reinterpret_cast<const float4 *>(table + o);
+                m4[k] = *reinterpret_cast<const float4 *>(m + o);
+                v4[k] = *reinterpret_cast<const float4 *>(v + o);
+            }
+        }
+        float acc[CPL][4];
+        seg_wide_accumulate<CPL, LISTS, true>(g, sorted_pos, p0, p1, SEG_CHUNK, chunk_base, partial, s, sub, acc, first);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            constexpr int KK = 0;
+            const int kk = PREFETCH ? k : KK;
+            if (!PREFETCH) {
+                const int64_t o = r * g.dim + (sub + LPR * k) * 4;
+                p4[0] = *reinterpret_cast<const float4 *>(table + o);
+                m4[0] = *reinterpret_cast<const float4 *>(m + o);
+                v4[0] = *reinterpret_cast<const float4 *>(v + o);
+            }
+            // (acc * scale) is what the two-kernel form stores as row_grad, (row_grad * coef) what its Adam kernel applies
+            const float gg[4] = {(acc[k][0] * scale) * coef, (acc[k][1] * scale) * coef, (acc[k][2] * scale) * coef,
+                                 (acc[k][3] * scale) * coef};
+            float pp[4] = {p4[kk].x, p4[kk].y, p4[kk].z, p4[kk].w};
+            float mm[4] = {m4[kk].x, m4[kk].y, m4[kk].z, m4[kk].w};
+            float vv[4] = {v4[kk].x, v4[kk].y, v4[kk].z, v4[kk].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) adam_elem(h, step_size, bc2_sqrt, gg[e], pp[e], mm[e], vv[e]);
+            const int64_t o = r * g.dim + (sub + LPR * k) * 4;
+            *reinterpret_cast<float4 *>(m + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            *reinterpret_cast<float4 *>(v + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            *reinterpret_cast<float4 *>(table + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+        }
     }
 }
 
@@ -598,6 +698,7 @@ extern "C" int tt_emb_segment_grad_workspace(int64_t n_pos, int dim, size_t *byt
     add(sizeof(int32_t) * 4);           // counters
     add(sizeof(float) * p.max_chunks * dim);
     add(p.cub_bytes);
+    add(sizeof(int32_t) * n_pos);       // first sorted value of every segment
     *bytes_host = tt::align_up(b, 256) + 256;
     return 0;
 }
@@ -628,6 +729,45 @@ struct KeySrc {
     const int32_t *pos_src;   // list form: per-position float4 gradient offsets (become the sort values)
 };
 
+// the workspace of one segment-gradient call (same carve-up in tt_emb_segment_grad_workspace)
+struct SegWs {
+    uint32_t *keys_in, *keys_out;
+    int32_t *vals_in, *vals_out, *head, *seg_id, *seg_start;
+    float *seg_sq;
+    int32_t *counters;
+    float *partial;
+    void *cub_tmp;
+    int32_t *seg_first;     // first sorted value of every segment (general path)
+    bool ok;
+    size_t used;
+};
+static SegWs seg_carve(void *workspace, size_t workspace_bytes, int64_t n, int dim, const SegPlan &plan) {
+    Workspace ws(workspace, workspace_bytes);
+    SegWs w;
+    w.keys_in = ws.take<uint32_t>(n);
+    w.keys_out = ws.take<uint32_t>(n);
+    w.vals_in = ws.take<int32_t>(n);
+    w.vals_out = ws.take<int32_t>(n);
+    w.head = ws.take<int32_t>(n);
+    w.seg_id = ws.take<int32_t>(n);
+    w.seg_start = ws.take<int32_t>(n + 1);
+    w.seg_sq = ws.take<float>(n);
+    w.counters = ws.take<int32_t>(4);
+    w.partial = ws.take<float>(plan.max_chunks * dim);
+    w.cub_tmp = ws.take<char>(plan.cub_bytes);
+    w.seg_first = ws.take<int32_t>(n);
+    w.ok = ws.ok();
+    w.used = ws.off;
+    return w;
+}
+
+// dims the 8-lane "wide" kernels cover: D / 32 float4 columns per lane
+static inline int seg_wide_cpl(int dim) {
+    const int vpr = dim / 4;
+    const int cpl = (dim % 4 == 0 && vpr % 8 == 0) ? vpr / 8 : 0;
+    return (cpl == 2 || cpl == 3 || cpl == 4 || cpl == 6 || cpl == 8) ? cpl : 0;
+}
+
 template <bool LISTS>
 static int segment_grad_run(const KeySrc &ks, const GradSrc &g, int64_t n, int64_t vocab, float scale,
                             int64_t *unique_rows, float *row_grad, int32_t *n_unique, float *sq_norm, void *workspace,
@@ -635,19 +775,14 @@ static int segment_grad_run(const KeySrc &ks, const GradSrc &g, int64_t n, int64
     const int dim = g.dim;
     const SegPlan plan = seg_plan(n);
 
-    Workspace ws(workspace, workspace_bytes);
-    uint32_t *keys_in = ws.take<uint32_t>(n);
-    uint32_t *keys_out = ws.take<uint32_t>(n);
-    int32_t *vals_in = ws.take<int32_t>(n);
-    int32_t *vals_out = ws.take<int32_t>(n);
-    int32_t *head = ws.take<int32_t>(n);
-    int32_t *seg_id = ws.take<int32_t>(n);
-    int32_t *seg_start = ws.take<int32_t>(n + 1);
-    float *seg_sq = ws.take<float>(n);
-    int32_t *counters = ws.take<int32_t>(4);
-    float *partial = ws.take<float>(plan.max_chunks * dim);
-    void *cub_tmp = ws.take<char>(plan.cub_bytes);
-    if (!ws.ok()) { set_error("segment_grad workspace too small: need %zu have %zu", ws.off, workspace_bytes); return TT_E_WORKSPACE; }
+    const SegWs sw = seg_carve(workspace, workspace_bytes, n, dim, plan);
+    if (!sw.ok) { set_error("segment_grad workspace too small: need %zu have %zu", sw.used, workspace_bytes); return TT_E_WORKSPACE; }
+    uint32_t *keys_in = sw.keys_in, *keys_out = sw.keys_out;
+    int32_t *vals_in = sw.vals_in, *vals_out = sw.vals_out, *head = sw.head, *seg_id = sw.seg_id, *seg_start = sw.seg_start;
+    float *seg_sq = sw.seg_sq;
+    int32_t *counters = sw.counters;
+    float *partial = sw.partial;
+    void *cub_tmp = sw.cub_tmp;
 
     const int threads = 256;
     const unsigned g1 = grid_for(n, threads);
@@ -682,7 +817,8 @@ static int segment_grad_run(const KeySrc &ks, const GradSrc &g, int64_t n, int64
         tmp = plan.cub_bytes;
         e = cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, head, seg_id, static_cast<int>(n), st);
         if (e != cudaSuccess) return cuda_status(e, "cub ExclusiveSum");
-        seg_starts<<<g1, threads, 0, st>>>(keys_out, head, seg_id, n, sentinel, seg_start, unique_rows, counters);
+        seg_starts<<<g1, threads, 0, st>>>(keys_out, head, seg_id, n, sentinel, seg_start, unique_rows, counters, vals_out,
+                                           sw.seg_first);
         TT_LAUNCH_CHECK("seg_starts");
         seg_chunk_counts<<<g1, threads, 0, st>>>(seg_start, counters, n, plan.chunk, n_chunks);
         TT_LAUNCH_CHECK("seg_chunk_counts");
@@ -694,6 +830,10 @@ static int segment_grad_run(const KeySrc &ks, const GradSrc &g, int64_t n, int64
     const bool vec = (dim % 4 == 0) && (g.grad_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(g.grad_out) % 16 == 0) &&
                      (reinterpret_cast<uintptr_t>(row_grad) % 16 == 0) && (g.piece_stride % 4 == 0);
     int rc = 0;
+    if (row_grad == nullptr && !(vec && seg_wide_cpl(dim) != 0)) {
+        set_error("segment_grad without row_grad (deferred form) needs dim in {64, 96, 128, 192, 256} and 16-byte aligned gradient rows");
+        return TT_E_UNSUPPORTED;
+    }
     if (!vec) {
         seg_reduce_rows_scalar<<<grid_for(n * dim, threads), threads, 0, st>>>(g, vals_out, seg_start, counters, scale,
                                                                                 row_grad);
@@ -702,8 +842,8 @@ static int segment_grad_run(const KeySrc &ks, const GradSrc &g, int64_t n, int64
         TT_LAUNCH_CHECK("seg_sq_scalar");
     } else {
         const int vpr = dim / 4;
-        const int cpl = (vpr % 8 == 0) ? vpr / 8 : 0;
-        if (cpl == 2 || cpl == 3 || cpl == 4 || cpl == 6 || cpl == 8) {
+        const int cpl = seg_wide_cpl(dim);
+        if (cpl != 0) {
             if (n > plan.chunk) {
                 seg_reduce_chunks<8, LISTS><<<grid_for(plan.max_chunks * 8, threads), threads, 0, st>>>(
                     g, vals_out, seg_start, chunk_base, counters, plan.chunk, partial);
@@ -770,7 +910,7 @@ extern "C" int tt_emb_segment_grad_lists(const int32_t *rows, int64_t n_pieces, 
                                          int32_t *n_unique, float *sq_norm, void *workspace, size_t workspace_bytes,
                                          void *stream) {
     using namespace tt;
-    TT_CHECK_ARG(rows && grad && unique_rows && row_grad && n_unique && workspace, "null pointer");
+    TT_CHECK_ARG(rows && grad && unique_rows && n_unique && workspace, "null pointer");   // row_grad NULL = deferred form
     TT_CHECK_ARG(n_pieces > 0 && piece_len > 0 && piece_stride >= piece_len && dim > 0 && vocab > 0, "bad size");
     TT_CHECK_ARG(grad_piece_rows > 0 && grad_piece_stride >= grad_piece_rows * dim, "bad gradient piece layout");
     TT_CHECK_ARG(vocab < (int64_t(1) << 31) - 1, "vocab must fit 31 bits");
@@ -780,6 +920,41 @@ extern "C" int tt_emb_segment_grad_lists(const int32_t *rows, int64_t n_pieces, 
     const GradSrc g{grad, dim, nullptr, 1, TT_POOL_SUM, dim, pos_src, grad_piece_rows, grad_piece_stride};
     return segment_grad_run<true>(ks, g, n, vocab, 1.0f, unique_rows, row_grad, n_unique, sq_norm, workspace,
                                   workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tt_emb_segment_adam_lists(int64_t n_positions, const int32_t *pos_src, const float *grad, int64_t grad_piece_rows,
+                                         int64_t grad_piece_stride, int dim, const int64_t *unique_rows, int64_t max_rows,
+                                         void *workspace, size_t workspace_bytes, float *table, float *exp_avg,
+                                         float *exp_avg_sq, const float *clip_coef, double lr, double beta1, double beta2,
+                                         double eps, const int64_t *step_dev, const double *lr_dev, void *stream) {
+    using namespace tt;
+    TT_CHECK_ARG(grad && unique_rows && workspace && table && exp_avg && exp_avg_sq && step_dev, "null pointer");
+    TT_CHECK_ARG(n_positions > 0 && n_positions < (int64_t(1) << 31) - 2 && dim > 0, "bad size");
+    TT_CHECK_ARG(grad_piece_rows > 0 && grad_piece_stride >= grad_piece_rows * dim, "bad gradient piece layout");
+    const int cpl = seg_wide_cpl(dim);
+    if (cpl == 0 || reinterpret_cast<uintptr_t>(grad) % 16 != 0 || grad_piece_stride % 4 != 0) {
+        set_error("tt_emb_segment_adam_lists needs dim in {64, 96, 128, 192, 256} and 16-byte aligned gradient rows");
+        return TT_E_UNSUPPORTED;
+    }
+    if (max_rows <= 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const SegPlan plan = seg_plan(n_positions);
+    const SegWs sw = seg_carve(workspace, workspace_bytes, n_positions, dim, plan);
+    if (!sw.ok) { set_error("segment_grad workspace too small: need %zu have %zu", sw.used, workspace_bytes); return TT_E_WORKSPACE; }
+    const GradSrc g{grad, dim, nullptr, 1, TT_POOL_SUM, dim, pos_src, grad_piece_rows, grad_piece_stride};
+    const AdamHyper hyper = make_adam(lr, beta1, beta2, eps, lr_dev);
+    int64_t blocks = (max_rows + 31) / 32;                      // 32 segments per 256-thread block
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    // seg_id holds the chunk bases after the first phase (segment_grad_run: chunk_base = seg_id)
+#define TT_WIDE_ADAM(C) seg_adam_rows_wide<C, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(                            \
+        g, sw.vals_out, sw.seg_start, sw.seg_id, sw.counters, sw.partial, 1.0f, plan.chunk, unique_rows, sw.seg_first,     \
+        table, exp_avg, exp_avg_sq, clip_coef, hyper, step_dev)
+    if (cpl == 2) TT_WIDE_ADAM(2); else if (cpl == 3) TT_WIDE_ADAM(3); else if (cpl == 4) TT_WIDE_ADAM(4);
+    else if (cpl == 6) TT_WIDE_ADAM(6); else TT_WIDE_ADAM(8);
+#undef TT_WIDE_ADAM
+    TT_LAUNCH_CHECK("seg_adam_rows_wide");
+    return 0;
 }
 
 namespace tt {

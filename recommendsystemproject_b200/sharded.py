@@ -95,6 +95,17 @@ class _CudaShardOps:
         ops._count(7)
 
     @staticmethod
+    def segment_adam_lists(n_pos, pos_src, grad, piece_rows, block_floats, dim, rows, ws, table, m, v, coef, lr, b1, b2, eps,
+                           step_dev, lr_dev=None):
+        """Second phase of the deferred form (include/tt_b200.h, tt_emb_segment_adam_lists): the first phase was
+        segment_grad_lists(..., row_grad=None, ...) over the same buffers."""
+        lib = _lib.load()
+        check(lib.tt_emb_segment_adam_lists(n_pos, _p(pos_src), _p(grad), piece_rows, block_floats, dim, _p(rows), rows.numel(),
+                                            _p(ws), ws.numel(), _p(table), _p(m), _p(v), _p(coef), lr, b1, b2, eps,
+                                            _p(step_dev), _p(lr_dev), _stream()), "tt_emb_segment_adam_lists")
+        ops._count()
+
+    @staticmethod
     def segment_ws_bytes(n_pos, dim):
         lib = _lib.load()
         nbytes = ctypes.c_size_t(0)
@@ -162,6 +173,11 @@ class ShardedTableGroup:
         # ~15 short launches per small table behind the big table's HBM-bound kernels.  TT_SHARD_LANES=0 disables.
         self.parallel_lanes = os.environ.get("TT_SHARD_LANES", "1") != "0"
         self._lanes: Dict = {}
+        # deferred segment gradient: the backward keeps only the sorted lists and the gradient norm, step() forms each
+        # touched row's gradient sum again inside the Adam kernel (no [U, D] row_grad buffer through HBM, and none
+        # allocated).  Per table, when the device ops offer it and the table is fp32 with dim in {64, 96, 128, 192, 256}.
+        # Set before the first lookup (the choice is part of the wire plan); TT_SEG_ADAM_FUSED=0 disables.
+        self.fused_adam = os.environ.get("TT_SEG_ADAM_FUSED", "1") != "0"
 
     @property
     def device(self):
@@ -264,8 +280,11 @@ class ShardedTableGroup:
             n_pos = W * s["cap"]
             pl.pos_src[name] = torch.empty(n_pos, dtype=torch.int32, device=dev)
             ws_bytes = self.ops.segment_ws_bytes(n_pos, t.dim)
+            deferred = (self.fused_adam and hasattr(self.ops, "segment_adam_lists") and t.dim in (64, 96, 128, 192, 256)
+                        and t.weight.dtype == torch.float32)
             pl.seg[name] = dict(rows=torch.empty(n_pos, dtype=torch.int64, device=dev),
-                                row_grad=torch.empty(n_pos, t.dim, dtype=torch.float32, device=dev),
+                                row_grad=None if deferred else torch.empty(n_pos, t.dim, dtype=torch.float32, device=dev),
+                                n_pos=n_pos,
                                 n_unique=torch.zeros(1, dtype=torch.int32, device=dev),
                                 ws=torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev))
         self._plans[key] = pl
@@ -388,6 +407,7 @@ class ShardedTableGroup:
         for name in todo:
             sg = pl.seg[name]
             self.tables[name].pending = (sg["rows"], sg["row_grad"], sg["n_unique"])
+            self.tables[name].pending_plan = (pl, name)       # deferred form: step() reads the lists / gradients again
             self.tables[name].pending_positions = pl.slots[name]["len"] * pl.B
 
     # ------------------------------------------------------------------ optimizer side
@@ -408,6 +428,12 @@ class ShardedTableGroup:
         def adam(t):
             rows, row_grad, n_unique = t.pending
             weight = t.weight.data if isinstance(t.weight, torch.nn.Parameter) else t.weight
+            if row_grad is None:        # deferred form: segment sum + Adam in one kernel over the backward's lists
+                pl, name = t.pending_plan
+                s, sg = pl.slots[name], pl.seg[name]
+                return lambda: self.ops.segment_adam_lists(sg["n_pos"], pl.pos_src[name], pl.g_in, s["vec_rows"], pl.block_floats,
+                                                           t.dim, rows, sg["ws"], weight, t.exp_avg, t.exp_avg_sq, clip_coef, lr,
+                                                           betas[0], betas[1], eps, step_dev, lr_dev)
             return lambda: self.ops.adam(weight, t.exp_avg, t.exp_avg_sq, rows, row_grad, n_unique, clip_coef, lr, betas[0],
                                          betas[1], eps, step_dev, lr_dev)
 

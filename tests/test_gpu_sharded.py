@@ -163,6 +163,7 @@ def test_group_world1_equals_unsharded_kernels_and_oracle():
     ids = _ids(gen, B, L, V, 0)
     up = torch.randn(B, D, generator=gen)
     grp = sharded.ShardedTableGroup(0, 1, DEV)
+    grp.fused_adam = False          # keep the per-row gradients (the deferred form never writes them): inspected below
     wd = w.to(DEV).clone()
     grp.add_table("hist", V, D, ops.POOL_MEAN, 0, wd, wd[0].clone())
     grp.zero_grad()
@@ -199,3 +200,47 @@ def test_group_lookup_under_cuda_graph_replays_with_new_ids():
     g.replay()
     torch.cuda.synchronize()
     assert torch.allclose(out, ops.gather_rows(w, new, "sum", 0), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("D", [64, 128, 256])
+def test_deferred_segment_adam_is_bitwise_the_two_kernel_form(D):
+    """tt_emb_segment_grad_lists(row_grad = NULL) + tt_emb_segment_adam_lists (the per-row gradient sum is formed again
+    inside the Adam kernel) against segment reduction -> row_grad -> tt_emb_rowwise_adam: same additions in the same
+    order, so weights, both moments and the gradient norm must be BITWISE equal -- pooled table with heavy-hitter rows
+    (segments far longer than a chunk) and a single-id table, two steps."""
+    from recommendsystemproject_b200 import ops, sharded
+    gen = torch.Generator().manual_seed(17 + D)
+    V, B, L = 3001, 600, 50
+    w = torch.randn(V, D, generator=gen)
+    w1 = torch.randn(V, D, generator=gen)
+    ids = _ids(gen, B, L, V, 0)
+    ids[:, :4] = 7                                   # one row with 2400 positions, more with dozens
+    ids[::3, 5] = 11
+    ids1 = torch.randint(1, V, (B,), generator=gen)
+    ids1[::5] = 42
+    up = torch.randn(2, B, D, generator=gen).to(DEV)
+    results = []
+    for fused in (False, True):
+        grp = sharded.ShardedTableGroup(0, 1, DEV)
+        grp.fused_adam = fused
+        wd, w1d = w.to(DEV).clone(), w1.to(DEV).clone()
+        grp.add_table("hist", V, D, ops.POOL_MEAN, 0, wd, wd[0].clone())
+        grp.add_table("uid", V, D, ops.POOL_NONE, 0, w1d, w1d[0].clone())
+        grp.init_state()
+        step_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+        coef = torch.tensor([0.37], device=DEV)
+        norms = []
+        for k in range(2):
+            grp.zero_grad()
+            out = grp.lookup({"hist": ids.to(DEV), "uid": ids1.to(DEV)})
+            ((out["hist"] * up[0]).sum() + (out["uid"] * up[1]).sum() * (k + 1)).backward()
+            grp.check_flags()
+            assert (grp.tables["hist"].pending[1] is None) == fused
+            norms.append(grp.sq_terms.clone())
+            step_dev += 1
+            grp.step(coef, 1e-2, step_dev)
+        results.append((wd, w1d, grp.tables["hist"].exp_avg, grp.tables["hist"].exp_avg_sq, grp.tables["uid"].exp_avg,
+                        grp.tables["uid"].exp_avg_sq, *norms))
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
+    assert not torch.equal(results[0][0], w.to(DEV))        # the step did move the table
