@@ -303,7 +303,51 @@ def kernel_rooflines(peaks, flush, quick=False):
                 "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": alg / ms / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg,
                 "traffic": None, "traffic_note": "ncu dram read+write for this shape: profiles/r1_hot_kernels_ncu.md (17.27 GB)"})
-    del table, m, v, ids, g, rows, row_grad, res
+    del m, v, rows, row_grad, res
+    torch.cuda.empty_cache()
+    # --- the same table through the row-sharded group at W = 1 (the path of the C3 step): deferred segment gradient --
+    # the backward keeps the sorted lists + the norm, step() forms each row's sum again inside the Adam kernel
+    try:
+        from recommendsystemproject_b200 import sharded
+        grp = sharded.ShardedTableGroup(0, 1, dev)
+        grp.add_table("hist", V, D, ops.POOL_MEAN, 0, table, table[0].clone())
+        grp.init_state()
+        tb, ts, U2 = [], [], U
+        for it in range(6):
+            grp.zero_grad()
+            loss = (grp.lookup({"hist": ids})["hist"] * g).sum()
+            flush()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            loss.backward()
+            ev[1].record()
+            if it == 0:
+                U2 = int(grp.tables["hist"].pending[2].item())
+            step += 1
+            grp.step(coef, 5e-4, step)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                tb.append(ev[0].elapsed_time(ev[1]))
+                ts.append(ev[1].elapsed_time(ev[2]))
+        deferred = any(sg["row_grad"] is None for pl in grp._plans.values() for sg in pl.seg.values())
+        ms_b, ms_s = sum(tb) / len(tb), sum(ts) / len(ts)
+        alg_b = n_valid * 8 + B * D * 4 + U2 * 8          # int32 rows + gradient offsets per entry, [B, D] gradients, unique rows out
+        alg_s = U2 * (D * 4 * 6 + 8 + 8) + n_valid * 4    # table / exp_avg / exp_avg_sq read + written, row ids, segment bounds, sorted entries
+        out.append({"kernel": "owner-side table backward of the sharded path (grad pack + keys + cub radix sort + scans + "
+                              + ("norm-only segment reduction: deferred form)" if deferred else "seg_reduce_rows_wide)"),
+                    "workload": f"same ids through ShardedTableGroup at W=1, U={U2}", "bound": "hbm", "ms": ms_b,
+                    "achieved": alg_b / ms_b / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_b / ms_b / 1e6 / peaks["hbm_gbs"],
+                    "alg_bytes": alg_b, "traffic": None})
+        out.append({"kernel": ("seg_adam_rows_wide (segment sum + row-wise Adam in ONE kernel, no row_grad buffer)" if deferred
+                               else "rowwise_adam_kernel via the group"),
+                    "workload": f"U={U2} rows x D={D}: 6 HBM streams of U x D x 4 bytes (two-kernel form: 9 incl. row_grad write + read)",
+                    "bound": "hbm", "ms": ms_s, "achieved": alg_s / ms_s / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": alg_s / ms_s / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg_s, "traffic": None})
+        del grp, loss
+    except Exception as ex:  # noqa: BLE001
+        out.append({"kernel": "sharded-path segment gradient + Adam", "error": repr(ex)})
+    del table, ids, g
     torch.cuda.empty_cache()
     # --- C4 fused CE, tcgen05/TMA bf16 path, forward + backward: the B x (B+H) logits live only in TMEM
     Bc, Hc, Dc = (8192, 1024, 128) if quick else (65536, 4096, 128)
