@@ -26,8 +26,16 @@ def main():
             if i - prev > 50:
                 starts.append(i)
             prev = i
-    s0, s1 = starts[-2], starts[-1]
-    step = rows[s0:s1]
+    if len(starts) >= 2:
+        s0, s1 = starts[-2], starts[-1]
+        step = rows[s0:s1]
+    else:
+        # a short capture (`--launch-skip N -c M` with M a little above one step): the steps are identical, so any
+        # window of one period holds one step's launches.  The period = the smallest shift that maps the list onto itself.
+        period = next((p for p in range(50, len(names) - 4) if names[:len(names) - p] == names[p:]), None)
+        if period is None:
+            raise SystemExit("no complete step and no period found in the launch list")
+        step = rows[:period]
     unit = step[0][2]
     scale = 1e-3 if unit in ("ns", "nsecond") else 1.0
     total = sum(v for _, v, _ in step) * scale
