@@ -334,11 +334,15 @@ def kernel_rooflines(peaks, flush, quick=False):
         ms_b, ms_s = sum(tb) / len(tb), sum(ts) / len(ts)
         alg_b = n_valid * 8 + B * D * 4 + U2 * 8          # int32 rows + gradient offsets per entry, [B, D] gradients, unique rows out
         alg_s = U2 * (D * 4 * 6 + 8 + 8) + n_valid * 4    # table / exp_avg / exp_avg_sq read + written, row ids, segment bounds, sorted entries
-        out.append({"kernel": "owner-side table backward of the sharded path (grad pack + keys + cub radix sort + scans + "
-                              + ("norm-only segment reduction: deferred form)" if deferred else "seg_reduce_rows_wide)"),
-                    "workload": f"same ids through ShardedTableGroup at W=1, U={U2}", "bound": "hbm", "ms": ms_b,
-                    "achieved": alg_b / ms_b / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_b / ms_b / 1e6 / peaks["hbm_gbs"],
-                    "alg_bytes": alg_b, "traffic": None})
+        ms_t = ms_b + ms_s
+        out.append({"kernel": "table backward + update through the sharded path: grad pack + keys + cub radix sort + scans + "
+                              + ("norm-only segment reduction, then segment sum + Adam in one kernel (deferred form)" if deferred
+                                 else "seg_reduce_rows_wide + rowwise_adam_kernel"),
+                    "workload": f"same ids through ShardedTableGroup at W=1, U={U2}", "bound": "hbm", "ms": ms_t, "backward_ms": ms_b,
+                    "step_ms": ms_s, "achieved": (alg_b + alg_s) / ms_t / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": (alg_b + alg_s) / ms_t / 1e6 / peaks["hbm_gbs"], "alg_bytes": alg_b + alg_s, "traffic": None,
+                    "note": "strict bytes: list entries + [B, D] gradients + six streams of U x D x 4 (row state read + written); the "
+                            "backward half is sort / L2-gather bound and moves almost nothing through HBM (profiles/r2b_new_kernels_ncu.md)"})
         out.append({"kernel": ("seg_adam_rows_wide (segment sum + row-wise Adam in ONE kernel, no row_grad buffer)" if deferred
                                else "rowwise_adam_kernel via the group"),
                     "workload": f"U={U2} rows x D={D}: 6 HBM streams of U x D x 4 bytes (two-kernel form: 9 incl. row_grad write + read)",
