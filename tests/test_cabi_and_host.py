@@ -132,3 +132,13 @@ def test_torch_custom_ops_are_registered_and_cuda_only():
         assert s.shape == (4, 10) and s.dtype == torch.float64 and i.dtype == torch.int64
     with pytest.raises((NotImplementedError, RuntimeError)):
         ns.gather_pool(torch.zeros(10, 8), torch.zeros(3, 2, dtype=torch.int64), ops.POOL_SUM, -1)
+
+
+def test_loss_kernel_host_rules():
+    """Pure host logic of the tensor-core loss: the declared id range and the single-pass range rule (include/tt_b200.h:
+    |u||w| / T * log2(e) <= 96 for unit-norm embeddings <=> T >= 0.0155 with the rounding margin)."""
+    from recommendsystemproject_b200 import ops
+    assert [ops.id_bits_for(v) for v in (1, 2, 3, 256, 257, 10_000_001, 100_000_001)] == [1, 1, 2, 8, 9, 24, 27]
+    assert ops.CE_FLAG_ID_RANGE == 8 and ops.CE_FLAG_LOGIT_RANGE == 16
+    if ops.SINGLE_PASS_DEFAULT:
+        assert ops.single_pass_ok(0.05) and ops.single_pass_ok(0.0155) and not ops.single_pass_ok(0.015)
