@@ -582,6 +582,8 @@ def c3_dominant_kernel(B_loc, B_glob, D, peaks, dev, temperature=0.05, v_item=10
             "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "peak_sustained": peaks["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["bf16_tflops"],
             "frac_of_sustained": flops / ms / 1e9 / peaks["bf16_tflops_sustained"], "alg_flops": flops, "traffic": None,
+            "traffic_note": "not measured in this run; ncu --set full at the 65536 x 65536 shape (profiles/r2b_new_kernels_ncu.md): DRAM read + "
+                            "write 35.8 MB (forward + dU pass) and 37.3 MB (dI pass) per launch -- the operands stay in L2, the logits in TMEM",
             "l2": "operands (B x D bf16, <= 17 MB) are L2-resident by design; inputs are not flushed between repetitions",
             "note": "algorithmic flops = 2 (fwd) + 4 (bwd) x B_loc x B_glob x D; the logits recomputed by the dI pass (and, in the "
                     "three-pass form, by the dU pass) are not counted"}
