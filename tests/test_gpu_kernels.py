@@ -445,7 +445,7 @@ def test_ce_tc_backward_matches_oracle_on_bf16_rounded_inputs(B, D, N, H, ids):
         close(hnd.grad, dhn_f, "dHN", rel=3e-2, elem=5e-2)
 
 
-def test_ce_tc_backward_large_properties():
+def test_ce_tc_backward_large_against_this_librarys_fp32_path():
     """B=8192, H=1024 (a 300 MB logit matrix if it were materialised) through the tensor-core fwd+bwd, compared
     with this library's exact fp32 SIMT path on the same inputs (itself oracle-checked at small sizes): loss within
     1e-2, every gradient within 3e-2 relative Frobenius error (bf16 operands + bf16 probabilities)."""
@@ -602,7 +602,7 @@ def test_topk_tc_history_mask_with_sampled_thresholds(Bq):
         assert torch.allclose(s_, s32, atol=1e-12)
 
 
-def test_topk_tc_equals_fp32_path_at_scale():
+def test_topk_tc_equals_this_librarys_fp32_path_at_scale():
     """Q=2048 x N=400k (an 3.3 GB score matrix if materialised): the tensor-core path and the fp32 SIMT path of this
     library must return identical rows (both claim the oracle's answer; the fp32 path is oracle-checked above)."""
     gen = torch.Generator(device=DEV).manual_seed(21)
