@@ -183,6 +183,10 @@ class ShardedTrainStep:
                 dist.all_reduce(bad, op=dist.ReduceOp.MAX)
             if not (self.single_pass and float(bad) > 0):
                 break
+            if not self.restore_tables and getattr(model, "shard_group", None) is not None and model.shard_group.tables:
+                raise ops.TTError("ShardedTrainStep: the towers' embeddings are outside the single-pass loss kernel's range and the "
+                                  "warm-up steps already updated the row-sharded tables (restore_tables=False); rebuild the model "
+                                  "and pass single_pass-incompatible towers through TT_CE_SINGLE_PASS=0")
             self.single_pass = False
             self.loss_flags.zero_()
         self.graph = None
