@@ -158,7 +158,9 @@ TT_API int tt_adam_flat(float *param, const float *grad, float *exp_avg, float *
  * item_ids (nullable): in-batch logits with item_ids[b]==item_ids[j], b!=j
  * are set to -1e9 after scaling.  hn_rows [B,N,D] is the reference's per-row
  * form; pool [H,D] is the shared-pool form (== hn_rows = pool expanded).
- * nan_flags bits: 1 user, 2 item, 4 hard negative (device int, OR-ed).
+ * nan_flags bits (device int, OR-ed): 1 NaN in user rows, 2 in item rows, 4 in hard negatives; tensor-core entry points also
+ * 8 = an item id outside the declared id range (tt_ce_fwd_tc_rect_bits), 16 = logits outside the single-pass form's range
+ * (tt_ce_fwd_tc_fused).
  * fp32 variant: exact SIMT path.  bf16 variant: tcgen05/TMA tensor-core path
  * (requires D == 64 or 128 and 16-byte aligned rows).
  * ---------------------------------------------------------------------- */
